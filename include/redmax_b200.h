@@ -1,0 +1,176 @@
+/*
+ * redmax_b200.h -- C ABI of the B200-native batched RedMax stepper.
+ *
+ * This is the drop-in boundary for the hot path of sueda/redmax `matlab-diff`: the time loop of
+ * driverRedMaxBDF1.m:57-91 / driverRedMaxBDF2.m:57-125 (simLoop + newton + evalBDF* + computeValues and
+ * every +redmax Joint/Body/Force method they call) and of driverRedMaxAdjointBDF1/2.m (simLoop + newton +
+ * Task*.calcStep/calcFinal), run for B independent rollouts on the GPU.  The reference has no FFI layer;
+ * the binding a maintainer adds is a MEX gateway (matlab/redmax_mex.cpp) that passes
+ * mxGetDoubles() pointers straight into these functions.  The same symbols are driven from Python (ctypes)
+ * by redmax_b200/_ffi.py for every test and benchmark.
+ *
+ * Conventions
+ *   - All matrices are column-major float64 exactly as MATLAB stores them; the batch is the trailing
+ *     dimension (q0 is nr x B, q_out is nr x nsteps x B).
+ *   - Joints are listed parents-before-children, as the reference requires (Joint.m:134-146).  Reduced
+ *     indices follow the reference's leaf-to-root numbering (Scene.m:69-71): the LAST joint in the list owns
+ *     q(1); the library computes that numbering itself from `ndof` implied by `jtype`.
+ *   - Host-pointer entry points copy H2D/D2H internally and block until done.  `_dev` entry points take
+ *     device pointers on the current CUDA device and enqueue on the given stream without synchronising.
+ *   - Errors: 0 on success, negative RMX_E* otherwise; rmx_last_error() returns a message.  No exceptions
+ *     cross the ABI.  Not re-entrant per scene handle (MATLAB calls from its single main thread).
+ *   - There is no CPU fallback: every compute entry point fails with RMX_ENOGPU when no CUDA device exists.
+ */
+#ifndef REDMAX_B200_H
+#define REDMAX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RMX_VERSION 100
+
+/* error codes */
+#define RMX_OK 0
+#define RMX_EINVAL (-1)  /* bad argument / unsupported scene */
+#define RMX_ENOGPU (-2)  /* no CUDA device / driver */
+#define RMX_ECUDA (-3)   /* CUDA runtime error (message in rmx_last_error) */
+#define RMX_ENOMEM (-4)
+#define RMX_ELIMIT (-5)  /* scene exceeds kernel limits (n <= 128 joints) */
+
+/* joint types (matlab-diff/+redmax/JointFixed.m, JointRevolute.m) */
+#define RMX_JOINT_FIXED 0
+#define RMX_JOINT_REVOLUTE 1
+
+/* integrators (driverRedMaxBDF1.m, driverRedMaxBDF2.m) */
+#define RMX_SCHEME_BDF1 1
+#define RMX_SCHEME_BDF2 2 /* one SDIRK2 step (two sub-solves) then BDF2, driverRedMaxBDF2.m:62-107 */
+
+/* Newton linear solve */
+#define RMX_LINSOLVE_LU 0  /* in-block partial-pivot LU == MATLAB `H\g` / lu(H,'vector') (parity path) */
+#define RMX_LINSOLVE_PCG 1 /* in-block preconditioned Krylov solve, projected block-Jacobi preconditioner
+                              after c++/PCG Solver.cpp:81 + ConstraintJoint.cpp:1236,1455 */
+
+/* per-rollout status bits (reference prints and continues, driverRedMaxBDF1.m:118-121,135-138,150-153) */
+#define RMX_ST_DIVERGED 1  /* 'Newton diverged'            (||dx|| > dxMax) in some step */
+#define RMX_ST_MAXITER 2   /* 'Newton did not converge'    (iter >= iterMax) in some step */
+#define RMX_ST_LSFAIL 4    /* line search exhausted iterLsMax halvings in some step (silent in reference) */
+#define RMX_ST_NAN 8       /* non-finite state produced */
+
+/* tau layout for rmx_rollout */
+#define RMX_TAU_NONE 0     /* tau == NULL: joint.tau = 0 */
+#define RMX_TAU_CONST 1    /* tau is nr x B: constant over the rollout (TaskBDF1PointPos.applyStep) */
+#define RMX_TAU_PER_STEP 2 /* tau is nr x nsteps x B */
+
+/*
+ * Flattened +redmax scene (what scenesRedMax.m builds with redmax.Scene / BodyCuboid / JointRevolute /
+ * JointFixed / ForceGroundCuboid after scene.init(), Scene.m:59-119).  All pointers are host pointers and are
+ * copied by rmx_scene_create.
+ */
+typedef struct rmx_scene_desc {
+    int32_t n;               /* number of joints == number of bodies (Scene.m:64) */
+    const int32_t* parent;   /* [n] index of parent joint, -1 for a root; parent[j] < j */
+    const int32_t* jtype;    /* [n] RMX_JOINT_* */
+    const double* E0_pj;     /* [16*n] joint wrt parent joint at q=0   (Joint.setJointTransform, Joint.m:95) */
+    const double* E0_ji;     /* [16*n] body wrt joint                  (Body.setBodyTransform, Body.m:46) */
+    const double* axis;      /* [3*n]  revolute axis, unit length      (JointRevolute.m:14); ignored if fixed */
+    const double* I_i;       /* [6*n]  diagonal body inertia [Ixx Iyy Izz m m m] (se3.inertiaCuboid, se3.m:366) */
+    const double* sides;     /* [3*n]  cuboid side lengths             (BodyCuboid.m:13) */
+    const double* stiffness; /* [n] Joint.m:102 */
+    const double* damping;   /* [n] Joint.m:108 */
+    const double* qRest;     /* [n] rest angle = q at scene.init()     (Joint.m:157); ignored if fixed */
+    const double* qLimL;     /* [n] Joint.m:114  (default -1e8) */
+    const double* qLimU;     /* [n] Joint.m:119  (default  1e8) */
+    const double* qLimK;     /* [n] Joint.m:124  (default  1e8) */
+    const double* qLimD;     /* [n] Joint.m:129  (default  0)   */
+    double grav[3];          /* Scene.m:48 */
+    int32_t nground;         /* number of ForceGroundCuboid forces (at most one per body) */
+    const int32_t* ground_body; /* [nground] body (== joint) index      (ForceGroundCuboid.m:18) */
+    const double* ground_E;  /* [16*nground] ground frame, Z-up        (ForceGroundCuboid.m:29) */
+    const double* ground_kn; /* [nground] normal stiffness             (ForceGroundCuboid.m:34) */
+    const double* ground_kt; /* [nground] tangential stiffness */
+    const double* ground_kd; /* [nground] damping                      (ForceGroundCuboid.m:40) */
+    const double* ground_mu; /* [nground] friction coefficient         (ForceGroundCuboid.m:45) */
+} rmx_scene_desc;
+
+/* Solver constants hard-coded in the reference's newton() (driverRedMaxBDF1.m:95-98;
+ * driverRedMaxAdjointBDF1.m:106-108).  rmx_opts_default() fills the reference's values. */
+typedef struct rmx_opts {
+    int32_t scheme;          /* RMX_SCHEME_* */
+    int32_t nsteps;          /* Scene.m:117  nsteps = ceil(tEnd/h) */
+    double h;                /* Scene.m:38 */
+    double tol;              /* 1e-9 */
+    double dxMax;            /* 1e3 */
+    int32_t iterMaxFactor;   /* forward: iterMax = 10*nr; adjoint driver: 5*nr */
+    int32_t iterLsMax;       /* 20 */
+    int32_t linsolve;        /* RMX_LINSOLVE_* */
+    int32_t ngpus;           /* host-pointer entry points only: shard the batch over this many devices (>=1) */
+    int32_t tau_mode;        /* RMX_TAU_* */
+    int32_t reserved;
+} rmx_opts;
+
+/* TaskBDF1PointPos / TaskBDF2PointPos (matlab-diff/+redmax/TaskBDF1PointPos.m:27-55) */
+typedef struct rmx_task_pointpos {
+    int32_t body;            /* task body (== joint) index, setBody */
+    int32_t reserved;
+    double xlocal[3];        /* setPoint */
+    double t_target;         /* setTime: objective sampled when |t_target - t| < 1e-6 (TaskBDF1PointPos.m:75) */
+    double pscale;           /* setScale */
+    double wreg;             /* setWeights(wreg, wpos) */
+    double wpos;
+} rmx_task_pointpos;
+
+typedef struct rmx_scene rmx_scene;
+
+int rmx_version(void);
+const char* rmx_last_error(void);
+int rmx_device_count(void);
+
+void rmx_opts_default(rmx_opts* o, int32_t scheme, int32_t adjoint);
+
+/* Scene.init() + flattening.  Replaces the object graph walked by Joint.update/computeJacobian etc. */
+int rmx_scene_create(const rmx_scene_desc* d, rmx_scene** out);
+void rmx_scene_destroy(rmx_scene* s);
+int rmx_scene_nr(const rmx_scene* s); /* redmax.Scene.countR(), Scene.m:411 */
+int rmx_scene_nm(const rmx_scene* s); /* redmax.Scene.countM(), Scene.m:398 */
+
+/* Forward rollouts: replaces simLoop(scene) of driverRedMaxBDF1.m:57 / driverRedMaxBDF2.m:57 for B scenes
+ * that differ in (q0, qdot0, tau).  q_out/qdot_out[:, k, b] = history(k+1).q/.qdot (Scene.m:136-137).
+ * status: B x int32 (RMX_ST_* bits).  iters: 2 x B int32 = total Newton iterations, total residual-only
+ * (line-search) evaluations; may be NULL.  qdot_out may be NULL. */
+int rmx_rollout(rmx_scene* s, const rmx_opts* o, int64_t B, const double* q0, const double* qdot0,
+                const double* tau, double* q_out, double* qdot_out, int32_t* status, int32_t* iters);
+int rmx_rollout_dev(rmx_scene* s, const rmx_opts* o, int64_t B, const double* q0, const double* qdot0,
+                    const double* tau, double* q_out, double* qdot_out, int32_t* status, int32_t* iters,
+                    void* cuda_stream);
+
+/* Objective + gradient: replaces taskObjective(p,scene) of driverRedMaxAdjointBDF1.m:39 / ...BDF2.m:39
+ * (scene.reset, task.init, adjoint simLoop with newton:105, saveHistory tape, task.calcStep, task.calcFinal).
+ * p: np x B with np == nr (TaskBDF1PointPos.m:18-24); xtarget: 3 x B; P: B; dPdp: np x B;
+ * q_out (nr x nsteps x B) optional. */
+int rmx_rollout_adjoint(rmx_scene* s, const rmx_opts* o, const rmx_task_pointpos* t, int64_t B,
+                        const double* q0, const double* qdot0, const double* p, const double* xtarget,
+                        double* P, double* dPdp, double* q_out, int32_t* status);
+int rmx_rollout_adjoint_dev(rmx_scene* s, const rmx_opts* o, const rmx_task_pointpos* t, int64_t B,
+                            const double* q0, const double* qdot0, const double* p, const double* xtarget,
+                            double* P, double* dPdp, double* q_out, int32_t* status, void* cuda_stream);
+/* bytes of device scratch (the adjoint tape) rmx_rollout_adjoint* needs for a batch of B */
+int64_t rmx_adjoint_tape_bytes(const rmx_scene* s, const rmx_opts* o, int64_t B);
+
+/* Test hook (B = 1, host pointers): one evaluation of the implicit-step residual and its Jacobian,
+ *   g = M*dqtmp - cK*f,  H = M - cD*D - cK*K + sum_i dMdq(:,:,i)*dqtmp      (driverRedMaxBDF1.m:173-185)
+ * at state (q, qdot) with qdot = beta*(q - const), i.e. cD = cK*beta.  Any of g,H,M,D,f may be NULL.
+ * H, M, D are nr x nr column-major; g, f are nr. */
+int rmx_eval(rmx_scene* s, const double* q, const double* qdot, const double* dqtmp, const double* tau,
+             double cK, double beta, double* g, double* H, double* M, double* D, double* f);
+
+/* Scene.saveHistory energies (Scene.m:155-160; Joint.m:616, Body.m:167, ForceGroundCuboid.m:156) for B states:
+ * T, V: B each. */
+int rmx_energies(rmx_scene* s, int64_t B, const double* q, const double* qdot, double* T, double* V);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REDMAX_B200_H */

@@ -1661,10 +1661,14 @@ def run_forward(scene, scheme, q0=None, qdot0=None, tau=None, nsteps=None, stats
         for j in scene.joints:
             j.tau = np.asarray(tau, dtype=float)[j.idxR].copy()
     nsteps = scene.nsteps if nsteps is None else nsteps
-    if scheme == 1:
-        sim_loop_bdf1(scene, nsteps, stats)
-    else:
-        sim_loop_bdf2(scene, nsteps, stats)
+    task, scene.task = scene.task, None  # forward drivers know no task (driverRedMaxBDF1.m)
+    try:
+        if scheme == 1:
+            sim_loop_bdf1(scene, nsteps, stats)
+        else:
+            sim_loop_bdf2(scene, nsteps, stats)
+    finally:
+        scene.task = task
     qs = np.array([r['q'] for r in scene.history[:nsteps]])
     qds = np.array([r['qdot'] for r in scene.history[:nsteps]])
     return qs, qds

@@ -1,0 +1,16 @@
+"""redmax_b200 -- B200-native batched RedMax stepper behind the reference's +redmax Scene/Joint/Body API.
+
+Host mirror of the object API (scene.py), scene factory (scenes.py), reference-named drivers (drivers.py) and the
+ctypes binding of the C ABI (_ffi.py) over the CUDA library built from csrc/.  No CPU compute path exists.
+"""
+from ._ffi import (RMX_LINSOLVE_LU, RMX_LINSOLVE_PCG, RMX_SCHEME_BDF1, RMX_SCHEME_BDF2, RMX_ST_DIVERGED,
+                   RMX_ST_LSFAIL, RMX_ST_MAXITER, RMX_ST_NAN, RmxError)
+from .scene import (Body, BodyCuboid, ForceGroundCuboid, Joint, JointFixed, JointRevolute, Scene,
+                    TaskBDF1PointPos, TaskBDF2PointPos, inertiaCuboid)
+from .scenes import BDF1, BDF2, chain_scene, hand_scene, scenesRedMax, synthetic_inputs
+
+__all__ = [
+    'Scene', 'Body', 'BodyCuboid', 'Joint', 'JointRevolute', 'JointFixed', 'ForceGroundCuboid',
+    'TaskBDF1PointPos', 'TaskBDF2PointPos', 'inertiaCuboid', 'scenesRedMax', 'chain_scene', 'hand_scene',
+    'synthetic_inputs', 'BDF1', 'BDF2', 'RmxError',
+]

@@ -1,0 +1,520 @@
+// rmx_api.cu -- host side of the C ABI declared in include/redmax_b200.h.
+//
+// Scene flattening follows Scene.init (matlab-diff/+redmax/Scene.m:59-119): joints listed parents-first,
+// reduced indices assigned leaf-to-root (Scene.m:69-71 + Joint.countDofs, Joint.m:149).  Internally joints are
+// renumbered in DFS preorder so that every subtree is a contiguous index range.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/redmax_b200.h"
+#include "rmx_adjoint.cuh"
+#include "rmx_rollout.cuh"
+
+using namespace rmx;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CUDA_TRY(x)                                                                                      \
+    do {                                                                                                 \
+        cudaError_t e_ = (x);                                                                            \
+        if (e_ != cudaSuccess) {                                                                         \
+            cudaGetLastError();                                                                          \
+            return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ? RMX_ENOGPU : RMX_ECUDA, \
+                        std::string(#x) + ": " + cudaGetErrorString(e_));                                \
+        }                                                                                                \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+struct DevCopy {
+    JointConst* jc = nullptr;
+    int* ends = nullptr;
+    cudaStream_t stream = nullptr;
+    DevBuf buf[12];
+};
+
+struct rmx_scene {
+    int n = 0, nr = 0, nm = 0;
+    int is_chain = 0, has_ground = 0;
+    double grav[3] = {0, 0, 0};
+    std::vector<JointConst> jc;   // internal (preorder) order
+    std::vector<int> ends_list;
+    std::vector<int> user2int;    // user joint index -> internal index
+    std::map<int, DevCopy> dev;   // per CUDA device
+};
+
+extern "C" int rmx_version(void) { return RMX_VERSION; }
+extern "C" const char* rmx_last_error(void) { return g_err.c_str(); }
+extern "C" int rmx_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" void rmx_opts_default(rmx_opts* o, int32_t scheme, int32_t adjoint) {
+    if (!o) return;
+    std::memset(o, 0, sizeof(*o));
+    o->scheme = scheme;
+    o->nsteps = 100;          // ceil(tEnd/h) with Scene.m:38,41 defaults
+    o->h = 1e-2;              // Scene.m:41
+    o->tol = 1e-9;            // driverRedMaxBDF1.m:95
+    o->dxMax = 1e3;           // :96
+    o->iterMaxFactor = adjoint ? 5 : 10;  // :97 ; driverRedMaxAdjointBDF1.m:108
+    o->iterLsMax = 20;        // :98
+    o->linsolve = RMX_LINSOLVE_LU;
+    o->ngpus = 1;
+    o->tau_mode = RMX_TAU_NONE;
+}
+
+static void colmajor4_to_Rp(const double* E, double* R, double* p) {
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) R[3 * r + c] = E[4 * c + r];
+        p[r] = E[12 + r];
+    }
+}
+
+extern "C" int rmx_scene_create(const rmx_scene_desc* d, rmx_scene** out) {
+    if (!d || !out) return fail(RMX_EINVAL, "rmx_scene_create: null argument");
+    *out = nullptr;
+    const int n = d->n;
+    if (n < 1) return fail(RMX_EINVAL, "rmx_scene_create: n < 1");
+    if (n > 128) return fail(RMX_ELIMIT, "rmx_scene_create: n > 128 joints not supported by the in-block solver");
+    if (!d->parent || !d->jtype || !d->E0_pj || !d->E0_ji || !d->axis || !d->I_i || !d->sides)
+        return fail(RMX_EINVAL, "rmx_scene_create: missing required array");
+    for (int j = 0; j < n; ++j) {
+        if (d->parent[j] >= j || d->parent[j] < -1)
+            return fail(RMX_EINVAL, "rmx_scene_create: joints must be listed parents-before-children (Joint.m:134)");
+        if (d->jtype[j] != RMX_JOINT_FIXED && d->jtype[j] != RMX_JOINT_REVOLUTE)
+            return fail(RMX_EINVAL, "rmx_scene_create: only JointFixed and JointRevolute are on the hot path");
+    }
+    rmx_scene* s = new rmx_scene();
+    s->n = n;
+    // reference numbering: countDofs is called for i = n..1 (Scene.m:69-71)
+    std::vector<int> idxR(n, -1);
+    int nr = 0;
+    for (int j = n - 1; j >= 0; --j) {
+        if (d->jtype[j] == RMX_JOINT_REVOLUTE) idxR[j] = nr++;
+    }
+    s->nr = nr;
+    s->nm = 6 * n;
+    if (nr < 1) {
+        delete s;
+        return fail(RMX_EINVAL, "rmx_scene_create: scene has no degrees of freedom");
+    }
+    // DFS preorder
+    std::vector<std::vector<int>> children(n);
+    std::vector<int> roots;
+    for (int j = 0; j < n; ++j) {
+        if (d->parent[j] < 0)
+            roots.push_back(j);
+        else
+            children[d->parent[j]].push_back(j);
+    }
+    std::vector<int> order;  // internal -> user
+    order.reserve(n);
+    {
+        std::vector<int> stack;
+        for (int ri = (int)roots.size() - 1; ri >= 0; --ri) stack.push_back(roots[ri]);
+        while (!stack.empty()) {
+            int j = stack.back();
+            stack.pop_back();
+            order.push_back(j);
+            for (int ci = (int)children[j].size() - 1; ci >= 0; --ci) stack.push_back(children[j][ci]);
+        }
+    }
+    s->user2int.assign(n, -1);
+    for (int k = 0; k < n; ++k) s->user2int[order[k]] = k;
+    s->jc.assign(n, JointConst());
+    std::vector<int> size(n, 1);
+    s->is_chain = 1;
+    for (int k = 0; k < n; ++k) {
+        const int j = order[k];
+        JointConst& J = s->jc[k];
+        std::memset(&J, 0, sizeof(J));
+        colmajor4_to_Rp(d->E0_pj + 16 * j, J.R0, J.p0);
+        colmajor4_to_Rp(d->E0_ji + 16 * j, J.Rji, J.pji);
+        for (int i = 0; i < 3; ++i) {
+            J.axis[i] = d->axis[3 * j + i];
+            J.hs[i] = 0.5 * d->sides[3 * j + i];  // ForceGroundCuboid.m:71
+        }
+        for (int i = 0; i < 6; ++i) J.I[i] = d->I_i[6 * j + i];
+        J.stiff = d->stiffness ? d->stiffness[j] : 0.0;
+        J.damp = d->damping ? d->damping[j] : 0.0;
+        J.qRest = d->qRest ? d->qRest[j] : 0.0;
+        J.qLimL = d->qLimL ? d->qLimL[j] : -1e8;  // Joint.m:77-80
+        J.qLimU = d->qLimU ? d->qLimU[j] : 1e8;
+        J.qLimK = d->qLimK ? d->qLimK[j] : 1e8;
+        J.qLimD = d->qLimD ? d->qLimD[j] : 0.0;
+        J.parent = d->parent[j] < 0 ? -1 : s->user2int[d->parent[j]];
+        if (J.parent != k - 1) s->is_chain = 0;
+        J.idx = idxR[j];
+        // se3.aaToMat classification (se3.m:118-176)
+        J.axtype = 0;
+        J.axsign = 1;
+        if (d->jtype[j] == RMX_JOINT_REVOLUTE) {
+            double ax = J.axis[0], ay = J.axis[1], az = J.axis[2];
+            double mag = std::sqrt(ax * ax + ay * ay + az * az);
+            if (!(mag > 1e-9)) {
+                delete s;
+                return fail(RMX_EINVAL, "rmx_scene_create: zero revolute axis");
+            }
+            mag = 1.0 / mag;
+            ax = ax * mag;
+            ay = ay * mag;
+            az = az * mag;
+            J.axn[0] = ax;
+            J.axn[1] = ay;
+            J.axn[2] = az;
+            const double TH = 1e-9;
+            if (std::fabs(ax) < TH && std::fabs(ay) < TH) {
+                J.axtype = 3;
+                J.axsign = az < 0 ? -1 : 1;
+            } else if (std::fabs(ay) < TH && std::fabs(az) < TH) {
+                J.axtype = 1;
+                J.axsign = ax < 0 ? -1 : 1;
+            } else if (std::fabs(az) < TH && std::fabs(ax) < TH) {
+                J.axtype = 2;
+                J.axsign = ay < 0 ? -1 : 1;
+            }
+        }
+    }
+    for (int k = n - 1; k >= 0; --k) {
+        s->jc[k].end = k + size[k];
+        if (s->jc[k].parent >= 0) size[s->jc[k].parent] += size[k];
+    }
+    // ends lists: for each index m, joints k (k < m) with end == m
+    {
+        std::vector<std::vector<int>> ends(n + 1);
+        for (int k = 0; k < n; ++k) ends[s->jc[k].end].push_back(k);
+        for (int m = 0; m < n; ++m) {
+            s->jc[m].ends_ptr = (int)s->ends_list.size();
+            s->jc[m].ends_cnt = (int)ends[m].size();
+            for (int k : ends[m]) s->ends_list.push_back(k);
+        }
+        if (s->ends_list.empty()) s->ends_list.push_back(0);
+    }
+    for (int i = 0; i < 3; ++i) s->grav[i] = d->grav[i];
+    for (int f = 0; f < d->nground; ++f) {
+        const int b = d->ground_body[f];
+        if (b < 0 || b >= n) {
+            delete s;
+            return fail(RMX_EINVAL, "rmx_scene_create: ground_body out of range");
+        }
+        JointConst& J = s->jc[s->user2int[b]];
+        if (J.has_ground) {
+            delete s;
+            return fail(RMX_EINVAL, "rmx_scene_create: at most one ForceGroundCuboid per body");
+        }
+        J.has_ground = 1;
+        const double* E = d->ground_E + 16 * f;
+        for (int i = 0; i < 3; ++i) {
+            J.gxg[i] = E[12 + i];  // E(1:3,4)  ForceGroundCuboid.m:56
+            J.gng[i] = E[8 + i];   // E(1:3,3)  ForceGroundCuboid.m:57
+        }
+        J.gkn = d->ground_kn[f];
+        J.gkt = d->ground_kt[f];
+        J.gkd = d->ground_kd[f];
+        J.gmu = d->ground_mu[f];
+        s->has_ground = 1;
+    }
+    *out = s;
+    return RMX_OK;
+}
+
+extern "C" void rmx_scene_destroy(rmx_scene* s) {
+    if (!s) return;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (auto& kv : s->dev) {
+        cudaSetDevice(kv.first);
+        cudaFree(kv.second.jc);
+        cudaFree(kv.second.ends);
+        for (auto& b : kv.second.buf) cudaFree(b.p);
+        if (kv.second.stream) cudaStreamDestroy(kv.second.stream);
+    }
+    cudaSetDevice(cur);
+    cudaGetLastError();
+    delete s;
+}
+extern "C" int rmx_scene_nr(const rmx_scene* s) { return s ? s->nr : 0; }
+extern "C" int rmx_scene_nm(const rmx_scene* s) { return s ? s->nm : 0; }
+
+static int scene_on_device(rmx_scene* s, int dev, DevCopy** out) {
+    auto it = s->dev.find(dev);
+    if (it == s->dev.end()) {
+        DevCopy dc;
+        CUDA_TRY(cudaMalloc(&dc.jc, sizeof(JointConst) * s->n));
+        CUDA_TRY(cudaMemcpy(dc.jc, s->jc.data(), sizeof(JointConst) * s->n, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc(&dc.ends, sizeof(int) * s->ends_list.size()));
+        CUDA_TRY(cudaMemcpy(dc.ends, s->ends_list.data(), sizeof(int) * s->ends_list.size(), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaStreamCreateWithFlags(&dc.stream, cudaStreamNonBlocking));
+        it = s->dev.emplace(dev, dc).first;
+    }
+    *out = &it->second;
+    return RMX_OK;
+}
+
+static int dev_reserve(DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return RMX_OK;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+    CUDA_TRY(cudaMalloc(&b.p, bytes));
+    b.cap = bytes;
+    return RMX_OK;
+}
+
+static DevScene make_devscene(const rmx_scene* s, const DevCopy* dc) {
+    DevScene ds;
+    ds.n = s->n;
+    ds.nr = s->nr;
+    ds.is_chain = s->is_chain;
+    ds.has_ground = s->has_ground;
+    for (int i = 0; i < 3; ++i) ds.grav[i] = s->grav[i];
+    ds.jc = dc->jc;
+    ds.ends_list = dc->ends;
+    return ds;
+}
+
+static int warps_for(const rmx_scene* s) {
+    const int m = s->n > s->nr ? s->n : s->nr;
+    if (m <= 32) return 1;
+    if (m <= 64) return 2;
+    return 4;
+}
+
+static int check_opts(const rmx_scene* s, const rmx_opts* o, StepOpts* so, int adjoint) {
+    if (!s || !o) return fail(RMX_EINVAL, "null scene/opts");
+    if (o->scheme != RMX_SCHEME_BDF1 && o->scheme != RMX_SCHEME_BDF2) return fail(RMX_EINVAL, "opts.scheme must be BDF1 or BDF2");
+    if (o->nsteps < 1) return fail(RMX_EINVAL, "opts.nsteps < 1");
+    if (!(o->h > 0)) return fail(RMX_EINVAL, "opts.h <= 0");
+    if (o->linsolve != RMX_LINSOLVE_LU && o->linsolve != RMX_LINSOLVE_PCG) return fail(RMX_EINVAL, "opts.linsolve");
+    so->scheme = o->scheme;
+    so->nsteps = o->nsteps;
+    so->iterMax = (o->iterMaxFactor > 0 ? o->iterMaxFactor : (adjoint ? 5 : 10)) * s->nr;
+    so->iterLsMax = o->iterLsMax > 0 ? o->iterLsMax : 20;
+    so->tau_mode = o->tau_mode;
+    so->adjoint_newton = adjoint;
+    so->h = o->h;
+    so->tol = o->tol > 0 ? o->tol : 1e-9;
+    so->dxMax = o->dxMax > 0 ? o->dxMax : 1e3;
+    return RMX_OK;
+}
+
+template <typename K>
+static int set_smem(K kernel, size_t bytes) {
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return RMX_OK;
+}
+
+template <int NW, bool GROUND>
+static int launch_fwd_t(const RolloutArgs& a, size_t smem, cudaStream_t st) {
+    int rc = set_smem(rollout_fwd_kernel<NW, GROUND>, smem);
+    if (rc) return rc;
+    const long long grid = a.B;
+    rollout_fwd_kernel<NW, GROUND><<<(unsigned)grid, 32 * NW, smem, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    return RMX_OK;
+}
+
+static int launch_fwd(const rmx_scene* s, const RolloutArgs& a, cudaStream_t st) {
+    const int nw = warps_for(s);
+    const bool g = s->has_ground != 0;
+    const size_t smem = smem_doubles(s->n, s->nr, g) * sizeof(double);
+    if (smem > 227 * 1024) return fail(RMX_ELIMIT, "scene does not fit the 227 KB shared memory of one SM");
+    if (nw == 1) return g ? launch_fwd_t<1, true>(a, smem, st) : launch_fwd_t<1, false>(a, smem, st);
+    if (nw == 2) return g ? launch_fwd_t<2, true>(a, smem, st) : launch_fwd_t<2, false>(a, smem, st);
+    return g ? launch_fwd_t<4, true>(a, smem, st) : launch_fwd_t<4, false>(a, smem, st);
+}
+
+extern "C" int rmx_rollout_dev(rmx_scene* s, const rmx_opts* o, int64_t B, const double* q0, const double* qdot0,
+                               const double* tau, double* q_out, double* qdot_out, int32_t* status, int32_t* iters,
+                               void* cuda_stream) {
+    StepOpts so;
+    int rc = check_opts(s, o, &so, 0);
+    if (rc) return rc;
+    if (B < 1 || !q0 || !qdot0 || !q_out || !status) return fail(RMX_EINVAL, "rmx_rollout_dev: bad arguments");
+    if (so.tau_mode != RMX_TAU_NONE && !tau) return fail(RMX_EINVAL, "rmx_rollout_dev: tau_mode set but tau == NULL");
+    if (o->linsolve == RMX_LINSOLVE_PCG) return fail(RMX_EINVAL, "linsolve=PCG is not built yet in this version; use LU");
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    DevCopy* dc;
+    rc = scene_on_device(s, dev, &dc);
+    if (rc) return rc;
+    RolloutArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.sc = make_devscene(s, dc);
+    a.op = so;
+    a.B = B;
+    a.q0 = q0;
+    a.qd0 = qdot0;
+    a.tau = tau;
+    a.q_out = q_out;
+    a.qd_out = qdot_out;
+    a.status = status;
+    a.iters = iters;
+    return launch_fwd(s, a, (cudaStream_t)cuda_stream);
+}
+
+// Host-pointer entry: shards the batch contiguously over o->ngpus devices (no communication during the rollout),
+// each device copying its slice of the trajectories straight back into the caller's buffers.
+extern "C" int rmx_rollout(rmx_scene* s, const rmx_opts* o, int64_t B, const double* q0, const double* qdot0,
+                           const double* tau, double* q_out, double* qdot_out, int32_t* status, int32_t* iters) {
+    StepOpts so;
+    int rc = check_opts(s, o, &so, 0);
+    if (rc) return rc;
+    if (B < 1 || !q0 || !qdot0 || !q_out || !status) return fail(RMX_EINVAL, "rmx_rollout: bad arguments");
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (ndev < 1) return fail(RMX_ENOGPU, "rmx_rollout: no CUDA device (there is no CPU fallback)");
+    int G = o->ngpus > 0 ? o->ngpus : 1;
+    if (G > ndev) G = ndev;
+    if (G > B) G = (int)B;
+    int cur = 0;
+    CUDA_TRY(cudaGetDevice(&cur));
+    const int nr = s->nr;
+    const size_t per = (size_t)nr * so.nsteps;
+    const size_t tau_per = so.tau_mode == RMX_TAU_PER_STEP ? per : (size_t)nr;
+    rmx_opts o1 = *o;
+    std::vector<int> devs;
+    for (int gi = 0; gi < G; ++gi) devs.push_back(G == 1 ? cur : gi);
+    int ret = RMX_OK;
+    for (int gi = 0; gi < G && ret == RMX_OK; ++gi) {
+        const int64_t b0 = B * gi / G, b1 = B * (gi + 1) / G, nb = b1 - b0;
+        CUDA_TRY(cudaSetDevice(devs[gi]));
+        DevCopy* dc;
+        ret = scene_on_device(s, devs[gi], &dc);
+        if (ret) break;
+        size_t sz[7] = {nb * nr * sizeof(double), nb * nr * sizeof(double), tau ? nb * tau_per * sizeof(double) : 0,
+                        nb * per * sizeof(double), qdot_out ? nb * per * sizeof(double) : 0, nb * sizeof(int),
+                        iters ? 2 * nb * sizeof(int) : 0};
+        for (int i = 0; i < 7 && ret == RMX_OK; ++i)
+            if (sz[i]) ret = dev_reserve(dc->buf[i], sz[i]);
+        if (ret) break;
+        cudaStream_t st = dc->stream;
+        CUDA_TRY(cudaMemcpyAsync(dc->buf[0].p, q0 + b0 * nr, sz[0], cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(dc->buf[1].p, qdot0 + b0 * nr, sz[1], cudaMemcpyHostToDevice, st));
+        if (tau) CUDA_TRY(cudaMemcpyAsync(dc->buf[2].p, tau + b0 * tau_per, sz[2], cudaMemcpyHostToDevice, st));
+        ret = rmx_rollout_dev(s, &o1, nb, (double*)dc->buf[0].p, (double*)dc->buf[1].p, tau ? (double*)dc->buf[2].p : nullptr,
+                              (double*)dc->buf[3].p, qdot_out ? (double*)dc->buf[4].p : nullptr, (int*)dc->buf[5].p,
+                              iters ? (int*)dc->buf[6].p : nullptr, st);
+        if (ret) break;
+        CUDA_TRY(cudaMemcpyAsync(q_out + b0 * per, dc->buf[3].p, sz[3], cudaMemcpyDeviceToHost, st));
+        if (qdot_out) CUDA_TRY(cudaMemcpyAsync(qdot_out + b0 * per, dc->buf[4].p, sz[4], cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(status + b0, dc->buf[5].p, sz[5], cudaMemcpyDeviceToHost, st));
+        if (iters) CUDA_TRY(cudaMemcpyAsync(iters + 2 * b0, dc->buf[6].p, sz[6], cudaMemcpyDeviceToHost, st));
+    }
+    for (int gi = 0; gi < G; ++gi) {
+        cudaSetDevice(devs[gi]);
+        auto it = s->dev.find(devs[gi]);
+        if (it != s->dev.end()) {
+            cudaError_t e = cudaStreamSynchronize(it->second.stream);
+            if (e != cudaSuccess && ret == RMX_OK) ret = fail(RMX_ECUDA, std::string("rollout: ") + cudaGetErrorString(e));
+        }
+    }
+    cudaSetDevice(cur);
+    return ret;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// rmx_eval test hook
+// ---------------------------------------------------------------------------------------------------
+template <int NW, bool GROUND>
+static int launch_eval_t(const EvalArgs& a, size_t smem) {
+    int rc = set_smem(eval_kernel<NW, GROUND>, smem);
+    if (rc) return rc;
+    eval_kernel<NW, GROUND><<<1, 32 * NW, smem>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaDeviceSynchronize());
+    return RMX_OK;
+}
+
+extern "C" int rmx_eval(rmx_scene* s, const double* q, const double* qdot, const double* dqtmp, const double* tau,
+                        double cK, double beta, double* g, double* H, double* M, double* D, double* f) {
+    if (!s || !q || !qdot || !dqtmp) return fail(RMX_EINVAL, "rmx_eval: null argument");
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (ndev < 1) return fail(RMX_ENOGPU, "rmx_eval: no CUDA device");
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    DevCopy* dc;
+    int rc = scene_on_device(s, dev, &dc);
+    if (rc) return rc;
+    const int nr = s->nr;
+    const size_t v = nr * sizeof(double), m = (size_t)nr * nr * sizeof(double);
+    double* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, 5 * v + 3 * m));
+    double* dq_ = d;
+    double* dqd = d + nr;
+    double* ddq = d + 2 * nr;
+    double* dtau = d + 3 * nr;
+    double* dg = d + 4 * nr;
+    double* dH = d + 5 * nr;
+    double* dM = dH + (size_t)nr * nr;
+    double* dD = dM + (size_t)nr * nr;
+    cudaMemcpy(dq_, q, v, cudaMemcpyHostToDevice);
+    cudaMemcpy(dqd, qdot, v, cudaMemcpyHostToDevice);
+    cudaMemcpy(ddq, dqtmp, v, cudaMemcpyHostToDevice);
+    if (tau)
+        cudaMemcpy(dtau, tau, v, cudaMemcpyHostToDevice);
+    else
+        cudaMemset(dtau, 0, v);
+    EvalArgs a;
+    a.sc = make_devscene(s, dc);
+    a.q = dq_;
+    a.qd = dqd;
+    a.dq = ddq;
+    a.tau = dtau;
+    a.cK = cK;
+    a.beta = beta;
+    a.g = dg;
+    a.H = dH;
+    a.M = dM;
+    a.D = dD;
+    const int nw = warps_for(s);
+    const bool gr = s->has_ground != 0;
+    const size_t smem = smem_doubles(s->n, s->nr, gr) * sizeof(double);
+    if (nw == 1)
+        rc = gr ? launch_eval_t<1, true>(a, smem) : launch_eval_t<1, false>(a, smem);
+    else if (nw == 2)
+        rc = gr ? launch_eval_t<2, true>(a, smem) : launch_eval_t<2, false>(a, smem);
+    else
+        rc = gr ? launch_eval_t<4, true>(a, smem) : launch_eval_t<4, false>(a, smem);
+    if (rc == RMX_OK) {
+        std::vector<double> hg(nr), hM((size_t)nr * nr);
+        cudaMemcpy(hg.data(), dg, v, cudaMemcpyDeviceToHost);
+        cudaMemcpy(hM.data(), dM, m, cudaMemcpyDeviceToHost);
+        if (g) std::memcpy(g, hg.data(), v);
+        if (H) cudaMemcpy(H, dH, m, cudaMemcpyDeviceToHost);
+        if (M) std::memcpy(M, hM.data(), m);
+        if (D) cudaMemcpy(D, dD, m, cudaMemcpyDeviceToHost);
+        if (f) {
+            // g = M*dqtmp - cK*f  =>  f = (M*dqtmp - g)/cK
+            for (int r = 0; r < nr; ++r) {
+                double acc = 0;
+                for (int c2 = 0; c2 < nr; ++c2) acc += hM[(size_t)c2 * nr + r] * dqtmp[c2];
+                f[r] = (acc - hg[r]) / cK;
+            }
+        }
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) rc = fail(RMX_ECUDA, cudaGetErrorString(e));
+    }
+    cudaFree(d);
+    return rc;
+}
+
+#include "rmx_api_adjoint.inc"

@@ -1,0 +1,440 @@
+"""Host-side mirror of the reference's `+redmax` object API (matlab-diff/+redmax/*.m), description only.
+
+The class and method names, argument meaning and defaults are the reference's, so a scene script written for
+`scenesRedMax.m` reads the same here:
+
+    scene = Scene()
+    scene.bodies.append(BodyCuboid(density, sides))
+    scene.joints.append(JointRevolute(parent, body, axis)); joint.setJointTransform(E); body.setBodyTransform(E)
+    scene.forces.append(ForceGroundCuboid(body)); ...
+    scene.init()
+
+`Scene.init()` (Scene.m:59-119) numbers the degrees of freedom leaf-to-root exactly as the reference does,
+flattens the object graph into `rmx_scene_desc` and hands it to the CUDA library through the C ABI.  All
+dynamics (Joint.update, computeJacobian, computeValues, newton, simLoop, Task.calcFinal ...) then run on the
+GPU for a whole batch of rollouts: `Scene.rollout(...)`, `Scene.rollout_adjoint(...)`.  Nothing in this file
+computes dynamics on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import RmxError, f64, i32, ptr
+
+
+def inertiaCuboid(whd, density):
+    """se3.inertiaCuboid (se3.m:366): diagonal inertia [Ixx Iyy Izz m m m]."""
+    whd = np.asarray(whd, dtype=float).reshape(3)
+    m = np.zeros(6)
+    mass = density * np.prod(whd)
+    m[0] = (1.0 / 12.0) * mass * (whd[[1, 2]] @ whd[[1, 2]])
+    m[1] = (1.0 / 12.0) * mass * (whd[[2, 0]] @ whd[[2, 0]])
+    m[2] = (1.0 / 12.0) * mass * (whd[[0, 1]] @ whd[[0, 1]])
+    m[3:6] = mass
+    return m
+
+
+class Body:
+    """+redmax/Body.m (description fields only)."""
+
+    def __init__(self, density):
+        self.name = ''
+        self.density = density
+        self.E0_ji = np.eye(4)
+        self.I_i = np.ones(6)
+        self.joint = None
+        self.idxM = None
+
+    def setBodyTransform(self, E):
+        """Body.m:46 -- transform of this body wrt its joint."""
+        self.E0_ji = np.array(E, dtype=float).reshape(4, 4)
+
+
+class BodyCuboid(Body):
+    """+redmax/BodyCuboid.m"""
+
+    def __init__(self, density, sides):
+        super().__init__(density)
+        self.sides = np.asarray(sides, dtype=float).reshape(3)
+
+    def computeInertia_(self):
+        self.I_i = inertiaCuboid(self.sides, self.density)
+
+
+class Joint:
+    """+redmax/Joint.m (description fields only)."""
+
+    def __init__(self, parent, body, ndof):
+        self.parent = parent
+        self.body = body
+        self.children = []
+        self.ndof = ndof
+        self.q = np.zeros(ndof)
+        self.qdot = np.zeros(ndof)
+        self.qRest = np.zeros(ndof)
+        self.qLimL = -1e8   # Joint.m:77-80
+        self.qLimU = 1e8
+        self.qLimK = 1e8
+        self.qLimD = 0.0
+        self.tau = np.zeros(ndof)
+        self.stiffness = 0.0
+        self.damping = 0.0
+        self.E0_pj = np.eye(4)
+        self.idxR = None
+        body.joint = self
+        if parent is not None:
+            parent.children.append(self)
+
+    def setJointTransform(self, E):
+        """Joint.m:95 -- transform of this joint wrt the parent joint at q = 0."""
+        self.E0_pj = np.array(E, dtype=float).reshape(4, 4)
+
+    def setStiffness(self, stiffness):
+        self.stiffness = float(stiffness)
+
+    def setDamping(self, damping):
+        self.damping = float(damping)
+
+    def setLimitLower(self, limit):
+        self.qLimL = float(limit)
+
+    def setLimitUpper(self, limit):
+        self.qLimU = float(limit)
+
+    def setLimitStiffness(self, K):
+        self.qLimK = float(K)
+
+    def setLimitDamping(self, D):
+        self.qLimD = float(D)
+
+
+class JointRevolute(Joint):
+    """+redmax/JointRevolute.m"""
+
+    def __init__(self, parent, body, axis):
+        super().__init__(parent, body, 1)
+        axis = np.asarray(axis, dtype=float).reshape(3)
+        self.axis = axis / np.linalg.norm(axis)  # JointRevolute.m:14
+
+
+class JointFixed(Joint):
+    """+redmax/JointFixed.m"""
+
+    def __init__(self, parent, body):
+        super().__init__(parent, body, 0)
+        self.axis = np.zeros(3)
+
+
+class ForceGroundCuboid:
+    """+redmax/ForceGroundCuboid.m:18-48"""
+
+    def __init__(self, cuboid):
+        self.cuboid = cuboid
+        self.E = np.eye(4)
+        self.kn = 1.0
+        self.kt = 0.0
+        self.mu = 0.0
+        self.kd = 0.0
+
+    def setTransform(self, E):
+        self.E = np.array(E, dtype=float).reshape(4, 4)
+
+    def setStiffness(self, kn, kt):
+        self.kn = float(kn)
+        self.kt = float(kt)
+
+    def setDamping(self, kd):
+        self.kd = float(kd)
+
+    def setFriction(self, mu):
+        self.mu = float(mu)
+
+
+class _TaskPointPos:
+    """+redmax/TaskBDF1PointPos.m / TaskBDF2PointPos.m (parameters = constant joint torques, objective = a body
+    point reaching a target at time t)."""
+    scheme = 1
+
+    def __init__(self, scene):
+        self.scene = scene
+        self.t = scene.tEnd
+        self.body = None
+        self.xlocal = np.zeros(3)
+        self.xtarget = np.zeros(3)
+        self.pscale = 1.0
+        self.wreg = 1.0
+        self.wpos = 1.0
+
+    def setTime(self, t):
+        self.t = float(t)
+
+    def setBody(self, body):
+        self.body = body
+
+    def setPoint(self, xlocal):
+        self.xlocal = np.asarray(xlocal, dtype=float).reshape(3)
+
+    def setTarget(self, xtarget):
+        self.xtarget = np.asarray(xtarget, dtype=float).reshape(3)
+
+    def setScale(self, pscale):
+        self.pscale = float(pscale)
+
+    def setWeights(self, wreg, wpos):
+        self.wreg = float(wreg)
+        self.wpos = float(wpos)
+
+
+class TaskBDF1PointPos(_TaskPointPos):
+    scheme = 1
+
+
+class TaskBDF2PointPos(_TaskPointPos):
+    scheme = 2
+
+
+class Scene:
+    """+redmax/Scene.m.  `init()` replaces Scene.init; `rollout*` replace the drivers' simLoop."""
+
+    def __init__(self):
+        self.name = ''
+        self.bodies = []
+        self.joints = []
+        self.forces = []
+        self.tEnd = 1.0        # Scene.m:38
+        self.h = 1e-2          # Scene.m:41
+        self.grav = np.array([0.0, 0.0, -980.0])  # Scene.m:48
+        self.Hexpected = np.zeros(2)
+        self.task = None
+        self.qInit = None
+        self.qdotInit = None
+        self.nsteps = 0
+        self.nr = 0
+        self.nm = 0
+        self._handle = None
+
+    # -- Scene.init, Scene.m:59-119 ---------------------------------------------------------------------
+    def init(self):
+        n = len(self.joints)
+        if n == 0 or len(self.bodies) != n:
+            raise ValueError('scene needs one body per joint')
+        index = {id(j): i for i, j in enumerate(self.joints)}
+        for i, j in enumerate(self.joints):
+            if j.parent is not None and index[id(j.parent)] >= i:
+                raise ValueError('joints must be listed parents-before-children (Joint.getTraversalOrder)')
+            if j.body is not self.bodies[i]:
+                raise ValueError('bodies must be listed in the same order as their joints (Scene.m:104)')
+        nr = 0
+        nm = 0
+        for i in range(n - 1, -1, -1):  # Scene.m:69-71: leaf-to-root numbering
+            j = self.joints[i]
+            j.idxR = nr + np.arange(j.ndof)
+            nr += j.ndof
+            j.body.idxM = nm + np.arange(6)
+            nm += 6
+            j.qRest = np.array(j.q[: j.ndof], dtype=float)  # Joint.m:157
+        self.nr, self.nm = nr, nm
+        for b in self.bodies:
+            b.computeInertia_()
+        self.qInit = np.zeros(nr)
+        self.qdotInit = np.zeros(nr)
+        for j in self.joints:
+            self.qInit[j.idxR] = j.q[: j.ndof]
+            self.qdotInit[j.idxR] = j.qdot[: j.ndof]
+        self.nsteps = int(math.ceil(self.tEnd / self.h))  # Scene.m:117
+        self._create_handle(index)
+        return self
+
+    def _create_handle(self, index):
+        n = len(self.joints)
+        L = _ffi.lib()
+        d = _ffi.rmx_scene_desc()
+        keep = []
+
+        def arr(a, conv):
+            a = conv(a)
+            keep.append(a)
+            return a.ctypes.data_as(_ffi._pd if a.dtype == np.float64 else _ffi._pi)
+        d.n = n
+        d.parent = arr([(-1 if j.parent is None else index[id(j.parent)]) for j in self.joints], i32)
+        d.jtype = arr([(_ffi.RMX_JOINT_REVOLUTE if j.ndof == 1 else _ffi.RMX_JOINT_FIXED) for j in self.joints], i32)
+        for j in self.joints:
+            if not isinstance(j, (JointRevolute, JointFixed)):
+                raise RmxError('only JointRevolute / JointFixed are on the GPU hot path (SURVEY.md section 8)')
+        # MATLAB stores 4x4 column-major: E.T.ravel()
+        d.E0_pj = arr(np.concatenate([j.E0_pj.T.ravel() for j in self.joints]), f64)
+        d.E0_ji = arr(np.concatenate([j.body.E0_ji.T.ravel() for j in self.joints]), f64)
+        d.axis = arr(np.concatenate([j.axis for j in self.joints]), f64)
+        d.I_i = arr(np.concatenate([j.body.I_i for j in self.joints]), f64)
+        d.sides = arr(np.concatenate([j.body.sides for j in self.joints]), f64)
+        d.stiffness = arr([j.stiffness for j in self.joints], f64)
+        d.damping = arr([j.damping for j in self.joints], f64)
+        d.qRest = arr([(j.qRest[0] if j.ndof else 0.0) for j in self.joints], f64)
+        d.qLimL = arr([j.qLimL for j in self.joints], f64)
+        d.qLimU = arr([j.qLimU for j in self.joints], f64)
+        d.qLimK = arr([j.qLimK for j in self.joints], f64)
+        d.qLimD = arr([j.qLimD for j in self.joints], f64)
+        d.grav = (C.c_double * 3)(*[float(x) for x in self.grav])
+        grounds = [f for f in self.forces if isinstance(f, ForceGroundCuboid)]
+        if len(grounds) != len(self.forces):
+            raise RmxError('only ForceGroundCuboid is on the GPU hot path (SURVEY.md section 8)')
+        d.nground = len(grounds)
+        if grounds:
+            d.ground_body = arr([index[id(f.cuboid.joint)] for f in grounds], i32)
+            d.ground_E = arr(np.concatenate([f.E.T.ravel() for f in grounds]), f64)
+            d.ground_kn = arr([f.kn for f in grounds], f64)
+            d.ground_kt = arr([f.kt for f in grounds], f64)
+            d.ground_kd = arr([f.kd for f in grounds], f64)
+            d.ground_mu = arr([f.mu for f in grounds], f64)
+        h = C.c_void_p()
+        _ffi.check(L.rmx_scene_create(C.byref(d), C.byref(h)), 'rmx_scene_create')
+        self.close()
+        self._handle = h
+        assert L.rmx_scene_nr(h) == self.nr and L.rmx_scene_nm(h) == self.nm
+
+    def close(self):
+        if self._handle is not None:
+            _ffi.lib().rmx_scene_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def countR(scene):
+        return scene.nr
+
+    # -- options ----------------------------------------------------------------------------------------
+    def opts(self, scheme=1, adjoint=False, nsteps=None, h=None, ngpus=1, tau_mode=_ffi.RMX_TAU_NONE,
+             linsolve=_ffi.RMX_LINSOLVE_LU, **kw):
+        o = _ffi.rmx_opts()
+        _ffi.lib().rmx_opts_default(C.byref(o), int(scheme), int(bool(adjoint)))
+        o.nsteps = int(self.nsteps if nsteps is None else nsteps)
+        o.h = float(self.h if h is None else h)
+        o.ngpus = int(ngpus)
+        o.tau_mode = int(tau_mode)
+        o.linsolve = int(linsolve)
+        for k, v in kw.items():
+            setattr(o, k, v)
+        return o
+
+    def _require(self):
+        if self._handle is None:
+            raise RmxError('call scene.init() first')
+        return _ffi.lib()
+
+    # -- forward rollouts: simLoop of driverRedMaxBDF1.m:57 / driverRedMaxBDF2.m:57, batched ----------------
+    def rollout(self, q0=None, qdot0=None, tau=None, scheme=1, nsteps=None, ngpus=1, want_qdot=True, **kw):
+        """Host-buffer call.  q0, qdot0: [B, nr] (row b = rollout b; memory layout nr x B column-major as the
+        C ABI wants).  tau: None, [B, nr] (constant) or [B, nsteps, nr].  Returns dict(q=[B,nsteps,nr],
+        qdot=..., status=[B], iters=[B,2])."""
+        L = self._require()
+        q0 = f64(self.qInit[None, :] if q0 is None else q0)
+        qdot0 = f64(self.qdotInit[None, :] if qdot0 is None else qdot0)
+        if q0.ndim == 1:
+            q0 = q0[None, :]
+        if qdot0.ndim == 1:
+            qdot0 = qdot0[None, :]
+        B = q0.shape[0]
+        assert q0.shape == (B, self.nr) and qdot0.shape == (B, self.nr)
+        tau_mode = _ffi.RMX_TAU_NONE
+        if tau is not None:
+            tau = f64(tau)
+            tau_mode = _ffi.RMX_TAU_CONST if tau.ndim == 2 else _ffi.RMX_TAU_PER_STEP
+        o = self.opts(scheme=scheme, nsteps=nsteps, ngpus=ngpus, tau_mode=tau_mode, **kw)
+        ns = o.nsteps
+        if tau is not None:
+            assert tau.shape == ((B, self.nr) if tau_mode == _ffi.RMX_TAU_CONST else (B, ns, self.nr))
+        q = np.empty((B, ns, self.nr))
+        qd = np.empty((B, ns, self.nr)) if want_qdot else None
+        status = np.empty(B, dtype=np.int32)
+        iters = np.empty((B, 2), dtype=np.int32)
+        _ffi.check(L.rmx_rollout(self._handle, C.byref(o), B, ptr(q0), ptr(qdot0), ptr(tau), ptr(q), ptr(qd),
+                                 ptr(status), ptr(iters)), 'rmx_rollout')
+        return dict(q=q, qdot=qd, status=status, iters=iters)
+
+    def rollout_dev(self, q0, qdot0, q_out, qdot_out, status, iters=None, tau=None, scheme=1, nsteps=None,
+                    stream=None, **kw):
+        """Device-buffer call (torch CUDA tensors or raw device addresses), enqueued on `stream` (a
+        torch.cuda.Stream, a raw cudaStream_t address, or None for the legacy default stream)."""
+        L = self._require()
+        B = int(q0.shape[0])
+        tau_mode = _ffi.RMX_TAU_NONE
+        if tau is not None:
+            tau_mode = _ffi.RMX_TAU_CONST if tau.dim() == 2 else _ffi.RMX_TAU_PER_STEP
+        o = self.opts(scheme=scheme, nsteps=nsteps, tau_mode=tau_mode, **kw)
+        st = None
+        if stream is not None:
+            st = C.c_void_p(int(getattr(stream, 'cuda_stream', stream)))
+        _ffi.check(L.rmx_rollout_dev(self._handle, C.byref(o), B, ptr(q0), ptr(qdot0), ptr(tau), ptr(q_out),
+                                     ptr(qdot_out), ptr(status), ptr(iters), st), 'rmx_rollout_dev')
+
+    # -- adjoint: taskObjective of driverRedMaxAdjointBDF1.m:39 / ...BDF2.m:39, batched ----------------------
+    def _task_struct(self):
+        if self.task is None or self.task.body is None:
+            raise RmxError('scene.task with a body is required for the adjoint path')
+        index = {id(b): i for i, b in enumerate(self.bodies)}
+        t = _ffi.rmx_task_pointpos()
+        t.body = index[id(self.task.body)]
+        t.xlocal = (C.c_double * 3)(*self.task.xlocal)
+        t.t_target = self.task.t
+        t.pscale = self.task.pscale
+        t.wreg = self.task.wreg
+        t.wpos = self.task.wpos
+        return t
+
+    def rollout_adjoint(self, p, xtarget=None, q0=None, qdot0=None, nsteps=None, ngpus=1, want_q=False, **kw):
+        """(P, dPdp) for B parameter vectors p: [B, nr]; xtarget: [B, 3] (default: the task's target)."""
+        L = self._require()
+        p = f64(p)
+        if p.ndim == 1:
+            p = p[None, :]
+        B = p.shape[0]
+        q0 = f64(np.broadcast_to(self.qInit, (B, self.nr)) if q0 is None else q0)
+        qdot0 = f64(np.broadcast_to(self.qdotInit, (B, self.nr)) if qdot0 is None else qdot0)
+        xt = f64(np.broadcast_to(self.task.xtarget, (B, 3)) if xtarget is None else xtarget)
+        o = self.opts(scheme=self.task.scheme, adjoint=True, nsteps=nsteps, ngpus=ngpus, **kw)
+        t = self._task_struct()
+        P = np.empty(B)
+        dPdp = np.empty((B, self.nr))
+        q = np.empty((B, o.nsteps, self.nr)) if want_q else None
+        status = np.empty(B, dtype=np.int32)
+        _ffi.check(L.rmx_rollout_adjoint(self._handle, C.byref(o), C.byref(t), B, ptr(q0), ptr(qdot0), ptr(p), ptr(xt),
+                                         ptr(P), ptr(dPdp), ptr(q), ptr(status)), 'rmx_rollout_adjoint')
+        return dict(P=P, dPdp=dPdp, q=q, status=status)
+
+    # -- test hooks ---------------------------------------------------------------------------------------
+    def eval(self, q, qdot, dqtmp, cK, beta, tau=None):
+        """One residual/Jacobian evaluation on the GPU (rmx_eval)."""
+        L = self._require()
+        nr = self.nr
+        q, qdot, dqtmp = f64(q), f64(qdot), f64(dqtmp)
+        tau = None if tau is None else f64(tau)
+        g = np.empty(nr)
+        f = np.empty(nr)
+        H = np.empty((nr, nr))
+        M = np.empty((nr, nr))
+        D = np.empty((nr, nr))
+        _ffi.check(L.rmx_eval(self._handle, ptr(q), ptr(qdot), ptr(dqtmp), ptr(tau), float(cK), float(beta),
+                              ptr(g), ptr(H), ptr(M), ptr(D), ptr(f)), 'rmx_eval')
+        # column-major nr x nr -> numpy [row, col]
+        return dict(g=g, f=f, H=H.T.copy(), M=M.T.copy(), D=D.T.copy())
+
+    def energies(self, q, qdot):
+        """T, V of Scene.saveHistory (Scene.m:155-160) for B states."""
+        L = self._require()
+        q, qdot = f64(q), f64(qdot)
+        if q.ndim == 1:
+            q, qdot = q[None, :], qdot[None, :]
+        B = q.shape[0]
+        T = np.empty(B)
+        V = np.empty(B)
+        _ffi.check(L.rmx_energies(self._handle, B, ptr(q), ptr(qdot), ptr(T), ptr(V)), 'rmx_energies')
+        return T, V

@@ -1,0 +1,255 @@
+"""Scene factory mirroring matlab-diff/scenesRedMax.m for the joint/force types on the GPU hot path, plus the
+synthetic benchmark scenes of SURVEY.md section 8(d).
+
+Every factory takes `api`: the namespace providing Scene / BodyCuboid / JointRevolute / JointFixed /
+ForceGroundCuboid / TaskBDF*PointPos.  The default is this package's host mirror (redmax_b200.scene); the tests
+pass the oracle module instead to build the identical scene on the checker's side.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from . import scene as _api
+
+BDF1 = 1
+BDF2 = 2
+
+
+def _trans(p):
+    E = np.eye(4)
+    E[0:3, 3] = p
+    return E
+
+
+def _rot(axis, angle):
+    """se3.aaToMat for the axis-aligned cases used by scenesRedMax.m."""
+    c, s = math.cos(angle), math.sin(angle)
+    ax = np.argmax(np.abs(axis))
+    R = np.eye(3)
+    if ax == 0:
+        R[1, 1], R[1, 2], R[2, 1], R[2, 2] = c, -s, s, c
+    elif ax == 1:
+        R[0, 0], R[0, 2], R[2, 0], R[2, 2] = c, s, -s, c
+    else:
+        R[0, 0], R[0, 1], R[1, 0], R[1, 1] = c, -s, s, c
+    E = np.eye(4)
+    E[0:3, 0:3] = R
+    return E
+
+
+def scenesRedMax(sceneID, api=None):
+    """scenesRedMax.m, scene IDs -2, -1, 0, 1, 2, 14, 100, 101 (revolute / fixed joints; the other IDs use joint
+    or force types outside the hot-path scope)."""
+    api = api or _api
+    scene = api.Scene()
+    density = 1.0
+    if sceneID == -2:  # scenesRedMax.m:13
+        scene.name = 'Single revolute'
+        b = api.BodyCuboid(density, [2, 0.2, 0.2])
+        j = api.JointRevolute(None, b, [0, 1, 0])
+        j.setJointTransform(np.eye(4))
+        j.q[0] = 0
+        j.qdot[0] = 1
+        b.setBodyTransform(_trans([1, 0, 0]))
+        scene.bodies.append(b)
+        scene.joints.append(j)
+    elif sceneID in (-1, 0):  # :27, :52
+        nbodies = 1 if sceneID == -1 else 5
+        scene.name = 'Simpler serial chain' if sceneID == -1 else 'Simple serial chain'
+        if sceneID == 0:
+            scene.Hexpected[:] = [-1.2705398823489915e+05, 2.6058008179021417e+03]
+        for i in range(1, nbodies + 1):
+            b = api.BodyCuboid(density, [10, 1, 1])
+            if i == 1:
+                j = api.JointRevolute(None, b, [0, 1, 0])
+                j.setJointTransform(np.eye(4))
+            else:
+                if sceneID == 0 and i % 2 == 0:
+                    j = api.JointFixed(scene.joints[i - 2], b)
+                else:
+                    j = api.JointRevolute(scene.joints[i - 2], b, [0, 1, 0])
+                j.setJointTransform(_trans([10, 0, 0]))
+            b.setBodyTransform(_trans([5, 0, 0]))
+            if sceneID == -1:
+                j.q[0] = 0 if i == 1 else math.pi / 4
+                j.qdot[0] = 1
+                j.setStiffness(1e6)
+                j.setDamping(1e4)
+            elif j.ndof:
+                j.q[0] = math.pi / 4 if i % 2 == 1 else 0.0
+            scene.bodies.append(b)
+            scene.joints.append(j)
+    elif sceneID == 1:  # :80
+        scene.name = 'Different revolute axes'
+        scene.Hexpected[:] = [-3.8359074258588909e+04, -9.7138545812971279e+02]
+        bs = [api.BodyCuboid(density, [10, 1, 1]) for _ in range(3)]
+        j1 = api.JointRevolute(None, bs[0], [0, 0, 1])
+        j2 = api.JointRevolute(j1, bs[1], [0, 1, 0])
+        j3 = api.JointRevolute(j2, bs[2], [0, 0, 1])
+        for b in bs:
+            b.setBodyTransform(_trans([5, 0, 0]))
+        j1.setJointTransform(np.eye(4))
+        j2.setJointTransform(_trans([10, 0, 0]))
+        j3.setJointTransform(_trans([10, 0, 0]))
+        j1.q[0] = 0
+        j2.q[0] = math.pi / 2
+        j3.q[0] = math.pi / 2
+        scene.bodies = bs
+        scene.joints = [j1, j2, j3]
+    elif sceneID == 2:  # :101
+        scene.name = 'Branching'
+        scene.Hexpected[:] = [-2.2826101928480086e+04, -2.4159349151742754e+02]
+        bs = [api.BodyCuboid(density, [1, 1, 10]), api.BodyCuboid(density, [1, 20, 1]),
+              api.BodyCuboid(density, [1, 1, 10]), api.BodyCuboid(density, [1, 1, 10])]
+        j1 = api.JointRevolute(None, bs[0], [1, 0, 0])
+        j2 = api.JointRevolute(j1, bs[1], [0, 0, 1])
+        j3 = api.JointRevolute(j2, bs[2], [1, 0, 0])
+        j4 = api.JointRevolute(j2, bs[3], [0, 1, 0])
+        bs[0].setBodyTransform(_trans([0, 0, -5]))
+        bs[1].setBodyTransform(_trans([0, 0, 0]))
+        bs[2].setBodyTransform(_trans([0, 0, -5]))
+        bs[3].setBodyTransform(_trans([0, 0, -5]))
+        j1.setJointTransform(_trans([0, 0, 15]))
+        j2.setJointTransform(_trans([0, 0, -10]))
+        j3.setJointTransform(_trans([0, -10, 0]))
+        j4.setJointTransform(_trans([0, 10, 0]))
+        j1.q[0] = 0
+        j2.q[0] = 0
+        j3.q[0] = math.pi / 4
+        j4.q[0] = math.pi / 4
+        scene.bodies = bs
+        scene.joints = [j1, j2, j3, j4]
+    elif sceneID == 14:  # :371
+        scene.name = 'Joint limits'
+        scene.Hexpected[:] = [-2.5928305306546572e+04, -1.8476279319765570e+04]
+        scene.h = 5e-3
+        for i in range(1, 4):
+            b = api.BodyCuboid(density, [10, 1, 1])
+            if i == 1:
+                j = api.JointRevolute(None, b, [0, 1, 0])
+                j.setJointTransform(_rot([0, 1, 0], math.pi / 2))
+                j.q[0] = 0
+            else:
+                j = api.JointRevolute(scene.joints[i - 2], b, [0, 1, 0])
+                j.setJointTransform(_trans([10, 0, 0]))
+                j.q[0] = -math.pi / 6
+            j.qdot[0] = 0
+            b.setBodyTransform(_trans([5, 0, 0]))
+            j.setLimitLower(-math.pi / 2)
+            j.setLimitUpper(0)
+            j.setLimitStiffness(1e5)
+            j.setLimitDamping(1e2)
+            j.setDamping(1e2)
+            scene.bodies.append(b)
+            scene.joints.append(j)
+    elif sceneID in (100, 101):  # :402, :437
+        scene.name = 'Adjoint BDF1' if sceneID == 100 else 'Adjoint BDF2'
+        for i in range(1, 3):
+            b = api.BodyCuboid(density, [10, 1, 1])
+            if i == 1:
+                j = api.JointRevolute(None, b, [0, 1, 0])
+                j.setJointTransform(np.eye(4))
+                j.q[0] = math.pi / 2
+            else:
+                j = api.JointRevolute(scene.joints[i - 2], b, [0, 1, 0])
+                j.setJointTransform(_trans([10, 0, 0]))
+                j.q[0] = math.pi / 4
+            j.qdot[0] = 1
+            b.setBodyTransform(_trans([5, 0, 0]))
+            j.setStiffness(1e4)
+            j.setDamping(1e4)
+            scene.bodies.append(b)
+            scene.joints.append(j)
+        scene.task = (api.TaskBDF1PointPos if sceneID == 100 else api.TaskBDF2PointPos)(scene)
+        scene.task.setTime(scene.tEnd)
+        scene.task.setBody(scene.bodies[-1])
+        scene.task.setPoint([5, 0, 0])
+        scene.task.setTarget([10, 0, -10] if sceneID == 100 else [-10, 0, -10])
+        scene.task.setScale(1e5)
+        scene.task.setWeights(1e-2, 1e2)
+    else:
+        raise ValueError('scene %r is outside the hot-path scope' % (sceneID,))
+    return scene
+
+
+def chain_scene(n, ground=False, h=1e-2, nsteps=100, axis=(0, 1, 0), ground_z=-40.0, api=None):
+    """C2/C3/C5 of BASELINE.json: n-link serial chain after the scene 0/-1 pattern (scenesRedMax.m:27-79), every
+    joint revolute; optional ForceGroundCuboid per link with scene 11's constants (scenesRedMax.m:306-311)."""
+    api = api or _api
+    scene = api.Scene()
+    scene.name = '%d-link chain%s' % (n, ' + ground' if ground else '')
+    scene.h = h
+    scene.tEnd = nsteps * h
+    for i in range(1, n + 1):
+        b = api.BodyCuboid(1.0, [10, 1, 1])
+        if i == 1:
+            j = api.JointRevolute(None, b, axis)
+            j.setJointTransform(np.eye(4))
+        else:
+            j = api.JointRevolute(scene.joints[i - 2], b, axis)
+            j.setJointTransform(_trans([10, 0, 0]))
+        b.setBodyTransform(_trans([5, 0, 0]))
+        j.q[0] = math.pi / 4 if i % 2 == 1 else 0.0
+        scene.bodies.append(b)
+        scene.joints.append(j)
+    if ground:
+        for b in scene.bodies:
+            f = api.ForceGroundCuboid(b)
+            f.setTransform(_trans([0, 0, ground_z]))
+            f.setStiffness(1e5, 1e2)
+            f.setDamping(3e1)
+            f.setFriction(0.5)
+            scene.forces.append(f)
+    return scene
+
+
+def hand_scene(h=1e-2, nsteps=100, scheme=1, api=None):
+    """C4: fixed palm + 5 fingers x 4 revolute phalanges, TaskBDF*PointPos on the index fingertip, joint stiffness
+    and damping as scene 100 (scenesRedMax.m:426-436)."""
+    api = api or _api
+    scene = api.Scene()
+    scene.name = 'hand'
+    scene.h = h
+    scene.tEnd = nsteps * h
+    palm = api.BodyCuboid(1.0, [8, 8, 1])
+    jp = api.JointFixed(None, palm)
+    jp.setJointTransform(np.eye(4))
+    palm.setBodyTransform(np.eye(4))
+    scene.bodies.append(palm)
+    scene.joints.append(jp)
+    tip = None
+    for fi, y in enumerate([-3.0, -1.5, 0.0, 1.5, 3.0]):
+        parent = jp
+        for k in range(4):
+            b = api.BodyCuboid(1.0, [3, 0.8, 0.8])
+            ax = [0, 0, 1] if (fi == 0 and k == 0) else [0, 1, 0]
+            j = api.JointRevolute(parent, b, ax)
+            j.setJointTransform(_trans([4, y, 0]) if k == 0 else _trans([3, 0, 0]))
+            b.setBodyTransform(_trans([1.5, 0, 0]))
+            j.setStiffness(1e4)
+            j.setDamping(1e4)
+            scene.bodies.append(b)
+            scene.joints.append(j)
+            parent = j
+        if fi == 1:
+            tip = scene.bodies[-1]
+    scene.task = (api.TaskBDF1PointPos if scheme == 1 else api.TaskBDF2PointPos)(scene)
+    scene.task.setTime(scene.tEnd)
+    scene.task.setBody(tip)
+    scene.task.setPoint([1.5, 0, 0])
+    scene.task.setTarget([10, -1.5, -5])
+    scene.task.setScale(1e5)
+    scene.task.setWeights(1e-2, 1e2)
+    return scene
+
+
+def synthetic_inputs(scene, B, seed):
+    """Per-rollout initial states of SURVEY.md section 8(d): q0 = qInit + 0.1*U(-1,1), qdot0 = U(-1,1), drawn from
+    numpy Generator(PCG64(seed)) so the oracle and the GPU see identical inputs.  Returns [B, nr] arrays."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    nr = scene.nr
+    q0 = scene.qInit[None, :] + 0.1 * rng.uniform(-1.0, 1.0, (B, nr))
+    qdot0 = rng.uniform(-1.0, 1.0, (B, nr))
+    return q0, qdot0

@@ -1,0 +1,152 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle on identical scenes and seeds.
+
+Bars: q(t) within 1e-10 relative (BASELINE.json north_star); single evaluations (g, H, M, D) within 1e-11."""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL_Q = 1e-10    # north_star: q(t) within 1e-10 relative of the reference on identical scenes and seeds
+TOL_EVAL = 1e-11
+
+
+def both(rb, oracle, factory, *a, **kw):
+    sg = factory(*a, **kw)
+    sg.init()
+    so = factory(*a, api=oracle, **kw)
+    so.init()
+    assert sg.nr == so.nr and sg.nm == so.nm
+    np.testing.assert_array_equal(sg.qInit, so.qInit)
+    return sg, so
+
+
+def oracle_eval(oracle, so, q, qdot0, q0, tau=None):
+    """BDF1 evaluation at q with history (q0, qdot0): returns g, H, M, D."""
+    so.setQ0(q0, qdot0)
+    for j in so.joints:
+        j.tau = (np.zeros(j.ndof) if tau is None else np.asarray(tau)[j.idxR].copy())
+    g, H, M, f, K, D, J = oracle.eval_bdf1(q, so, True, True)
+    return g, H, M, D, f
+
+
+CASES = [
+    ('scene0', lambda rb: (rb.scenesRedMax, (0,), {})),
+    ('scene1', lambda rb: (rb.scenesRedMax, (1,), {})),
+    ('scene2', lambda rb: (rb.scenesRedMax, (2,), {})),
+    ('scene14', lambda rb: (rb.scenesRedMax, (14,), {})),
+    ('hand', lambda rb: (rb.hand_scene, (), {})),
+    ('chain10', lambda rb: (rb.chain_scene, (10,), {})),
+    ('chain32', lambda rb: (rb.chain_scene, (32,), {})),
+    ('chain6ground', lambda rb: (rb.chain_scene, (6,), dict(ground=True, h=5e-4, ground_z=-48.5))),
+    ('chain40', lambda rb: (rb.chain_scene, (40,), {})),
+]
+
+
+@pytest.mark.parametrize('name,mk', CASES, ids=[c[0] for c in CASES])
+def test_eval_matches_oracle(rb, oracle, name, mk):
+    factory, a, kw = mk(rb)
+    sg, so = both(rb, oracle, factory, *a, **kw)
+    rng = np.random.default_rng(42)
+    nr = sg.nr
+    h = sg.h
+    for trial in range(2):
+        q = sg.qInit + 0.3 * rng.uniform(-1, 1, nr)
+        q0 = q - 0.02 * rng.uniform(-1, 1, nr)
+        qdot0 = rng.uniform(-1, 1, nr)
+        tau = 100 * rng.uniform(-1, 1, nr)
+        if name == 'scene14':
+            q[0] = -2.0   # below the lower limit: exercises Joint.computeForce's hitL branch
+            q[1] = 0.4    # above the upper limit
+        g, H, M, D, f = oracle_eval(oracle, so, q, qdot0, q0, tau)
+        out = sg.eval(q, (q - q0) / h, q - q0 - h * qdot0, h * h, 1.0 / h, tau=tau)
+        assert rel_err(out['g'], g) < TOL_EVAL, ('g', rel_err(out['g'], g))
+        assert rel_err(out['H'], H) < TOL_EVAL, ('H', rel_err(out['H'], H))
+        assert rel_err(out['M'], M) < TOL_EVAL, ('M', rel_err(out['M'], M))
+        assert rel_err(out['D'], D) < 1e-10, ('D', rel_err(out['D'], D))
+        assert rel_err(out['f'], f) < 1e-9, ('f', rel_err(out['f'], f))
+
+
+def test_ground_contact_active(rb, oracle):
+    """The ground case above really has corners in contact (otherwise it would test nothing)."""
+    so = rb.chain_scene(6, ground=True, h=5e-4, ground_z=-48.5, api=oracle)
+    so.init()
+    so.update()
+    fm = np.zeros(so.nm)
+    for f in so.forces:
+        f.computeValues_(None, fm)
+    assert np.linalg.norm(fm) > 0
+
+
+ROLL = [
+    ('scene0', 1), ('scene0', 2), ('scene1', 1), ('scene1', 2), ('scene2', 1), ('scene2', 2),
+    ('scene14', 1), ('scene14', 2), ('hand', 1), ('chain10', 1), ('chain10', 2),
+]
+
+
+@pytest.mark.parametrize('name,scheme', ROLL, ids=['%s-bdf%d' % r for r in ROLL])
+def test_rollout_matches_oracle(rb, oracle, name, scheme):
+    factory, a, kw = dict(CASES)[name](rb)
+    sg, so = both(rb, oracle, factory, *a, **kw)
+    ns = sg.nsteps if sg.nr <= 5 else 25
+    # rollout 0: the scene's own initial state (the reference run); rollouts 1..: seeded perturbations
+    q0, qd0 = rb.synthetic_inputs(sg, 3, seed=20260000 + len(name))
+    q0[0], qd0[0] = sg.qInit, sg.qdotInit
+    out = sg.rollout(q0, qd0, scheme=scheme, nsteps=ns)
+    assert out['status'].tolist() == [0, 0, 0]
+    for b in range(3 if sg.nr <= 5 else 2):
+        stats = []
+        qs, qds = oracle.run_forward(so, scheme, q0[b], qd0[b], nsteps=ns, stats=stats)
+        assert rel_err(out['q'][b], qs) < TOL_Q, (b, rel_err(out['q'][b], qs))
+        assert rel_err(out['qdot'][b], qds) < 1e-8, (b, rel_err(out['qdot'][b], qds))
+        it = np.array(stats)
+        assert out['iters'][b, 0] == it[:, 0].sum(), (out['iters'][b], it[:, 0].sum())
+        assert out['iters'][b, 1] == it[:, 1].sum()
+
+
+def test_rollout_chain32_bdf1_short(rb, oracle):
+    """Headline shape (32-link chain, BDF1), a few steps against the dense oracle."""
+    sg, so = both(rb, oracle, rb.chain_scene, 32)
+    q0, qd0 = rb.synthetic_inputs(sg, 2, seed=20260003)
+    ns = 6
+    out = sg.rollout(q0, qd0, scheme=1, nsteps=ns)
+    for b in range(2):
+        qs, _ = oracle.run_forward(so, 1, q0[b], qd0[b], nsteps=ns)
+        assert rel_err(out['q'][b], qs) < TOL_Q, rel_err(out['q'][b], qs)
+
+
+def test_rollout_ground_bdf2(rb, oracle):
+    """C3 pattern at a size the oracle finishes quickly: chain + ForceGroundCuboid per link (normal spring/damper,
+    static and dynamic Coulomb friction), SDIRK2 start + BDF2.  The plane sits 1.4 mm inside the lowest corner
+    of the rest pose, so the chain starts in light contact and keeps bouncing/sliding."""
+    kw = dict(ground=True, h=5e-4, ground_z=-48.5)
+    sg, so = both(rb, oracle, rb.chain_scene, 6, **kw)
+    q0, qd0 = rb.synthetic_inputs(sg, 3, seed=20260002)
+    q0[0], qd0[0] = sg.qInit, sg.qdotInit
+    ns = 80
+    out = sg.rollout(q0, qd0, scheme=2, nsteps=ns)
+    for b in range(3):
+        stats = []
+        qs, _ = oracle.run_forward(so, 2, q0[b], qd0[b], nsteps=ns, stats=stats)
+        it = np.array(stats)
+        err = rel_err(out['q'][b], qs)
+        print('ground rollout %d: rel err %.2e, newton %d vs %d, status %d vs %d'
+              % (b, err, out['iters'][b, 0], it[:, 0].sum(), out['status'][b], np.bitwise_or.reduce(it[:, 2])))
+        assert err < TOL_Q, err
+
+
+def test_batch_independence_and_determinism(rb):
+    """Size-independent property at full batch: every rollout depends only on its own inputs (bitwise), and a
+    rerun is bitwise identical."""
+    sg = rb.chain_scene(32, nsteps=10)
+    sg.init()
+    B = 1024
+    q0, qd0 = rb.synthetic_inputs(sg, B, seed=7)
+    a = sg.rollout(q0, qd0, scheme=1)
+    b = sg.rollout(q0, qd0, scheme=1)
+    np.testing.assert_array_equal(a['q'], b['q'])
+    perm = np.random.default_rng(0).permutation(B)
+    c = sg.rollout(q0[perm], qd0[perm], scheme=1)
+    np.testing.assert_array_equal(a['q'][perm], c['q'])
+    assert (a['status'] == 0).all()

@@ -1,0 +1,116 @@
+"""CPU: pin the oracle against every golden vector the reference holds for the hot path.
+
+Golden end-of-run energies Hexpected(BDF1/BDF2) from matlab-diff/scenesRedMax.m:54-55, 82-83, 108-109, 292-293,
+373-374; pass criterion |H(end) - Hexpected| <= 1e-2 as Scene.plotEnergies (Scene.m:171-177)."""
+import numpy as np
+import pytest
+
+PINS = {
+    0: (-1.2705398823489915e+05, 2.6058008179021417e+03),
+    1: (-3.8359074258588909e+04, -9.7138545812971279e+02),
+    2: (-2.2826101928480086e+04, -2.4159349151742754e+02),
+    14: (-2.5928305306546572e+04, -1.8476279319765570e+04),
+    11: (-4.4208045000000002e+03, -2.7811251900394832e+03),
+}
+
+
+@pytest.mark.parametrize('sid', [0, 1, 2, 14])
+@pytest.mark.parametrize('itype', [1, 2])
+def test_hexpected(oracle, sid, itype):
+    s = oracle.scenes(sid)
+    s.init()
+    assert s.Hexpected[itype - 1] == PINS[sid][itype - 1]
+    (oracle.sim_loop_bdf1 if itype == 1 else oracle.sim_loop_bdf2)(s)
+    ok, H = s.checkEnergy(itype)
+    assert ok, (sid, itype, H)
+    # far tighter than the reference's 1e-2: the restatement reproduces the printed 17 digits to ~1e-8
+    assert abs(H - PINS[sid][itype - 1]) < 1e-6
+
+
+@pytest.mark.parametrize('itype', [2, 1])
+def test_hexpected_scene11_ground_contact(oracle, itype):
+    """The only end-to-end pin of ForceGroundCuboid (Free2D body bouncing on the ground, 1200 steps)."""
+    s = oracle.scenes(11)
+    s.init()
+    assert s.nsteps == 1200
+    (oracle.sim_loop_bdf1 if itype == 1 else oracle.sim_loop_bdf2)(s)
+    ok, H = s.checkEnergy(itype)
+    assert ok, H
+    assert abs(H - PINS[11][itype - 1]) < 1e-4
+
+
+def _fd_check(name, analytic, numeric, tol=1e-6):
+    """redmax.Scene.printError (Scene.m:424-450): relative error below 1e-6."""
+    e = np.linalg.norm(analytic - numeric)
+    n0, n1 = np.linalg.norm(analytic), np.linalg.norm(numeric)
+    if n0 > 1e-4 and n1 > 1e-4:
+        e = e / min(n0, n1)
+    assert e < tol, (name, e)
+
+
+@pytest.mark.parametrize('sid', [0, 1, 2, 14])
+def test_scene_test_fd_selfcheck(oracle, sid):
+    """Scene.test (Scene.m:224-378) restated with a fixed seed: H is the derivative of g, K and D of f."""
+    s = oracle.scenes(sid)
+    s.init()
+    rng = np.random.default_rng(100 + sid)
+    nr = s.nr
+    q1 = s.qInit + 0.3 * rng.uniform(-1, 1, nr)
+    q0 = q1 - 0.01 * rng.uniform(-1, 1, nr)
+    s.setQ0(q0, rng.uniform(-1, 1, nr))
+    g, H = oracle.eval_bdf1(q1, s, True)
+    eps = np.sqrt(np.finfo(float).eps)
+    Hn = np.zeros_like(H)
+    for i in range(nr):
+        x = q1.copy()
+        x[i] += eps
+        Hn[:, i] = (oracle.eval_bdf1(x, s, False) - g) / eps
+    _fd_check('H', H, Hn, 2e-6)
+
+
+def test_ground_contact_fd(oracle):
+    """ForceGroundCuboid.test/test3/test4 (ForceGroundCuboid.m:197-423) restated: Km, Dm are the derivatives of fm
+    in a state with corners in contact (static and dynamic friction both occur along the chain)."""
+    s = oracle.chain_scene(6, ground=True, h=1e-3)
+    for f in s.forces:
+        f.E[2, 3] = -12.0
+    s.init()
+    rng = np.random.default_rng(5)
+    nr = s.nr
+    q1 = s.qInit + 0.2 * rng.uniform(-1, 1, nr)
+    q0 = q1 - 1e-3 * rng.uniform(-1, 1, nr) * 5
+    s.setQ0(q0, rng.uniform(-1, 1, nr))
+    g, H = oracle.eval_bdf1(q1, s, True)
+    # some corner must be in contact for this to test anything
+    fm = np.zeros(s.nm)
+    for f in s.forces:
+        f.computeValues_(None, fm)
+    assert np.linalg.norm(fm) > 0
+    eps = 1e-7
+    Hn = np.zeros_like(H)
+    for i in range(nr):
+        x = q1.copy()
+        x[i] += eps
+        Hn[:, i] = (oracle.eval_bdf1(x, s, False) - g) / eps
+    _fd_check('H(ground)', H, Hn, 1e-5)
+
+
+def test_adjoint_gradient_fd(oracle):
+    """The reference's own check of the adjoint (driverRedMaxAdjointBDF1.m:47-61): dP/dp against forward
+    differences of P obtained by re-simulating.  Scenes 100/101 carry no golden number."""
+    for sid, scheme in ((100, 1), (101, 2)):
+        s = oracle.scenes(sid)
+        s.tEnd = 0.2
+        s.init()
+        s.task.setTime(s.tEnd)
+        p = np.array([0.02, -0.01])
+        P, dPdp = oracle.task_objective(p, s, scheme)
+        d = np.zeros_like(dPdp)
+        eps = 1e-6
+        for i in range(len(p)):
+            pp = p.copy()
+            pp[i] += eps
+            d[i] = (oracle.task_objective(pp, s, scheme)[0] - P) / eps
+        rel = np.linalg.norm(d - dPdp) / np.linalg.norm(d)
+        # BDF2's first-step dgdp coefficient is knowingly inexact in the reference (SURVEY note N7)
+        assert rel < (1e-4 if scheme == 1 else 5e-2), (sid, rel, d, dPdp)
