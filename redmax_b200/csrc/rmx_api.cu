@@ -41,7 +41,7 @@ struct DevCopy {
     JointConst* jc = nullptr;
     int* ends = nullptr;
     cudaStream_t stream = nullptr;
-    DevBuf buf[12];
+    DevBuf buf[16];
 };
 
 struct rmx_scene {
@@ -323,10 +323,10 @@ static int set_smem(K kernel, size_t bytes) {
 
 template <int NW, bool GROUND>
 static int launch_fwd_t(const RolloutArgs& a, size_t smem, cudaStream_t st) {
-    int rc = set_smem(rollout_fwd_kernel<NW, GROUND>, smem);
+    int rc = set_smem(rollout_fwd_kernel<NW, GROUND, false>, smem);
     if (rc) return rc;
     const long long grid = a.B;
-    rollout_fwd_kernel<NW, GROUND><<<(unsigned)grid, 32 * NW, smem, st>>>(a);
+    rollout_fwd_kernel<NW, GROUND, false><<<(unsigned)grid, 32 * NW, smem, st>>>(a);
     CUDA_TRY(cudaGetLastError());
     return RMX_OK;
 }

@@ -5,17 +5,22 @@
 namespace rmx {
 
 struct TapeArgs {
-    // adjoint tape, per rollout b and step k (internal layout, consumed only by adjoint_bwd_kernel):
-    //   LU   : nr*nr   column-major LU factors of H (unit-lower L below the diagonal)      [b][k][nr*nr]
-    //   perm : nr      int32 (Hp of lu(H,'vector'), 0-based)                               [b][k][nr]
-    //   M, D : nr*nr   row-major (i.e. transposed) so that M'z is a coalesced column sweep [b][k][nr*nr]
-    //   dPdq : nr                                                                          [b][k][nr]
-    double* LU;
+    // adjoint tape, per rollout b and step k (internal layout, consumed only by adjoint_bwd_kernel).
+    // What Scene.saveHistory keeps for Task*.calcFinal (Scene.m:141-148; only Hl,Hu,Hp,M,D are consumed):
+    //   A[b][k][sza] : one 16B-aligned record  { LU[nr*ld] | dPdq[nr] | perm int32[nr] (+pad) }
+    //                  LU = the shared-memory image of the factored H (column-major, ld = nr|1, unit-lower L
+    //                  below the diagonal) so the backward kernel can bulk-copy (TMA) it straight into smem;
+    //                  perm = Hp of lu(H,'vector') (0-based)
+    //   M[b][k][nr*nr], D[b][k][nr*nr] : row-major, so thread i streams column i of M' with coalesced loads
+    double* A;
     double* M;
     double* D;
-    double* dPdq;
-    int* perm;
+    int sza;  // doubles per A record
 };
+__host__ __device__ inline int tape_sza(int nr) {
+    int d = nr * h_ld(nr) + nr + (nr + 1) / 2;
+    return (d + 1) & ~1;
+}
 
 struct TaskArgs {
     int body;  // internal joint index of the task body
@@ -105,9 +110,87 @@ __device__ __forceinline__ int newton_forward(Ctx& c, const StepOpts& op, int* p
 }
 
 // ---------------------------------------------------------------------------------------------
-// Forward rollout kernel: simLoop of driverRedMaxBDF1.m:57-91 / driverRedMaxBDF2.m:57-125, one block per rollout.
+// newton() of driverRedMaxAdjointBDF1.m:105-146 (= driverRedMaxAdjointBDF2.m:139-180): LU with row permutation,
+// no line search, convergence test on the PRE-update residual, so one more full step is always taken after
+// ||g|| < tol and the returned tape (LU(H), Hp, M, D, J) belongs to the last evaluation point.
+// If `save`, that tape is written to global memory; if `want_J`, the task body's rows of J (6 x nr, the only rows
+// TaskBDF1PointPos.calcStep reads) are left in shared memory behind H.
 // ---------------------------------------------------------------------------------------------
+template <int NW>
+__device__ __forceinline__ void store_rowmajor(const Ctx& c, const double* H, double* __restrict__ dst) {
+    const int nr = c.nr, ld = c.ld;
+    for (int e = threadIdx.x; e < nr * nr; e += 32 * NW) {
+        const int r = e / nr, i = e - r * nr;
+        dst[e] = H[(size_t)i * ld + r];
+    }
+}
+
 template <int NW, bool GROUND>
+__device__ __forceinline__ int newton_adjoint(Ctx& c, const StepOpts& op, int* perm, int& n_iter, bool save,
+                                              double* __restrict__ tA, double* __restrict__ tM,
+                                              double* __restrict__ tD, bool want_J, int jb) {
+    const int t = threadIdx.x;
+    const int nr = c.nr, ld = c.ld;
+    int status = 0;
+    int iter = 1;
+    while (true) {
+        eval_base<NW, GROUND>(c, true);
+        const double gt = (t < nr) ? c.g[t] : 0.0;
+        const double gsum = block_sum<NW>(gt * gt, c.red);
+        eval_columns<NW, GROUND>(c, 1.0, c.beta, 1.0, 1.0, c.H);
+        lu_factor<NW>(c, c.H, perm);
+        lu_solve<NW>(c, c.H, perm, c.g, c.dx, -1.0);
+        const double dxt = (t < nr) ? c.dx[t] : 0.0;
+        const double dxn = sqrt(block_sum<NW>(dxt * dxt, c.red));
+        ++n_iter;
+        const bool diverged = dxn > op.dxMax;
+        const bool conv = sqrt(gsum) < op.tol;
+        const bool last = diverged || conv || iter >= op.iterMax;
+        if (last && save) {
+            for (int e = t; e < nr * ld; e += 32 * NW) tA[e] = c.H[e];
+            if (t < nr) reinterpret_cast<int*>(tA + (size_t)nr * ld + nr)[t] = perm[t];
+            bsync<NW>();
+            eval_columns<NW, GROUND>(c, 0.0, 0.0, 1.0, 1.0, c.H);  // M = dg/d(dqtmp)
+            store_rowmajor<NW>(c, c.H, tM);
+            bsync<NW>();
+            eval_columns<NW, GROUND>(c, 0.0, 1.0, 0.0, -1.0 / c.c, c.H);  // D = df/dqdot = -(1/cK) dg/dqdot
+            store_rowmajor<NW>(c, c.H, tD);
+            if (want_J) {
+                // J(idxM(body), :) : column of joint k is Ad(E_body^-1) s_k for ancestors-or-self k of the body, else 0
+                double* Jb = c.H + (size_t)nr * ld;
+                if (t < c.n && c.jc[t].idx >= 0) {
+                    double col[6] = {0, 0, 0, 0, 0, 0};
+                    if (t <= jb && jb < c.jc[t].end) {
+                        const double* rb = c.rec1 + (size_t)jb * REC1;
+                        xm_w2b(rb, rb + 9, c.rec1 + (size_t)t * REC1 + 18, col);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) Jb[6 * c.jc[t].idx + i] = col[i];
+                }
+            }
+            bsync<NW>();
+        }
+        if (diverged) {
+            status |= 1;
+            break;
+        }
+        if (t < nr) c.q[t] = __dadd_rn(c.q[t], dxt);
+        bsync<NW>();
+        if (conv) break;
+        if (iter >= op.iterMax) {
+            status |= 2;
+            break;
+        }
+        ++iter;
+    }
+    return status;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Forward rollout kernel: simLoop of driverRedMaxBDF1.m:57-91 / driverRedMaxBDF2.m:57-125 (ADJ = false) and of
+// driverRedMaxAdjointBDF1.m:65-102 / driverRedMaxAdjointBDF2.m:65-136 (ADJ = true), one block per rollout.
+// ---------------------------------------------------------------------------------------------
+template <int NW, bool GROUND, bool ADJ>
 __global__ void __launch_bounds__(32 * NW) rollout_fwd_kernel(RolloutArgs a) {
     extern __shared__ double2 smem_raw[];
     double* sm = reinterpret_cast<double*>(smem_raw);
@@ -133,13 +216,20 @@ __global__ void __launch_bounds__(32 * NW) rollout_fwd_kernel(RolloutArgs a) {
         if (t < nr) {
             qc = a.q0[b * nr + t];
             qdc = a.qd0[b * nr + t];
-            c.tau[t] = (op.tau_mode == 1) ? a.tau[b * nr + t] : 0.0;
+            if (ADJ)  // task.applyStep: joints{i}.tau = pscale*p(idxR)   (TaskBDF1PointPos.m:58-64)
+                c.tau[t] = __dmul_rn(a.task.pscale, a.task.p[b * nr + t]);
+            else
+                c.tau[t] = (op.tau_mode == 1) ? a.tau[b * nr + t] : 0.0;
             c.hq1[t] = qc;
             c.hqd1[t] = qdc;
         }
         int status = 0, n_iter = 0, n_ls = 0;
+        double tcur = 0.0, Pacc = 0.0;  // scene.t (Scene.m:122), task.P
         for (int k = 0; k < op.nsteps; ++k) {
-            if (op.tau_mode == 2 && t < nr) c.tau[t] = a.tau[((size_t)b * op.nsteps + k) * nr + t];
+            if (!ADJ && op.tau_mode == 2 && t < nr) c.tau[t] = a.tau[((size_t)b * op.nsteps + k) * nr + t];
+            // scene.t after this step; TaskBDF1PointPos.calcStep samples the objective when |t_target - t| < 1e-6
+            const double tnext = __dadd_rn(tcur, h);
+            const bool is_obj = ADJ && (fabs(__dsub_rn(a.task.t_target, tnext)) < 1e-6);
             const int nsub = (op.scheme == 2 && k == 0) ? 2 : 1;
             for (int sub = 0; sub < nsub; ++sub) {
                 const int stage = (op.scheme == 1) ? ST_BDF1 : (k == 0 ? (sub == 0 ? ST_SDIRK_A : ST_SDIRK_B) : ST_BDF2);
@@ -172,7 +262,16 @@ __global__ void __launch_bounds__(32 * NW) rollout_fwd_kernel(RolloutArgs a) {
                 }
                 stage_coef(c, stage, h);
                 bsync<NW>();
-                status |= newton_forward<NW, GROUND>(c, op, perm_s, n_iter, n_ls);
+                if (ADJ) {
+                    // the BDF2 adjoint driver keeps only the second SDIRK sub-solve's tape (driverRedMaxAdjointBDF2.m:88,96)
+                    const bool save = stage != ST_SDIRK_A;
+                    const size_t rec = (size_t)b * op.nsteps + k;
+                    status |= newton_adjoint<NW, GROUND>(c, op, perm_s, n_iter, save, a.tape.A + rec * a.tape.sza,
+                                                         a.tape.M + rec * nr * nr, a.tape.D + rec * nr * nr,
+                                                         save && is_obj, a.task.body);
+                } else {
+                    status |= newton_forward<NW, GROUND>(c, op, perm_s, n_iter, n_ls);
+                }
                 // ---- new state ----------------------------------------------------------------------------
                 if (t < nr) {
                     const double x = c.q[t];
@@ -191,10 +290,38 @@ __global__ void __launch_bounds__(32 * NW) rollout_fwd_kernel(RolloutArgs a) {
                     qc = x;
                 }
             }
+            tcur = tnext;
             if (t < nr) {
                 const size_t o = ((size_t)b * op.nsteps + k) * nr + t;
-                a.q_out[o] = qc;
+                if (a.q_out) a.q_out[o] = qc;
                 if (a.qd_out) a.qd_out[o] = qdc;
+            }
+            if (ADJ) {
+                // task.calcStep (TaskBDF1PointPos.m:67-107): objective and dP/dq_k at the stored (final) q, with the
+                // tape's J, i.e. the Jacobian of the last Newton evaluation point (note N4 of SURVEY.md)
+                double dPdq = 0.0;
+                if (is_obj) {
+                    bsync<NW>();
+                    eval_base<NW, GROUND>(c, false);  // c.q holds the final iterate: FK at history(k).q
+                    const double* rb = c.rec1 + (size_t)a.task.body * REC1;
+                    double xw[3], dx3[3], y[3], v6[6];
+                    mat3_vec(rb, a.task.xlocal, xw);
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) dx3[i] = (xw[i] + rb[9 + i]) - a.task.xtarget[3 * b + i];
+                    Pacc += a.task.wpos * 0.5 * (dx3[0] * dx3[0] + dx3[1] * dx3[1] + dx3[2] * dx3[2]);
+                    mat3T_vec(rb, dx3, y);               // R' dx
+                    cross3(a.task.xlocal, y, v6);        // Gamma' y = [xlocal x y ; y]
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        v6[i] *= a.task.wpos;
+                        v6[3 + i] = y[i] * a.task.wpos;
+                    }
+                    if (t < nr) dPdq = dot6(c.H + (size_t)nr * c.ld + 6 * t, v6);
+                }
+                if (t < nr) {
+                    double* recA = a.tape.A + ((size_t)b * op.nsteps + k) * a.tape.sza;
+                    recA[(size_t)nr * c.ld + t] = dPdq;
+                }
             }
             bsync<NW>();
         }
@@ -207,6 +334,7 @@ __global__ void __launch_bounds__(32 * NW) rollout_fwd_kernel(RolloutArgs a) {
                 a.iters[2 * b] = n_iter;
                 a.iters[2 * b + 1] = n_ls;
             }
+            if (ADJ) a.task.P[b] = Pacc;  // objective part; the regulariser is added by the backward kernel
         }
         bsync<NW>();
     }

@@ -360,6 +360,26 @@ class Scene:
                                  ptr(status), ptr(iters)), 'rmx_rollout')
         return dict(q=q, qdot=qd, status=status, iters=iters)
 
+    def rollout_into(self, q0, qdot0, q_out, qdot_out=None, tau=None, scheme=1, nsteps=None, ngpus=1, **kw):
+        """rmx_rollout with caller-owned host buffers (e.g. pinned memory): q0, qdot0 [B, nr] float64 C-contiguous,
+        q_out / qdot_out [B, nsteps, nr].  Returns dict(status, iters)."""
+        L = self._require()
+        B = q0.shape[0]
+        tau_mode = _ffi.RMX_TAU_NONE
+        if tau is not None:
+            tau_mode = _ffi.RMX_TAU_CONST if tau.ndim == 2 else _ffi.RMX_TAU_PER_STEP
+        o = self.opts(scheme=scheme, nsteps=nsteps, ngpus=ngpus, tau_mode=tau_mode, **kw)
+        for a in (q0, qdot0, q_out, qdot_out, tau):
+            if a is not None and not (a.dtype == np.float64 and a.flags['C_CONTIGUOUS']):
+                raise ValueError('rollout_into needs C-contiguous float64 arrays')
+        if q0.shape != (B, self.nr) or qdot0.shape != (B, self.nr) or q_out.shape != (B, o.nsteps, self.nr):
+            raise ValueError('rollout_into: shape mismatch')
+        status = np.empty(B, dtype=np.int32)
+        iters = np.empty((B, 2), dtype=np.int32)
+        _ffi.check(L.rmx_rollout(self._handle, C.byref(o), B, ptr(q0), ptr(qdot0), ptr(tau), ptr(q_out), ptr(qdot_out),
+                                 ptr(status), ptr(iters)), 'rmx_rollout')
+        return dict(status=status, iters=iters)
+
     def rollout_dev(self, q0, qdot0, q_out, qdot_out, status, iters=None, tau=None, scheme=1, nsteps=None,
                     stream=None, **kw):
         """Device-buffer call (torch CUDA tensors or raw device addresses), enqueued on `stream` (a

@@ -38,8 +38,7 @@ def run(n, B, nsteps, scheme, ground=False, h=1e-2, reps=3):
 
 if __name__ == '__main__':
     print(torch.cuda.get_device_name(0))
-    run(10, 1024, 100, 1)
-    run(32, 4096, 100, 1)
-    run(32, 4096, 100, 2)
-    run(32, 4096, 100, 2, ground=True, h=1e-3)
-    run(64, 8192, 20, 1)
+    run(10, 1024, 100, 1, h=1e-3)
+    run(32, 4096, 100, 1, h=1e-3)
+    run(32, 4096, 100, 2, h=1e-3)
+    run(64, 8192, 50, 1, h=2e-4)
