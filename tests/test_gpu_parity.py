@@ -150,3 +150,49 @@ def test_batch_independence_and_determinism(rb):
     c = sg.rollout(q0[perm], qd0[perm], scheme=1)
     np.testing.assert_array_equal(a['q'][perm], c['q'])
     assert (a['status'] == 0).all()
+
+
+@pytest.fixture(scope='module')
+def oc():
+    """compiled twin of the oracle (oracle/redmax_oracle_c.c), prebuilt by __graft_entry__.build()"""
+    import oracle_c
+    if not oracle_c.available():
+        import __graft_entry__ as ge
+        ge.build_oracle()
+    return oracle_c
+
+
+@pytest.mark.parametrize('scheme', [1, 2])
+def test_headline_workload_full_length_vs_c_oracle(rb, oracle, oc, scheme):
+    """BASELINE.json's headline shape at full length: 32-link chain, 100 steps, h = 1e-3 (bench.py's workload), a
+    sample of the seeded batch against the reference's dense algorithm (C twin of the oracle; the NumPy oracle needs
+    minutes per rollout at this size)."""
+    sg, so = both(rb, oracle, rb.chain_scene, 32, h=1e-3)
+    B = 8
+    q0, qd0 = rb.synthetic_inputs(sg, B, seed=20260003)
+    out = sg.rollout(q0, qd0, scheme=scheme)
+    q, qd, st = oc.run_forward_batch(so, scheme, q0, qd0, threads=min(B, oc.max_threads()))
+    assert (out['status'] == 0).all() and (st[:, 2] == 0).all()
+    assert rel_err(out['q'], q) < TOL_Q, rel_err(out['q'], q)
+    np.testing.assert_array_equal(out['iters'], st[:, :2])
+
+
+def test_c3_ground_friction_bdf2_vs_c_oracle(rb, oracle, oc):
+    """Config C3 pattern: 32-link chain with a ForceGroundCuboid on every link, SDIRK2 start + BDF2, contacts active."""
+    kw = dict(ground=True, h=5e-4, ground_z=-40.0)
+    sg, so = both(rb, oracle, rb.chain_scene, 32, **kw)
+    B = 4
+    q0, qd0 = rb.synthetic_inputs(sg, B, seed=20260002)
+    ns = 40
+    out = sg.rollout(q0, qd0, scheme=2, nsteps=ns)
+    q, qd, st = oc.run_forward_batch(so, 2, q0, qd0, nsteps=ns, threads=min(B, oc.max_threads()))
+    free = rb.chain_scene(32, h=5e-4)
+    free.init()
+    assert rel_err(free.rollout(q0, qd0, scheme=2, nsteps=ns)['q'], out['q']) > 1e-6  # the ground really acts
+    for b in range(B):
+        err = rel_err(out['q'][b], q[b])
+        print('C3 rollout %d: rel err %.2e newton %d vs %d status %d vs %d' % (b, err, out['iters'][b, 0], st[b, 0],
+                                                                              out['status'][b], st[b, 2]))
+    ok = st[:, 2] == 0  # compare where the reference's Newton converged in every step
+    assert ok.any()
+    assert rel_err(out['q'][ok], q[ok]) < TOL_Q
