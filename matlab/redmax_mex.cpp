@@ -1,0 +1,180 @@
+// redmax_mex.cpp -- MEX gateway from MATLAB to the C ABI of include/redmax_b200.h.
+//
+// Build on a machine with MATLAB (mex.h is not present in the build image, so this file is compiled there only):
+//     mex -R2018a CXXFLAGS='$CXXFLAGS -std=c++14' -I<repo>/include redmax_mex.cpp -L<repo>/redmax_b200/lib -lredmax_b200
+//
+// Usage from MATLAB (all arrays double, column-major as MATLAB stores them; batch is the trailing dimension):
+//     h        = redmax_mex('create', desc)                    desc: struct produced by +redmax/Scene.flatten
+//     [q,qdot,status,iters] = redmax_mex('rollout', h, opts, q0, qdot0, tau)     q0,qdot0: nr x B ; q: nr x nsteps x B
+//     [P,dPdp,status,q]     = redmax_mex('adjoint', h, opts, task, q0, qdot0, p, xtarget)
+//     [T,V]    = redmax_mex('energies', h, q, qdot)
+//     redmax_mex('destroy', h)
+// The handle is a uint64 scalar.  Errors from the library are raised as MATLAB errors with rmx_last_error().
+#ifdef MATLAB_MEX_FILE
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mex.h"
+#include "redmax_b200.h"
+
+static std::vector<rmx_scene*> g_scenes;
+
+static void cleanup() {
+    for (rmx_scene* s : g_scenes)
+        if (s) rmx_scene_destroy(s);
+    g_scenes.clear();
+}
+
+static const mxArray* field(const mxArray* s, const char* name, bool required = true) {
+    const mxArray* f = mxGetField(s, 0, name);
+    if (!f && required) mexErrMsgIdAndTxt("redmax:arg", "missing field '%s'", name);
+    return f;
+}
+static double scalar(const mxArray* s, const char* name, double dflt) {
+    const mxArray* f = mxGetField(s, 0, name);
+    return f ? mxGetScalar(f) : dflt;
+}
+static std::vector<int32_t> to_i32(const mxArray* a) {
+    const size_t n = mxGetNumberOfElements(a);
+    std::vector<int32_t> v(n);
+    const double* p = mxGetDoubles(a);
+    for (size_t i = 0; i < n; ++i) v[i] = (int32_t)p[i];
+    return v;
+}
+static void check(int rc, const char* what) {
+    if (rc != RMX_OK) mexErrMsgIdAndTxt("redmax:lib", "%s failed (%d): %s", what, rc, rmx_last_error());
+}
+static rmx_scene* handle(const mxArray* a) {
+    const uint64_t h = *(const uint64_t*)mxGetData(a);
+    return (rmx_scene*)(uintptr_t)h;
+}
+static rmx_opts opts_from(const mxArray* o, int adjoint) {
+    rmx_opts r;
+    rmx_opts_default(&r, (int32_t)scalar(o, "scheme", 1), adjoint);
+    r.nsteps = (int32_t)scalar(o, "nsteps", r.nsteps);
+    r.h = scalar(o, "h", r.h);
+    r.tol = scalar(o, "tol", r.tol);
+    r.dxMax = scalar(o, "dxMax", r.dxMax);
+    r.iterMaxFactor = (int32_t)scalar(o, "iterMaxFactor", r.iterMaxFactor);
+    r.iterLsMax = (int32_t)scalar(o, "iterLsMax", r.iterLsMax);
+    r.linsolve = (int32_t)scalar(o, "linsolve", r.linsolve);
+    r.ngpus = (int32_t)scalar(o, "ngpus", 1);
+    return r;
+}
+
+void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+    if (nrhs < 1 || !mxIsChar(prhs[0])) mexErrMsgIdAndTxt("redmax:arg", "first argument must be a command string");
+    char cmd[32];
+    mxGetString(prhs[0], cmd, sizeof(cmd));
+    static bool locked = false;
+    if (!locked) {
+        mexLock();
+        mexAtExit(cleanup);
+        locked = true;
+    }
+    if (!std::strcmp(cmd, "create")) {
+        const mxArray* d = prhs[1];
+        rmx_scene_desc sd;
+        std::memset(&sd, 0, sizeof(sd));
+        std::vector<int32_t> parent = to_i32(field(d, "parent")), jtype = to_i32(field(d, "jtype")), gbody;
+        sd.n = (int32_t)parent.size();
+        sd.parent = parent.data();
+        sd.jtype = jtype.data();
+        sd.E0_pj = mxGetDoubles(field(d, "E0_pj"));  // 4 x 4 x n, column-major == what rmx_scene_desc wants
+        sd.E0_ji = mxGetDoubles(field(d, "E0_ji"));
+        sd.axis = mxGetDoubles(field(d, "axis"));    // 3 x n
+        sd.I_i = mxGetDoubles(field(d, "I_i"));      // 6 x n
+        sd.sides = mxGetDoubles(field(d, "sides"));  // 3 x n
+        sd.stiffness = mxGetDoubles(field(d, "stiffness"));
+        sd.damping = mxGetDoubles(field(d, "damping"));
+        sd.qRest = mxGetDoubles(field(d, "qRest"));
+        sd.qLimL = mxGetDoubles(field(d, "qLimL"));
+        sd.qLimU = mxGetDoubles(field(d, "qLimU"));
+        sd.qLimK = mxGetDoubles(field(d, "qLimK"));
+        sd.qLimD = mxGetDoubles(field(d, "qLimD"));
+        std::memcpy(sd.grav, mxGetDoubles(field(d, "grav")), 3 * sizeof(double));
+        const mxArray* gb = field(d, "ground_body", false);
+        if (gb && mxGetNumberOfElements(gb) > 0) {
+            gbody = to_i32(gb);
+            sd.nground = (int32_t)gbody.size();
+            sd.ground_body = gbody.data();
+            sd.ground_E = mxGetDoubles(field(d, "ground_E"));
+            sd.ground_kn = mxGetDoubles(field(d, "ground_kn"));
+            sd.ground_kt = mxGetDoubles(field(d, "ground_kt"));
+            sd.ground_kd = mxGetDoubles(field(d, "ground_kd"));
+            sd.ground_mu = mxGetDoubles(field(d, "ground_mu"));
+        }
+        rmx_scene* s = nullptr;
+        check(rmx_scene_create(&sd, &s), "rmx_scene_create");
+        g_scenes.push_back(s);
+        plhs[0] = mxCreateNumericMatrix(1, 1, mxUINT64_CLASS, mxREAL);
+        *(uint64_t*)mxGetData(plhs[0]) = (uint64_t)(uintptr_t)s;
+    } else if (!std::strcmp(cmd, "destroy")) {
+        rmx_scene* s = handle(prhs[1]);
+        for (auto& p : g_scenes)
+            if (p == s) p = nullptr;
+        rmx_scene_destroy(s);
+    } else if (!std::strcmp(cmd, "rollout")) {
+        rmx_scene* s = handle(prhs[1]);
+        rmx_opts o = opts_from(prhs[2], 0);
+        const int nr = rmx_scene_nr(s);
+        const mwSize B = mxGetN(prhs[3]);
+        const mxArray* tau = nrhs > 5 && !mxIsEmpty(prhs[5]) ? prhs[5] : nullptr;
+        o.tau_mode = !tau ? RMX_TAU_NONE : (mxGetNumberOfElements(tau) == (size_t)nr * B ? RMX_TAU_CONST : RMX_TAU_PER_STEP);
+        const mwSize dims[3] = {(mwSize)nr, (mwSize)o.nsteps, B};
+        plhs[0] = mxCreateNumericArray(3, dims, mxDOUBLE_CLASS, mxREAL);
+        mxArray* qd = mxCreateNumericArray(3, dims, mxDOUBLE_CLASS, mxREAL);
+        mxArray* st = mxCreateNumericMatrix(B, 1, mxINT32_CLASS, mxREAL);
+        mxArray* it = mxCreateNumericMatrix(2, B, mxINT32_CLASS, mxREAL);
+        check(rmx_rollout(s, &o, (int64_t)B, mxGetDoubles(prhs[3]), mxGetDoubles(prhs[4]), tau ? mxGetDoubles(tau) : nullptr,
+                          mxGetDoubles(plhs[0]), mxGetDoubles(qd), (int32_t*)mxGetData(st), (int32_t*)mxGetData(it)),
+              "rmx_rollout");
+        if (nlhs > 1) plhs[1] = qd; else mxDestroyArray(qd);
+        if (nlhs > 2) plhs[2] = st; else mxDestroyArray(st);
+        if (nlhs > 3) plhs[3] = it; else mxDestroyArray(it);
+    } else if (!std::strcmp(cmd, "adjoint")) {
+        rmx_scene* s = handle(prhs[1]);
+        rmx_opts o = opts_from(prhs[2], 1);
+        const mxArray* t = prhs[3];
+        rmx_task_pointpos tk;
+        std::memset(&tk, 0, sizeof(tk));
+        tk.body = (int32_t)scalar(t, "body", 1) - 1;  // MATLAB index -> 0-based
+        std::memcpy(tk.xlocal, mxGetDoubles(field(t, "xlocal")), 3 * sizeof(double));
+        tk.t_target = scalar(t, "t", 0);
+        tk.pscale = scalar(t, "pscale", 1);
+        tk.wreg = scalar(t, "wreg", 1);
+        tk.wpos = scalar(t, "wpos", 1);
+        const int nr = rmx_scene_nr(s);
+        const mwSize B = mxGetN(prhs[6]);
+        plhs[0] = mxCreateDoubleMatrix(B, 1, mxREAL);
+        mxArray* G = mxCreateDoubleMatrix(nr, B, mxREAL);
+        mxArray* st = mxCreateNumericMatrix(B, 1, mxINT32_CLASS, mxREAL);
+        mxArray* q = nullptr;
+        if (nlhs > 3) {
+            const mwSize dims[3] = {(mwSize)nr, (mwSize)o.nsteps, B};
+            q = mxCreateNumericArray(3, dims, mxDOUBLE_CLASS, mxREAL);
+        }
+        check(rmx_rollout_adjoint(s, &o, &tk, (int64_t)B, mxGetDoubles(prhs[4]), mxGetDoubles(prhs[5]), mxGetDoubles(prhs[6]),
+                                  mxGetDoubles(prhs[7]), mxGetDoubles(plhs[0]), mxGetDoubles(G), q ? mxGetDoubles(q) : nullptr,
+                                  (int32_t*)mxGetData(st)),
+              "rmx_rollout_adjoint");
+        if (nlhs > 1) plhs[1] = G; else mxDestroyArray(G);
+        if (nlhs > 2) plhs[2] = st; else mxDestroyArray(st);
+        if (nlhs > 3) plhs[3] = q;
+    } else if (!std::strcmp(cmd, "energies")) {
+        rmx_scene* s = handle(prhs[1]);
+        const mwSize B = mxGetN(prhs[2]);
+        plhs[0] = mxCreateDoubleMatrix(B, 1, mxREAL);
+        mxArray* V = mxCreateDoubleMatrix(B, 1, mxREAL);
+        check(rmx_energies(s, (int64_t)B, mxGetDoubles(prhs[2]), mxGetDoubles(prhs[3]), mxGetDoubles(plhs[0]), mxGetDoubles(V)),
+              "rmx_energies");
+        if (nlhs > 1) plhs[1] = V; else mxDestroyArray(V);
+    } else {
+        mexErrMsgIdAndTxt("redmax:arg", "unknown command '%s'", cmd);
+    }
+}
+#else
+// Not a MEX build: nothing to compile (mex.h exists only where MATLAB is installed).
+#endif

@@ -1,0 +1,52 @@
+function [q,qdot,status,iters] = rolloutBatch(scene,scheme,q0,qdot0,tau)
+% rolloutBatch  GPU replacement of simLoop(scene) of driverRedMaxBDF1.m:57 / driverRedMaxBDF2.m:57 for B rollouts.
+%   scene   redmax.Scene after scene.init()  (built by scenesRedMax.m unchanged)
+%   scheme  1 = BDF1, 2 = SDIRK2 start + BDF2
+%   q0,qdot0  nr x B initial states (column b = rollout b); tau: [] | nr x B | nr x nsteps x B
+%   q,qdot  nr x nsteps x B == history(k).q / history(k).qdot of each rollout (Scene.m:136-137)
+% See INTEGRATION.md.  Requires redmax_mex (matlab/redmax_mex.cpp) and libredmax_b200.so.
+if nargin < 5, tau = []; end
+h = redmax_mex('create',flattenScene(scene));
+opts = struct('scheme',scheme,'nsteps',scene.nsteps,'h',scene.h);
+[q,qdot,status,iters] = redmax_mex('rollout',h,opts,q0,qdot0,tau);
+redmax_mex('destroy',h);
+end
+
+function d = flattenScene(scene)
+% Flattens the +redmax object graph into the arrays of rmx_scene_desc (include/redmax_b200.h).
+n = length(scene.joints);
+d.parent = zeros(1,n); d.jtype = zeros(1,n);
+d.E0_pj = zeros(4,4,n); d.E0_ji = zeros(4,4,n); d.axis = zeros(3,n); d.I_i = zeros(6,n); d.sides = zeros(3,n);
+d.stiffness = zeros(1,n); d.damping = zeros(1,n); d.qRest = zeros(1,n);
+d.qLimL = zeros(1,n); d.qLimU = zeros(1,n); d.qLimK = zeros(1,n); d.qLimD = zeros(1,n);
+for i = 1 : n
+	j = scene.joints{i};
+	if isempty(j.parent)
+		d.parent(i) = -1;
+	else
+		d.parent(i) = find(cellfun(@(x) x == j.parent, scene.joints)) - 1;
+	end
+	if isa(j,'redmax.JointRevolute')
+		d.jtype(i) = 1; d.axis(:,i) = j.axis; d.qRest(i) = j.qRest;
+	elseif isa(j,'redmax.JointFixed')
+		d.jtype(i) = 0;
+	else
+		error('only JointRevolute / JointFixed are on the GPU hot path');
+	end
+	d.E0_pj(:,:,i) = j.E0_pj; d.E0_ji(:,:,i) = j.body.E0_ji; d.I_i(:,i) = j.body.I_i; d.sides(:,i) = j.body.sides;
+	d.stiffness(i) = j.stiffness; d.damping(i) = j.damping;
+	d.qLimL(i) = j.qLimL; d.qLimU(i) = j.qLimU; d.qLimK(i) = j.qLimK; d.qLimD(i) = j.qLimD;
+end
+d.grav = scene.grav;
+gb = []; gE = zeros(4,4,0); kn = []; kt = []; kd = []; mu = [];
+for i = 1 : length(scene.forces)
+	f = scene.forces{i};
+	if isa(f,'redmax.ForceGroundCuboid')
+		gb(end+1) = find(cellfun(@(x) x == f.cuboid, scene.bodies)) - 1; %#ok<AGROW>
+		gE(:,:,end+1) = f.E; kn(end+1) = f.kn; kt(end+1) = f.kt; kd(end+1) = f.kd; mu(end+1) = f.mu; %#ok<AGROW>
+	elseif ~isa(f,'redmax.ForceNull')
+		error('only ForceGroundCuboid is on the GPU hot path');
+	end
+end
+d.ground_body = gb; d.ground_E = gE; d.ground_kn = kn; d.ground_kt = kt; d.ground_kd = kd; d.ground_mu = mu;
+end
