@@ -172,20 +172,15 @@ struct EnergyArgs {
     double* V;
 };
 
-template <int NW, bool GROUND>
+template <int NW, bool GROUND, int IMPL>
 __global__ void __launch_bounds__(32 * NW) energies_kernel(EnergyArgs a) {
+    typedef Eval<IMPL, NW, GROUND> E;
     extern __shared__ double2 smem_raw[];
     double* sm = reinterpret_cast<double*>(smem_raw);
     const int t = threadIdx.x;
     const int n = a.sc.n, nr = a.sc.nr;
-    Ctx c;
-    ctx_carve(c, sm, n, nr, GROUND);
-    c.jc = a.sc.jc;
-    c.ends_list = a.sc.ends_list;
-    c.gx = a.sc.grav[0];
-    c.gy = a.sc.grav[1];
-    c.gz = a.sc.grav[2];
-    c.is_chain = a.sc.is_chain;
+    typename E::C c;
+    E::setup(c, sm, a.sc);
     c.stage = ST_DIRECT;
     c.h = 1.0;
     c.c = 1.0;
@@ -200,12 +195,13 @@ __global__ void __launch_bounds__(32 * NW) energies_kernel(EnergyArgs a) {
             c.tau[t] = 0;
         }
         bsync<NW>();
-        eval_base<NW, GROUND>(c, false);
+        E::base(c, false);
         double T = 0.0, V = 0.0;
         if (t < n) {
             const JointConst& J = c.jc[t];
-            const double* r1 = c.rec1 + (size_t)t * REC1;
-            const double* phi = r1 + 12;
+            double r1[12], phi[6];
+            E::body_frame(c, t, r1, r1 + 9);
+            E::body_phi(c, t, phi);
             double acc = 0.0;
 #pragma unroll
             for (int i = 0; i < 6; ++i) acc += phi[i] * (J.I[i] * phi[i]);

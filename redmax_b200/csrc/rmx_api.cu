@@ -7,6 +7,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -40,6 +41,7 @@ struct DevBuf {
 struct DevCopy {
     JointConst* jc = nullptr;
     int* ends = nullptr;
+    int* anc = nullptr;
     cudaStream_t stream = nullptr;
     DevBuf buf[16];
 };
@@ -51,6 +53,9 @@ struct rmx_scene {
     std::vector<JointConst> jc;   // internal (preorder) order
     std::vector<int> ends_list;
     std::vector<int> user2int;    // user joint index -> internal index
+    std::vector<int> anc;         // [nrounds][n] 2^r-th ancestors (internal indices) for the pointer-jumping scans
+    int nrounds = 0;
+    int impl = 2;                 // 1 = sweep kernels (rmx_device.cuh), 2 = composite kernels (rmx_fast.cuh)
     std::map<int, DevCopy> dev;   // per CUDA device
 };
 
@@ -207,6 +212,27 @@ extern "C" int rmx_scene_create(const rmx_scene_desc* d, rmx_scene** out) {
         }
         if (s->ends_list.empty()) s->ends_list.push_back(0);
     }
+    // ancestor tables: anc[0] = parent, anc[r+1][j] = anc[r][anc[r][j]]
+    {
+        std::vector<int> cur(n);
+        for (int k = 0; k < n; ++k) cur[k] = s->jc[k].parent;
+        while (true) {
+            bool any = false;
+            for (int k = 0; k < n; ++k) any = any || cur[k] >= 0;
+            if (!any) break;
+            s->anc.insert(s->anc.end(), cur.begin(), cur.end());
+            s->nrounds++;
+            std::vector<int> nxt(n);
+            for (int k = 0; k < n; ++k) nxt[k] = cur[k] >= 0 ? cur[cur[k]] : -1;
+            cur.swap(nxt);
+        }
+        if (s->anc.empty()) s->anc.push_back(-1);
+    }
+    {
+        const char* e = std::getenv("RMX_IMPL");  // developer switch: 1 forces the sweep kernels
+        s->impl = (e && e[0] == '1') ? 1 : 2;
+        if (n > 64) s->impl = 1;  // the composite path keeps ~90 doubles per joint in shared memory
+    }
     for (int i = 0; i < 3; ++i) s->grav[i] = d->grav[i];
     for (int f = 0; f < d->nground; ++f) {
         const int b = d->ground_body[f];
@@ -243,6 +269,7 @@ extern "C" void rmx_scene_destroy(rmx_scene* s) {
         cudaSetDevice(kv.first);
         cudaFree(kv.second.jc);
         cudaFree(kv.second.ends);
+        cudaFree(kv.second.anc);
         for (auto& b : kv.second.buf) cudaFree(b.p);
         if (kv.second.stream) cudaStreamDestroy(kv.second.stream);
     }
@@ -261,6 +288,8 @@ static int scene_on_device(rmx_scene* s, int dev, DevCopy** out) {
         CUDA_TRY(cudaMemcpy(dc.jc, s->jc.data(), sizeof(JointConst) * s->n, cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMalloc(&dc.ends, sizeof(int) * s->ends_list.size()));
         CUDA_TRY(cudaMemcpy(dc.ends, s->ends_list.data(), sizeof(int) * s->ends_list.size(), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc(&dc.anc, sizeof(int) * s->anc.size()));
+        CUDA_TRY(cudaMemcpy(dc.anc, s->anc.data(), sizeof(int) * s->anc.size(), cudaMemcpyHostToDevice));
         CUDA_TRY(cudaStreamCreateWithFlags(&dc.stream, cudaStreamNonBlocking));
         it = s->dev.emplace(dev, dc).first;
     }
@@ -287,6 +316,8 @@ static DevScene make_devscene(const rmx_scene* s, const DevCopy* dc) {
     for (int i = 0; i < 3; ++i) ds.grav[i] = s->grav[i];
     ds.jc = dc->jc;
     ds.ends_list = dc->ends;
+    ds.anc = dc->anc;
+    ds.nrounds = s->nrounds;
     return ds;
 }
 
@@ -295,6 +326,11 @@ static int warps_for(const rmx_scene* s) {
     if (m <= 32) return 1;
     if (m <= 64) return 2;
     return 4;
+}
+
+static size_t scene_smem_doubles(const rmx_scene* s) {
+    const bool g = s->has_ground != 0;
+    return s->impl == 2 ? smem_doubles2(s->n, s->nr, g) : smem_doubles(s->n, s->nr, g);
 }
 
 static int check_opts(const rmx_scene* s, const rmx_opts* o, StepOpts* so, int adjoint) {
@@ -321,24 +357,29 @@ static int set_smem(K kernel, size_t bytes) {
     return RMX_OK;
 }
 
-template <int NW, bool GROUND>
+template <int NW, bool GROUND, bool ADJ, int IMPL>
 static int launch_fwd_t(const RolloutArgs& a, size_t smem, cudaStream_t st) {
-    int rc = set_smem(rollout_fwd_kernel<NW, GROUND, false>, smem);
+    int rc = set_smem(rollout_fwd_kernel<NW, GROUND, ADJ, IMPL>, smem);
     if (rc) return rc;
     const long long grid = a.B;
-    rollout_fwd_kernel<NW, GROUND, false><<<(unsigned)grid, 32 * NW, smem, st>>>(a);
+    rollout_fwd_kernel<NW, GROUND, ADJ, IMPL><<<(unsigned)grid, 32 * NW, smem, st>>>(a);
     CUDA_TRY(cudaGetLastError());
     return RMX_OK;
 }
 
+template <bool ADJ>
 static int launch_fwd(const rmx_scene* s, const RolloutArgs& a, cudaStream_t st) {
     const int nw = warps_for(s);
     const bool g = s->has_ground != 0;
-    const size_t smem = smem_doubles(s->n, s->nr, g) * sizeof(double);
+    const size_t smem = (scene_smem_doubles(s) + (ADJ ? 6 * (size_t)s->nr : 0)) * sizeof(double);
     if (smem > 227 * 1024) return fail(RMX_ELIMIT, "scene does not fit the 227 KB shared memory of one SM");
-    if (nw == 1) return g ? launch_fwd_t<1, true>(a, smem, st) : launch_fwd_t<1, false>(a, smem, st);
-    if (nw == 2) return g ? launch_fwd_t<2, true>(a, smem, st) : launch_fwd_t<2, false>(a, smem, st);
-    return g ? launch_fwd_t<4, true>(a, smem, st) : launch_fwd_t<4, false>(a, smem, st);
+    if (s->impl == 2) {
+        if (nw == 1) return g ? launch_fwd_t<1, true, ADJ, 2>(a, smem, st) : launch_fwd_t<1, false, ADJ, 2>(a, smem, st);
+        return g ? launch_fwd_t<2, true, ADJ, 2>(a, smem, st) : launch_fwd_t<2, false, ADJ, 2>(a, smem, st);
+    }
+    if (nw == 1) return g ? launch_fwd_t<1, true, ADJ, 1>(a, smem, st) : launch_fwd_t<1, false, ADJ, 1>(a, smem, st);
+    if (nw == 2) return g ? launch_fwd_t<2, true, ADJ, 1>(a, smem, st) : launch_fwd_t<2, false, ADJ, 1>(a, smem, st);
+    return g ? launch_fwd_t<4, true, ADJ, 1>(a, smem, st) : launch_fwd_t<4, false, ADJ, 1>(a, smem, st);
 }
 
 extern "C" int rmx_rollout_dev(rmx_scene* s, const rmx_opts* o, int64_t B, const double* q0, const double* qdot0,
@@ -367,7 +408,7 @@ extern "C" int rmx_rollout_dev(rmx_scene* s, const rmx_opts* o, int64_t B, const
     a.qd_out = qdot_out;
     a.status = status;
     a.iters = iters;
-    return launch_fwd(s, a, (cudaStream_t)cuda_stream);
+    return launch_fwd<false>(s, a, (cudaStream_t)cuda_stream);
 }
 
 // Host-pointer entry: shards the batch contiguously over o->ngpus devices (no communication during the rollout),
@@ -433,11 +474,11 @@ extern "C" int rmx_rollout(rmx_scene* s, const rmx_opts* o, int64_t B, const dou
 // ---------------------------------------------------------------------------------------------------
 // rmx_eval test hook
 // ---------------------------------------------------------------------------------------------------
-template <int NW, bool GROUND>
+template <int NW, bool GROUND, int IMPL>
 static int launch_eval_t(const EvalArgs& a, size_t smem) {
-    int rc = set_smem(eval_kernel<NW, GROUND>, smem);
+    int rc = set_smem(eval_kernel<NW, GROUND, IMPL>, smem);
     if (rc) return rc;
-    eval_kernel<NW, GROUND><<<1, 32 * NW, smem>>>(a);
+    eval_kernel<NW, GROUND, IMPL><<<1, 32 * NW, smem>>>(a);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaDeviceSynchronize());
     return RMX_OK;
@@ -487,13 +528,18 @@ extern "C" int rmx_eval(rmx_scene* s, const double* q, const double* qdot, const
     a.D = dD;
     const int nw = warps_for(s);
     const bool gr = s->has_ground != 0;
-    const size_t smem = smem_doubles(s->n, s->nr, gr) * sizeof(double);
-    if (nw == 1)
-        rc = gr ? launch_eval_t<1, true>(a, smem) : launch_eval_t<1, false>(a, smem);
+    const size_t smem = scene_smem_doubles(s) * sizeof(double);
+    if (s->impl == 2) {
+        if (nw == 1)
+            rc = gr ? launch_eval_t<1, true, 2>(a, smem) : launch_eval_t<1, false, 2>(a, smem);
+        else
+            rc = gr ? launch_eval_t<2, true, 2>(a, smem) : launch_eval_t<2, false, 2>(a, smem);
+    } else if (nw == 1)
+        rc = gr ? launch_eval_t<1, true, 1>(a, smem) : launch_eval_t<1, false, 1>(a, smem);
     else if (nw == 2)
-        rc = gr ? launch_eval_t<2, true>(a, smem) : launch_eval_t<2, false>(a, smem);
+        rc = gr ? launch_eval_t<2, true, 1>(a, smem) : launch_eval_t<2, false, 1>(a, smem);
     else
-        rc = gr ? launch_eval_t<4, true>(a, smem) : launch_eval_t<4, false>(a, smem);
+        rc = gr ? launch_eval_t<4, true, 1>(a, smem) : launch_eval_t<4, false, 1>(a, smem);
     if (rc == RMX_OK) {
         std::vector<double> hg(nr), hM((size_t)nr * nr);
         cudaMemcpy(hg.data(), dg, v, cudaMemcpyDeviceToHost);

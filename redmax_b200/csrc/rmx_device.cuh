@@ -57,6 +57,8 @@ struct DevScene {
     double grav[3];
     const JointConst* jc;
     const int* ends_list;
+    const int* anc;   // [nrounds][n] 2^r-th ancestor of joint j or -1 (pointer-jumping scans of the fast path)
+    int nrounds;
 };
 
 struct StepOpts {

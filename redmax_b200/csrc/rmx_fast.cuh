@@ -1,0 +1,638 @@
+// rmx_fast.cuh -- the composite ("v2") evaluation of the implicit-step residual and Newton matrix, and the warp-register LU.
+//
+// Same mathematics as rmx_device.cuh's eval_base / eval_columns (world-frame screws), reorganised so
+// that nothing is a serial sweep over the joints any more:
+//   * forward kinematics, V and U are prefix products / sums along root paths -> pointer-jumping scans, log2(depth) rounds
+//     (ancestor tables anc[r][j] = 2^r-th ancestor of j come with the scene);
+//   * the tangent wrench of body j for column i is linear in three per-column vectors,
+//         T^i_j = B_j c2_i + A_j c1_i + sq C_j s_i ,     B_j = X' M X,  A_j = -c X'(M ad(phi) + dfcor/dphi + Dext) X,  C_j = -c X'(Kgrav + Kext) X
+//     so with subtree-composite blocks B^C_k, A^C_k, C^C_k (one leaves->root accumulation, parallel over components)
+//         H[k][i] = (B^C_k s_k).c2_i + (A^C_k' s_k).c1_i + sq (C^C_k' s_k).s_i          k in sub(i)
+//                 = s_k.(B^C_i c2_i + A^C_i c1_i + sq C^C_i s_i + sq ad*(s_i) F^C_i)    k a proper ancestor of i
+//     i.e. 12 (18 with ground contact) multiply-adds per matrix entry instead of a 330-flop body evaluation per (i,j) pair;
+//   * without external forces A_j, B_j, C_j have closed forms needing 22 numbers per body (rotated inertia, m p, m, a 3x3
+//     block and the linear momentum); ground contact adds two dense 6x6 blocks per body.
+// Shared memory is structure-of-arrays (field-major, joint index fastest): every phase is bank-conflict free.
+// The prototype tools/proto_composite.py checks these formulas against the dense oracle (1e-15 on g, H, M, D).
+#pragma once
+#include "rmx_device.cuh"
+
+namespace rmx {
+
+// field offsets in the SoA block (units: NS doubles)
+template <bool GROUND>
+struct Fld {
+    static constexpr int RW = 0;     // 9  joint frame rotation (scan)
+    static constexpr int PW = 9;     // 3
+    static constexpr int S = 12;     // 6  world screw
+    static constexpr int V = 18;     // 6
+    static constexpr int U = 24;     // 6
+    static constexpr int RB = 30;    // 9  body frame
+    static constexpr int PB = 39;    // 3
+    static constexpr int PHI = 42;   // 6
+    static constexpr int CF = 48;    // 6  F (composite after the accumulation)
+    static constexpr int JB = 54;    // 6  sum (R I3 R' - m [p][p]) : xx xy xz yy yz zz
+    static constexpr int MP = 60;    // 3  sum m p
+    static constexpr int MS = 63;    // 1  sum m
+    static constexpr int ATL = 64;   // 9  sum -c (R Ptl R' + 2 m [p][vc])
+    static constexpr int MV = 73;    // 3  sum m vc
+    static constexpr int AEXT = 76;  // 36 sum -c X' Dext X   (GROUND only)
+    static constexpr int CEXT = 112; // 36 sum -c X' Kext X   (GROUND only)
+    static constexpr int NCOMP = GROUND ? 100 : 28;  // composite components starting at CF
+    static constexpr int LK = GROUND ? 148 : 76;     // L_k: 12 (18 with ground)
+    static constexpr int NL = GROUND ? 18 : 12;
+    static constexpr int TOTAL = LK + NL;
+};
+
+__host__ __device__ inline size_t smem_doubles2(int n, int nr, bool ground) {
+    const size_t tot = ground ? Fld<true>::TOTAL : Fld<false>::TOTAL;
+    size_t d = (size_t)n * tot + (size_t)NVEC * nr + (size_t)nr * h_ld(nr) + 16 + 8;
+    d += (size_t)(3 * n + 1) / 2 + 1;  // int tables idx/end/parent
+    return (d + 1) & ~(size_t)1;
+}
+
+struct Ctx2 : Ctx {
+    double* sa;  // SoA block
+    int NS;      // stride (= n)
+    int* idx_s;  // [n] reduced index or -1
+    int* end_s;  // [n] subtree end
+    int* par_s;  // [n] parent
+    const int* __restrict__ anc;  // [nrounds][n] ancestor tables (global)
+    int nrounds;
+};
+
+__device__ __forceinline__ void ctx2_carve(Ctx2& c, double* sm, int n, int nr, bool ground) {
+    c.n = n;
+    c.nr = nr;
+    c.ld = h_ld(nr);
+    c.NS = n;
+    double* p = sm;
+    c.sa = p;
+    p += (size_t)n * (ground ? Fld<true>::TOTAL : Fld<false>::TOTAL);
+    c.rec1 = nullptr;
+    c.rec2 = nullptr;
+    c.KD = nullptr;
+    c.q = p; p += nr;
+    c.qd = p; p += nr;
+    c.dq = p; p += nr;
+    c.g = p; p += nr;
+    c.dx = p; p += nr;
+    c.x0 = p; p += nr;
+    c.tau = p; p += nr;
+    c.hq0 = p; p += nr;
+    c.hqd0 = p; p += nr;
+    c.hq1 = p; p += nr;
+    c.hqd1 = p; p += nr;
+    c.sp0 = p; p += nr;
+    c.sp1 = p; p += nr;
+    c.sp2 = p; p += nr;
+    c.red = p;
+    p += 16;
+    c.idx_s = reinterpret_cast<int*>(p);
+    c.end_s = c.idx_s + n;
+    c.par_s = c.end_s + n;
+    p += (size_t)(3 * n + 1) / 2 + 1;
+    p = (double*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
+    c.H = p;
+}
+
+#define SA(f, k, j) c.sa[(size_t)((f) + (k)) * NS + (j)]
+
+// X' M X (scaled) for a dense body-frame 6x6 M (row-major), X = Ad(E^-1): column m of the result is
+// xf_b2w(M * xm_w2b(e_m)).  Adds into the SoA field `fld` (row-major 6x6) of joint j.
+__device__ __forceinline__ void xtmx_store(double* sa, int NS, int fld, int j, const double* R, const double* p, const double* M,
+                                           double scale) {
+#pragma unroll
+    for (int m = 0; m < 6; ++m) {
+        double e[6] = {0, 0, 0, 0, 0, 0}, xe[6], y[6], wv[6];
+        e[m] = 1.0;
+        xm_w2b(R, p, e, xe);
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            double acc = 0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) acc += M[6 * r + k] * xe[k];
+            y[r] = acc;
+        }
+        xf_b2w(R, p, y, wv);
+#pragma unroll
+        for (int r = 0; r < 6; ++r) sa[(size_t)(fld + 6 * r + m) * NS + j] = scale * wv[r];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// eval_base2: residual g at iterate c.q (and, if deriv, the composite blocks eval_columns2 needs).
+// ---------------------------------------------------------------------------------------------
+template <int NW, bool GROUND>
+__device__ void eval_base2(Ctx2& c, bool deriv) {
+    typedef Fld<GROUND> F;
+    const int t = threadIdx.x;
+    const int n = c.n, NS = c.NS;
+    const int NT = 32 * NW;
+    // ---- stage kinematics + joint-local transforms --------------------------------------------------------
+    if (t < c.nr) {
+        double qd, dq;
+        stage_kin(c.stage, c.h, c.q[t], c.hq0[t], c.hqd0[t], c.hq1[t], c.hqd1[t], qd, dq);
+        c.qd[t] = qd;
+        c.dq[t] = dq;
+    }
+    double Rj[9], pj[3];  // this joint's (partial) world frame, kept in registers through the scan
+    int myidx = -1;
+    if (t < n) {
+        const JointConst& J = c.jc[t];
+        myidx = J.idx;
+        if (myidx >= 0) {
+            double Rq[9];
+            aa_to_mat(J, c.q[myidx], Rq);
+            mat3_mul(J.R0, Rq, Rj);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) Rj[i] = J.R0[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) pj[i] = J.p0[i];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) SA(F::RW, i, t) = Rj[i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) SA(F::PW, i, t) = pj[i];
+    }
+    bsync<NW>();
+    // ---- world frames: pointer-jumping prefix product  E_w,j = E_w,anc o E_(anc, j] -----------------------------
+    for (int r = 0; r < c.nrounds; ++r) {
+        const int a = (t < n) ? __ldg(c.anc + r * n + t) : -1;
+        if (a >= 0) {
+            double Ra[9], pa[3], Rn[9], pn[3];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) Ra[i] = SA(F::RW, i, a);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) pa[i] = SA(F::PW, i, a);
+            mat3_mul(Ra, Rj, Rn);
+            mat3_vec(Ra, pj, pn);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) Rj[i] = Rn[i];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) pj[i] = pn[i] + pa[i];
+        }
+        bsync<NW>();
+        if (a >= 0) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) SA(F::RW, i, t) = Rj[i];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) SA(F::PW, i, t) = pj[i];
+        }
+        bsync<NW>();
+    }
+    // ---- screws, V = prefix sum of s qd ------------------------------------------------------------------------
+    double s[6] = {0, 0, 0, 0, 0, 0}, Vj[6] = {0, 0, 0, 0, 0, 0}, Uj[6] = {0, 0, 0, 0, 0, 0};
+    double qdk = 0.0, dqk = 0.0;
+    if (t < n) {
+        if (myidx >= 0) {
+            const JointConst& J = c.jc[t];
+            mat3_vec(Rj, J.axis, s);
+            cross3(pj, s, s + 3);
+            qdk = c.qd[myidx];
+            dqk = c.dq[myidx];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) Vj[i] = s[i] * qdk;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            SA(F::S, i, t) = s[i];
+            SA(F::V, i, t) = Vj[i];
+        }
+    }
+    bsync<NW>();
+    for (int r = 0; r < c.nrounds; ++r) {
+        const int a = (t < n) ? __ldg(c.anc + r * n + t) : -1;
+        if (a >= 0) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) Vj[i] += SA(F::V, i, a);
+        }
+        bsync<NW>();
+        if (a >= 0) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) SA(F::V, i, t) = Vj[i];
+        }
+        bsync<NW>();
+    }
+    // ---- U = prefix sum of (s dq + c qd ad(Vp) s) --------------------------------------------------------------
+    if (t < n) {
+        if (myidx >= 0) {
+            const int par = c.par_s[t];
+            double Vp[6] = {0, 0, 0, 0, 0, 0}, sd[6];
+            if (par >= 0) {
+#pragma unroll
+                for (int i = 0; i < 6; ++i) Vp[i] = SA(F::V, i, par);
+            }
+            ad_mv(Vp, s, sd);
+            const double cq = c.c * qdk;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) Uj[i] = s[i] * dqk + cq * sd[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) SA(F::U, i, t) = Uj[i];
+    }
+    bsync<NW>();
+    for (int r = 0; r < c.nrounds; ++r) {
+        const int a = (t < n) ? __ldg(c.anc + r * n + t) : -1;
+        if (a >= 0) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) Uj[i] += SA(F::U, i, a);
+        }
+        bsync<NW>();
+        if (a >= 0) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) SA(F::U, i, t) = Uj[i];
+        }
+        bsync<NW>();
+    }
+    // ---- per body: frame, twist, wrench, and (deriv) the world-frame blocks ------------------------------------
+    if (t < n) {
+        const JointConst& J = c.jc[t];
+        double Rb[9], pb[3];
+        mat3_mul(Rj, J.Rji, Rb);
+        mat3_vec(Rj, J.pji, pb);
+        pb[0] += pj[0]; pb[1] += pj[1]; pb[2] += pj[2];
+        double phi[6], u[6];
+        xm_w2b(Rb, pb, Vj, phi);
+        xm_w2b(Rb, pb, Uj, u);
+        const double m = J.I[3];
+        double Iw[3] = {J.I[0] * phi[0], J.I[1] * phi[1], J.I[2] * phi[2]};
+        double mv[3] = {m * phi[3], m * phi[4], m * phi[5]};
+        double fb[6];  // fcor + fgrav + fext (Body.m:98-107)
+        cross3(Iw, phi, fb);
+        cross3(mv, phi, fb + 3);
+        double gw[3] = {c.gx, c.gy, c.gz}, gb[3];
+        mat3T_vec(Rb, gw, gb);
+        fb[3] += m * gb[0]; fb[4] += m * gb[1]; fb[5] += m * gb[2];
+        if (GROUND) {
+            if (J.has_ground) {
+                if (deriv) {
+                    double K[36], D[36];
+#pragma unroll
+                    for (int i = 0; i < 36; ++i) K[i] = D[i] = 0;
+                    ground_body<true>(J, Rb, pb, phi, fb, K, D);
+                    xtmx_store(c.sa, NS, F::AEXT, t, Rb, pb, D, -c.c);
+                    xtmx_store(c.sa, NS, F::CEXT, t, Rb, pb, K, -c.c);
+                } else {
+                    ground_body<false>(J, Rb, pb, phi, fb, nullptr, nullptr);
+                }
+            } else if (deriv) {
+                for (int i = 0; i < 72; ++i) SA(F::AEXT, i, t) = 0.0;
+            }
+        }
+        double Fb[6], Fw[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) Fb[i] = J.I[i] * u[i] - c.c * fb[i];
+        xf_b2w(Rb, pb, Fb, Fw);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) SA(F::RB, i, t) = Rb[i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) SA(F::PB, i, t) = pb[i];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            SA(F::PHI, i, t) = phi[i];
+            SA(F::CF, i, t) = Fw[i];
+        }
+        if (deriv) {
+            // Jb = R I3 R' - m [p][p]   (symmetric: xx xy xz yy yz zz);  [p][p] = p p' - |p|^2 I
+            const double pp = pb[0] * pb[0] + pb[1] * pb[1] + pb[2] * pb[2];
+            int e = 0;
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = a; b < 3; ++b) {
+                    double v = Rb[3 * a] * J.I[0] * Rb[3 * b] + Rb[3 * a + 1] * J.I[1] * Rb[3 * b + 1] + Rb[3 * a + 2] * J.I[2] * Rb[3 * b + 2];
+                    v -= m * (pb[a] * pb[b] - (a == b ? pp : 0.0));
+                    SA(F::JB, e, t) = v;
+                    ++e;
+                }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) SA(F::MP, i, t) = m * pb[i];
+            SA(F::MS, 0, t) = m;
+            // Ptl = I3[w] - [w]I3 + [I3 w]  (body frame);  Atl = -c (R Ptl R' + 2 m [p][vc]),  vc = R v_b
+            double Ptl[9], W[9], IW[9], T1[9], T2[9], vc[3];
+            brac3(phi, W);
+            brac3(Iw, IW);
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b) Ptl[3 * a + b] = J.I[a] * W[3 * a + b] - W[3 * a + b] * J.I[b] + IW[3 * a + b];
+            mat3_mul(Rb, Ptl, T1);
+            // T2 = T1 * Rb'
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b) T2[3 * a + b] = T1[3 * a] * Rb[3 * b] + T1[3 * a + 1] * Rb[3 * b + 1] + T1[3 * a + 2] * Rb[3 * b + 2];
+            mat3_vec(Rb, phi + 3, vc);
+            // [p][vc] = vc p' - (p.vc) I
+            const double pv = pb[0] * vc[0] + pb[1] * vc[1] + pb[2] * vc[2];
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b)
+                    SA(F::ATL, 3 * a + b, t) = -c.c * (T2[3 * a + b] + 2.0 * m * (vc[a] * pb[b] - (a == b ? pv : 0.0)));
+#pragma unroll
+            for (int i = 0; i < 3; ++i) SA(F::MV, i, t) = m * vc[i];
+        }
+    }
+    bsync<NW>();
+    // ---- composite sums, leaves -> root (one thread per component) ---------------------------------------------
+    {
+        const int ncomp = deriv ? F::NCOMP : 6;
+        for (int comp = t; comp < ncomp; comp += NT) {
+            double* col = c.sa + (size_t)(F::CF + comp) * NS;
+            if (c.is_chain) {
+                double acc = 0.0;
+                for (int j = n - 1; j >= 0; --j) {
+                    acc += col[j];
+                    col[j] = acc;
+                }
+            } else {
+                for (int j = n - 1; j > 0; --j) {
+                    const int par = c.par_s[j];
+                    if (par >= 0) col[par] += col[j];
+                }
+            }
+        }
+    }
+    bsync<NW>();
+    // ---- reduced residual ---------------------------------------------------------------------------------------
+    if (t < n && myidx >= 0) {
+        const JointConst& J = c.jc[t];
+        const int r = myidx;
+        const double qk = c.q[r];
+        double fr = c.tau[r] + J.stiff * (J.qRest - qk) - J.damp * qdk;  // Joint.computeForce (Joint.m:448-454, 470-481)
+        double dK = -J.stiff, dD = -J.damp;
+        if (qk < J.qLimL) {
+            fr += J.qLimK * (J.qLimL - qk) - J.qLimD * qdk;
+            dK -= J.qLimK;
+            dD -= J.qLimD;
+        }
+        if (qk > J.qLimU) {
+            fr += J.qLimK * (J.qLimU - qk) - J.qLimD * qdk;
+            dK -= J.qLimK;
+            dD -= J.qLimD;
+        }
+        double Fc[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) Fc[i] = SA(F::CF, i, t);
+        c.g[r] = dot6(s, Fc) - c.c * fr;
+        c.sp2[r] = dK;
+        c.sp1[r] = dD;
+    }
+    bsync<NW>();
+}
+
+// ---------------------------------------------------------------------------------------------
+// eval_columns2: out (nr x ld column-major) = scale * ( sq dg/dq + sqd dg/dqdot + sd dg/d(dqtmp) ), from the composite blocks.
+// ---------------------------------------------------------------------------------------------
+template <int NW, bool GROUND>
+__device__ void eval_columns2(Ctx2& c, double sq, double sqd, double sd, double scale, double* out) {
+    typedef Fld<GROUND> F;
+    const int t = threadIdx.x;
+    const int n = c.n, NS = c.NS, ld = c.ld;
+    const double cc = c.c;
+    const int myidx = (t < n) ? c.idx_s[t] : -1;
+    double Rt[F::NL];  // [c2 (6) ; c1 (3 or 6) ; sq s (3 or 6)]
+    double Z[6];
+    if (myidx >= 0) {
+        double s[6], Vp[6] = {0, 0, 0, 0, 0, 0}, Up[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < 6; ++i) s[i] = SA(F::S, i, t);
+        const int par = c.par_s[t];
+        if (par >= 0) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                Vp[i] = SA(F::V, i, par);
+                Up[i] = SA(F::U, i, par);
+            }
+        }
+        double a1[6], a2[6], a3[6], a4[6], c1[6], c2[6];
+        ad_mv(s, Vp, a1);
+        ad_mv(s, Up, a2);
+        ad_mv(Vp, s, a3);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) c1[i] = sqd * s[i] - sq * a1[i];
+        ad_mv(c1, Vp, a4);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) c2[i] = sd * s[i] - sq * a2[i] + cc * (sqd * a3[i] - a4[i]);
+        // composite blocks of this joint
+        double Jb[6], mp[3], Atl[9], mv[3], Fc[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            Jb[i] = SA(F::JB, i, t);
+            Fc[i] = SA(F::CF, i, t);
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            mp[i] = SA(F::MP, i, t);
+            mv[i] = SA(F::MV, i, t);
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Atl[i] = SA(F::ATL, i, t);
+        const double Ms = SA(F::MS, 0, t);
+        const double gw[3] = {c.gx, c.gy, c.gz};
+        // a = B^C s ;  B^C x = [Jb xw + mp x xv ; -mp x xw + Ms xv]
+        double L[F::NL];
+        {
+            double t1[3], t2[3];
+            cross3(mp, s + 3, t1);
+            cross3(mp, s, t2);
+            L[0] = Jb[0] * s[0] + Jb[1] * s[1] + Jb[2] * s[2] + t1[0];
+            L[1] = Jb[1] * s[0] + Jb[3] * s[1] + Jb[4] * s[2] + t1[1];
+            L[2] = Jb[2] * s[0] + Jb[4] * s[1] + Jb[5] * s[2] + t1[2];
+            L[3] = Ms * s[3] - t2[0];
+            L[4] = Ms * s[4] - t2[1];
+            L[5] = Ms * s[5] - t2[2];
+            // b = A^C' s : first three = Atl' sw + 2c (mv x sv)
+            double t3[3], bw[3];
+            cross3(mv, s + 3, t3);
+            mat3T_vec(Atl, s, bw);
+            L[6] = bw[0] + 2.0 * cc * t3[0];
+            L[7] = bw[1] + 2.0 * cc * t3[1];
+            L[8] = bw[2] + 2.0 * cc * t3[2];
+            // e = C^C' s : first three = -c g x (mp x sw - Ms sv)
+            double y[3] = {t2[0] - Ms * s[3], t2[1] - Ms * s[4], t2[2] - Ms * s[5]}, ew[3];
+            cross3(gw, y, ew);
+            const int EO = GROUND ? 12 : 9;
+            L[EO] = -cc * ew[0];
+            L[EO + 1] = -cc * ew[1];
+            L[EO + 2] = -cc * ew[2];
+            if (GROUND) {
+                L[9] = L[10] = L[11] = 0.0;
+                L[15] = L[16] = L[17] = 0.0;
+            }
+        }
+        // Z = B^C c2 + A^C c1 + sq C^C s + sq ad*(s) F^C
+        {
+            double t1[3], t2[3], t3[3], t4[3], t5[3];
+            cross3(mp, c2 + 3, t1);
+            cross3(mp, c2, t2);
+            Z[0] = Jb[0] * c2[0] + Jb[1] * c2[1] + Jb[2] * c2[2] + t1[0];
+            Z[1] = Jb[1] * c2[0] + Jb[3] * c2[1] + Jb[4] * c2[2] + t1[1];
+            Z[2] = Jb[2] * c2[0] + Jb[4] * c2[1] + Jb[5] * c2[2] + t1[2];
+            Z[3] = Ms * c2[3] - t2[0];
+            Z[4] = Ms * c2[4] - t2[1];
+            Z[5] = Ms * c2[5] - t2[2];
+            mat3_vec(Atl, c1, t3);
+            cross3(mv, c1, t4);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                Z[i] += t3[i];
+                Z[3 + i] -= 2.0 * cc * t4[i];
+            }
+            if (sq != 0.0) {
+                double gs[3], az[6];
+                cross3(gw, s, gs);  // g x sw
+                cross3(mp, gs, t5);
+                adstar_fv(s, Fc, az);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    Z[i] += sq * (az[i] - cc * t5[i]);
+                    Z[3 + i] += sq * (az[3 + i] - cc * Ms * gs[i]);
+                }
+            }
+        }
+        if (GROUND) {
+            // dense external blocks: b += Aext' s ; e += Cext' s ; Z += Aext c1 + sq Cext s
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+                double zr = 0.0;
+#pragma unroll
+                for (int m = 0; m < 6; ++m) {
+                    const double av = SA(F::AEXT, 6 * r + m, t);
+                    const double cv = SA(F::CEXT, 6 * r + m, t);
+                    L[6 + m] += av * s[r];
+                    L[12 + m] += cv * s[r];
+                    zr += av * c1[m] + sq * cv * s[m];
+                }
+                Z[r] += zr;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < F::NL; ++i) SA(F::LK, i, t) = L[i];
+        // Rt
+#pragma unroll
+        for (int i = 0; i < 6; ++i) Rt[i] = c2[i];
+        if (GROUND) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                Rt[6 + i] = c1[i];
+                Rt[12 + i] = sq * s[i];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                Rt[6 + i] = c1[i];
+                Rt[9 + i] = sq * s[i];
+            }
+        }
+    }
+    bsync<NW>();
+    // ---- entries of column idx[t] -----------------------------------------------------------------------------------
+    if (myidx >= 0) {
+        const int i = t, iend = c.end_s[t];
+        double* col = out + (size_t)myidx * ld;
+        for (int k = 0; k < n; ++k) {
+            const int rk = c.idx_s[k];
+            if (rk < 0) continue;
+            double v = 0.0;
+            if (k >= i && k < iend) {
+#pragma unroll
+                for (int e = 0; e < F::NL; ++e) v += SA(F::LK, e, k) * Rt[e];
+            } else if (k < i && i < c.end_s[k]) {
+#pragma unroll
+                for (int e = 0; e < 6; ++e) v += SA(F::S, e, k) * Z[e];
+            }
+            if (k == i) v += -cc * (sq * c.sp2[myidx] + sqd * c.sp1[myidx]);  // Kr, Dr of Joint.m:470-481
+            col[rk] = scale * v;
+        }
+    }
+    bsync<NW>();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Warp-register LU with partial pivoting + solve for one warp (nr <= 32).  Lane r holds row r of H; rows never move:
+// the pivot row of step k is broadcast with shuffles, `pos` tracks each row's LAPACK position so that ties are broken
+// exactly like dgetf2's idamax (first maximum in the current row order).  Solves H x = scale * rhs, x -> dx (shared).
+// If write_back, the factored image (unit-lower L below the diagonal, rows in pivot order) goes back to H and
+// perm[k] = original row in position k (== Hp of lu(H,'vector')).
+// ---------------------------------------------------------------------------------------------
+template <int NR>
+__device__ __noinline__ void lu_solve_warp_t(int nr, int ld, double* H, int* perm, const double* rhs, double scale, double* dx,
+                                                bool write_back) {
+    // The matrix is padded to NR x NR with an identity block (lanes/columns >= nr), so no loop below needs a runtime
+    // bound: padding rows are never chosen before the real ones (their column entries are exactly 0) and eliminate nothing.
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    double a[NR];
+#pragma unroll
+    for (int cI = 0; cI < NR; ++cI) a[cI] = (cI < nr && lane < nr) ? H[(size_t)cI * ld + lane] : ((cI == lane) ? 1.0 : 0.0);
+    double b = (lane < nr) ? scale * rhs[lane] : 0.0;
+    bool done = lane >= NR;
+    int pos = lane, mypos = -1;
+    double rdiag = 1.0;
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+        const double v = fabs(a[k]);
+        const unsigned hi = done ? 0u : (unsigned)__double2hiint(v);
+        const unsigned mh = __reduce_max_sync(FULL, hi);
+        const bool c1 = !done && hi == mh;
+        const unsigned lo = c1 ? (unsigned)__double2loint(v) : 0u;
+        const unsigned ml = __reduce_max_sync(FULL, lo);
+        const bool c2 = c1 && lo == ml;
+        const unsigned pm = __reduce_min_sync(FULL, c2 ? (unsigned)pos : 0xffffu);
+        const int src = __ffs(__ballot_sync(FULL, c2 && (unsigned)pos == pm)) - 1;
+        const int kl = __ffs(__ballot_sync(FULL, !done && pos == k)) - 1;
+        const int pos_src = __shfl_sync(FULL, pos, src);
+        if (lane == kl) pos = pos_src;
+        if (lane == src) {
+            pos = k;
+            done = true;
+            mypos = k;
+        }
+        if (lane == k) perm[k] = src;
+        const double piv = __shfl_sync(FULL, a[k], src);
+        const double rp = 1.0 / piv;
+        rdiag = (lane == src) ? rp : rdiag;
+        const double l = done ? 0.0 : a[k] * rp;
+        a[k] = done ? a[k] : l;
+#pragma unroll
+        for (int cI = k + 1; cI < NR; ++cI) {
+            const double u = __shfl_sync(FULL, a[cI], src);
+            a[cI] = fma(-l, u, a[cI]);  // l == 0 for rows that are already pivots
+        }
+        const double ub = __shfl_sync(FULL, b, src);
+        b = fma(-l, ub, b);
+    }
+    __syncwarp();
+    if (write_back && lane < nr) {
+#pragma unroll
+        for (int cI = 0; cI < NR; ++cI)
+            if (cI < nr) H[(size_t)cI * ld + mypos] = a[cI];
+    }
+    // back substitution U x = y : row `mypos` of U lives in this lane, y_mypos = b
+#pragma unroll
+    for (int k = NR - 1; k >= 0; --k) {
+        const int src = perm[k];
+        const double xk = __shfl_sync(FULL, b * rdiag, src);
+        b = (mypos < k) ? fma(-a[k], xk, b) : b;
+        if (lane == k && k < nr) dx[k] = xk;
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void lu_solve_warp(int nr, int ld, double* H, int* perm, const double* rhs, double scale, double* dx,
+                                              bool write_back) {
+    if (nr <= 8)
+        lu_solve_warp_t<8>(nr, ld, H, perm, rhs, scale, dx, write_back);
+    else if (nr <= 16)
+        lu_solve_warp_t<16>(nr, ld, H, perm, rhs, scale, dx, write_back);
+    else if (nr <= 24)
+        lu_solve_warp_t<24>(nr, ld, H, perm, rhs, scale, dx, write_back);
+    else
+        lu_solve_warp_t<32>(nr, ld, H, perm, rhs, scale, dx, write_back);
+}
+
+}  // namespace rmx

@@ -1,6 +1,7 @@
 // rmx_rollout.cuh -- Newton iteration, time loop and the __global__ entry points.
 #pragma once
 #include "rmx_device.cuh"
+#include "rmx_fast.cuh"
 
 namespace rmx {
 
@@ -48,12 +49,111 @@ struct RolloutArgs {
 };
 
 // ---------------------------------------------------------------------------------------------
+// Two implementations of the evaluation behind one interface:
+//   IMPL 1 : rmx_device.cuh  -- serial tree sweeps + per-(column, body) tangent sweep (kept for n > 64 and as cross-check)
+//   IMPL 2 : rmx_fast.cuh    -- scans + composite blocks + (one warp) register LU
+// ---------------------------------------------------------------------------------------------
+template <int IMPL, int NW, bool GROUND>
+struct Eval;
+
+template <int NW, bool GROUND>
+struct Eval<1, NW, GROUND> {
+    typedef Ctx C;
+    static __device__ __forceinline__ size_t extra_off(const C& c) { return (size_t)c.nr * c.ld; }
+    static __device__ __forceinline__ void setup(C& c, double* sm, const DevScene& sc) {
+        ctx_carve(c, sm, sc.n, sc.nr, GROUND);
+        c.jc = sc.jc;
+        c.ends_list = sc.ends_list;
+        c.gx = sc.grav[0];
+        c.gy = sc.grav[1];
+        c.gz = sc.grav[2];
+        c.is_chain = sc.is_chain;
+    }
+    static __device__ __forceinline__ void base(C& c, bool deriv) { eval_base<NW, GROUND>(c, deriv); }
+    static __device__ __forceinline__ void columns(C& c, double sq, double sqd, double sd, double scale, double* out) {
+        eval_columns<NW, GROUND>(c, sq, sqd, sd, scale, out);
+    }
+    // dx = scale * H \ rhs ; H is overwritten by its LU image, perm = row permutation
+    static __device__ __forceinline__ void factor_solve(C& c, int* perm, double scale, bool /*write_back*/) {
+        lu_factor<NW>(c, c.H, perm);
+        lu_solve<NW>(c, c.H, perm, c.g, c.dx, scale);
+    }
+    static __device__ __forceinline__ void body_frame(const C& c, int j, double* R, double* p) {
+        const double* r1 = c.rec1 + (size_t)j * REC1;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) R[i] = r1[i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) p[i] = r1[9 + i];
+    }
+    static __device__ __forceinline__ void screw(const C& c, int j, double* s) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) s[i] = c.rec1[(size_t)j * REC1 + 18 + i];
+    }
+    static __device__ __forceinline__ void body_phi(const C& c, int j, double* phi) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) phi[i] = c.rec1[(size_t)j * REC1 + 12 + i];
+    }
+};
+
+template <int NW, bool GROUND>
+struct Eval<2, NW, GROUND> {
+    typedef Ctx2 C;
+    typedef Fld<GROUND> F;
+    static __device__ __forceinline__ void setup(C& c, double* sm, const DevScene& sc) {
+        ctx2_carve(c, sm, sc.n, sc.nr, GROUND);
+        c.jc = sc.jc;
+        c.ends_list = sc.ends_list;
+        c.gx = sc.grav[0];
+        c.gy = sc.grav[1];
+        c.gz = sc.grav[2];
+        c.is_chain = sc.is_chain;
+        c.anc = sc.anc;
+        c.nrounds = sc.nrounds;
+        for (int j = threadIdx.x; j < sc.n; j += 32 * NW) {
+            c.idx_s[j] = sc.jc[j].idx;
+            c.end_s[j] = sc.jc[j].end;
+            c.par_s[j] = sc.jc[j].parent;
+        }
+        bsync<NW>();
+    }
+    static __device__ __forceinline__ void base(C& c, bool deriv) { eval_base2<NW, GROUND>(c, deriv); }
+    static __device__ __forceinline__ void columns(C& c, double sq, double sqd, double sd, double scale, double* out) {
+        eval_columns2<NW, GROUND>(c, sq, sqd, sd, scale, out);
+    }
+    static __device__ __forceinline__ void factor_solve(C& c, int* perm, double scale, bool write_back) {
+        if (NW == 1) {
+            lu_solve_warp(c.nr, c.ld, c.H, perm, c.g, scale, c.dx, write_back);
+        } else {
+            lu_factor<NW>(c, c.H, perm);
+            lu_solve<NW>(c, c.H, perm, c.g, c.dx, scale);
+        }
+    }
+    static __device__ __forceinline__ void body_frame(const C& c, int j, double* R, double* p) {
+        const int NS = c.NS;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) R[i] = SA(F::RB, i, j);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) p[i] = SA(F::PB, i, j);
+    }
+    static __device__ __forceinline__ void screw(const C& c, int j, double* s) {
+        const int NS = c.NS;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) s[i] = SA(F::S, i, j);
+    }
+    static __device__ __forceinline__ void body_phi(const C& c, int j, double* phi) {
+        const int NS = c.NS;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) phi[i] = SA(F::PHI, i, j);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
 // newton() of driverRedMaxBDF1.m:94-157 (forward drivers: damped Newton + backtracking line search).
 // Written as a two-state machine (FULL evaluation with H / residual-only line-search trial) so that the
 // evaluation code has a single call site.
 // ---------------------------------------------------------------------------------------------
-template <int NW, bool GROUND>
-__device__ __forceinline__ int newton_forward(Ctx& c, const StepOpts& op, int* perm, int& n_iter, int& n_ls) {
+template <class E, int NW>
+__device__ __forceinline__ int newton_forward(typename E::C& c, const StepOpts& op, int* perm, int& n_iter, int& n_ls) {
     const int t = threadIdx.x;
     const int nr = c.nr;
     int status = 0;
@@ -62,15 +162,14 @@ __device__ __forceinline__ int newton_forward(Ctx& c, const StepOpts& op, int* p
     double f0 = 0.0, x0t = 0.0, dxt = 0.0, alpha = 1.0;
     int iterLs = 1;
     while (true) {
-        eval_base<NW, GROUND>(c, full);
+        E::base(c, full);
         const double gt = (t < nr) ? c.g[t] : 0.0;
         const double gsum = block_sum<NW>(gt * gt, c.red);
         if (full) {
-            eval_columns<NW, GROUND>(c, 1.0, c.beta, 1.0, 1.0, c.H);
+            E::columns(c, 1.0, c.beta, 1.0, 1.0, c.H);
             f0 = 0.5 * gsum;
             // dx = -H\g
-            lu_factor<NW>(c, c.H, perm);
-            lu_solve<NW>(c, c.H, perm, c.g, c.dx, -1.0);
+            E::factor_solve(c, perm, -1.0, false);
             dxt = (t < nr) ? c.dx[t] : 0.0;
             const double dxn = sqrt(block_sum<NW>(dxt * dxt, c.red));
             ++n_iter;
@@ -125,8 +224,8 @@ __device__ __forceinline__ void store_rowmajor(const Ctx& c, const double* H, do
     }
 }
 
-template <int NW, bool GROUND>
-__device__ __forceinline__ int newton_adjoint(Ctx& c, const StepOpts& op, int* perm, int& n_iter, bool save,
+template <class E, int NW>
+__device__ __forceinline__ int newton_adjoint(typename E::C& c, const StepOpts& op, int* perm, int& n_iter, bool save,
                                               double* __restrict__ tA, double* __restrict__ tM,
                                               double* __restrict__ tD, bool want_J, int jb) {
     const int t = threadIdx.x;
@@ -134,12 +233,11 @@ __device__ __forceinline__ int newton_adjoint(Ctx& c, const StepOpts& op, int* p
     int status = 0;
     int iter = 1;
     while (true) {
-        eval_base<NW, GROUND>(c, true);
+        E::base(c, true);
         const double gt = (t < nr) ? c.g[t] : 0.0;
         const double gsum = block_sum<NW>(gt * gt, c.red);
-        eval_columns<NW, GROUND>(c, 1.0, c.beta, 1.0, 1.0, c.H);
-        lu_factor<NW>(c, c.H, perm);
-        lu_solve<NW>(c, c.H, perm, c.g, c.dx, -1.0);
+        E::columns(c, 1.0, c.beta, 1.0, 1.0, c.H);
+        E::factor_solve(c, perm, -1.0, save);
         const double dxt = (t < nr) ? c.dx[t] : 0.0;
         const double dxn = sqrt(block_sum<NW>(dxt * dxt, c.red));
         ++n_iter;
@@ -150,10 +248,10 @@ __device__ __forceinline__ int newton_adjoint(Ctx& c, const StepOpts& op, int* p
             for (int e = t; e < nr * ld; e += 32 * NW) tA[e] = c.H[e];
             if (t < nr) reinterpret_cast<int*>(tA + (size_t)nr * ld + nr)[t] = perm[t];
             bsync<NW>();
-            eval_columns<NW, GROUND>(c, 0.0, 0.0, 1.0, 1.0, c.H);  // M = dg/d(dqtmp)
+            E::columns(c, 0.0, 0.0, 1.0, 1.0, c.H);  // M = dg/d(dqtmp)
             store_rowmajor<NW>(c, c.H, tM);
             bsync<NW>();
-            eval_columns<NW, GROUND>(c, 0.0, 1.0, 0.0, -1.0 / c.c, c.H);  // D = df/dqdot = -(1/cK) dg/dqdot
+            E::columns(c, 0.0, 1.0, 0.0, -1.0 / c.c, c.H);  // D = df/dqdot = -(1/cK) dg/dqdot
             store_rowmajor<NW>(c, c.H, tD);
             if (want_J) {
                 // J(idxM(body), :) : column of joint k is Ad(E_body^-1) s_k for ancestors-or-self k of the body, else 0
@@ -161,8 +259,10 @@ __device__ __forceinline__ int newton_adjoint(Ctx& c, const StepOpts& op, int* p
                 if (t < c.n && c.jc[t].idx >= 0) {
                     double col[6] = {0, 0, 0, 0, 0, 0};
                     if (t <= jb && jb < c.jc[t].end) {
-                        const double* rb = c.rec1 + (size_t)jb * REC1;
-                        xm_w2b(rb, rb + 9, c.rec1 + (size_t)t * REC1 + 18, col);
+                        double Rb[9], pb[3], st[6];
+                        E::body_frame(c, jb, Rb, pb);
+                        E::screw(c, t, st);
+                        xm_w2b(Rb, pb, st, col);
                     }
 #pragma unroll
                     for (int i = 0; i < 6; ++i) Jb[6 * c.jc[t].idx + i] = col[i];
@@ -190,21 +290,16 @@ __device__ __forceinline__ int newton_adjoint(Ctx& c, const StepOpts& op, int* p
 // Forward rollout kernel: simLoop of driverRedMaxBDF1.m:57-91 / driverRedMaxBDF2.m:57-125 (ADJ = false) and of
 // driverRedMaxAdjointBDF1.m:65-102 / driverRedMaxAdjointBDF2.m:65-136 (ADJ = true), one block per rollout.
 // ---------------------------------------------------------------------------------------------
-template <int NW, bool GROUND, bool ADJ>
+template <int NW, bool GROUND, bool ADJ, int IMPL>
 __global__ void __launch_bounds__(32 * NW) rollout_fwd_kernel(RolloutArgs a) {
+    typedef Eval<IMPL, NW, GROUND> E;
     extern __shared__ double2 smem_raw[];
     double* sm = reinterpret_cast<double*>(smem_raw);
     __shared__ int perm_s[32 * NW];
     const int t = threadIdx.x;
-    const int n = a.sc.n, nr = a.sc.nr;
-    Ctx c;
-    ctx_carve(c, sm, n, nr, GROUND);
-    c.jc = a.sc.jc;
-    c.ends_list = a.sc.ends_list;
-    c.gx = a.sc.grav[0];
-    c.gy = a.sc.grav[1];
-    c.gz = a.sc.grav[2];
-    c.is_chain = a.sc.is_chain;
+    const int nr = a.sc.nr;
+    typename E::C c;
+    E::setup(c, sm, a.sc);
     const StepOpts op = a.op;
     const double h = op.h;
     const double ah = __dmul_rn(SDIRK_A_CONST, h);
@@ -266,11 +361,11 @@ __global__ void __launch_bounds__(32 * NW) rollout_fwd_kernel(RolloutArgs a) {
                     // the BDF2 adjoint driver keeps only the second SDIRK sub-solve's tape (driverRedMaxAdjointBDF2.m:88,96)
                     const bool save = stage != ST_SDIRK_A;
                     const size_t rec = (size_t)b * op.nsteps + k;
-                    status |= newton_adjoint<NW, GROUND>(c, op, perm_s, n_iter, save, a.tape.A + rec * a.tape.sza,
+                    status |= newton_adjoint<E, NW>(c, op, perm_s, n_iter, save, a.tape.A + rec * a.tape.sza,
                                                          a.tape.M + rec * nr * nr, a.tape.D + rec * nr * nr,
                                                          save && is_obj, a.task.body);
                 } else {
-                    status |= newton_forward<NW, GROUND>(c, op, perm_s, n_iter, n_ls);
+                    status |= newton_forward<E, NW>(c, op, perm_s, n_iter, n_ls);
                 }
                 // ---- new state ----------------------------------------------------------------------------
                 if (t < nr) {
@@ -302,12 +397,13 @@ __global__ void __launch_bounds__(32 * NW) rollout_fwd_kernel(RolloutArgs a) {
                 double dPdq = 0.0;
                 if (is_obj) {
                     bsync<NW>();
-                    eval_base<NW, GROUND>(c, false);  // c.q holds the final iterate: FK at history(k).q
-                    const double* rb = c.rec1 + (size_t)a.task.body * REC1;
+                    E::base(c, false);  // c.q holds the final iterate: FK at history(k).q
+                    double rb[9], pbt[3];
+                    E::body_frame(c, a.task.body, rb, pbt);
                     double xw[3], dx3[3], y[3], v6[6];
                     mat3_vec(rb, a.task.xlocal, xw);
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) dx3[i] = (xw[i] + rb[9 + i]) - a.task.xtarget[3 * b + i];
+                    for (int i = 0; i < 3; ++i) dx3[i] = (xw[i] + pbt[i]) - a.task.xtarget[3 * b + i];
                     Pacc += a.task.wpos * 0.5 * (dx3[0] * dx3[0] + dx3[1] * dx3[1] + dx3[2] * dx3[2]);
                     mat3T_vec(rb, dx3, y);               // R' dx
                     cross3(a.task.xlocal, y, v6);        // Gamma' y = [xlocal x y ; y]
@@ -356,20 +452,15 @@ struct EvalArgs {
     double* D;
 };
 
-template <int NW, bool GROUND>
+template <int NW, bool GROUND, int IMPL>
 __global__ void __launch_bounds__(32 * NW) eval_kernel(EvalArgs a) {
+    typedef Eval<IMPL, NW, GROUND> E;
     extern __shared__ double2 smem_raw[];
     double* sm = reinterpret_cast<double*>(smem_raw);
     const int t = threadIdx.x;
-    const int n = a.sc.n, nr = a.sc.nr;
-    Ctx c;
-    ctx_carve(c, sm, n, nr, GROUND);
-    c.jc = a.sc.jc;
-    c.ends_list = a.sc.ends_list;
-    c.gx = a.sc.grav[0];
-    c.gy = a.sc.grav[1];
-    c.gz = a.sc.grav[2];
-    c.is_chain = a.sc.is_chain;
+    const int nr = a.sc.nr;
+    typename E::C c;
+    E::setup(c, sm, a.sc);
     c.stage = ST_DIRECT;  // direct: qd = hqd0, dq = hq1
     c.h = 1.0;
     c.c = a.cK;
@@ -383,15 +474,15 @@ __global__ void __launch_bounds__(32 * NW) eval_kernel(EvalArgs a) {
         c.tau[t] = a.tau ? a.tau[t] : 0.0;
     }
     bsync<NW>();
-    eval_base<NW, GROUND>(c, true);
+    E::base(c, true);
     if (t < nr && a.g) a.g[t] = c.g[t];
     const int ld = c.ld;
     for (int pass = 0; pass < 3; ++pass) {
         double* dst = pass == 0 ? a.H : (pass == 1 ? a.M : a.D);
         if (!dst) continue;
-        if (pass == 0) eval_columns<NW, GROUND>(c, 1.0, c.beta, 1.0, 1.0, c.H);
-        if (pass == 1) eval_columns<NW, GROUND>(c, 0.0, 0.0, 1.0, 1.0, c.H);
-        if (pass == 2) eval_columns<NW, GROUND>(c, 0.0, 1.0, 0.0, -1.0 / c.c, c.H);
+        if (pass == 0) E::columns(c, 1.0, c.beta, 1.0, 1.0, c.H);
+        if (pass == 1) E::columns(c, 0.0, 0.0, 1.0, 1.0, c.H);
+        if (pass == 2) E::columns(c, 0.0, 1.0, 0.0, -1.0 / c.c, c.H);
         for (int e = t; e < nr * nr; e += blockDim.x) {
             const int col = e / nr, row = e % nr;
             dst[e] = c.H[(size_t)col * ld + row];

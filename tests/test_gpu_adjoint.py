@@ -121,7 +121,7 @@ def test_energies_match_oracle_with_ground(rb, oracle):
         so.setQ(q[b], qd[b])
         so.update()
         To, Vo = so.computeEnergies()
-        assert abs(T[b] - To) <= 1e-12 * abs(To) and abs(V[b] - Vo) <= 1e-12 * abs(Vo)
+        assert abs(T[b] - To) <= 1e-11 * abs(To) and abs(V[b] - Vo) <= 1e-11 * abs(Vo)
     so.setQ(q[0], qd[0])
     so.update()
     Vg = 0.0
