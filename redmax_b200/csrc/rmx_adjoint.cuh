@@ -174,7 +174,7 @@ struct EnergyArgs {
 
 template <int NW, bool GROUND, int IMPL>
 __global__ void __launch_bounds__(32 * NW) energies_kernel(EnergyArgs a) {
-    typedef Eval<IMPL, NW, GROUND> E;
+    typedef Eval<IMPL, NW, GROUND, true> E;
     extern __shared__ double2 smem_raw[];
     double* sm = reinterpret_cast<double*>(smem_raw);
     const int t = threadIdx.x;

@@ -328,9 +328,9 @@ static int warps_for(const rmx_scene* s) {
     return 4;
 }
 
-static size_t scene_smem_doubles(const rmx_scene* s) {
+static size_t scene_smem_doubles(const rmx_scene* s, bool keep = true) {
     const bool g = s->has_ground != 0;
-    return s->impl == 2 ? smem_doubles2(s->n, s->nr, g) : smem_doubles(s->n, s->nr, g);
+    return s->impl == 2 ? smem_doubles2(s->n, s->nr, g, keep) : smem_doubles(s->n, s->nr, g);
 }
 
 static int check_opts(const rmx_scene* s, const rmx_opts* o, StepOpts* so, int adjoint) {
@@ -371,7 +371,7 @@ template <bool ADJ>
 static int launch_fwd(const rmx_scene* s, const RolloutArgs& a, cudaStream_t st) {
     const int nw = warps_for(s);
     const bool g = s->has_ground != 0;
-    const size_t smem = (scene_smem_doubles(s) + (ADJ ? 6 * (size_t)s->nr : 0)) * sizeof(double);
+    const size_t smem = (scene_smem_doubles(s, ADJ) + (ADJ ? 6 * (size_t)s->nr : 0)) * sizeof(double);
     if (smem > 227 * 1024) return fail(RMX_ELIMIT, "scene does not fit the 227 KB shared memory of one SM");
     if (s->impl == 2) {
         if (nw == 1) return g ? launch_fwd_t<1, true, ADJ, 2>(a, smem, st) : launch_fwd_t<1, false, ADJ, 2>(a, smem, st);

@@ -19,56 +19,68 @@
 
 namespace rmx {
 
-// field offsets in the SoA block (units: NS doubles)
-template <bool GROUND>
+// Field offsets in the SoA block (units: NS doubles, NS = n|1).  KEEP = body frames stay in shared memory and H has its
+// own storage (adjoint / test kernels); otherwise H aliases the fields that are dead once the Newton matrix is assembled.
+template <bool GROUND, bool KEEP>
 struct Fld {
-    static constexpr int RW = 0;     // 9  joint frame rotation (scan)
-    static constexpr int PW = 9;     // 3
-    static constexpr int S = 12;     // 6  world screw
-    static constexpr int V = 18;     // 6
-    static constexpr int U = 24;     // 6
-    static constexpr int RB = 30;    // 9  body frame
-    static constexpr int PB = 39;    // 3
-    static constexpr int PHI = 42;   // 6
-    static constexpr int CF = 48;    // 6  F (composite after the accumulation)
-    static constexpr int JB = 54;    // 6  sum (R I3 R' - m [p][p]) : xx xy xz yy yz zz
-    static constexpr int MP = 60;    // 3  sum m p
-    static constexpr int MS = 63;    // 1  sum m
-    static constexpr int ATL = 64;   // 9  sum -c (R Ptl R' + 2 m [p][vc])
-    static constexpr int MV = 73;    // 3  sum m vc
-    static constexpr int AEXT = 76;  // 36 sum -c X' Dext X   (GROUND only)
-    static constexpr int CEXT = 112; // 36 sum -c X' Kext X   (GROUND only)
+    static constexpr int NL = GROUND ? 18 : 12;  // length of L_k
+    static constexpr int NW_ = NL + 6;           // W_k = [L_k ; s_k], stored joint-major (AoS) in region XA
+    static constexpr int RW = 0;                 // 9  joint frame rotation (scan only; region XA)
+    static constexpr int PW = 9;                 // 3
+    static constexpr int XA = NW_;               // size of region XA in fields
+    static constexpr int S = XA;                 // 6  world screw
+    static constexpr int V = S + 6;              // 6
+    static constexpr int U = V + 6;              // 6
+    static constexpr int CF = U + 6;             // 6  F (composite after the accumulation)
+    static constexpr int JB = CF + 6;            // 6  sum (R I3 R' - m [p][p]) : xx xy xz yy yz zz
+    static constexpr int MP = JB + 6;            // 3  sum m p
+    static constexpr int MS = MP + 3;            // 1  sum m
+    static constexpr int ATL = MS + 1;           // 9  sum -c (R Ptl R' + 2 m [p][vc])
+    static constexpr int MV = ATL + 9;           // 3  sum m vc
+    static constexpr int AEXT = MV + 3;          // 36 sum -c X' Dext X   (GROUND only)
+    static constexpr int CEXT = AEXT + 36;       // 36 sum -c X' Kext X   (GROUND only)
     static constexpr int NCOMP = GROUND ? 100 : 28;  // composite components starting at CF
-    static constexpr int LK = GROUND ? 148 : 76;     // L_k: 12 (18 with ground)
-    static constexpr int NL = GROUND ? 18 : 12;
-    static constexpr int TOTAL = LK + NL;
+    static constexpr int RB = CF + NCOMP;        // 9  body frame            (KEEP only)
+    static constexpr int PB = RB + 9;            // 3
+    static constexpr int PHI = PB + 3;           // 6
+    static constexpr int TOTAL = CF + NCOMP + (KEEP ? 18 : 0);
+    static constexpr int HALIAS = V;             // H may live in [V, CF + NCOMP) when !KEEP
+    static constexpr int HROOM = 12 + NCOMP;
 };
 
-__host__ __device__ inline size_t smem_doubles2(int n, int nr, bool ground) {
-    const size_t tot = ground ? Fld<true>::TOTAL : Fld<false>::TOTAL;
-    size_t d = (size_t)n * tot + (size_t)NVEC * nr + (size_t)nr * h_ld(nr) + 16 + 8;
-    d += (size_t)(3 * n + 1) / 2 + 1;  // int tables idx/end/parent
+__host__ __device__ inline int fld_total(bool ground, bool keep) {
+    return ground ? (keep ? Fld<true, true>::TOTAL : Fld<true, false>::TOTAL)
+                  : (keep ? Fld<false, true>::TOTAL : Fld<false, false>::TOTAL);
+}
+__host__ __device__ inline bool h_aliased(int n, int nr, bool ground, bool keep) {
+    const int room = ground ? Fld<true, false>::HROOM : Fld<false, false>::HROOM;
+    return !keep && (size_t)nr * h_ld(nr) <= (size_t)room * (n | 1);
+}
+
+__host__ __device__ inline size_t smem_doubles2(int n, int nr, bool ground, bool keep) {
+    size_t d = (size_t)(n | 1) * fld_total(ground, keep) + (size_t)NVEC * nr + 16 + 8;
+    if (!h_aliased(n, nr, ground, keep)) d += (size_t)nr * h_ld(nr);
+    d += (size_t)(3 * n + 1) / 2 + 1;  // int tables {idx,end}/parent
     return (d + 1) & ~(size_t)1;
 }
 
 struct Ctx2 : Ctx {
     double* sa;  // SoA block
-    int NS;      // stride (= n)
-    int* idx_s;  // [n] reduced index or -1
-    int* end_s;  // [n] subtree end
+    int NS;      // stride (= n|1: odd, so that component-major accesses are conflict free too)
+    int2* ie_s;  // [n] {reduced index or -1, subtree end}
     int* par_s;  // [n] parent
     const int* __restrict__ anc;  // [nrounds][n] ancestor tables (global)
     int nrounds;
 };
 
-__device__ __forceinline__ void ctx2_carve(Ctx2& c, double* sm, int n, int nr, bool ground) {
+__device__ __forceinline__ void ctx2_carve(Ctx2& c, double* sm, int n, int nr, bool ground, bool keep) {
     c.n = n;
     c.nr = nr;
     c.ld = h_ld(nr);
-    c.NS = n;
+    c.NS = n | 1;
     double* p = sm;
     c.sa = p;
-    p += (size_t)n * (ground ? Fld<true>::TOTAL : Fld<false>::TOTAL);
+    p += (size_t)c.NS * fld_total(ground, keep);
     c.rec1 = nullptr;
     c.rec2 = nullptr;
     c.KD = nullptr;
@@ -88,12 +100,15 @@ __device__ __forceinline__ void ctx2_carve(Ctx2& c, double* sm, int n, int nr, b
     c.sp2 = p; p += nr;
     c.red = p;
     p += 16;
-    c.idx_s = reinterpret_cast<int*>(p);
-    c.end_s = c.idx_s + n;
-    c.par_s = c.end_s + n;
+    c.ie_s = reinterpret_cast<int2*>(p);
+    c.par_s = reinterpret_cast<int*>(p) + 2 * n;
     p += (size_t)(3 * n + 1) / 2 + 1;
-    p = (double*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
-    c.H = p;
+    if (h_aliased(n, nr, ground, keep)) {
+        c.H = c.sa + (size_t)(ground ? Fld<true, false>::HALIAS : Fld<false, false>::HALIAS) * c.NS;
+    } else {
+        p = (double*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
+        c.H = p;
+    }
 }
 
 #define SA(f, k, j) c.sa[(size_t)((f) + (k)) * NS + (j)]
@@ -123,9 +138,9 @@ __device__ __forceinline__ void xtmx_store(double* sa, int NS, int fld, int j, c
 // ---------------------------------------------------------------------------------------------
 // eval_base2: residual g at iterate c.q (and, if deriv, the composite blocks eval_columns2 needs).
 // ---------------------------------------------------------------------------------------------
-template <int NW, bool GROUND>
+template <int NW, bool GROUND, bool KEEP>
 __device__ void eval_base2(Ctx2& c, bool deriv) {
-    typedef Fld<GROUND> F;
+    typedef Fld<GROUND, KEEP> F;
     const int t = threadIdx.x;
     const int n = c.n, NS = c.NS;
     const int NT = 32 * NW;
@@ -285,15 +300,16 @@ __device__ void eval_base2(Ctx2& c, bool deriv) {
 #pragma unroll
         for (int i = 0; i < 6; ++i) Fb[i] = J.I[i] * u[i] - c.c * fb[i];
         xf_b2w(Rb, pb, Fb, Fw);
+        if (KEEP) {
 #pragma unroll
-        for (int i = 0; i < 9; ++i) SA(F::RB, i, t) = Rb[i];
+            for (int i = 0; i < 9; ++i) SA(F::RB, i, t) = Rb[i];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) SA(F::PB, i, t) = pb[i];
+            for (int i = 0; i < 3; ++i) SA(F::PB, i, t) = pb[i];
 #pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            SA(F::PHI, i, t) = phi[i];
-            SA(F::CF, i, t) = Fw[i];
+            for (int i = 0; i < 6; ++i) SA(F::PHI, i, t) = phi[i];
         }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) SA(F::CF, i, t) = Fw[i];
         if (deriv) {
             // Jb = R I3 R' - m [p][p]   (symmetric: xx xy xz yy yz zz);  [p][p] = p p' - |p|^2 I
             const double pp = pb[0] * pb[0] + pb[1] * pb[1] + pb[2] * pb[2];
@@ -387,13 +403,13 @@ __device__ void eval_base2(Ctx2& c, bool deriv) {
 // ---------------------------------------------------------------------------------------------
 // eval_columns2: out (nr x ld column-major) = scale * ( sq dg/dq + sqd dg/dqdot + sd dg/d(dqtmp) ), from the composite blocks.
 // ---------------------------------------------------------------------------------------------
-template <int NW, bool GROUND>
+template <int NW, bool GROUND, bool KEEP>
 __device__ void eval_columns2(Ctx2& c, double sq, double sqd, double sd, double scale, double* out) {
-    typedef Fld<GROUND> F;
+    typedef Fld<GROUND, KEEP> F;
     const int t = threadIdx.x;
     const int n = c.n, NS = c.NS, ld = c.ld;
     const double cc = c.c;
-    const int myidx = (t < n) ? c.idx_s[t] : -1;
+    const int myidx = (t < n) ? c.ie_s[t].x : -1;
     double Rt[F::NL];  // [c2 (6) ; c1 (3 or 6) ; sq s (3 or 6)]
     double Z[6];
     if (myidx >= 0) {
@@ -510,8 +526,14 @@ __device__ void eval_columns2(Ctx2& c, double sq, double sqd, double sd, double 
                 Z[r] += zr;
             }
         }
+        // W_t = [L_t ; s_t], joint-major so that the rows below are fetched with 128-bit broadcast loads
+        {
+            double* W = c.sa + (size_t)t * F::NW_;
 #pragma unroll
-        for (int i = 0; i < F::NL; ++i) SA(F::LK, i, t) = L[i];
+            for (int i = 0; i < F::NL; ++i) W[i] = L[i];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) W[F::NL + i] = s[i];
+        }
         // Rt
 #pragma unroll
         for (int i = 0; i < 6; ++i) Rt[i] = c2[i];
@@ -530,23 +552,33 @@ __device__ void eval_columns2(Ctx2& c, double sq, double sqd, double sd, double 
         }
     }
     bsync<NW>();
-    // ---- entries of column idx[t] -----------------------------------------------------------------------------------
+    // ---- entries of column idx[t]: row k is L_k.Rt_i for k in sub(i), s_k.Z_i for k a proper ancestor of i ------------
     if (myidx >= 0) {
-        const int i = t, iend = c.end_s[t];
+        const int i = t, iend = c.ie_s[t].y;
         double* col = out + (size_t)myidx * ld;
+        const double dg = -cc * (sq * c.sp2[myidx] + sqd * c.sp1[myidx]);  // Kr, Dr of Joint.m:470-481
         for (int k = 0; k < n; ++k) {
-            const int rk = c.idx_s[k];
-            if (rk < 0) continue;
+            const int2 ie = c.ie_s[k];
+            if (ie.x < 0) continue;
+            const double2* W = reinterpret_cast<const double2*>(c.sa + (size_t)k * F::NW_);
             double v = 0.0;
             if (k >= i && k < iend) {
 #pragma unroll
-                for (int e = 0; e < F::NL; ++e) v += SA(F::LK, e, k) * Rt[e];
-            } else if (k < i && i < c.end_s[k]) {
+                for (int e = 0; e < F::NL / 2; ++e) {
+                    const double2 w = W[e];
+                    v = fma(w.x, Rt[2 * e], v);
+                    v = fma(w.y, Rt[2 * e + 1], v);
+                }
+                if (k == i) v += dg;
+            } else if (k < i && i < ie.y) {
 #pragma unroll
-                for (int e = 0; e < 6; ++e) v += SA(F::S, e, k) * Z[e];
+                for (int e = 0; e < 3; ++e) {
+                    const double2 w = W[F::NL / 2 + e];
+                    v = fma(w.x, Z[2 * e], v);
+                    v = fma(w.y, Z[2 * e + 1], v);
+                }
             }
-            if (k == i) v += -cc * (sq * c.sp2[myidx] + sqd * c.sp1[myidx]);  // Kr, Dr of Joint.m:470-481
-            col[rk] = scale * v;
+            col[ie.x] = scale * v;
         }
     }
     bsync<NW>();
@@ -594,7 +626,7 @@ __device__ __noinline__ void lu_solve_warp_t(int nr, int ld, double* H, int* per
         }
         if (lane == k) perm[k] = src;
         const double piv = __shfl_sync(FULL, a[k], src);
-        const double rp = 1.0 / piv;
+        const double rp = __drcp_rn(piv);  // == 1.0 / piv, correctly rounded
         rdiag = (lane == src) ? rp : rdiag;
         const double l = done ? 0.0 : a[k] * rp;
         a[k] = done ? a[k] : l;

@@ -53,11 +53,11 @@ struct RolloutArgs {
 //   IMPL 1 : rmx_device.cuh  -- serial tree sweeps + per-(column, body) tangent sweep (kept for n > 64 and as cross-check)
 //   IMPL 2 : rmx_fast.cuh    -- scans + composite blocks + (one warp) register LU
 // ---------------------------------------------------------------------------------------------
-template <int IMPL, int NW, bool GROUND>
+template <int IMPL, int NW, bool GROUND, bool KEEP>
 struct Eval;
 
-template <int NW, bool GROUND>
-struct Eval<1, NW, GROUND> {
+template <int NW, bool GROUND, bool KEEP>
+struct Eval<1, NW, GROUND, KEEP> {
     typedef Ctx C;
     static __device__ __forceinline__ size_t extra_off(const C& c) { return (size_t)c.nr * c.ld; }
     static __device__ __forceinline__ void setup(C& c, double* sm, const DevScene& sc) {
@@ -95,12 +95,12 @@ struct Eval<1, NW, GROUND> {
     }
 };
 
-template <int NW, bool GROUND>
-struct Eval<2, NW, GROUND> {
+template <int NW, bool GROUND, bool KEEP>
+struct Eval<2, NW, GROUND, KEEP> {
     typedef Ctx2 C;
-    typedef Fld<GROUND> F;
+    typedef Fld<GROUND, KEEP> F;
     static __device__ __forceinline__ void setup(C& c, double* sm, const DevScene& sc) {
-        ctx2_carve(c, sm, sc.n, sc.nr, GROUND);
+        ctx2_carve(c, sm, sc.n, sc.nr, GROUND, KEEP);
         c.jc = sc.jc;
         c.ends_list = sc.ends_list;
         c.gx = sc.grav[0];
@@ -110,15 +110,14 @@ struct Eval<2, NW, GROUND> {
         c.anc = sc.anc;
         c.nrounds = sc.nrounds;
         for (int j = threadIdx.x; j < sc.n; j += 32 * NW) {
-            c.idx_s[j] = sc.jc[j].idx;
-            c.end_s[j] = sc.jc[j].end;
+            c.ie_s[j] = make_int2(sc.jc[j].idx, sc.jc[j].end);
             c.par_s[j] = sc.jc[j].parent;
         }
         bsync<NW>();
     }
-    static __device__ __forceinline__ void base(C& c, bool deriv) { eval_base2<NW, GROUND>(c, deriv); }
+    static __device__ __forceinline__ void base(C& c, bool deriv) { eval_base2<NW, GROUND, KEEP>(c, deriv); }
     static __device__ __forceinline__ void columns(C& c, double sq, double sqd, double sd, double scale, double* out) {
-        eval_columns2<NW, GROUND>(c, sq, sqd, sd, scale, out);
+        eval_columns2<NW, GROUND, KEEP>(c, sq, sqd, sd, scale, out);
     }
     static __device__ __forceinline__ void factor_solve(C& c, int* perm, double scale, bool write_back) {
         if (NW == 1) {
@@ -154,56 +153,53 @@ struct Eval<2, NW, GROUND> {
 // ---------------------------------------------------------------------------------------------
 template <class E, int NW>
 __device__ __forceinline__ int newton_forward(typename E::C& c, const StepOpts& op, int* perm, int& n_iter, int& n_ls) {
+    // The reference evaluates g at every line-search trial (nargout == 1) and then [g,H] again at the accepted point when
+    // the next iteration starts.  Both evaluations see the same x, so the trial evaluation here also produces what the
+    // Newton matrix needs; an accepted, not yet converged trial is reused as the next iteration's evaluation (bitwise the
+    // same numbers, one forward-kinematics pass less per iteration).  n_iter / n_ls count what the reference would do.
     const int t = threadIdx.x;
     const int nr = c.nr;
     int status = 0;
     int iter = 1;
-    bool full = true;
-    double f0 = 0.0, x0t = 0.0, dxt = 0.0, alpha = 1.0;
-    int iterLs = 1;
+    E::base(c, true);
+    double gt = (t < nr) ? c.g[t] : 0.0;
+    double gsum = block_sum<NW>(gt * gt, c.red);
     while (true) {
-        E::base(c, full);
-        const double gt = (t < nr) ? c.g[t] : 0.0;
-        const double gsum = block_sum<NW>(gt * gt, c.red);
-        if (full) {
-            E::columns(c, 1.0, c.beta, 1.0, 1.0, c.H);
-            f0 = 0.5 * gsum;
-            // dx = -H\g
-            E::factor_solve(c, perm, -1.0, false);
-            dxt = (t < nr) ? c.dx[t] : 0.0;
-            const double dxn = sqrt(block_sum<NW>(dxt * dxt, c.red));
-            ++n_iter;
-            if (dxn > op.dxMax) {
-                status |= 1;  // 'Newton diverged': x stays at the evaluation point (driverRedMaxBDF1.m:118-121)
-                break;
-            }
-            if (t < nr) x0t = c.q[t];
-            alpha = 1.0;
-            iterLs = 1;
-            full = false;
-        } else {
+        E::columns(c, 1.0, c.beta, 1.0, 1.0, c.H);
+        const double f0 = 0.5 * gsum;
+        // dx = -H\g
+        E::factor_solve(c, perm, -1.0, false);
+        const double dxt = (t < nr) ? c.dx[t] : 0.0;
+        const double dxn = sqrt(block_sum<NW>(dxt * dxt, c.red));
+        ++n_iter;
+        if (dxn > op.dxMax) {
+            status |= 1;  // 'Newton diverged': x stays at the evaluation point (driverRedMaxBDF1.m:118-121)
+            break;
+        }
+        const double x0t = (t < nr) ? c.q[t] : 0.0;
+        double alpha = 1.0;
+        int iterLs = 1;
+        while (true) {  // driverRedMaxBDF1.m:123-141
+            if (t < nr) c.q[t] = __dadd_rn(x0t, __dmul_rn(alpha, dxt));
+            bsync<NW>();
+            E::base(c, true);
             ++n_ls;
-            const double f = 0.5 * gsum;
-            bool accept = f < f0;
-            if (!accept && iterLs >= op.iterLsMax) {
+            gt = (t < nr) ? c.g[t] : 0.0;
+            gsum = block_sum<NW>(gt * gt, c.red);
+            if (0.5 * gsum < f0) break;
+            if (iterLs >= op.iterLsMax) {
                 status |= 4;  // line search exhausted: keep the last trial (driverRedMaxBDF1.m:135-138)
-                accept = true;
-            }
-            if (accept) {
-                if (sqrt(gsum) < op.tol) break;
-                if (iter >= op.iterMax) {
-                    status |= 2;
-                    break;
-                }
-                ++iter;
-                full = true;
-                continue;
+                break;
             }
             alpha = 0.5 * alpha;
             ++iterLs;
         }
-        if (t < nr) c.q[t] = __dadd_rn(x0t, __dmul_rn(alpha, dxt));
-        bsync<NW>();
+        if (sqrt(gsum) < op.tol) break;
+        if (iter >= op.iterMax) {
+            status |= 2;
+            break;
+        }
+        ++iter;
     }
     return status;
 }
@@ -292,7 +288,7 @@ __device__ __forceinline__ int newton_adjoint(typename E::C& c, const StepOpts& 
 // ---------------------------------------------------------------------------------------------
 template <int NW, bool GROUND, bool ADJ, int IMPL>
 __global__ void __launch_bounds__(32 * NW) rollout_fwd_kernel(RolloutArgs a) {
-    typedef Eval<IMPL, NW, GROUND> E;
+    typedef Eval<IMPL, NW, GROUND, ADJ> E;
     extern __shared__ double2 smem_raw[];
     double* sm = reinterpret_cast<double*>(smem_raw);
     __shared__ int perm_s[32 * NW];
@@ -454,7 +450,7 @@ struct EvalArgs {
 
 template <int NW, bool GROUND, int IMPL>
 __global__ void __launch_bounds__(32 * NW) eval_kernel(EvalArgs a) {
-    typedef Eval<IMPL, NW, GROUND> E;
+    typedef Eval<IMPL, NW, GROUND, true> E;
     extern __shared__ double2 smem_raw[];
     double* sm = reinterpret_cast<double*>(smem_raw);
     const int t = threadIdx.x;
