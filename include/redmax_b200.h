@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RMX_VERSION 100
+#define RMX_VERSION 101
 
 /* error codes */
 #define RMX_OK 0
@@ -50,8 +50,9 @@ extern "C" {
 
 /* Newton linear solve */
 #define RMX_LINSOLVE_LU 0  /* in-block partial-pivot LU == MATLAB `H\g` / lu(H,'vector') (parity path) */
-#define RMX_LINSOLVE_PCG 1 /* in-block preconditioned Krylov solve, projected block-Jacobi preconditioner
-                              after c++/PCG Solver.cpp:81 + ConstraintJoint.cpp:1236,1455 */
+#define RMX_LINSOLVE_PCG 1 /* in-block preconditioned Krylov solve (BiCGStab: the BDF Newton matrix is unsymmetric) with the
+                              projected block-Jacobi preconditioner of c++/PCG Solver.cpp:81 + ConstraintJoint.cpp:1236,1455;
+                              forward rollouts only (the adjoint tape stores LU factors) */
 
 /* per-rollout status bits (reference prints and continues, driverRedMaxBDF1.m:118-121,135-138,150-153) */
 #define RMX_ST_DIVERGED 1  /* 'Newton diverged'            (||dx|| > dxMax) in some step */
@@ -108,7 +109,8 @@ typedef struct rmx_opts {
     int32_t linsolve;        /* RMX_LINSOLVE_* */
     int32_t ngpus;           /* host-pointer entry points only: shard the batch over this many devices (>=1) */
     int32_t tau_mode;        /* RMX_TAU_* */
-    int32_t reserved;
+    int32_t pcg_maxit;       /* RMX_LINSOLVE_PCG: max Krylov iterations per solve (c++/PCG Solver.h:43: 1000; default here 4*nr) */
+    double pcg_tol;          /* RMX_LINSOLVE_PCG: relative residual tolerance ||r|| < tol ||r0|| (Solver.h:43, Solver.cpp:137: 1e-6) */
 } rmx_opts;
 
 /* TaskBDF1PointPos / TaskBDF2PointPos (matlab-diff/+redmax/TaskBDF1PointPos.m:27-55) */
@@ -145,6 +147,10 @@ int rmx_rollout(rmx_scene* s, const rmx_opts* o, int64_t B, const double* q0, co
 int rmx_rollout_dev(rmx_scene* s, const rmx_opts* o, int64_t B, const double* q0, const double* qdot0,
                     const double* tau, double* q_out, double* qdot_out, int32_t* status, int32_t* iters,
                     void* cuda_stream);
+
+/* Total Krylov iterations of the last rmx_rollout* call with linsolve = RMX_LINSOLVE_PCG on this scene (summed over
+ * rollouts, steps and Newton iterations; the counterpart of SolverDataTracker::num_iterations, c++/PCG Solver.h:19-23). */
+int rmx_linsolve_stats(rmx_scene* s, int64_t* krylov_iterations);
 
 /* Objective + gradient: replaces taskObjective(p,scene) of driverRedMaxAdjointBDF1.m:39 / ...BDF2.m:39
  * (scene.reset, task.init, adjoint simLoop with newton:105, saveHistory tape, task.calcStep, task.calcFinal).

@@ -52,7 +52,7 @@ class rmx_opts(C.Structure):
         ('scheme', C.c_int32), ('nsteps', C.c_int32),
         ('h', C.c_double), ('tol', C.c_double), ('dxMax', C.c_double),
         ('iterMaxFactor', C.c_int32), ('iterLsMax', C.c_int32), ('linsolve', C.c_int32),
-        ('ngpus', C.c_int32), ('tau_mode', C.c_int32), ('reserved', C.c_int32),
+        ('ngpus', C.c_int32), ('tau_mode', C.c_int32), ('pcg_maxit', C.c_int32), ('pcg_tol', C.c_double),
     ]
 
 
@@ -69,7 +69,7 @@ SYMBOLS = [
     'rmx_version', 'rmx_last_error', 'rmx_device_count', 'rmx_opts_default',
     'rmx_scene_create', 'rmx_scene_destroy', 'rmx_scene_nr', 'rmx_scene_nm',
     'rmx_rollout', 'rmx_rollout_dev', 'rmx_rollout_adjoint', 'rmx_rollout_adjoint_dev',
-    'rmx_adjoint_tape_bytes', 'rmx_eval', 'rmx_energies',
+    'rmx_adjoint_tape_bytes', 'rmx_eval', 'rmx_energies', 'rmx_linsolve_stats',
 ]
 
 _lib = None
@@ -109,6 +109,7 @@ def lib():
     L.rmx_adjoint_tape_bytes.restype = C.c_int64
     L.rmx_eval.argtypes = [vp, vp, vp, vp, vp, C.c_double, C.c_double, vp, vp, vp, vp, vp]
     L.rmx_energies.argtypes = [vp, C.c_int64, vp, vp, vp, vp]
+    L.rmx_linsolve_stats.argtypes = [vp, C.POINTER(C.c_int64)]
     _lib = L
     return L
 

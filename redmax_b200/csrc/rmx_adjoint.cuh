@@ -174,13 +174,16 @@ struct EnergyArgs {
 
 template <int NW, bool GROUND, int IMPL>
 __global__ void __launch_bounds__(32 * NW) energies_kernel(EnergyArgs a) {
-    typedef Eval<IMPL, NW, GROUND, true> E;
+    typedef Eval<IMPL, NW, GROUND, true, 0> E;
     extern __shared__ double2 smem_raw[];
     double* sm = reinterpret_cast<double*>(smem_raw);
     const int t = threadIdx.x;
     const int n = a.sc.n, nr = a.sc.nr;
     typename E::C c;
-    E::setup(c, sm, a.sc);
+    StepOpts op0;
+    op0.lin_tol = 0.0;
+    op0.lin_maxit = 0;
+    E::setup(c, sm, a.sc, op0);
     c.stage = ST_DIRECT;
     c.h = 1.0;
     c.c = 1.0;

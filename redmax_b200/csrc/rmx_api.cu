@@ -42,6 +42,7 @@ struct DevCopy {
     JointConst* jc = nullptr;
     int* ends = nullptr;
     int* anc = nullptr;
+    unsigned long long* kry = nullptr;  // Krylov iteration counter
     cudaStream_t stream = nullptr;
     DevBuf buf[16];
 };
@@ -57,6 +58,7 @@ struct rmx_scene {
     int nrounds = 0;
     int impl = 2;                 // 1 = sweep kernels (rmx_device.cuh), 2 = composite kernels (rmx_fast.cuh)
     std::map<int, DevCopy> dev;   // per CUDA device
+    std::vector<int> kry_devs;    // devices that ran the last Krylov-solve rollout
 };
 
 extern "C" int rmx_version(void) { return RMX_VERSION; }
@@ -83,6 +85,8 @@ extern "C" void rmx_opts_default(rmx_opts* o, int32_t scheme, int32_t adjoint) {
     o->linsolve = RMX_LINSOLVE_LU;
     o->ngpus = 1;
     o->tau_mode = RMX_TAU_NONE;
+    o->pcg_maxit = 0;         // 0 -> 4*nr
+    o->pcg_tol = 1e-6;        // c++/PCG Solver.h:43
 }
 
 static void colmajor4_to_Rp(const double* E, double* R, double* p) {
@@ -270,6 +274,7 @@ extern "C" void rmx_scene_destroy(rmx_scene* s) {
         cudaFree(kv.second.jc);
         cudaFree(kv.second.ends);
         cudaFree(kv.second.anc);
+        cudaFree(kv.second.kry);
         for (auto& b : kv.second.buf) cudaFree(b.p);
         if (kv.second.stream) cudaStreamDestroy(kv.second.stream);
     }
@@ -290,6 +295,8 @@ static int scene_on_device(rmx_scene* s, int dev, DevCopy** out) {
         CUDA_TRY(cudaMemcpy(dc.ends, s->ends_list.data(), sizeof(int) * s->ends_list.size(), cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMalloc(&dc.anc, sizeof(int) * s->anc.size()));
         CUDA_TRY(cudaMemcpy(dc.anc, s->anc.data(), sizeof(int) * s->anc.size(), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc(&dc.kry, sizeof(unsigned long long)));
+        CUDA_TRY(cudaMemset(dc.kry, 0, sizeof(unsigned long long)));
         CUDA_TRY(cudaStreamCreateWithFlags(&dc.stream, cudaStreamNonBlocking));
         it = s->dev.emplace(dev, dc).first;
     }
@@ -348,23 +355,38 @@ static int check_opts(const rmx_scene* s, const rmx_opts* o, StepOpts* so, int a
     so->h = o->h;
     so->tol = o->tol > 0 ? o->tol : 1e-9;
     so->dxMax = o->dxMax > 0 ? o->dxMax : 1e3;
+    so->lin_tol = o->pcg_tol > 0 ? o->pcg_tol : 1e-6;
+    so->lin_maxit = o->pcg_maxit > 0 ? o->pcg_maxit : 4 * s->nr;
     return RMX_OK;
 }
 
 template <typename K>
 static int set_smem(K kernel, size_t bytes) {
     CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    // as many rollouts per SM as shared memory allows: ask for the full shared-memory carve-out
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     return RMX_OK;
 }
 
-template <int NW, bool GROUND, bool ADJ, int IMPL>
+template <int NW, bool GROUND, bool ADJ, int IMPL, int LIN = 0>
 static int launch_fwd_t(const RolloutArgs& a, size_t smem, cudaStream_t st) {
-    int rc = set_smem(rollout_fwd_kernel<NW, GROUND, ADJ, IMPL>, smem);
+    int rc = set_smem(rollout_fwd_kernel<NW, GROUND, ADJ, IMPL, LIN>, smem);
     if (rc) return rc;
     const long long grid = a.B;
-    rollout_fwd_kernel<NW, GROUND, ADJ, IMPL><<<(unsigned)grid, 32 * NW, smem, st>>>(a);
+    rollout_fwd_kernel<NW, GROUND, ADJ, IMPL, LIN><<<(unsigned)grid, 32 * NW, smem, st>>>(a);
     CUDA_TRY(cudaGetLastError());
     return RMX_OK;
+}
+
+// forward rollout with the Krylov linear solve (fast path only: it needs the world-frame fields of rmx_fast.cuh)
+static int launch_fwd_pcg(const rmx_scene* s, const RolloutArgs& a, cudaStream_t st) {
+    if (s->impl != 2) return fail(RMX_ELIMIT, "linsolve=PCG needs the composite kernels (n <= 64 joints)");
+    const int nw = warps_for(s);
+    const bool g = s->has_ground != 0;
+    const size_t smem = (smem_doubles2(s->n, s->nr, g, true) + pcg_doubles(s->n, s->nr)) * sizeof(double);
+    if (smem > 227 * 1024) return fail(RMX_ELIMIT, "scene does not fit the 227 KB shared memory of one SM");
+    if (nw == 1) return g ? launch_fwd_t<1, true, false, 2, 1>(a, smem, st) : launch_fwd_t<1, false, false, 2, 1>(a, smem, st);
+    return g ? launch_fwd_t<2, true, false, 2, 1>(a, smem, st) : launch_fwd_t<2, false, false, 2, 1>(a, smem, st);
 }
 
 template <bool ADJ>
@@ -390,7 +412,6 @@ extern "C" int rmx_rollout_dev(rmx_scene* s, const rmx_opts* o, int64_t B, const
     if (rc) return rc;
     if (B < 1 || !q0 || !qdot0 || !q_out || !status) return fail(RMX_EINVAL, "rmx_rollout_dev: bad arguments");
     if (so.tau_mode != RMX_TAU_NONE && !tau) return fail(RMX_EINVAL, "rmx_rollout_dev: tau_mode set but tau == NULL");
-    if (o->linsolve == RMX_LINSOLVE_PCG) return fail(RMX_EINVAL, "linsolve=PCG is not built yet in this version; use LU");
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     DevCopy* dc;
@@ -408,6 +429,14 @@ extern "C" int rmx_rollout_dev(rmx_scene* s, const rmx_opts* o, int64_t B, const
     a.qd_out = qdot_out;
     a.status = status;
     a.iters = iters;
+    if (o->linsolve == RMX_LINSOLVE_PCG) {
+        CUDA_TRY(cudaMemsetAsync(dc->kry, 0, sizeof(unsigned long long), (cudaStream_t)cuda_stream));
+        a.kry_total = dc->kry;
+        bool seen = false;
+        for (int d2 : s->kry_devs) seen = seen || d2 == dev;
+        if (!seen) s->kry_devs.push_back(dev);
+        return launch_fwd_pcg(s, a, (cudaStream_t)cuda_stream);
+    }
     return launch_fwd<false>(s, a, (cudaStream_t)cuda_stream);
 }
 
@@ -431,6 +460,7 @@ extern "C" int rmx_rollout(rmx_scene* s, const rmx_opts* o, int64_t B, const dou
     const size_t per = (size_t)nr * so.nsteps;
     const size_t tau_per = so.tau_mode == RMX_TAU_PER_STEP ? per : (size_t)nr;
     rmx_opts o1 = *o;
+    s->kry_devs.clear();
     std::vector<int> devs;
     for (int gi = 0; gi < G; ++gi) devs.push_back(G == 1 ? cur : gi);
     int ret = RMX_OK;
@@ -469,6 +499,25 @@ extern "C" int rmx_rollout(rmx_scene* s, const rmx_opts* o, int64_t B, const dou
     }
     cudaSetDevice(cur);
     return ret;
+}
+
+extern "C" int rmx_linsolve_stats(rmx_scene* s, int64_t* krylov_iterations) {
+    if (!s || !krylov_iterations) return fail(RMX_EINVAL, "rmx_linsolve_stats: null argument");
+    int cur = 0;
+    CUDA_TRY(cudaGetDevice(&cur));
+    int64_t total = 0;
+    for (int d : s->kry_devs) {
+        auto it = s->dev.find(d);
+        if (it == s->dev.end()) continue;
+        unsigned long long v = 0;
+        CUDA_TRY(cudaSetDevice(d));
+        CUDA_TRY(cudaDeviceSynchronize());
+        CUDA_TRY(cudaMemcpy(&v, it->second.kry, sizeof(v), cudaMemcpyDeviceToHost));
+        total += (int64_t)v;
+    }
+    cudaSetDevice(cur);
+    *krylov_iterations = total;
+    return RMX_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -64,6 +64,8 @@ struct DevScene {
 struct StepOpts {
     int scheme, nsteps, iterMax, iterLsMax, tau_mode, adjoint_newton;
     double h, tol, dxMax;
+    double lin_tol;  // Krylov linear solve: relative residual tolerance (c++/PCG Solver.h:43: 1e-6)
+    int lin_maxit;
 };
 
 // stages of the implicit step

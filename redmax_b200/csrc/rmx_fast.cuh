@@ -561,13 +561,13 @@ __device__ void eval_columns2(Ctx2& c, double sq, double sqd, double sd, double 
             const int2 ie = c.ie_s[k];
             if (ie.x < 0) continue;
             const double2* W = reinterpret_cast<const double2*>(c.sa + (size_t)k * F::NW_);
-            double v = 0.0;
+            double v = 0.0, v2 = 0.0;
             if (k >= i && k < iend) {
 #pragma unroll
                 for (int e = 0; e < F::NL / 2; ++e) {
                     const double2 w = W[e];
                     v = fma(w.x, Rt[2 * e], v);
-                    v = fma(w.y, Rt[2 * e + 1], v);
+                    v2 = fma(w.y, Rt[2 * e + 1], v2);
                 }
                 if (k == i) v += dg;
             } else if (k < i && i < ie.y) {
@@ -575,10 +575,10 @@ __device__ void eval_columns2(Ctx2& c, double sq, double sqd, double sd, double 
                 for (int e = 0; e < 3; ++e) {
                     const double2 w = W[F::NL / 2 + e];
                     v = fma(w.x, Z[2 * e], v);
-                    v = fma(w.y, Z[2 * e + 1], v);
+                    v2 = fma(w.y, Z[2 * e + 1], v2);
                 }
             }
-            col[ie.x] = scale * v;
+            col[ie.x] = scale * (v + v2);
         }
     }
     bsync<NW>();
@@ -607,15 +607,22 @@ __device__ __noinline__ void lu_solve_warp_t(int nr, int ld, double* H, int* per
     double rdiag = 1.0;
 #pragma unroll
     for (int k = 0; k < NR; ++k) {
+        // argmax |a[k]| over the rows that are not pivots yet; ties -> smallest LAPACK position.  |v| >= 0, so the IEEE bit
+        // pattern orders like the value: one warp reduction on the high words decides unless two rows agree in their
+        // top 32 bits, and only then the low words and the positions are consulted (warp-uniform branch).
         const double v = fabs(a[k]);
         const unsigned hi = done ? 0u : (unsigned)__double2hiint(v);
         const unsigned mh = __reduce_max_sync(FULL, hi);
         const bool c1 = !done && hi == mh;
-        const unsigned lo = c1 ? (unsigned)__double2loint(v) : 0u;
-        const unsigned ml = __reduce_max_sync(FULL, lo);
-        const bool c2 = c1 && lo == ml;
-        const unsigned pm = __reduce_min_sync(FULL, c2 ? (unsigned)pos : 0xffffu);
-        const int src = __ffs(__ballot_sync(FULL, c2 && (unsigned)pos == pm)) - 1;
+        unsigned cand = __ballot_sync(FULL, c1);
+        if (cand & (cand - 1)) {
+            const unsigned lo = c1 ? (unsigned)__double2loint(v) : 0u;
+            const unsigned ml = __reduce_max_sync(FULL, lo);
+            const bool c2 = c1 && lo == ml;
+            const unsigned pm = __reduce_min_sync(FULL, c2 ? (unsigned)pos : 0xffffu);
+            cand = __ballot_sync(FULL, c2 && (unsigned)pos == pm);
+        }
+        const int src = __ffs(cand) - 1;
         const int kl = __ffs(__ballot_sync(FULL, !done && pos == k)) - 1;
         const int pos_src = __shfl_sync(FULL, pos, src);
         if (lane == kl) pos = pos_src;

@@ -2,6 +2,7 @@
 #pragma once
 #include "rmx_device.cuh"
 #include "rmx_fast.cuh"
+#include "rmx_pcg.cuh"
 
 namespace rmx {
 
@@ -46,21 +47,32 @@ struct RolloutArgs {
     int* iters;
     TapeArgs tape;
     TaskArgs task;
+    unsigned long long* kry_total;  // total Krylov iterations of the launch (LIN == 1) or null
 };
+
+__device__ __forceinline__ int krylov_count(const Ctx&) { return 0; }
+__device__ __forceinline__ void krylov_reset(Ctx&) {}
 
 // ---------------------------------------------------------------------------------------------
 // Two implementations of the evaluation behind one interface:
 //   IMPL 1 : rmx_device.cuh  -- serial tree sweeps + per-(column, body) tangent sweep (kept for n > 64 and as cross-check)
 //   IMPL 2 : rmx_fast.cuh    -- scans + composite blocks + (one warp) register LU
 // ---------------------------------------------------------------------------------------------
-template <int IMPL, int NW, bool GROUND, bool KEEP>
+template <int IMPL, int NW, bool GROUND, bool KEEP, int LIN>
 struct Eval;
 
-template <int NW, bool GROUND, bool KEEP>
-struct Eval<1, NW, GROUND, KEEP> {
+struct Ctx2L : Ctx2 {  // fast-path context + state of the Krylov linear solve (LIN == 1)
+    PcgMem pm;
+    double lin_tol;
+    int lin_maxit;
+    int kry_iters;
+};
+
+template <int NW, bool GROUND, bool KEEP, int LIN>
+struct Eval<1, NW, GROUND, KEEP, LIN> {
     typedef Ctx C;
     static __device__ __forceinline__ size_t extra_off(const C& c) { return (size_t)c.nr * c.ld; }
-    static __device__ __forceinline__ void setup(C& c, double* sm, const DevScene& sc) {
+    static __device__ __forceinline__ void setup(C& c, double* sm, const DevScene& sc, const StepOpts&) {
         ctx_carve(c, sm, sc.n, sc.nr, GROUND);
         c.jc = sc.jc;
         c.ends_list = sc.ends_list;
@@ -95,12 +107,16 @@ struct Eval<1, NW, GROUND, KEEP> {
     }
 };
 
-template <int NW, bool GROUND, bool KEEP>
-struct Eval<2, NW, GROUND, KEEP> {
-    typedef Ctx2 C;
+template <int NW, bool GROUND, bool KEEP, int LIN>
+struct Eval<2, NW, GROUND, KEEP, LIN> {
+    typedef Ctx2L C;
     typedef Fld<GROUND, KEEP> F;
-    static __device__ __forceinline__ void setup(C& c, double* sm, const DevScene& sc) {
+    static __device__ __forceinline__ void setup(C& c, double* sm, const DevScene& sc, const StepOpts& op) {
         ctx2_carve(c, sm, sc.n, sc.nr, GROUND, KEEP);
+        c.lin_tol = op.lin_tol;
+        c.lin_maxit = op.lin_maxit;
+        c.kry_iters = 0;
+        if (LIN == 1) pcg_carve(c.pm, c.H + (size_t)c.nr * c.ld, sc.n, sc.nr);
         c.jc = sc.jc;
         c.ends_list = sc.ends_list;
         c.gx = sc.grav[0];
@@ -120,7 +136,9 @@ struct Eval<2, NW, GROUND, KEEP> {
         eval_columns2<NW, GROUND, KEEP>(c, sq, sqd, sd, scale, out);
     }
     static __device__ __forceinline__ void factor_solve(C& c, int* perm, double scale, bool write_back) {
-        if (NW == 1) {
+        if (LIN == 1) {
+            c.kry_iters += krylov_solve<NW, GROUND>(c, c.pm, c.H, c.g, scale, c.lin_tol, c.lin_maxit);
+        } else if (NW == 1) {
             lu_solve_warp(c.nr, c.ld, c.H, perm, c.g, scale, c.dx, write_back);
         } else {
             lu_factor<NW>(c, c.H, perm);
@@ -146,6 +164,9 @@ struct Eval<2, NW, GROUND, KEEP> {
     }
 };
 
+__device__ __forceinline__ int krylov_count(const Ctx2L& c) { return c.kry_iters; }
+__device__ __forceinline__ void krylov_reset(Ctx2L& c) { c.kry_iters = 0; }
+
 // ---------------------------------------------------------------------------------------------
 // newton() of driverRedMaxBDF1.m:94-157 (forward drivers: damped Newton + backtracking line search).
 // Written as a two-state machine (FULL evaluation with H / residual-only line-search trial) so that the
@@ -157,49 +178,58 @@ __device__ __forceinline__ int newton_forward(typename E::C& c, const StepOpts& 
     // the next iteration starts.  Both evaluations see the same x, so the trial evaluation here also produces what the
     // Newton matrix needs; an accepted, not yet converged trial is reused as the next iteration's evaluation (bitwise the
     // same numbers, one forward-kinematics pass less per iteration).  n_iter / n_ls count what the reference would do.
+    // Written as a state machine so that the evaluation, assembly and LU code each have a single call site.
     const int t = threadIdx.x;
     const int nr = c.nr;
     int status = 0;
     int iter = 1;
-    E::base(c, true);
-    double gt = (t < nr) ? c.g[t] : 0.0;
-    double gsum = block_sum<NW>(gt * gt, c.red);
+    bool trial = false;  // false: first evaluation of the solve; true: line-search trial at x0 + alpha dx
+    double f0 = 0.0, x0t = 0.0, dxt = 0.0, alpha = 1.0;
+    int iterLs = 1;
     while (true) {
+        E::base(c, true);
+        const double gt = (t < nr) ? c.g[t] : 0.0;
+        const double gsum = block_sum<NW>(gt * gt, c.red);
+        if (trial) {  // driverRedMaxBDF1.m:123-141
+            ++n_ls;
+            bool accept = 0.5 * gsum < f0;
+            if (!accept && iterLs >= op.iterLsMax) {
+                status |= 4;  // line search exhausted: keep the last trial (driverRedMaxBDF1.m:135-138)
+                accept = true;
+            }
+            if (!accept) {
+                alpha = 0.5 * alpha;
+                ++iterLs;
+                if (t < nr) c.q[t] = __dadd_rn(x0t, __dmul_rn(alpha, dxt));
+                bsync<NW>();
+                continue;
+            }
+            if (sqrt(gsum) < op.tol) break;
+            if (iter >= op.iterMax) {
+                status |= 2;
+                break;
+            }
+            ++iter;
+        }
         E::columns(c, 1.0, c.beta, 1.0, 1.0, c.H);
-        const double f0 = 0.5 * gsum;
+        f0 = 0.5 * gsum;
         // dx = -H\g
         E::factor_solve(c, perm, -1.0, false);
-        const double dxt = (t < nr) ? c.dx[t] : 0.0;
+        dxt = (t < nr) ? c.dx[t] : 0.0;
         const double dxn = sqrt(block_sum<NW>(dxt * dxt, c.red));
         ++n_iter;
         if (dxn > op.dxMax) {
             status |= 1;  // 'Newton diverged': x stays at the evaluation point (driverRedMaxBDF1.m:118-121)
             break;
         }
-        const double x0t = (t < nr) ? c.q[t] : 0.0;
-        double alpha = 1.0;
-        int iterLs = 1;
-        while (true) {  // driverRedMaxBDF1.m:123-141
-            if (t < nr) c.q[t] = __dadd_rn(x0t, __dmul_rn(alpha, dxt));
-            bsync<NW>();
-            E::base(c, true);
-            ++n_ls;
-            gt = (t < nr) ? c.g[t] : 0.0;
-            gsum = block_sum<NW>(gt * gt, c.red);
-            if (0.5 * gsum < f0) break;
-            if (iterLs >= op.iterLsMax) {
-                status |= 4;  // line search exhausted: keep the last trial (driverRedMaxBDF1.m:135-138)
-                break;
-            }
-            alpha = 0.5 * alpha;
-            ++iterLs;
+        if (t < nr) {
+            x0t = c.q[t];
+            c.q[t] = __dadd_rn(x0t, dxt);  // alpha = 1
         }
-        if (sqrt(gsum) < op.tol) break;
-        if (iter >= op.iterMax) {
-            status |= 2;
-            break;
-        }
-        ++iter;
+        alpha = 1.0;
+        iterLs = 1;
+        trial = true;
+        bsync<NW>();
     }
     return status;
 }
@@ -286,16 +316,16 @@ __device__ __forceinline__ int newton_adjoint(typename E::C& c, const StepOpts& 
 // Forward rollout kernel: simLoop of driverRedMaxBDF1.m:57-91 / driverRedMaxBDF2.m:57-125 (ADJ = false) and of
 // driverRedMaxAdjointBDF1.m:65-102 / driverRedMaxAdjointBDF2.m:65-136 (ADJ = true), one block per rollout.
 // ---------------------------------------------------------------------------------------------
-template <int NW, bool GROUND, bool ADJ, int IMPL>
+template <int NW, bool GROUND, bool ADJ, int IMPL, int LIN>
 __global__ void __launch_bounds__(32 * NW) rollout_fwd_kernel(RolloutArgs a) {
-    typedef Eval<IMPL, NW, GROUND, ADJ> E;
+    typedef Eval<IMPL, NW, GROUND, ADJ || LIN == 1, LIN> E;
     extern __shared__ double2 smem_raw[];
     double* sm = reinterpret_cast<double*>(smem_raw);
     __shared__ int perm_s[32 * NW];
     const int t = threadIdx.x;
     const int nr = a.sc.nr;
     typename E::C c;
-    E::setup(c, sm, a.sc);
+    E::setup(c, sm, a.sc, a.op);
     const StepOpts op = a.op;
     const double h = op.h;
     const double ah = __dmul_rn(SDIRK_A_CONST, h);
@@ -427,6 +457,10 @@ __global__ void __launch_bounds__(32 * NW) rollout_fwd_kernel(RolloutArgs a) {
                 a.iters[2 * b + 1] = n_ls;
             }
             if (ADJ) a.task.P[b] = Pacc;  // objective part; the regulariser is added by the backward kernel
+            if (LIN == 1 && IMPL == 2 && a.kry_total) {
+                atomicAdd(a.kry_total, (unsigned long long)krylov_count(c));
+                krylov_reset(c);
+            }
         }
         bsync<NW>();
     }
@@ -450,13 +484,16 @@ struct EvalArgs {
 
 template <int NW, bool GROUND, int IMPL>
 __global__ void __launch_bounds__(32 * NW) eval_kernel(EvalArgs a) {
-    typedef Eval<IMPL, NW, GROUND, true> E;
+    typedef Eval<IMPL, NW, GROUND, true, 0> E;
     extern __shared__ double2 smem_raw[];
     double* sm = reinterpret_cast<double*>(smem_raw);
     const int t = threadIdx.x;
     const int nr = a.sc.nr;
     typename E::C c;
-    E::setup(c, sm, a.sc);
+    StepOpts op0;
+    op0.lin_tol = 0.0;
+    op0.lin_maxit = 0;
+    E::setup(c, sm, a.sc, op0);
     c.stage = ST_DIRECT;  // direct: qd = hqd0, dq = hq1
     c.h = 1.0;
     c.c = a.cK;

@@ -396,6 +396,13 @@ class Scene:
         _ffi.check(L.rmx_rollout_dev(self._handle, C.byref(o), B, ptr(q0), ptr(qdot0), ptr(tau), ptr(q_out),
                                      ptr(qdot_out), ptr(status), ptr(iters), st), 'rmx_rollout_dev')
 
+    def linsolve_stats(self):
+        """Total Krylov iterations of the last rollout with linsolve=RMX_LINSOLVE_PCG (rmx_linsolve_stats)."""
+        L = self._require()
+        v = C.c_int64(0)
+        _ffi.check(L.rmx_linsolve_stats(self._handle, C.byref(v)), 'rmx_linsolve_stats')
+        return int(v.value)
+
     # -- adjoint: taskObjective of driverRedMaxAdjointBDF1.m:39 / ...BDF2.m:39, batched ----------------------
     def _task_struct(self):
         if self.task is None or self.task.body is None:
