@@ -221,6 +221,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     import redmax_b200 as rb
+    from redmax_b200 import shard
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -239,8 +240,8 @@ def run_ours(args):
     nr = sc.nr
     # per-rank shard of the global seeded batch: rollouts [rank*B, (rank+1)*B)
     q0_all, qd0_all = rb.synthetic_inputs(sc, B * world, seed=SEED)
-    q0 = np.ascontiguousarray(q0_all[rank * B:(rank + 1) * B])
-    qd0 = np.ascontiguousarray(qd0_all[rank * B:(rank + 1) * B])
+    q0 = np.ascontiguousarray(shard.take_shard(q0_all, world, rank))
+    qd0 = np.ascontiguousarray(shard.take_shard(qd0_all, world, rank))
     dq0 = torch.from_numpy(q0).to(dev)
     dqd0 = torch.from_numpy(qd0).to(dev)
     qo = torch.empty((B, nsteps, nr), dtype=torch.float64, device=dev)
@@ -306,12 +307,11 @@ def run_ours(args):
     # ---- trajectory gather the north star asks for (timed separately) -----------------------------------------
     gather_ms = None
     if world > 1:
-        gathered = torch.empty((world * B, nsteps, nr), dtype=torch.float64, device=dev)
-        dist.all_gather_into_tensor(gathered, qo)
+        gathered = shard.gather_trajectories(qo, B=world * B)
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
-        dist.all_gather_into_tensor(gathered, qo)
+        gathered = shard.gather_trajectories(qo, B=world * B)
         g1.record()
         torch.cuda.synchronize()
         gather_ms = g0.elapsed_time(g1)
