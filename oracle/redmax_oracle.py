@@ -521,6 +521,101 @@ class JointFixed(Joint):
         super().__init__(parent, body, 0)
 
 
+class JointPrismatic(Joint):
+    def __init__(self, parent, body, axis):
+        """JointPrismatic.m:12"""
+        super().__init__(parent, body, 1)
+        axis = np.asarray(axis, dtype=float).reshape(3)
+        self.axis = axis / np.linalg.norm(axis)
+
+    def update_(self, deriv):
+        """JointPrismatic.m:28"""
+        a = self.axis
+        self.Q[0:3, 3] = a * self.q[0]
+        self.A = se3_Ad(self.Q)
+        self.S = np.concatenate([np.zeros(3), a]).reshape(6, 1)
+        abrac = se3_brac(a)
+        self.Adot[3:6, 0:3] = abrac * self.qdot[0]
+        if deriv:
+            self.dAdq[3:6, 0:3, 0] = abrac
+
+
+class JointPlanar(Joint):
+    def __init__(self, parent, body, plane=None):
+        """JointPlanar.m:11 -- `plane` is 3 x 2 (columns = the two in-plane directions)."""
+        super().__init__(parent, body, 2)
+        if plane is None:
+            plane = np.array([[1.0, 0.0, 0.0], [0.0, 1.0, 0.0]]).T
+        plane = np.array(plane, dtype=float).reshape(3, 2)
+        self.plane = np.stack([plane[:, 0] / np.linalg.norm(plane[:, 0]), plane[:, 1] / np.linalg.norm(plane[:, 1])], axis=1)
+
+    def update_(self, deriv):
+        """JointPlanar.m:24"""
+        B = self.plane
+        self.Q[0:3, 3] = B @ self.q
+        self.A = se3_Ad(self.Q)
+        self.S = np.vstack([np.zeros((3, 2)), B])
+        self.Adot[3:6, 0:3] = se3_brac(B @ self.qdot)
+        if deriv:
+            for k in range(2):
+                self.dAdq[3:6, 0:3, k] = se3_brac(B[:, k])
+
+
+class JointTranslational(Joint):
+    def __init__(self, parent, body):
+        """JointTranslational.m:12"""
+        super().__init__(parent, body, 3)
+
+    def update_(self, deriv):
+        """JointTranslational.m:20"""
+        self.Q[0:3, 3] = self.q
+        self.A = se3_Ad(self.Q)
+        self.S = np.vstack([np.zeros((3, 3)), np.eye(3)])
+        self.Adot[3:6, 0:3] = se3_brac(self.qdot)
+        if deriv:
+            for k in range(3):
+                ek = np.zeros(3)
+                ek[k] = 1.0
+                self.dAdq[3:6, 0:3, k] = se3_brac(ek)
+
+
+class JointUniversal(Joint):
+    """JointUniversal.m -- rotation about X then Y, R = X(q1) Y(q2); the entries below are the reference's generated
+    closed forms (JointUniversal.m:122-182, `XY`), written out per matrix instead of through the t-temporaries."""
+
+    def __init__(self, parent, body):
+        super().__init__(parent, body, 2)
+
+    def update_(self, deriv):
+        """JointUniversal.m:19"""
+        q1, q2 = self.q
+        qd1, qd2 = self.qdot
+        c1, s1, c2, s2 = math.cos(q1), math.sin(q1), math.cos(q2), math.sin(q2)
+        R = np.array([[c2, 0.0, s2], [s1 * s2, c1, -c2 * s1], [-c1 * s2, s1, c1 * c2]])
+        dR1 = np.array([[0.0, 0.0, 0.0], [c1 * s2, -s1, -c1 * c2], [s1 * s2, c1, -c2 * s1]])
+        dR2 = np.array([[-s2, 0.0, c2], [c2 * s1, 0.0, s1 * s2], [-c1 * c2, 0.0, -c1 * s2]])
+        Rdot = dR1 * qd1 + dR2 * qd2
+        self.Q[0:3, 0:3] = R
+        self.A = se3_Ad(self.Q)
+        self.Adot[0:3, 0:3] = Rdot
+        self.Adot[3:6, 3:6] = Rdot
+        self.S[0:3, 0:2] = [[c2, 0.0], [0.0, 1.0], [s2, 0.0]]
+        self.Sdot[0:3, 0:2] = [[-s2 * qd2, 0.0], [0.0, 0.0], [c2 * qd2, 0.0]]
+        if deriv:
+            # d(Rdot)/dq_i = d2R/dq_i dq_1 qd1 + d2R/dq_i dq_2 qd2
+            d11 = np.array([[0.0, 0.0, 0.0], [-s1 * s2, -c1, c2 * s1], [c1 * s2, -s1, -c1 * c2]])
+            d12 = np.array([[0.0, 0.0, 0.0], [c1 * c2, 0.0, c1 * s2], [c2 * s1, 0.0, s1 * s2]])
+            d22 = np.array([[-c2, 0.0, -s2], [-s1 * s2, 0.0, c2 * s1], [c1 * s2, 0.0, -c1 * c2]])
+            dRdot = [d11 * qd1 + d12 * qd2, d12 * qd1 + d22 * qd2]
+            for i, (dR, dRd) in enumerate(((dR1, dRdot[0]), (dR2, dRdot[1]))):
+                self.dAdq[0:3, 0:3, i] = dR
+                self.dAdq[3:6, 3:6, i] = dR
+                self.dAdotdq[0:3, 0:3, i] = dRd
+                self.dAdotdq[3:6, 3:6, i] = dRd
+            self.dSdq[0:3, 0:2, 1] = [[-s2, 0.0], [0.0, 0.0], [c2, 0.0]]
+            self.dSdotdq[0:3, 0:2, 1] = [[-c2 * qd2, 0.0], [0.0, 0.0], [-s2 * qd2, 0.0]]
+
+
 class JointFree2D(Joint):
     """JointFree2D.m -- 2D free joint in XY (only used to reach the scene-11 pin for ForceGroundCuboid)."""
 

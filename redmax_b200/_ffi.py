@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libredmax_b200.so')
+# RMX_LIB: developer override to A/B a tagged build of the same CUDA library (tools/build_variant.sh); never a CPU path
+LIB_PATH = os.environ.get('RMX_LIB') or os.path.join(_HERE, 'lib', 'libredmax_b200.so')
 
 RMX_OK = 0
 RMX_JOINT_FIXED = 0

@@ -139,7 +139,7 @@ struct Eval<2, NW, GROUND, KEEP, LIN> {
         if (LIN == 1) {
             c.kry_iters += krylov_solve<NW, GROUND>(c, c.pm, c.H, c.g, scale, c.lin_tol, c.lin_maxit);
         } else if (NW == 1) {
-            lu_solve_warp(c.nr, c.ld, c.H, perm, c.g, scale, c.dx, write_back);
+            lu_solve_warp(c.nr, c.ld, c.H, perm, c.g, scale, c.dx, write_back, c.lubuf);
         } else {
             lu_factor<NW>(c, c.H, perm);
             lu_solve<NW>(c, c.H, perm, c.g, c.dx, scale);
@@ -316,8 +316,15 @@ __device__ __forceinline__ int newton_adjoint(typename E::C& c, const StepOpts& 
 // Forward rollout kernel: simLoop of driverRedMaxBDF1.m:57-91 / driverRedMaxBDF2.m:57-125 (ADJ = false) and of
 // driverRedMaxAdjointBDF1.m:65-102 / driverRedMaxAdjointBDF2.m:65-136 (ADJ = true), one block per rollout.
 // ---------------------------------------------------------------------------------------------
+#ifndef RMX_MINB_FWD
+// resident blocks per SM asked of ptxas for the one-warp forward kernel (register cap 65536/(32*MINB)).  Measured
+// (profiles/r01_ab_lu_occupancy.log): 10 blocks/SM at 168 registers spills ~500 B per thread and is 8-12 % slower than
+// 8 blocks/SM at 230 registers without spills, so the cap stays off.
+#define RMX_MINB_FWD 1
+#endif
 template <int NW, bool GROUND, bool ADJ, int IMPL, int LIN>
-__global__ void __launch_bounds__(32 * NW) rollout_fwd_kernel(RolloutArgs a) {
+__global__ void __launch_bounds__(32 * NW, (NW == 1 && !ADJ && !GROUND && LIN == 0 && IMPL == 2) ? RMX_MINB_FWD : 1)
+rollout_fwd_kernel(RolloutArgs a) {
     typedef Eval<IMPL, NW, GROUND, ADJ || LIN == 1, LIN> E;
     extern __shared__ double2 smem_raw[];
     double* sm = reinterpret_cast<double*>(smem_raw);

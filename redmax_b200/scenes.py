@@ -40,8 +40,9 @@ def _rot(axis, angle):
 
 
 def scenesRedMax(sceneID, api=None):
-    """scenesRedMax.m, scene IDs -2, -1, 0, 1, 2, 14, 100, 101 (revolute / fixed joints; the other IDs use joint
-    or force types outside the hot-path scope)."""
+    """scenesRedMax.m, scene IDs -2, -1, 0, 1, 2, 3, 4, 5, 6, 8, 11, 14, 100, 101 (revolute / fixed / prismatic / planar /
+    translational / Free2D / universal joints, ground contact; the other IDs use joint or force types outside the
+    hot-path scope)."""
     api = api or _api
     scene = api.Scene()
     density = 1.0
@@ -121,6 +122,89 @@ def scenesRedMax(sceneID, api=None):
         j4.q[0] = math.pi / 4
         scene.bodies = bs
         scene.joints = [j1, j2, j3, j4]
+    elif sceneID == 3:  # :130
+        scene.name = 'Prismatic joint'
+        scene.Hexpected[:] = [-3.7579402399569808e+04, -6.1132876082600706e+02]
+        b1 = api.BodyCuboid(density, [20, 1, 1])
+        j1 = api.JointPrismatic(None, b1, [1, 0, 0])
+        j1.setJointTransform(np.eye(4))
+        b1.setBodyTransform(np.eye(4))
+        b2 = api.BodyCuboid(density, [1, 1, 10])
+        j2 = api.JointRevolute(j1, b2, [0, 1, 0])
+        j2.setJointTransform(_trans([-10, 0, 0]))
+        b2.setBodyTransform(_trans([0, 0, -5]))
+        j2.q[0] = math.pi / 2
+        scene.bodies = [b1, b2]
+        scene.joints = [j1, j2]
+    elif sceneID in (4, 5):  # :144 planar, :164 translational
+        scene.name = 'Planar joint' if sceneID == 4 else 'Translational joint'
+        if sceneID == 4:
+            scene.Hexpected[:] = [-4.5738939646068720e+04, -4.7000178355609387e+02]
+        else:
+            scene.Hexpected[:] = [3.3661704151378050e+04, 3.3377464890219308e+04]
+            scene.tEnd = 2.0
+            scene.grav = np.array([0.0, 0.0, 0.0])
+        b1 = api.BodyCuboid(density, [10, 10, 1])
+        j1 = api.JointPlanar(None, b1) if sceneID == 4 else api.JointTranslational(None, b1)
+        j1.setJointTransform(np.eye(4))
+        b1.setBodyTransform(np.eye(4))
+        b2 = api.BodyCuboid(density, [1, 1, 10])
+        j2 = api.JointRevolute(j1, b2, [0, 1, 0])
+        j2.setJointTransform(_trans([-5, 0, 0]))
+        b2.setBodyTransform(_trans([0, 0, -5]))
+        b3 = api.BodyCuboid(density, [1, 1, 10])
+        j3 = api.JointRevolute(j1, b3, [1, 0, 0])
+        j3.setJointTransform(_trans([0, -5, 0]))
+        b3.setBodyTransform(_trans([0, 0, -5]))
+        if sceneID == 4:
+            j2.q[0] = math.pi / 2
+            j3.q[0] = math.pi / 4
+        else:
+            j2.qdot[0] = -10.0
+            j3.qdot[0] = 10.0
+        scene.bodies = [b1, b2, b3]
+        scene.joints = [j1, j2, j3]
+    elif sceneID in (6, 11):  # :188 Free2D, :290 Free2D with ground
+        free = sceneID == 6
+        scene.name = 'Free2D joint' if free else 'Free2D with ground'
+        scene.Hexpected[:] = ([2.0322933333333378e+04, 2.1283333333333332e+04] if free
+                              else [-4.4208045000000002e+03, -2.7811251900394832e+03])
+        scene.h = 5e-3 if free else 5e-4
+        scene.tEnd = 0.4 if free else 0.6
+        scene.grav = np.array([0.0, -980.0, 0.0])
+        b = api.BodyCuboid(density, [1, 1, 1] if free else [3, 1, 1])
+        j = api.JointFree2D(None, b)
+        j.q[:] = [-10, -10, 0] if free else [-1, 2, 0]
+        j.qdot[:] = [50, 200, 20] if free else [5, 70, 2]
+        j.setJointTransform(np.eye(4))
+        b.setBodyTransform(np.eye(4))
+        scene.bodies = [b]
+        scene.joints = [j]
+        if not free:
+            f = api.ForceGroundCuboid(b)
+            f.setTransform(_rot([1, 0, 0], -math.pi / 2))
+            f.setStiffness(1e5, 1e2)
+            f.setDamping(3e1)
+            f.setFriction(0.5)
+            scene.forces = [f]
+    elif sceneID == 8:  # :233
+        scene.name = 'Universal joint'
+        scene.Hexpected[:] = [-2.5276246935781084e+04, -1.3781281283808785e+03]
+        for i in range(1, 4):
+            b = api.BodyCuboid(density, [1, 1, 10])
+            if i == 1:
+                j = api.JointUniversal(None, b)
+                j.setJointTransform(np.eye(4))
+            else:
+                j = api.JointUniversal(scene.joints[i - 2], b)
+                j.setJointTransform(_trans([0, 0, -10]))
+            b.setBodyTransform(_trans([0, 0, -5]))
+            if i % 2 == 1:
+                j.q[0] = math.pi / 8
+            else:
+                j.q[1] = math.pi / 8
+            scene.bodies.append(b)
+            scene.joints.append(j)
     elif sceneID == 14:  # :371
         scene.name = 'Joint limits'
         scene.Hexpected[:] = [-2.5928305306546572e+04, -1.8476279319765570e+04]

@@ -41,4 +41,5 @@ if __name__ == '__main__':
     run(10, 1024, 100, 1, h=1e-3)
     run(32, 4096, 100, 1, h=1e-3)
     run(32, 4096, 100, 2, h=1e-3)
-    run(64, 8192, 50, 1, h=2e-4)
+    if os.environ.get("RMX_QUICK_BIG"):
+        run(64, 8192, 50, 1, h=2e-4)
