@@ -14,7 +14,8 @@
  *     dimension (q0 is nr x B, q_out is nr x nsteps x B).
  *   - Joints are listed parents-before-children, as the reference requires (Joint.m:134-146).  Reduced
  *     indices follow the reference's leaf-to-root numbering (Scene.m:69-71): the LAST joint in the list owns
- *     q(1); the library computes that numbering itself from `ndof` implied by `jtype`.
+ *     q(1), a joint's own DOFs are consecutive (Joint.m:152); the library computes that numbering itself from
+ *     the `ndof` implied by `jtype`.
  *   - Host-pointer entry points copy H2D/D2H internally and block until done.  `_dev` entry points take
  *     device pointers on the current CUDA device and enqueue on the given stream without synchronising.
  *   - Errors: 0 on success, negative RMX_E* otherwise; rmx_last_error() returns a message.  No exceptions
@@ -30,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RMX_VERSION 101
+#define RMX_VERSION 102
 
 /* error codes */
 #define RMX_OK 0
@@ -40,9 +41,15 @@ extern "C" {
 #define RMX_ENOMEM (-4)
 #define RMX_ELIMIT (-5)  /* scene exceeds kernel limits (n <= 128 joints) */
 
-/* joint types (matlab-diff/+redmax/JointFixed.m, JointRevolute.m) */
-#define RMX_JOINT_FIXED 0
-#define RMX_JOINT_REVOLUTE 1
+/* joint types (matlab-diff/+redmax/Joint*.m); ndof in brackets */
+#define RMX_JOINT_FIXED 0         /* JointFixed.m          [0] */
+#define RMX_JOINT_REVOLUTE 1      /* JointRevolute.m       [1] rotation about `axis` */
+#define RMX_JOINT_PRISMATIC 2     /* JointPrismatic.m      [1] translation along `axis` */
+#define RMX_JOINT_PLANAR 3        /* JointPlanar.m         [2] translation in the plane spanned by `axis`, `axis2` */
+#define RMX_JOINT_TRANSLATIONAL 4 /* JointTranslational.m  [3] translation x, y, z */
+#define RMX_JOINT_FREE2D 5        /* JointFree2D.m         [3] translation x, y then rotation about z */
+#define RMX_JOINT_UNIVERSAL 6     /* JointUniversal.m      [2] rotation about x then y */
+#define RMX_MAX_JOINT_DOF 3
 
 /* integrators (driverRedMaxBDF1.m, driverRedMaxBDF2.m) */
 #define RMX_SCHEME_BDF1 1
@@ -66,8 +73,9 @@ extern "C" {
 #define RMX_TAU_PER_STEP 2 /* tau is nr x nsteps x B */
 
 /*
- * Flattened +redmax scene (what scenesRedMax.m builds with redmax.Scene / BodyCuboid / JointRevolute /
- * JointFixed / ForceGroundCuboid after scene.init(), Scene.m:59-119).  All pointers are host pointers and are
+ * Flattened +redmax scene (what scenesRedMax.m builds with redmax.Scene / BodyCuboid / JointRevolute / JointFixed /
+ * JointPrismatic / JointPlanar / JointTranslational / JointFree2D / JointUniversal / ForceGroundCuboid after
+ * scene.init(), Scene.m:59-119).  All pointers are host pointers and are
  * copied by rmx_scene_create.
  */
 typedef struct rmx_scene_desc {
@@ -76,12 +84,16 @@ typedef struct rmx_scene_desc {
     const int32_t* jtype;    /* [n] RMX_JOINT_* */
     const double* E0_pj;     /* [16*n] joint wrt parent joint at q=0   (Joint.setJointTransform, Joint.m:95) */
     const double* E0_ji;     /* [16*n] body wrt joint                  (Body.setBodyTransform, Body.m:46) */
-    const double* axis;      /* [3*n]  revolute axis, unit length      (JointRevolute.m:14); ignored if fixed */
+    const double* axis;      /* [3*n]  revolute / prismatic axis, unit length (JointRevolute.m:14, JointPrismatic.m:14);
+                                       planar: first in-plane direction (JointPlanar.m:16); ignored otherwise */
+    const double* axis2;     /* [3*n]  planar: second in-plane direction (JointPlanar.m:17); may be NULL when the scene
+                                       has no planar joint (default [0 1 0]) */
     const double* I_i;       /* [6*n]  diagonal body inertia [Ixx Iyy Izz m m m] (se3.inertiaCuboid, se3.m:366) */
     const double* sides;     /* [3*n]  cuboid side lengths             (BodyCuboid.m:13) */
     const double* stiffness; /* [n] Joint.m:102 */
     const double* damping;   /* [n] Joint.m:108 */
-    const double* qRest;     /* [n] rest angle = q at scene.init()     (Joint.m:157); ignored if fixed */
+    const double* qRest;     /* [RMX_MAX_JOINT_DOF*n] rest configuration = q at scene.init() (Joint.m:157): entry
+                                       [RMX_MAX_JOINT_DOF*j + d] belongs to DOF d of joint j; unused entries ignored */
     const double* qLimL;     /* [n] Joint.m:114  (default -1e8) */
     const double* qLimU;     /* [n] Joint.m:119  (default  1e8) */
     const double* qLimK;     /* [n] Joint.m:124  (default  1e8) */

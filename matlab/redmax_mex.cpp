@@ -85,11 +85,12 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         sd.E0_pj = mxGetDoubles(field(d, "E0_pj"));  // 4 x 4 x n, column-major == what rmx_scene_desc wants
         sd.E0_ji = mxGetDoubles(field(d, "E0_ji"));
         sd.axis = mxGetDoubles(field(d, "axis"));    // 3 x n
+        sd.axis2 = mxGetDoubles(field(d, "axis2"));  // 3 x n
         sd.I_i = mxGetDoubles(field(d, "I_i"));      // 6 x n
         sd.sides = mxGetDoubles(field(d, "sides"));  // 3 x n
         sd.stiffness = mxGetDoubles(field(d, "stiffness"));
         sd.damping = mxGetDoubles(field(d, "damping"));
-        sd.qRest = mxGetDoubles(field(d, "qRest"));
+        sd.qRest = mxGetDoubles(field(d, "qRest"));  // RMX_MAX_JOINT_DOF x n
         sd.qLimL = mxGetDoubles(field(d, "qLimL"));
         sd.qLimU = mxGetDoubles(field(d, "qLimU"));
         sd.qLimK = mxGetDoubles(field(d, "qLimK"));

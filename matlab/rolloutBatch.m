@@ -17,7 +17,8 @@ function d = flattenScene(scene)
 n = length(scene.joints);
 d.parent = zeros(1,n); d.jtype = zeros(1,n);
 d.E0_pj = zeros(4,4,n); d.E0_ji = zeros(4,4,n); d.axis = zeros(3,n); d.I_i = zeros(6,n); d.sides = zeros(3,n);
-d.stiffness = zeros(1,n); d.damping = zeros(1,n); d.qRest = zeros(1,n);
+d.axis2 = repmat([0;1;0],1,n);
+d.stiffness = zeros(1,n); d.damping = zeros(1,n); d.qRest = zeros(3,n); % RMX_MAX_JOINT_DOF x n
 d.qLimL = zeros(1,n); d.qLimU = zeros(1,n); d.qLimK = zeros(1,n); d.qLimD = zeros(1,n);
 for i = 1 : n
 	j = scene.joints{i};
@@ -26,12 +27,23 @@ for i = 1 : n
 	else
 		d.parent(i) = find(cellfun(@(x) x == j.parent, scene.joints)) - 1;
 	end
+	d.qRest(1:j.ndof,i) = j.qRest;
 	if isa(j,'redmax.JointRevolute')
-		d.jtype(i) = 1; d.axis(:,i) = j.axis; d.qRest(i) = j.qRest;
+		d.jtype(i) = 1; d.axis(:,i) = j.axis;
 	elseif isa(j,'redmax.JointFixed')
 		d.jtype(i) = 0;
+	elseif isa(j,'redmax.JointPrismatic')
+		d.jtype(i) = 2; d.axis(:,i) = j.axis;
+	elseif isa(j,'redmax.JointPlanar')
+		d.jtype(i) = 3; d.axis(:,i) = j.plane(:,1); d.axis2(:,i) = j.plane(:,2);
+	elseif isa(j,'redmax.JointTranslational')
+		d.jtype(i) = 4;
+	elseif isa(j,'redmax.JointFree2D')
+		d.jtype(i) = 5;
+	elseif isa(j,'redmax.JointUniversal')
+		d.jtype(i) = 6;
 	else
-		error('only JointRevolute / JointFixed are on the GPU hot path');
+		error('joint type %s is not on the GPU hot path',class(j));
 	end
 	d.E0_pj(:,:,i) = j.E0_pj; d.E0_ji(:,:,i) = j.body.E0_ji; d.I_i(:,i) = j.body.I_i; d.sides(:,i) = j.body.sides;
 	d.stiffness(i) = j.stiffness; d.damping(i) = j.damping;

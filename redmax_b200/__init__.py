@@ -5,12 +5,14 @@ ctypes binding of the C ABI (_ffi.py) over the CUDA library built from csrc/.  N
 """
 from ._ffi import (RMX_LINSOLVE_LU, RMX_LINSOLVE_PCG, RMX_SCHEME_BDF1, RMX_SCHEME_BDF2, RMX_ST_DIVERGED,
                    RMX_ST_LSFAIL, RMX_ST_MAXITER, RMX_ST_NAN, RmxError)
-from .scene import (Body, BodyCuboid, ForceGroundCuboid, Joint, JointFixed, JointRevolute, Scene,
-                    TaskBDF1PointPos, TaskBDF2PointPos, inertiaCuboid)
+from .scene import (Body, BodyCuboid, ForceGroundCuboid, Joint, JointFixed, JointFree2D, JointPlanar, JointPrismatic,
+                    JointRevolute, JointTranslational, JointUniversal, Scene, TaskBDF1PointPos, TaskBDF2PointPos,
+                    inertiaCuboid)
 from .scenes import BDF1, BDF2, chain_scene, hand_scene, scenesRedMax, synthetic_inputs
 
 __all__ = [
-    'Scene', 'Body', 'BodyCuboid', 'Joint', 'JointRevolute', 'JointFixed', 'ForceGroundCuboid',
+    'Scene', 'Body', 'BodyCuboid', 'Joint', 'JointRevolute', 'JointFixed', 'JointPrismatic', 'JointPlanar',
+    'JointTranslational', 'JointFree2D', 'JointUniversal', 'ForceGroundCuboid',
     'TaskBDF1PointPos', 'TaskBDF2PointPos', 'inertiaCuboid', 'scenesRedMax', 'chain_scene', 'hand_scene',
     'synthetic_inputs', 'BDF1', 'BDF2', 'RmxError',
 ]

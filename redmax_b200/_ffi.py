@@ -18,6 +18,12 @@ LIB_PATH = os.environ.get('RMX_LIB') or os.path.join(_HERE, 'lib', 'libredmax_b2
 RMX_OK = 0
 RMX_JOINT_FIXED = 0
 RMX_JOINT_REVOLUTE = 1
+RMX_JOINT_PRISMATIC = 2
+RMX_JOINT_PLANAR = 3
+RMX_JOINT_TRANSLATIONAL = 4
+RMX_JOINT_FREE2D = 5
+RMX_JOINT_UNIVERSAL = 6
+RMX_MAX_JOINT_DOF = 3
 RMX_SCHEME_BDF1 = 1
 RMX_SCHEME_BDF2 = 2
 RMX_LINSOLVE_LU = 0
@@ -38,7 +44,7 @@ class rmx_scene_desc(C.Structure):
     _fields_ = [
         ('n', C.c_int32),
         ('parent', _pi), ('jtype', _pi),
-        ('E0_pj', _pd), ('E0_ji', _pd), ('axis', _pd), ('I_i', _pd), ('sides', _pd),
+        ('E0_pj', _pd), ('E0_ji', _pd), ('axis', _pd), ('axis2', _pd), ('I_i', _pd), ('sides', _pd),
         ('stiffness', _pd), ('damping', _pd), ('qRest', _pd),
         ('qLimL', _pd), ('qLimU', _pd), ('qLimK', _pd), ('qLimD', _pd),
         ('grav', C.c_double * 3),

@@ -53,7 +53,8 @@ struct rmx_scene {
     double grav[3] = {0, 0, 0};
     std::vector<JointConst> jc;   // internal (preorder) order
     std::vector<int> ends_list;
-    std::vector<int> user2int;    // user joint index -> internal index
+    std::vector<int> user2int;    // expanded (virtual) joint index -> internal (preorder) index
+    std::vector<int> body2int;    // user joint/body index -> internal index of the virtual joint that carries the body
     std::vector<int> anc;         // [nrounds][n] 2^r-th ancestors (internal indices) for the pointer-jumping scans
     int nrounds = 0;
     int impl = 2;                 // 1 = sweep kernels (rmx_device.cuh), 2 = composite kernels (rmx_fast.cuh)
@@ -96,30 +97,109 @@ static void colmajor4_to_Rp(const double* E, double* R, double* p) {
     }
 }
 
+// A multi-DOF joint whose Q(q) is a product of one-parameter motions is integrated as a chain of one-DOF "virtual"
+// joints; only the last one carries the body (the others have zero inertia):
+//   JointPlanar        Q = trans(B q)                 -> prismatic b1, prismatic b2          (JointPlanar.m:24-28)
+//   JointTranslational Q = trans(q)                   -> prismatic x, y, z                   (JointTranslational.m:20-23)
+//   JointFree2D        Q = [Rz(q3) [q1 q2 0]'; 0 1]   -> prismatic x, prismatic y, revolute z (JointFree2D.m:20-31)
+//   JointUniversal     R = X(q1) Y(q2)                -> revolute x, revolute y              (JointUniversal.m:73-75)
+// g(q) and H = dg/dq are functions of the motion only, so the reference's S(q), Sdot, dSdq ... of these joints are
+// reproduced by the world-frame screws of the virtual joints (parity: tests/test_gpu_joints.py vs the oracle's restatement
+// of the reference classes).
+struct ExpandedScene {
+    int n = 0;
+    std::vector<int> parent, type, idx, user;  // type: RMX_JOINT_FIXED / REVOLUTE / PRISMATIC; idx: reduced index or -1
+    std::vector<double> E0_pj, E0_ji, axis, I_i, sides, stiffness, damping, qRest, qLimL, qLimU, qLimK, qLimD;
+    std::vector<int> body_of_user;             // user joint/body -> index (in this list) of the virtual joint carrying the body
+};
+
+static int joint_ndof(int jtype) {
+    switch (jtype) {
+        case RMX_JOINT_FIXED: return 0;
+        case RMX_JOINT_REVOLUTE: case RMX_JOINT_PRISMATIC: return 1;
+        case RMX_JOINT_PLANAR: case RMX_JOINT_UNIVERSAL: return 2;
+        case RMX_JOINT_TRANSLATIONAL: case RMX_JOINT_FREE2D: return 3;
+        default: return -1;
+    }
+}
+
+static void expand_scene(const rmx_scene_desc* d, const std::vector<int>& base, ExpandedScene& x) {
+    static const double ID4[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    static const double EX[3] = {1, 0, 0}, EY[3] = {0, 1, 0}, EZ[3] = {0, 0, 1}, Z3[3] = {0, 0, 0};
+    const int n = d->n;
+    x.body_of_user.assign(n, -1);
+    for (int j = 0; j < n; ++j) {
+        const int jt = d->jtype[j];
+        const double* ax1 = d->axis + 3 * j;
+        const double* ax2 = d->axis2 ? d->axis2 + 3 * j : EY;
+        int vt[3] = {RMX_JOINT_FIXED, 0, 0};
+        const double* va[3] = {Z3, Z3, Z3};
+        int nv = 1;
+        switch (jt) {
+            case RMX_JOINT_REVOLUTE: vt[0] = RMX_JOINT_REVOLUTE; va[0] = ax1; break;
+            case RMX_JOINT_PRISMATIC: vt[0] = RMX_JOINT_PRISMATIC; va[0] = ax1; break;
+            case RMX_JOINT_PLANAR: nv = 2; vt[0] = vt[1] = RMX_JOINT_PRISMATIC; va[0] = ax1; va[1] = ax2; break;
+            case RMX_JOINT_TRANSLATIONAL: nv = 3; vt[0] = vt[1] = vt[2] = RMX_JOINT_PRISMATIC; va[0] = EX; va[1] = EY; va[2] = EZ; break;
+            case RMX_JOINT_FREE2D: nv = 3; vt[0] = vt[1] = RMX_JOINT_PRISMATIC; vt[2] = RMX_JOINT_REVOLUTE; va[0] = EX; va[1] = EY; va[2] = EZ; break;
+            case RMX_JOINT_UNIVERSAL: nv = 2; vt[0] = vt[1] = RMX_JOINT_REVOLUTE; va[0] = EX; va[1] = EY; break;
+            default: break;
+        }
+        for (int v = 0; v < nv; ++v) {
+            const bool first = v == 0, last = v == nv - 1;
+            x.parent.push_back(first ? (d->parent[j] < 0 ? -1 : x.body_of_user[d->parent[j]]) : x.n - 1);
+            x.type.push_back(vt[v]);
+            x.user.push_back(j);
+            x.idx.push_back(vt[v] == RMX_JOINT_FIXED ? -1 : base[j] + v);
+            const double* Epj = first ? d->E0_pj + 16 * j : ID4;
+            const double* Eji = last ? d->E0_ji + 16 * j : ID4;
+            x.E0_pj.insert(x.E0_pj.end(), Epj, Epj + 16);
+            x.E0_ji.insert(x.E0_ji.end(), Eji, Eji + 16);
+            x.axis.insert(x.axis.end(), va[v], va[v] + 3);
+            for (int i = 0; i < 6; ++i) x.I_i.push_back(last ? d->I_i[6 * j + i] : 0.0);
+            for (int i = 0; i < 3; ++i) x.sides.push_back(last ? d->sides[3 * j + i] : 0.0);
+            x.stiffness.push_back(d->stiffness ? d->stiffness[j] : 0.0);
+            x.damping.push_back(d->damping ? d->damping[j] : 0.0);
+            x.qRest.push_back(d->qRest ? d->qRest[RMX_MAX_JOINT_DOF * j + v] : 0.0);
+            x.qLimL.push_back(d->qLimL ? d->qLimL[j] : -1e8);  // Joint.m:77-80
+            x.qLimU.push_back(d->qLimU ? d->qLimU[j] : 1e8);
+            x.qLimK.push_back(d->qLimK ? d->qLimK[j] : 1e8);
+            x.qLimD.push_back(d->qLimD ? d->qLimD[j] : 0.0);
+            if (last) x.body_of_user[j] = x.n;
+            x.n++;
+        }
+    }
+}
+
 extern "C" int rmx_scene_create(const rmx_scene_desc* d, rmx_scene** out) {
     if (!d || !out) return fail(RMX_EINVAL, "rmx_scene_create: null argument");
     *out = nullptr;
-    const int n = d->n;
-    if (n < 1) return fail(RMX_EINVAL, "rmx_scene_create: n < 1");
-    if (n > 128) return fail(RMX_ELIMIT, "rmx_scene_create: n > 128 joints not supported by the in-block solver");
+    const int n_user = d->n;
+    if (n_user < 1) return fail(RMX_EINVAL, "rmx_scene_create: n < 1");
     if (!d->parent || !d->jtype || !d->E0_pj || !d->E0_ji || !d->axis || !d->I_i || !d->sides)
         return fail(RMX_EINVAL, "rmx_scene_create: missing required array");
-    for (int j = 0; j < n; ++j) {
+    for (int j = 0; j < n_user; ++j) {
         if (d->parent[j] >= j || d->parent[j] < -1)
             return fail(RMX_EINVAL, "rmx_scene_create: joints must be listed parents-before-children (Joint.m:134)");
-        if (d->jtype[j] != RMX_JOINT_FIXED && d->jtype[j] != RMX_JOINT_REVOLUTE)
-            return fail(RMX_EINVAL, "rmx_scene_create: only JointFixed and JointRevolute are on the hot path");
+        if (joint_ndof(d->jtype[j]) < 0)
+            return fail(RMX_EINVAL, "rmx_scene_create: joint type is not on the hot path (fixed, revolute, prismatic, planar, "
+                                    "translational, free2d, universal are)");
     }
+    // reference numbering: countDofs is called for i = n..1 (Scene.m:69-71); a joint's DOFs are consecutive (Joint.m:152)
+    std::vector<int> base(n_user, 0);
+    int nr = 0;
+    for (int j = n_user - 1; j >= 0; --j) {
+        base[j] = nr;
+        nr += joint_ndof(d->jtype[j]);
+    }
+    ExpandedScene x;
+    expand_scene(d, base, x);
+    const int n = x.n;
+    if (n > 128) return fail(RMX_ELIMIT, "rmx_scene_create: more than 128 (virtual) joints not supported by the in-block solver");
     rmx_scene* s = new rmx_scene();
     s->n = n;
-    // reference numbering: countDofs is called for i = n..1 (Scene.m:69-71)
-    std::vector<int> idxR(n, -1);
-    int nr = 0;
-    for (int j = n - 1; j >= 0; --j) {
-        if (d->jtype[j] == RMX_JOINT_REVOLUTE) idxR[j] = nr++;
-    }
+    const std::vector<int>& idxR = x.idx;
     s->nr = nr;
-    s->nm = 6 * n;
+    s->nm = 6 * n_user;
     if (nr < 1) {
         delete s;
         return fail(RMX_EINVAL, "rmx_scene_create: scene has no degrees of freedom");
@@ -128,10 +208,10 @@ extern "C" int rmx_scene_create(const rmx_scene_desc* d, rmx_scene** out) {
     std::vector<std::vector<int>> children(n);
     std::vector<int> roots;
     for (int j = 0; j < n; ++j) {
-        if (d->parent[j] < 0)
+        if (x.parent[j] < 0)
             roots.push_back(j);
         else
-            children[d->parent[j]].push_back(j);
+            children[x.parent[j]].push_back(j);
     }
     std::vector<int> order;  // internal -> user
     order.reserve(n);
@@ -154,27 +234,35 @@ extern "C" int rmx_scene_create(const rmx_scene_desc* d, rmx_scene** out) {
         const int j = order[k];
         JointConst& J = s->jc[k];
         std::memset(&J, 0, sizeof(J));
-        colmajor4_to_Rp(d->E0_pj + 16 * j, J.R0, J.p0);
-        colmajor4_to_Rp(d->E0_ji + 16 * j, J.Rji, J.pji);
+        colmajor4_to_Rp(x.E0_pj.data() + 16 * j, J.R0, J.p0);
+        colmajor4_to_Rp(x.E0_ji.data() + 16 * j, J.Rji, J.pji);
         for (int i = 0; i < 3; ++i) {
-            J.axis[i] = d->axis[3 * j + i];
-            J.hs[i] = 0.5 * d->sides[3 * j + i];  // ForceGroundCuboid.m:71
+            J.axis[i] = x.axis[3 * j + i];
+            J.hs[i] = 0.5 * x.sides[3 * j + i];  // ForceGroundCuboid.m:71
         }
-        for (int i = 0; i < 6; ++i) J.I[i] = d->I_i[6 * j + i];
-        J.stiff = d->stiffness ? d->stiffness[j] : 0.0;
-        J.damp = d->damping ? d->damping[j] : 0.0;
-        J.qRest = d->qRest ? d->qRest[j] : 0.0;
-        J.qLimL = d->qLimL ? d->qLimL[j] : -1e8;  // Joint.m:77-80
-        J.qLimU = d->qLimU ? d->qLimU[j] : 1e8;
-        J.qLimK = d->qLimK ? d->qLimK[j] : 1e8;
-        J.qLimD = d->qLimD ? d->qLimD[j] : 0.0;
-        J.parent = d->parent[j] < 0 ? -1 : s->user2int[d->parent[j]];
+        for (int i = 0; i < 6; ++i) J.I[i] = x.I_i[6 * j + i];
+        J.stiff = x.stiffness[j];
+        J.damp = x.damping[j];
+        J.qRest = x.qRest[j];
+        J.qLimL = x.qLimL[j];
+        J.qLimU = x.qLimU[j];
+        J.qLimK = x.qLimK[j];
+        J.qLimD = x.qLimD[j];
+        J.parent = x.parent[j] < 0 ? -1 : s->user2int[x.parent[j]];
         if (J.parent != k - 1) s->is_chain = 0;
+        J.prismatic = x.type[j] == RMX_JOINT_PRISMATIC;
         J.idx = idxR[j];
         // se3.aaToMat classification (se3.m:118-176)
         J.axtype = 0;
         J.axsign = 1;
-        if (d->jtype[j] == RMX_JOINT_REVOLUTE) {
+        if (x.type[j] == RMX_JOINT_PRISMATIC) {
+            const double mag = std::sqrt(J.axis[0] * J.axis[0] + J.axis[1] * J.axis[1] + J.axis[2] * J.axis[2]);
+            if (!(mag > 1e-9)) {
+                delete s;
+                return fail(RMX_EINVAL, "rmx_scene_create: zero prismatic axis");
+            }
+        }
+        if (x.type[j] == RMX_JOINT_REVOLUTE) {
             double ax = J.axis[0], ay = J.axis[1], az = J.axis[2];
             double mag = std::sqrt(ax * ax + ay * ay + az * az);
             if (!(mag > 1e-9)) {
@@ -236,15 +324,21 @@ extern "C" int rmx_scene_create(const rmx_scene_desc* d, rmx_scene** out) {
         const char* e = std::getenv("RMX_IMPL");  // developer switch: 1 forces the sweep kernels
         s->impl = (e && e[0] == '1') ? 1 : 2;
         if (n > 64) s->impl = 1;  // the composite path keeps ~90 doubles per joint in shared memory
+        bool any_prismatic = false;
+        for (int k = 0; k < n; ++k) any_prismatic = any_prismatic || s->jc[k].prismatic;
+        if (s->impl == 1 && any_prismatic) {
+            delete s;
+            return fail(RMX_ELIMIT, "rmx_scene_create: translational joint DOFs need the composite kernels (at most 64 virtual joints)");
+        }
     }
     for (int i = 0; i < 3; ++i) s->grav[i] = d->grav[i];
     for (int f = 0; f < d->nground; ++f) {
         const int b = d->ground_body[f];
-        if (b < 0 || b >= n) {
+        if (b < 0 || b >= n_user) {
             delete s;
             return fail(RMX_EINVAL, "rmx_scene_create: ground_body out of range");
         }
-        JointConst& J = s->jc[s->user2int[b]];
+        JointConst& J = s->jc[s->user2int[x.body_of_user[b]]];
         if (J.has_ground) {
             delete s;
             return fail(RMX_EINVAL, "rmx_scene_create: at most one ForceGroundCuboid per body");
@@ -261,6 +355,8 @@ extern "C" int rmx_scene_create(const rmx_scene_desc* d, rmx_scene** out) {
         J.gmu = d->ground_mu[f];
         s->has_ground = 1;
     }
+    s->body2int.assign(n_user, -1);
+    for (int j = 0; j < n_user; ++j) s->body2int[j] = s->user2int[x.body_of_user[j]];
     *out = s;
     return RMX_OK;
 }

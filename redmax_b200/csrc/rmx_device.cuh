@@ -46,6 +46,7 @@ struct JointConst {
     int axtype;     // 0 general, 1 X, 2 Y, 3 Z (se3.aaToMat special cases); sign in axsign
     int axsign;     // +1 / -1
     int has_ground;
+    int prismatic;  // 1: Q = trans(axis q), S = [0; axis] (JointPrismatic.m:28-34); 0: revolute (or fixed if idx < 0)
     int ends_ptr;   // CSR into DevScene.ends_list: joints k whose subtree ends exactly at this index
     int ends_cnt;
 };

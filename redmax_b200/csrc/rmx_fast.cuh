@@ -161,7 +161,7 @@ __device__ void eval_base2(Ctx2& c, bool deriv) {
     if (t < n) {
         const JointConst& J = c.jc[t];
         myidx = J.idx;
-        if (myidx >= 0) {
+        if (myidx >= 0 && !J.prismatic) {
             double Rq[9];
             aa_to_mat(J, c.q[myidx], Rq);
             mat3_mul(J.R0, Rq, Rj);
@@ -171,6 +171,11 @@ __device__ void eval_base2(Ctx2& c, bool deriv) {
         }
 #pragma unroll
         for (int i = 0; i < 3; ++i) pj[i] = J.p0[i];
+        if (myidx >= 0 && J.prismatic) {  // E_pj = E0_pj * trans(axis q)   (JointPrismatic.m:29-32)
+            double aq[3] = {J.axis[0] * c.q[myidx], J.axis[1] * c.q[myidx], J.axis[2] * c.q[myidx]}, t3[3];
+            mat3_vec(J.R0, aq, t3);
+            pj[0] += t3[0]; pj[1] += t3[1]; pj[2] += t3[2];
+        }
 #pragma unroll
         for (int i = 0; i < 9; ++i) SA(F::RW, i, t) = Rj[i];
 #pragma unroll
@@ -208,8 +213,12 @@ __device__ void eval_base2(Ctx2& c, bool deriv) {
     if (t < n) {
         if (myidx >= 0) {
             const JointConst& J = c.jc[t];
-            mat3_vec(Rj, J.axis, s);
-            cross3(pj, s, s + 3);
+            if (J.prismatic) {  // S = [0; a]  ->  world screw [0; R a]
+                mat3_vec(Rj, J.axis, s + 3);
+            } else {            // S = [a; 0]  ->  [R a; p x R a]
+                mat3_vec(Rj, J.axis, s);
+                cross3(pj, s, s + 3);
+            }
             qdk = c.qd[myidx];
             dqk = c.dq[myidx];
 #pragma unroll
@@ -405,20 +414,17 @@ __device__ void eval_base2(Ctx2& c, bool deriv) {
     bsync<NW>();
 }
 
-// ---------------------------------------------------------------------------------------------
-// eval_columns2: out (nr x ld column-major) = scale * ( sq dg/dq + sqd dg/dqdot + sd dg/d(dqtmp) ), from the composite blocks.
-// ---------------------------------------------------------------------------------------------
-template <int NW, bool GROUND, bool KEEP>
-__device__ void eval_columns2(Ctx2& c, double sq, double sqd, double sd, double scale, double* out) {
+// Per-joint part of the Newton-matrix assembly: from joint t's screw, its parent's V and U and its composite blocks, the
+// row vector L_t (so that H[t][i] = L_t . Rt_i for t in sub(i)), and the column vectors Rt_t = [c2 ; c1 ; sq s] and Z_t
+// (H[k][t] = s_k . Z_t for proper ancestors k).  Reads shared memory only; results stay in registers.
+template <bool GROUND, bool KEEP>
+__device__ __forceinline__ void columns_joint(Ctx2& c, int t, int myidx, double sq, double sqd, double sd, double* L, double* s,
+                                              double* Rt, double* Z) {
     typedef Fld<GROUND, KEEP> F;
-    const int t = threadIdx.x;
-    const int n = c.n, NS = c.NS, ld = c.ld;
+    const int NS = c.NS;
     const double cc = c.c;
-    const int myidx = (t < n) ? c.ie_s[t].x : -1;
-    double Rt[F::NL];  // [c2 (6) ; c1 (3 or 6) ; sq s (3 or 6)]
-    double Z[6];
     if (myidx >= 0) {
-        double s[6], Vp[6] = {0, 0, 0, 0, 0, 0}, Up[6] = {0, 0, 0, 0, 0, 0};
+        double Vp[6] = {0, 0, 0, 0, 0, 0}, Up[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
         for (int i = 0; i < 6; ++i) s[i] = SA(F::S, i, t);
         const int par = c.par_s[t];
@@ -455,7 +461,6 @@ __device__ void eval_columns2(Ctx2& c, double sq, double sqd, double sd, double 
         const double Ms = SA(F::MS, 0, t);
         const double gw[3] = {c.gx, c.gy, c.gz};
         // a = B^C s ;  B^C x = [Jb xw + mp x xv ; -mp x xw + Ms xv]
-        double L[F::NL];
         {
             double t1[3], t2[3];
             cross3(mp, s + 3, t1);
@@ -531,14 +536,6 @@ __device__ void eval_columns2(Ctx2& c, double sq, double sqd, double sd, double 
                 Z[r] += zr;
             }
         }
-        // W_t = [L_t ; s_t], joint-major so that the rows below are fetched with 128-bit broadcast loads
-        {
-            double* W = c.sa + (size_t)t * F::NW_;
-#pragma unroll
-            for (int i = 0; i < F::NL; ++i) W[i] = L[i];
-#pragma unroll
-            for (int i = 0; i < 6; ++i) W[F::NL + i] = s[i];
-        }
         // Rt
 #pragma unroll
         for (int i = 0; i < 6; ++i) Rt[i] = c2[i];
@@ -554,6 +551,31 @@ __device__ void eval_columns2(Ctx2& c, double sq, double sqd, double sd, double 
                 Rt[6 + i] = c1[i];
                 Rt[9 + i] = sq * s[i];
             }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// eval_columns2: out (nr x ld column-major) = scale * ( sq dg/dq + sqd dg/dqdot + sd dg/d(dqtmp) ), from the composite blocks.
+// ---------------------------------------------------------------------------------------------
+template <int NW, bool GROUND, bool KEEP>
+__device__ void eval_columns2(Ctx2& c, double sq, double sqd, double sd, double scale, double* out) {
+    typedef Fld<GROUND, KEEP> F;
+    const int t = threadIdx.x;
+    const int n = c.n, NS = c.NS, ld = c.ld;
+    const double cc = c.c;
+    const int myidx = (t < n) ? c.ie_s[t].x : -1;
+    double Rt[F::NL];  // [c2 (6) ; c1 (3 or 6) ; sq s (3 or 6)]
+    double Z[6], L[F::NL], s[6];
+    columns_joint<GROUND, KEEP>(c, t, myidx, sq, sqd, sd, L, s, Rt, Z);
+    if (myidx >= 0) {
+        // W_t = [L_t ; s_t], joint-major so that the rows below are fetched with 128-bit broadcast loads
+        {
+            double* W = c.sa + (size_t)t * F::NW_;
+#pragma unroll
+            for (int i = 0; i < F::NL; ++i) W[i] = L[i];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) W[F::NL + i] = s[i];
         }
     }
     bsync<NW>();

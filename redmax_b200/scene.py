@@ -114,6 +114,7 @@ class Joint:
 
 class JointRevolute(Joint):
     """+redmax/JointRevolute.m"""
+    jtype = _ffi.RMX_JOINT_REVOLUTE
 
     def __init__(self, parent, body, axis):
         super().__init__(parent, body, 1)
@@ -123,9 +124,61 @@ class JointRevolute(Joint):
 
 class JointFixed(Joint):
     """+redmax/JointFixed.m"""
+    jtype = _ffi.RMX_JOINT_FIXED
 
     def __init__(self, parent, body):
         super().__init__(parent, body, 0)
+        self.axis = np.zeros(3)
+
+
+class JointPrismatic(Joint):
+    """+redmax/JointPrismatic.m"""
+    jtype = _ffi.RMX_JOINT_PRISMATIC
+
+    def __init__(self, parent, body, axis):
+        super().__init__(parent, body, 1)
+        axis = np.asarray(axis, dtype=float).reshape(3)
+        self.axis = axis / np.linalg.norm(axis)  # JointPrismatic.m:14
+
+
+class JointPlanar(Joint):
+    """+redmax/JointPlanar.m -- `plane` is 3 x 2, columns = the two in-plane directions (default x, y)."""
+    jtype = _ffi.RMX_JOINT_PLANAR
+
+    def __init__(self, parent, body, plane=None):
+        super().__init__(parent, body, 2)
+        if plane is None:
+            plane = np.array([[1.0, 0.0, 0.0], [0.0, 1.0, 0.0]]).T  # JointPlanar.m:14
+        plane = np.array(plane, dtype=float).reshape(3, 2)
+        self.plane = np.stack([plane[:, 0] / np.linalg.norm(plane[:, 0]), plane[:, 1] / np.linalg.norm(plane[:, 1])], axis=1)
+        self.axis = self.plane[:, 0].copy()
+        self.axis2 = self.plane[:, 1].copy()
+
+
+class JointTranslational(Joint):
+    """+redmax/JointTranslational.m"""
+    jtype = _ffi.RMX_JOINT_TRANSLATIONAL
+
+    def __init__(self, parent, body):
+        super().__init__(parent, body, 3)
+        self.axis = np.zeros(3)
+
+
+class JointFree2D(Joint):
+    """+redmax/JointFree2D.m -- q = [x y theta]"""
+    jtype = _ffi.RMX_JOINT_FREE2D
+
+    def __init__(self, parent, body):
+        super().__init__(parent, body, 3)
+        self.axis = np.zeros(3)
+
+
+class JointUniversal(Joint):
+    """+redmax/JointUniversal.m -- rotation about X then Y"""
+    jtype = _ffi.RMX_JOINT_UNIVERSAL
+
+    def __init__(self, parent, body):
+        super().__init__(parent, body, 2)
         self.axis = np.zeros(3)
 
 
@@ -261,19 +314,23 @@ class Scene:
             return a.ctypes.data_as(_ffi._pd if a.dtype == np.float64 else _ffi._pi)
         d.n = n
         d.parent = arr([(-1 if j.parent is None else index[id(j.parent)]) for j in self.joints], i32)
-        d.jtype = arr([(_ffi.RMX_JOINT_REVOLUTE if j.ndof == 1 else _ffi.RMX_JOINT_FIXED) for j in self.joints], i32)
         for j in self.joints:
-            if not isinstance(j, (JointRevolute, JointFixed)):
-                raise RmxError('only JointRevolute / JointFixed are on the GPU hot path (SURVEY.md section 8)')
+            if getattr(j, 'jtype', None) is None:
+                raise RmxError('joint type %s is not on the GPU hot path (SURVEY.md section 8)' % type(j).__name__)
+        d.jtype = arr([j.jtype for j in self.joints], i32)
         # MATLAB stores 4x4 column-major: E.T.ravel()
         d.E0_pj = arr(np.concatenate([j.E0_pj.T.ravel() for j in self.joints]), f64)
         d.E0_ji = arr(np.concatenate([j.body.E0_ji.T.ravel() for j in self.joints]), f64)
         d.axis = arr(np.concatenate([j.axis for j in self.joints]), f64)
+        d.axis2 = arr(np.concatenate([getattr(j, 'axis2', np.array([0.0, 1.0, 0.0])) for j in self.joints]), f64)
         d.I_i = arr(np.concatenate([j.body.I_i for j in self.joints]), f64)
         d.sides = arr(np.concatenate([j.body.sides for j in self.joints]), f64)
         d.stiffness = arr([j.stiffness for j in self.joints], f64)
         d.damping = arr([j.damping for j in self.joints], f64)
-        d.qRest = arr([(j.qRest[0] if j.ndof else 0.0) for j in self.joints], f64)
+        qrest = np.zeros((n, _ffi.RMX_MAX_JOINT_DOF))
+        for i, j in enumerate(self.joints):
+            qrest[i, : j.ndof] = j.qRest
+        d.qRest = arr(qrest, f64)
         d.qLimL = arr([j.qLimL for j in self.joints], f64)
         d.qLimU = arr([j.qLimU for j in self.joints], f64)
         d.qLimK = arr([j.qLimK for j in self.joints], f64)

@@ -1,7 +1,7 @@
 """CPU: pin the oracle against every golden vector the reference holds for the hot path.
 
 Golden end-of-run energies Hexpected(BDF1/BDF2) from matlab-diff/scenesRedMax.m:54-55, 82-83, 108-109, 292-293,
-373-374; pass criterion |H(end) - Hexpected| <= 1e-2 as Scene.plotEnergies (Scene.m:171-177)."""
+373-374 and 132-133, 146-147, 166-167, 190-191, 238-239; pass criterion |H(end) - Hexpected| <= 1e-2 as Scene.plotEnergies (Scene.m:171-177)."""
 import numpy as np
 import pytest
 
@@ -11,6 +11,13 @@ PINS = {
     2: (-2.2826101928480086e+04, -2.4159349151742754e+02),
     14: (-2.5928305306546572e+04, -1.8476279319765570e+04),
     11: (-4.4208045000000002e+03, -2.7811251900394832e+03),
+    # prismatic / planar / translational / Free2D / universal joints (scenesRedMax.m:132-133,
+    # 146-147, 166-167, 190-191, 238-239)
+    3: (-3.7579402399569808e+04, -6.1132876082600706e+02),
+    4: (-4.5738939646068720e+04, -4.7000178355609387e+02),
+    5: (3.3661704151378050e+04, 3.3377464890219308e+04),
+    6: (2.0322933333333378e+04, 2.1283333333333332e+04),
+    8: (-2.5276246935781084e+04, -1.3781281283808785e+03),
 }
 
 
@@ -24,6 +31,21 @@ def test_hexpected(oracle, sid, itype):
     ok, H = s.checkEnergy(itype)
     assert ok, (sid, itype, H)
     # far tighter than the reference's 1e-2: the restatement reproduces the printed 17 digits to ~1e-8
+    assert abs(H - PINS[sid][itype - 1]) < 1e-6
+
+
+@pytest.mark.parametrize('sid', [3, 4, 5, 6, 8])
+@pytest.mark.parametrize('itype', [1, 2])
+def test_hexpected_more_joint_types(oracle, sid, itype):
+    """JointPrismatic / JointPlanar / JointTranslational / JointFree2D / JointUniversal restatements against the
+    reference's recorded end-of-run energies (scenes built by the api-agnostic factory the GPU path uses too)."""
+    import redmax_b200.scenes as scenes
+    s = scenes.scenesRedMax(sid, api=oracle)
+    s.init()
+    assert s.Hexpected[itype - 1] == PINS[sid][itype - 1]
+    (oracle.sim_loop_bdf1 if itype == 1 else oracle.sim_loop_bdf2)(s)
+    ok, H = s.checkEnergy(itype)
+    assert ok, (sid, itype, H)
     assert abs(H - PINS[sid][itype - 1]) < 1e-6
 
 
