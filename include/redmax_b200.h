@@ -184,6 +184,12 @@ int64_t rmx_adjoint_tape_bytes(const rmx_scene* s, const rmx_opts* o, int64_t B)
 int rmx_eval(rmx_scene* s, const double* q, const double* qdot, const double* dqtmp, const double* tau,
              double cK, double beta, double* g, double* H, double* M, double* D, double* f);
 
+/* Test hook (B = 1, host pointers): the Newton linear system exactly as the forward rollout kernel forms and solves it
+ * (the same assembly and in-block LU code path, which rmx_eval's M / D passes do not take): H = dg/dq (nr x nr
+ * column-major, before factorisation) and dx = -H \ g  (driverRedMaxBDF1.m:115).  H or dx may be NULL. */
+int rmx_eval_newton(rmx_scene* s, const double* q, const double* qdot, const double* dqtmp, const double* tau,
+                    double cK, double beta, double* H, double* dx);
+
 /* Scene.saveHistory energies (Scene.m:155-160; Joint.m:616, Body.m:167, ForceGroundCuboid.m:156) for B states:
  * T, V: B each. */
 int rmx_energies(rmx_scene* s, int64_t B, const double* q, const double* qdot, double* T, double* V);

@@ -8,11 +8,14 @@ from ._ffi import (RMX_LINSOLVE_LU, RMX_LINSOLVE_PCG, RMX_SCHEME_BDF1, RMX_SCHEM
 from .scene import (Body, BodyCuboid, ForceGroundCuboid, Joint, JointFixed, JointFree2D, JointPlanar, JointPrismatic,
                     JointRevolute, JointTranslational, JointUniversal, Scene, TaskBDF1PointPos, TaskBDF2PointPos,
                     inertiaCuboid)
+from .drivers import (driverRedMaxAdjointBDF1, driverRedMaxAdjointBDF2, driverRedMaxBDF1, driverRedMaxBDF2, plotEnergies,
+                      simLoop, taskObjective)
 from .scenes import BDF1, BDF2, chain_scene, hand_scene, scenesRedMax, synthetic_inputs
 
 __all__ = [
     'Scene', 'Body', 'BodyCuboid', 'Joint', 'JointRevolute', 'JointFixed', 'JointPrismatic', 'JointPlanar',
     'JointTranslational', 'JointFree2D', 'JointUniversal', 'ForceGroundCuboid',
     'TaskBDF1PointPos', 'TaskBDF2PointPos', 'inertiaCuboid', 'scenesRedMax', 'chain_scene', 'hand_scene',
-    'synthetic_inputs', 'BDF1', 'BDF2', 'RmxError',
+    'synthetic_inputs', 'BDF1', 'BDF2', 'RmxError', 'driverRedMaxBDF1', 'driverRedMaxBDF2', 'driverRedMaxAdjointBDF1',
+    'driverRedMaxAdjointBDF2', 'taskObjective', 'simLoop', 'plotEnergies',
 ]

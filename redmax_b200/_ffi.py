@@ -76,7 +76,7 @@ SYMBOLS = [
     'rmx_version', 'rmx_last_error', 'rmx_device_count', 'rmx_opts_default',
     'rmx_scene_create', 'rmx_scene_destroy', 'rmx_scene_nr', 'rmx_scene_nm',
     'rmx_rollout', 'rmx_rollout_dev', 'rmx_rollout_adjoint', 'rmx_rollout_adjoint_dev',
-    'rmx_adjoint_tape_bytes', 'rmx_eval', 'rmx_energies', 'rmx_linsolve_stats',
+    'rmx_adjoint_tape_bytes', 'rmx_eval', 'rmx_eval_newton', 'rmx_energies', 'rmx_linsolve_stats',
 ]
 
 _lib = None
@@ -115,6 +115,7 @@ def lib():
     L.rmx_adjoint_tape_bytes.argtypes = [vp, C.POINTER(rmx_opts), C.c_int64]
     L.rmx_adjoint_tape_bytes.restype = C.c_int64
     L.rmx_eval.argtypes = [vp, vp, vp, vp, vp, C.c_double, C.c_double, vp, vp, vp, vp, vp]
+    L.rmx_eval_newton.argtypes = [vp, vp, vp, vp, vp, C.c_double, C.c_double, vp, vp]
     L.rmx_energies.argtypes = [vp, C.c_int64, vp, vp, vp, vp]
     L.rmx_linsolve_stats.argtypes = [vp, C.POINTER(C.c_int64)]
     _lib = L

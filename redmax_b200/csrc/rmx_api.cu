@@ -708,4 +708,69 @@ extern "C" int rmx_eval(rmx_scene* s, const double* q, const double* qdot, const
     return rc;
 }
 
+// rmx_eval_newton test hook: H and dx = -H\g through the forward kernel's own assembly + factorisation path
+template <int NW, bool GROUND>
+static int launch_eval_newton_t(const EvalArgs& a, double* dx, size_t smem) {
+    int rc = set_smem(eval_newton_kernel<NW, GROUND>, smem);
+    if (rc) return rc;
+    eval_newton_kernel<NW, GROUND><<<1, 32 * NW, smem>>>(a, dx);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaDeviceSynchronize());
+    return RMX_OK;
+}
+
+extern "C" int rmx_eval_newton(rmx_scene* s, const double* q, const double* qdot, const double* dqtmp, const double* tau,
+                               double cK, double beta, double* H, double* dx) {
+    if (!s || !q || !qdot || !dqtmp) return fail(RMX_EINVAL, "rmx_eval_newton: null argument");
+    int ndev = 0;
+    cudaError_t e0 = cudaGetDeviceCount(&ndev);
+    if (e0 != cudaSuccess || ndev < 1) {
+        cudaGetLastError();
+        return fail(RMX_ENOGPU, "rmx_eval_newton: no CUDA device");
+    }
+    if (s->impl != 2) return fail(RMX_ELIMIT, "rmx_eval_newton: composite kernels only (n <= 64 joints)");
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    DevCopy* dc;
+    int rc = scene_on_device(s, dev, &dc);
+    if (rc) return rc;
+    const int nr = s->nr;
+    const size_t v = nr * sizeof(double), m = (size_t)nr * nr * sizeof(double);
+    double* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, 5 * v + m));
+    double *dq_ = d, *dqd = d + nr, *ddq = d + 2 * nr, *dtau = d + 3 * nr, *ddx = d + 4 * nr, *dH = d + 5 * nr;
+    cudaMemcpy(dq_, q, v, cudaMemcpyHostToDevice);
+    cudaMemcpy(dqd, qdot, v, cudaMemcpyHostToDevice);
+    cudaMemcpy(ddq, dqtmp, v, cudaMemcpyHostToDevice);
+    if (tau)
+        cudaMemcpy(dtau, tau, v, cudaMemcpyHostToDevice);
+    else
+        cudaMemset(dtau, 0, v);
+    EvalArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.sc = make_devscene(s, dc);
+    a.q = dq_;
+    a.qd = dqd;
+    a.dq = ddq;
+    a.tau = dtau;
+    a.cK = cK;
+    a.beta = beta;
+    a.H = dH;
+    const int nw = warps_for(s);
+    const bool gr = s->has_ground != 0;
+    const size_t smem = scene_smem_doubles(s, false) * sizeof(double);
+    if (nw == 1)
+        rc = gr ? launch_eval_newton_t<1, true>(a, ddx, smem) : launch_eval_newton_t<1, false>(a, ddx, smem);
+    else
+        rc = gr ? launch_eval_newton_t<2, true>(a, ddx, smem) : launch_eval_newton_t<2, false>(a, ddx, smem);
+    if (rc == RMX_OK) {
+        if (H) cudaMemcpy(H, dH, m, cudaMemcpyDeviceToHost);
+        if (dx) cudaMemcpy(dx, ddx, v, cudaMemcpyDeviceToHost);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) rc = fail(RMX_ECUDA, cudaGetErrorString(e));
+    }
+    cudaFree(d);
+    return rc;
+}
+
 #include "rmx_api_adjoint.inc"

@@ -48,21 +48,43 @@ struct Fld {
     static constexpr int HROOM = 12 + NCOMP;
 };
 
+// Joint stride of the SoA block.  One-warp kernels (n, nr <= 32) always use 33, so that every field offset is a compile-time
+// immediate there (const int NS = NW == 1 ? 33 : c.NS): no address arithmetic per shared-memory access.
+__host__ __device__ inline int soa_stride(int n, int nr) { return (n <= 32 && nr <= 32) ? 33 : (n | 1); }
+// leading dimension of H: the tensor-core forward path fixes it at 33 for the same reason
+__host__ __device__ inline int h_ld2(int n, int nr, bool keep) { return (!keep && n <= 32 && nr <= 32) ? 33 : h_ld(nr); }
+
 __host__ __device__ inline int fld_total(bool ground, bool keep) {
     return ground ? (keep ? Fld<true, true>::TOTAL : Fld<true, false>::TOTAL)
                   : (keep ? Fld<false, true>::TOTAL : Fld<false, false>::TOTAL);
 }
+// Tensor-core forward path (rmx_tc.cuh; one warp, n <= 32, nr <= 32, !KEEP): during the assembly the SoA block is overlaid by
+//   W  [n][NW_] at 0 (rows [L_k ; s_k]),  RZ [n][NW_] at n*NW_ (rows [Rt_i ; Z_i]),  H [nr][ld] at tc_h_offset (column-major)
+__host__ __device__ inline bool tc_layout(int n, int nr, bool keep) { return !keep && n <= 32 && nr <= 32; }
+__host__ __device__ inline size_t tc_h_offset(int n, bool ground) {
+    const size_t o = 2 * (size_t)n * (ground ? Fld<true, false>::NW_ : Fld<false, false>::NW_);
+    return (o + 1) & ~(size_t)1;
+}
 __host__ __device__ inline bool h_aliased(int n, int nr, bool ground, bool keep) {
+    if (tc_layout(n, nr, keep)) return true;
     const int room = ground ? Fld<true, false>::HROOM : Fld<false, false>::HROOM;
-    return !keep && (size_t)nr * h_ld(nr) <= (size_t)room * (n | 1);
+    return !keep && (size_t)nr * h_ld(nr) <= (size_t)room * soa_stride(n, nr);
+}
+__host__ __device__ inline size_t soa_doubles(int n, int nr, bool ground, bool keep) {
+    size_t d = (size_t)soa_stride(n, nr) * fld_total(ground, keep);
+    if (tc_layout(n, nr, keep)) {
+        const size_t need = tc_h_offset(n, ground) + (size_t)((nr + 7) & ~7) * h_ld2(n, nr, keep);  // H padded to whole 8x8 tiles
+        if (need > d) d = need;
+    }
+    return (d + 1) & ~(size_t)1;
 }
 
 constexpr int LUBUF = 2 * (32 / 2 + 1) * 2;  // doubles: two pivot-row buffers of the warp LU (lu_solve_warp_sm), 16B aligned
 
 __host__ __device__ inline size_t smem_doubles2(int n, int nr, bool ground, bool keep) {
-    size_t d = (size_t)(n | 1) * fld_total(ground, keep) + LUBUF + (size_t)NVEC * nr + 16 + 8;
-    if (!h_aliased(n, nr, ground, keep)) d += (size_t)nr * h_ld(nr);
-    d += (size_t)(3 * n + 1) / 2 + 1;  // int tables {idx,end}/parent
+    size_t d = soa_doubles(n, nr, ground, keep) + (tc_layout(n, nr, keep) ? 0 : LUBUF) + (size_t)NVEC * nr + 16 + 8;
+    if (!h_aliased(n, nr, ground, keep)) d += (size_t)nr * h_ld2(n, nr, keep);
+    d += (size_t)(3 * n + 1) / 2 + 1 + 16;  // int tables {idx,end}/parent, rem[32]
     return (d + 1) & ~(size_t)1;
 }
 
@@ -72,6 +94,7 @@ struct Ctx2 : Ctx {
     int NS;      // stride (= n|1: odd, so that component-major accesses are conflict free too)
     int2* ie_s;  // [n] {reduced index or -1, subtree end}
     int* par_s;  // [n] parent
+    int* rem_s;  // [32] rows still to be eliminated (blocked LU, rmx_tc.cuh)
     const int* __restrict__ anc;  // [nrounds][n] ancestor tables (global)
     int nrounds;
 };
@@ -79,13 +102,13 @@ struct Ctx2 : Ctx {
 __device__ __forceinline__ void ctx2_carve(Ctx2& c, double* sm, int n, int nr, bool ground, bool keep) {
     c.n = n;
     c.nr = nr;
-    c.ld = h_ld(nr);
-    c.NS = n | 1;
+    c.ld = h_ld2(n, nr, keep);
+    c.NS = soa_stride(n, nr);
     double* p = sm;
     c.sa = p;
-    p += (size_t)c.NS * fld_total(ground, keep);  // even number of doubles: p stays 16B aligned
+    p += soa_doubles(n, nr, ground, keep);  // even number of doubles: p stays 16B aligned
     c.lubuf = reinterpret_cast<double2*>(p);
-    p += LUBUF;
+    if (!tc_layout(n, nr, keep)) p += LUBUF;  // the tensor-core LU keeps no row buffers
     c.rec1 = nullptr;
     c.rec2 = nullptr;
     c.KD = nullptr;
@@ -108,7 +131,11 @@ __device__ __forceinline__ void ctx2_carve(Ctx2& c, double* sm, int n, int nr, b
     c.ie_s = reinterpret_cast<int2*>(p);
     c.par_s = reinterpret_cast<int*>(p) + 2 * n;
     p += (size_t)(3 * n + 1) / 2 + 1;
-    if (h_aliased(n, nr, ground, keep)) {
+    c.rem_s = reinterpret_cast<int*>(p);
+    p += 16;
+    if (tc_layout(n, nr, keep)) {
+        c.H = c.sa + tc_h_offset(n, ground);
+    } else if (h_aliased(n, nr, ground, keep)) {
         c.H = c.sa + (size_t)(ground ? Fld<true, false>::HALIAS : Fld<false, false>::HALIAS) * c.NS;
     } else {
         p = (double*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
@@ -147,7 +174,7 @@ template <int NW, bool GROUND, bool KEEP>
 __device__ void eval_base2(Ctx2& c, bool deriv) {
     typedef Fld<GROUND, KEEP> F;
     const int t = threadIdx.x;
-    const int n = c.n, NS = c.NS;
+    const int n = c.n, NS = (NW == 1) ? 33 : c.NS;
     const int NT = 32 * NW;
     // ---- stage kinematics + joint-local transforms --------------------------------------------------------
     if (t < c.nr) {
@@ -417,11 +444,11 @@ __device__ void eval_base2(Ctx2& c, bool deriv) {
 // Per-joint part of the Newton-matrix assembly: from joint t's screw, its parent's V and U and its composite blocks, the
 // row vector L_t (so that H[t][i] = L_t . Rt_i for t in sub(i)), and the column vectors Rt_t = [c2 ; c1 ; sq s] and Z_t
 // (H[k][t] = s_k . Z_t for proper ancestors k).  Reads shared memory only; results stay in registers.
-template <bool GROUND, bool KEEP>
+template <int NW, bool GROUND, bool KEEP>
 __device__ __forceinline__ void columns_joint(Ctx2& c, int t, int myidx, double sq, double sqd, double sd, double* L, double* s,
                                               double* Rt, double* Z) {
     typedef Fld<GROUND, KEEP> F;
-    const int NS = c.NS;
+    const int NS = (NW == 1) ? 33 : c.NS;
     const double cc = c.c;
     if (myidx >= 0) {
         double Vp[6] = {0, 0, 0, 0, 0, 0}, Up[6] = {0, 0, 0, 0, 0, 0};
@@ -562,12 +589,12 @@ template <int NW, bool GROUND, bool KEEP>
 __device__ void eval_columns2(Ctx2& c, double sq, double sqd, double sd, double scale, double* out) {
     typedef Fld<GROUND, KEEP> F;
     const int t = threadIdx.x;
-    const int n = c.n, NS = c.NS, ld = c.ld;
+    const int n = c.n, NS = (NW == 1) ? 33 : c.NS, ld = c.ld;
     const double cc = c.c;
     const int myidx = (t < n) ? c.ie_s[t].x : -1;
     double Rt[F::NL];  // [c2 (6) ; c1 (3 or 6) ; sq s (3 or 6)]
     double Z[6], L[F::NL], s[6];
-    columns_joint<GROUND, KEEP>(c, t, myidx, sq, sqd, sd, L, s, Rt, Z);
+    columns_joint<NW, GROUND, KEEP>(c, t, myidx, sq, sqd, sd, L, s, Rt, Z);
     if (myidx >= 0) {
         // W_t = [L_t ; s_t], joint-major so that the rows below are fetched with 128-bit broadcast loads
         {

@@ -2,6 +2,7 @@
 #pragma once
 #include "rmx_device.cuh"
 #include "rmx_fast.cuh"
+#include "rmx_tc.cuh"
 #include "rmx_pcg.cuh"
 
 namespace rmx {
@@ -131,12 +132,19 @@ struct Eval<2, NW, GROUND, KEEP, LIN> {
         }
         bsync<NW>();
     }
+    // one-warp forward kernels assemble and factor the Newton matrix on the FP64 tensor cores (rmx_tc.cuh)
+    static constexpr bool TC = (NW == 1 && !KEEP && LIN == 0);
     static __device__ __forceinline__ void base(C& c, bool deriv) { eval_base2<NW, GROUND, KEEP>(c, deriv); }
     static __device__ __forceinline__ void columns(C& c, double sq, double sqd, double sd, double scale, double* out) {
-        eval_columns2<NW, GROUND, KEEP>(c, sq, sqd, sd, scale, out);
+        if (TC)
+            eval_columns_tc<GROUND>(c, sq, sqd, sd, scale, out);
+        else
+            eval_columns2<NW, GROUND, KEEP>(c, sq, sqd, sd, scale, out);
     }
     static __device__ __forceinline__ void factor_solve(C& c, int* perm, double scale, bool write_back) {
-        if (LIN == 1) {
+        if (TC) {
+            lu_solve_warp_tc(c.nr, c.H, perm, c.rem_s, c.g, scale, c.dx);
+        } else if (LIN == 1) {
             c.kry_iters += krylov_solve<NW, GROUND>(c, c.pm, c.H, c.g, scale, c.lin_tol, c.lin_maxit);
         } else if (NW == 1) {
             lu_solve_warp(c.nr, c.ld, c.H, perm, c.g, scale, c.dx, write_back, c.lubuf);
@@ -529,6 +537,51 @@ __global__ void __launch_bounds__(32 * NW) eval_kernel(EvalArgs a) {
         }
         bsync<NW>();
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Test hook: one Newton linear system exactly as the forward rollout kernel forms and solves it (same Eval instance:
+// tensor-core assembly + blocked LU for one warp) -> H (before factorisation, nr x nr column-major) and dx = -H \ g.
+// ---------------------------------------------------------------------------------------------
+template <int NW, bool GROUND>
+__global__ void __launch_bounds__(32 * NW) eval_newton_kernel(EvalArgs a, double* dx_out) {
+    typedef Eval<2, NW, GROUND, false, 0> E;
+    extern __shared__ double2 smem_raw[];
+    double* sm = reinterpret_cast<double*>(smem_raw);
+    __shared__ int perm_s[32 * NW];
+    const int t = threadIdx.x;
+    const int nr = a.sc.nr;
+    typename E::C c;
+    StepOpts op0;
+    op0.lin_tol = 0.0;
+    op0.lin_maxit = 0;
+    E::setup(c, sm, a.sc, op0);
+    c.stage = ST_DIRECT;
+    c.h = 1.0;
+    c.c = a.cK;
+    c.beta = a.beta;
+    if (t < nr) {
+        c.q[t] = a.q[t];
+        c.hqd0[t] = a.qd[t];
+        c.hq1[t] = a.dq[t];
+        c.hq0[t] = 0;
+        c.hqd1[t] = 0;
+        c.tau[t] = a.tau ? a.tau[t] : 0.0;
+    }
+    bsync<NW>();
+    E::base(c, true);
+    E::columns(c, 1.0, c.beta, 1.0, 1.0, c.H);
+    const int ld = c.ld;
+    if (a.H) {
+        for (int e = t; e < nr * nr; e += blockDim.x) {
+            const int col = e / nr, row = e % nr;
+            a.H[e] = c.H[(size_t)col * ld + row];
+        }
+    }
+    bsync<NW>();
+    E::factor_solve(c, perm_s, -1.0, false);
+    bsync<NW>();
+    if (t < nr && dx_out) dx_out[t] = c.dx[t];
 }
 
 }  // namespace rmx

@@ -1,0 +1,284 @@
+// rmx_tc.cuh -- FP64 tensor-core (DMMA.8x8x4, mma.sync m8n8k4 f64) forms of the two hot phases of the one-warp forward
+// kernel: assembly of the Newton matrix from the composite blocks, and its partial-pivot LU.
+//
+// Why: the scalar forms (rmx_fast.cuh eval_columns2 / lu_solve_warp_t) spend 2 x 32-bit shuffles plus register moves per
+// trailing LU entry and 18 broadcast multiply-adds per matrix entry; measured on B200 (profiles/r01_dmma_dfma_shfl_probe.log)
+// one DMMA (256 multiply-adds, 1 issue slot) costs the FP64 pipe what 8 DFMAs cost, and a shuffle occupies the SM-wide
+// shuffle unit for 2 cycles.  Here
+//   * H = [L | S] [Rt ; Z] restricted by the tree relation is 8x8 output tiles of k = 12 (18 with ground contact) + 8:
+//     5 (7) DMMAs per tile, operands fetched as fragments straight from two joint-major arrays in shared memory;
+//   * the LU is right-looking in 8-column panels: rows never move (perm[] / rem[] indirection), a panel is factored in
+//     registers (8 entries per lane) with LAPACK's idamax tie rule, U12 by one forward substitution per trailing column,
+//     and the trailing update A22 -= L21 U12 by 2 DMMAs per 8x8 tile on the shared-memory image of H.
+// H is padded with an identity block to a multiple of 8 rows/columns (the assembly writes the padding), its leading
+// dimension and all strides are compile-time constants, and every index is a 32-bit offset into shared memory, so the
+// loops below carry no bounds checks and almost no address arithmetic.
+// tools/proto_dmma_lu.py emulates the LU lane by lane (fragment layouts included) and checks pivots and factors against
+// LAPACK.  PTX fragment layout (g = lane >> 2, t = lane & 3): A[g][t], B[t][g], C[g][2t], C[g][2t+1].
+#pragma once
+#include "rmx_fast.cuh"
+
+namespace rmx {
+
+constexpr int TC_LD = 33;  // leading dimension of H on this path (h_ld2)
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    // volatile: a .sync.aligned instruction must stay where the warp is converged (never sunk into a divergent consumer)
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// ---------------------------------------------------------------------------------------------
+// eval_columns_tc: same result as eval_columns2 (out = scale * (sq dg/dq + sqd dg/dqdot + sd dg/d(dqtmp))), one warp,
+// plus the identity padding of rows / columns nr .. 8*ceil(nr/8)-1.
+// ---------------------------------------------------------------------------------------------
+template <bool GROUND>
+__device__ __forceinline__ void eval_columns_tc(Ctx2& c, double sq, double sqd, double sd, double scale, double* out) {
+    typedef Fld<GROUND, false> F;
+    constexpr int NL = F::NL, NWD = F::NW_, LD = TC_LD;
+    constexpr int KS1 = (NL + 3) / 4;  // k-steps of the subtree part (k = NL, zero padded)
+    const int lane = threadIdx.x & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int n = c.n, nr = c.nr;
+    const double cc = c.c;
+    __builtin_assume(__isShared(c.sa));
+    __builtin_assume(__isShared(out));
+    const int myidx = (lane < n) ? c.ie_s[lane].x : -1;
+    double* __restrict__ Wb = c.sa;
+    double* __restrict__ RZb = c.sa + n * NWD;
+    {
+        double Rt[NL], Z[6], L[NL], s[6];
+        columns_joint<1, GROUND, false>(c, lane, myidx, sq, sqd, sd, L, s, Rt, Z);
+        __syncwarp();  // every lane has read S, V, U and its composite blocks: the SoA block may be overwritten
+        if (lane < n) {
+            double* W = Wb + lane * NWD;
+            double* RZ = RZb + lane * NWD;
+            if (myidx >= 0) {
+#pragma unroll
+                for (int i = 0; i < NL; ++i) {
+                    W[i] = L[i];
+                    RZ[i] = Rt[i];
+                }
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    W[NL + i] = s[i];
+                    RZ[NL + i] = Z[i];
+                }
+            } else {  // fixed joint: no row / column of H
+#pragma unroll
+                for (int i = 0; i < NWD; ++i) {
+                    W[i] = 0.0;
+                    RZ[i] = 0.0;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    const int nT = (n + 7) >> 3;
+    const bool chain = c.is_chain != 0;
+    // rows >= n of W / RZ are never written: whatever is there only reaches C rows / columns >= n, which are not stored
+    for (int I = 0; I < nT; ++I) {
+        const int k = 8 * I + g;  // row joint of this lane's A fragments and C elements
+        const double* wk = Wb + k * NWD + t4;
+        double a1[KS1], a2[2];
+#pragma unroll
+        for (int ks = 0; ks < KS1; ++ks) a1[ks] = (4 * ks + 3 < NL || 4 * ks + t4 < NL) ? wk[4 * ks] : 0.0;
+        a2[0] = wk[NL];
+        a2[1] = (t4 < 2) ? wk[NL + 4] : 0.0;
+        const int2 iek = (k < n) ? c.ie_s[k] : make_int2(-1, 0);
+        double* orow = out + iek.x;
+        for (int J = 0; J < nT; ++J) {
+            // serial chain: a tile strictly above the diagonal holds ancestor entries only, strictly below subtree entries only
+            const bool need_sub = !chain || I >= J;
+            const bool need_anc = !chain || I <= J;
+            const double* rz = RZb + (8 * J + g) * NWD + t4;  // column joint 8J+g of this lane's B fragments
+            double s0 = 0.0, s1 = 0.0, z0 = 0.0, z1 = 0.0;
+            if (need_sub) {
+#pragma unroll
+                for (int ks = 0; ks < KS1; ++ks) {
+                    const double bf = (4 * ks + 3 < NL || 4 * ks + t4 < NL) ? rz[4 * ks] : 0.0;
+                    dmma884(s0, s1, a1[ks], bf);
+                }
+            }
+            if (need_anc) {
+                const double b0 = rz[NL];
+                const double b1 = (t4 < 2) ? rz[NL + 4] : 0.0;
+                dmma884(z0, z1, a2[0], b0);
+                dmma884(z0, z1, a2[1], b1);
+            }
+            const int i0 = 8 * J + 2 * t4;  // column joints i0, i0+1 of this lane's C elements
+            if (k < n && iek.x >= 0) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int i = i0 + e;
+                    if (i < n) {
+                        const int2 iei = c.ie_s[i];
+                        if (iei.x >= 0) {
+                            double v = 0.0;
+                            if (i <= k && k < iei.y)
+                                v = e ? s1 : s0;  // k in sub(i):  L_k . Rt_i
+                            else if (k < i && i < iek.y)
+                                v = e ? z1 : z0;  // k a proper ancestor of i:  s_k . Z_i
+                            if (k == i) v += -cc * (sq * c.sp2[iei.x] + sqd * c.sp1[iei.x]);  // Kr, Dr of Joint.m:470-481
+                            orow[iei.x * LD] = scale * v;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    // identity padding up to a multiple of 8 (the blocked LU runs whole panels and whole tiles)
+    const int np8 = (nr + 7) & ~7;
+    for (int col = nr; col < np8; ++col) out[col * LD + lane] = (lane == col) ? 1.0 : 0.0;
+    if (lane < nr)
+        for (int row = nr; row < np8; ++row) out[lane * LD + row] = 0.0;
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
+// lu_solve_warp_tc: dx = scale * H \ rhs for one warp, nr <= 32.  H: column-major, leading dimension 33, padded with an
+// identity block to np8 = 8*ceil(nr/8) rows and columns, in shared memory; overwritten by its factors (rows stay where they
+// are: row perm[k] is the k-th pivot row, unit-lower multipliers left of the diagonal position).  perm, rem: int[32] shared.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void lu_solve_warp_tc(int nr, double* H, int* perm, int* rem, const double* rhs, double scale,
+                                                 double* dx) {
+    constexpr int LD = TC_LD;
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    __builtin_assume(__isShared(H));
+    __builtin_assume(__isShared(perm));
+    __builtin_assume(__isShared(rem));
+    __builtin_assume(__isShared(rhs));
+    __builtin_assume(__isShared(dx));
+    const int NP = (nr + 7) >> 3;
+    const int np8 = 8 * NP;
+    bool done = lane >= np8;  // lanes beyond the padded matrix never take part
+    int pos = lane, mypos = -1;
+    double b = (lane < nr) ? scale * rhs[lane] : 0.0;
+    double rdiag = 1.0;
+    double* Hrow = H + lane;  // this lane's row: entry c at Hrow[c * LD]
+    for (int p = 0; p < NP; ++p) {
+        const int c0 = 8 * p;
+        // ---- panel: columns c0 .. c0+7 of every row, 8 entries per lane ---------------------------------------------
+        double* Hp = Hrow + c0 * LD;
+        double a[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = Hp[i * LD];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int k = c0 + i;
+            // argmax |a[i]| over the rows that are not pivots yet; ties -> smallest LAPACK position (dgetf2's idamax).
+            // |v| >= 0, so the IEEE bit pattern orders like the value: one warp reduction on the high words decides unless two
+            // rows agree in their top 32 bits; only then the low words and the positions are consulted (warp-uniform branch).
+            const double v = fabs(a[i]);
+            const unsigned hi = done ? 0u : (unsigned)__double2hiint(v);
+            const unsigned mh = __reduce_max_sync(FULL, hi);
+            const bool c1 = !done && hi == mh;
+            unsigned cand = __ballot_sync(FULL, c1);
+            if (cand & (cand - 1)) {
+                const unsigned lo = c1 ? (unsigned)__double2loint(v) : 0u;
+                const unsigned ml = __reduce_max_sync(FULL, lo);
+                const bool c2 = c1 && lo == ml;
+                const unsigned pm = __reduce_min_sync(FULL, c2 ? (unsigned)pos : 0xffffu);
+                cand = __ballot_sync(FULL, c2 && (unsigned)pos == pm);
+            }
+            const int src = __ffs(cand) - 1;
+            const int kl = __ffs(__ballot_sync(FULL, !done && pos == k)) - 1;
+            const int pos_src = __shfl_sync(FULL, pos, src);
+            if (lane == kl) pos = pos_src;
+            if (lane == src) {
+                pos = k;
+                done = true;
+                mypos = k;
+            }
+            if (lane == k) perm[k] = src;
+            const double piv = __shfl_sync(FULL, a[i], src);
+            const double rp = __drcp_rn(piv);  // == 1.0 / piv, correctly rounded
+            rdiag = (lane == src) ? rp : rdiag;
+            const double l = done ? 0.0 : a[i] * rp;
+            a[i] = done ? a[i] : l;
+#pragma unroll
+            for (int j = i + 1; j < 8; ++j) {
+                const double u = __shfl_sync(FULL, a[j], src);
+                a[j] = fma(-l, u, a[j]);  // l == 0 for rows that are already pivots
+            }
+            const double ub = __shfl_sync(FULL, b, src);
+            b = fma(-l, ub, b);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) Hp[i * LD] = a[i];
+        const int nt = NP - p - 1;  // trailing tile rows == trailing tile columns
+        if (nt == 0) break;         // warp-uniform
+        // ---- compact list of the rows still to be eliminated: exactly 8*nt of them ----------------------------------
+        const unsigned live = __ballot_sync(FULL, !done);
+        if (!done) rem[__popc(live & ((1u << lane) - 1u))] = lane;
+        __syncwarp();
+        // ---- U12 = L11^-1 A12(pivot rows): lane = trailing column ------------------------------------------------
+        int pr[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pr[i] = perm[c0 + i];
+        if (lane < 8 * nt) {
+            double* colp = H + (c0 + 8 + lane) * LD;
+            const double* Lp = H + c0 * LD;
+            double x[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = colp[pr[i]];
+#pragma unroll
+            for (int i = 1; i < 8; ++i) {
+#pragma unroll
+                for (int j = 0; j < i; ++j) x[i] = fma(-Lp[j * LD + pr[i]], x[j], x[i]);
+            }
+#pragma unroll
+            for (int i = 1; i < 8; ++i) colp[pr[i]] = x[i];
+        }
+        __syncwarp();
+        // ---- A22 -= L21 U12 : 8x8 tiles, 2 DMMAs each ----------------------------------------------------------------
+        // pivot rows of this lane's k-indices t4 and 4 + t4 (B fragments)
+        const int prt0 = (t4 == 0) ? pr[0] : (t4 == 1) ? pr[1] : (t4 == 2) ? pr[2] : pr[3];
+        const int prt1 = (t4 == 0) ? pr[4] : (t4 == 1) ? pr[5] : (t4 == 2) ? pr[6] : pr[7];
+        const double* La = H + (c0 + t4) * LD;  // multipliers of k-index t4 (column c0 + t4): row r at La[r]; 4 + t4 at La[4 LD + r]
+        double af0[3], af1[3];
+        int rI[3];
+#pragma unroll
+        for (int I = 0; I < 3; ++I) {
+            if (I < nt) {
+                const int r = rem[8 * I + g];
+                rI[I] = r;
+                af0[I] = -La[r];
+                af1[I] = -La[4 * LD + r];
+            }
+        }
+        for (int J = 0; J < nt; ++J) {
+            const int cJ = c0 + 8 + 8 * J;
+            const double* Ub = H + (cJ + g) * LD;  // B fragments: U12[k-index][column cJ + g]
+            const double bf0 = Ub[prt0], bf1 = Ub[prt1];
+            double* Cc = H + (cJ + 2 * t4) * LD;   // C elements: columns cJ + 2 t4, + 1
+#pragma unroll
+            for (int I = 0; I < 3; ++I) {
+                if (I < nt) {
+                    double v0 = Cc[rI[I]], v1 = Cc[LD + rI[I]];
+                    dmma884(v0, v1, af0[I], bf0);
+                    dmma884(v0, v1, af1[I], bf1);
+                    Cc[rI[I]] = v0;
+                    Cc[LD + rI[I]] = v1;
+                }
+            }
+        }
+        __syncwarp();
+    }
+    __syncwarp();
+    // ---- back substitution U x = y: the row with pivot position k lives in lane perm[k], y there is b (padding rows: x = 0) --
+#pragma unroll 4
+    for (int k = nr - 1; k >= 0; --k) {
+        const int src = perm[k];
+        const double xk = __shfl_sync(FULL, b * rdiag, src);
+        const double u = Hrow[k * LD];
+        b = (mypos >= 0 && mypos < k) ? fma(-u, xk, b) : b;
+        if (lane == k) dx[k] = xk;
+    }
+    __syncwarp();
+}
+
+}  // namespace rmx

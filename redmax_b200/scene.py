@@ -511,6 +511,18 @@ class Scene:
         # column-major nr x nr -> numpy [row, col]
         return dict(g=g, f=f, H=H.T.copy(), M=M.T.copy(), D=D.T.copy())
 
+    def eval_newton(self, q, qdot, dqtmp, cK, beta, tau=None):
+        """H and dx = -H\\g through the forward kernel's own assembly + LU path (rmx_eval_newton)."""
+        L = self._require()
+        nr = self.nr
+        q, qdot, dqtmp = f64(q), f64(qdot), f64(dqtmp)
+        tau = None if tau is None else f64(tau)
+        H = np.empty((nr, nr))
+        dx = np.empty(nr)
+        _ffi.check(L.rmx_eval_newton(self._handle, ptr(q), ptr(qdot), ptr(dqtmp), ptr(tau), float(cK), float(beta),
+                                     ptr(H), ptr(dx)), 'rmx_eval_newton')
+        return dict(H=H.T.copy(), dx=dx)
+
     def energies(self, q, qdot):
         """T, V of Scene.saveHistory (Scene.m:155-160) for B states."""
         L = self._require()

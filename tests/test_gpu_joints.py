@@ -116,3 +116,20 @@ def test_planar_with_oblique_plane_and_limits(rb, oracle):
     so.update()
     To, Vo = so.computeEnergies()
     assert abs(V[0] - Vo) <= 1e-10 * max(1.0, abs(Vo)) and abs(T[0] - To) <= 1e-10 * max(1.0, abs(To))
+
+
+@pytest.mark.parametrize('sid', SCENES)
+def test_newton_system_through_the_rollout_path(rb, oracle, sid):
+    sg, so = both(rb, oracle, rb.scenesRedMax, sid)
+    rng = np.random.default_rng(900 + sid)
+    nr, h = sg.nr, sg.h
+    q = sg.qInit + 0.4 * rng.uniform(-1, 1, nr)
+    if sid == 11:
+        q[1] = 0.4
+    q0 = q - 0.02 * rng.uniform(-1, 1, nr)
+    qdot0 = rng.uniform(-1, 1, nr)
+    g, H, M, D, f = oracle_eval(oracle, so, q, qdot0, q0, None)
+    out = sg.eval_newton(q, (q - q0) / h, q - q0 - h * qdot0, h * h, 1.0 / h)
+    assert rel_err(out['H'], H) < TOL_EVAL, rel_err(out['H'], H)
+    dx = np.linalg.solve(H, -g)
+    assert rel_err(out['dx'], dx) < 1e-12 * max(10.0, np.linalg.cond(H))

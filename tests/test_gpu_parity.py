@@ -196,3 +196,36 @@ def test_c3_ground_friction_bdf2_vs_c_oracle(rb, oracle, oc):
     ok = st[:, 2] == 0  # compare where the reference's Newton converged in every step
     assert ok.any()
     assert rel_err(out['q'][ok], q[ok]) < TOL_Q
+
+
+NEWTON_CASES = [c for c in CASES if c[0] != 'chain40'] + [
+    ('chain40', dict(CASES)['chain40']),
+    ('chain20ground', lambda rb: (rb.chain_scene, (20,), dict(ground=True, h=5e-4, ground_z=-48.5))),
+    ('chain9', lambda rb: (rb.chain_scene, (9,), {})),
+    ('chain17', lambda rb: (rb.chain_scene, (17,), {})),
+    ('chain31', lambda rb: (rb.chain_scene, (31,), {})),
+]
+
+
+@pytest.mark.parametrize('name,mk', NEWTON_CASES, ids=[c[0] for c in NEWTON_CASES])
+def test_newton_system_through_the_rollout_path(rb, oracle, name, mk):
+    """rmx_eval_newton: H assembled and dx = -H\\g solved by the very code path the forward rollout kernel runs (FP64
+    tensor-core tiles + blocked partial-pivot LU for one warp; the scalar path for two warps), against the oracle's dense
+    H and LAPACK's solve.  Sizes cover partial 8x8 tiles and partial LU panels."""
+    factory, a, kw = mk(rb)
+    sg, so = both(rb, oracle, factory, *a, **kw)
+    rng = np.random.default_rng(4242)
+    nr, h = sg.nr, sg.h
+    for trial in range(2):
+        q = sg.qInit + 0.3 * rng.uniform(-1, 1, nr)
+        q0 = q - 0.02 * rng.uniform(-1, 1, nr)
+        qdot0 = rng.uniform(-1, 1, nr)
+        tau = 100 * rng.uniform(-1, 1, nr)
+        g, H, M, D, f = oracle_eval(oracle, so, q, qdot0, q0, tau)
+        out = sg.eval_newton(q, (q - q0) / h, q - q0 - h * qdot0, h * h, 1.0 / h, tau=tau)
+        assert rel_err(out['H'], H) < TOL_EVAL, ('H', rel_err(out['H'], H))
+        dx = np.linalg.solve(H, -g)
+        # backward error of the in-block LU, then the forward error on the scale the conditioning allows
+        back = np.linalg.norm(H @ out['dx'] + g) / (np.linalg.norm(H, 2) * np.linalg.norm(out['dx']) + np.linalg.norm(g))
+        assert back < 1e-14, back
+        assert rel_err(out['dx'], dx) < 1e-12 * max(10.0, np.linalg.cond(H)), (rel_err(out['dx'], dx), np.linalg.cond(H))
