@@ -79,12 +79,15 @@ __host__ __device__ inline size_t soa_doubles(int n, int nr, bool ground, bool k
     return (d + 1) & ~(size_t)1;
 }
 
+// tensor-core path extras (doubles): idx[32] + submask[32] + ancmask[32] ints, two 10-double pivot-row buffers (16B aligned)
+constexpr int TC_TABLES = 48 + 24;
 constexpr int LUBUF = 2 * (32 / 2 + 1) * 2;  // doubles: two pivot-row buffers of the warp LU (lu_solve_warp_sm), 16B aligned
 
 __host__ __device__ inline size_t smem_doubles2(int n, int nr, bool ground, bool keep) {
     size_t d = soa_doubles(n, nr, ground, keep) + (tc_layout(n, nr, keep) ? 0 : LUBUF) + (size_t)NVEC * nr + 16 + 8;
     if (!h_aliased(n, nr, ground, keep)) d += (size_t)nr * h_ld2(n, nr, keep);
     d += (size_t)(3 * n + 1) / 2 + 1 + 16;  // int tables {idx,end}/parent, rem[32]
+    if (tc_layout(n, nr, keep)) d += TC_TABLES;
     return (d + 1) & ~(size_t)1;
 }
 
@@ -95,6 +98,10 @@ struct Ctx2 : Ctx {
     int2* ie_s;  // [n] {reduced index or -1, subtree end}
     int* par_s;  // [n] parent
     int* rem_s;  // [32] rows still to be eliminated (blocked LU, rmx_tc.cuh)
+    int* tcidx_s;         // [32] reduced index of joint i or -1            (tensor-core path only)
+    unsigned* tcsub_s;    // [32] bit i set: joint k is in sub(i)
+    unsigned* tcanc_s;    // [32] bit i set: joint k is a proper ancestor of i
+    double2* tcrow_s;     // [2][5] pivot-row buffers of the blocked LU
     const int* __restrict__ anc;  // [nrounds][n] ancestor tables (global)
     int nrounds;
 };
@@ -133,6 +140,19 @@ __device__ __forceinline__ void ctx2_carve(Ctx2& c, double* sm, int n, int nr, b
     p += (size_t)(3 * n + 1) / 2 + 1;
     c.rem_s = reinterpret_cast<int*>(p);
     p += 16;
+    c.tcidx_s = nullptr;
+    c.tcsub_s = nullptr;
+    c.tcanc_s = nullptr;
+    c.tcrow_s = nullptr;
+    if (tc_layout(n, nr, keep)) {
+        p = (double*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
+        c.tcrow_s = reinterpret_cast<double2*>(p);
+        p += 20;
+        c.tcidx_s = reinterpret_cast<int*>(p);
+        c.tcsub_s = reinterpret_cast<unsigned*>(p) + 32;
+        c.tcanc_s = reinterpret_cast<unsigned*>(p) + 64;
+        p += 48;
+    }
     if (tc_layout(n, nr, keep)) {
         c.H = c.sa + tc_h_offset(n, ground);
     } else if (h_aliased(n, nr, ground, keep)) {

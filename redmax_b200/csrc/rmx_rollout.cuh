@@ -112,6 +112,8 @@ template <int NW, bool GROUND, bool KEEP, int LIN>
 struct Eval<2, NW, GROUND, KEEP, LIN> {
     typedef Ctx2L C;
     typedef Fld<GROUND, KEEP> F;
+    // one-warp forward kernels assemble and factor the Newton matrix on the FP64 tensor cores (rmx_tc.cuh)
+    static constexpr bool TC = (NW == 1 && !KEEP && LIN == 0);
     static __device__ __forceinline__ void setup(C& c, double* sm, const DevScene& sc, const StepOpts& op) {
         ctx2_carve(c, sm, sc.n, sc.nr, GROUND, KEEP);
         c.lin_tol = op.lin_tol;
@@ -131,9 +133,24 @@ struct Eval<2, NW, GROUND, KEEP, LIN> {
             c.par_s[j] = sc.jc[j].parent;
         }
         bsync<NW>();
+        if (TC) {  // tree relation as bit masks (lane = joint k): the tile epilogue tests one bit per matrix entry
+            const int k = threadIdx.x;
+            unsigned sub = 0u, anc = 0u;
+            int idx = -1;
+            if (k < sc.n) {
+                idx = c.ie_s[k].x;
+                const int endk = c.ie_s[k].y;
+                for (int i = 0; i < sc.n; ++i) {
+                    if (i <= k && k < c.ie_s[i].y) sub |= 1u << i;
+                    if (k < i && i < endk) anc |= 1u << i;
+                }
+            }
+            c.tcidx_s[k] = idx;
+            c.tcsub_s[k] = sub;
+            c.tcanc_s[k] = anc;
+            bsync<NW>();
+        }
     }
-    // one-warp forward kernels assemble and factor the Newton matrix on the FP64 tensor cores (rmx_tc.cuh)
-    static constexpr bool TC = (NW == 1 && !KEEP && LIN == 0);
     static __device__ __forceinline__ void base(C& c, bool deriv) { eval_base2<NW, GROUND, KEEP>(c, deriv); }
     static __device__ __forceinline__ void columns(C& c, double sq, double sqd, double sd, double scale, double* out) {
         if (TC)
@@ -143,7 +160,7 @@ struct Eval<2, NW, GROUND, KEEP, LIN> {
     }
     static __device__ __forceinline__ void factor_solve(C& c, int* perm, double scale, bool write_back) {
         if (TC) {
-            lu_solve_warp_tc(c.nr, c.H, perm, c.rem_s, c.g, scale, c.dx);
+            lu_solve_warp_tc(c.nr, c.H, perm, c.rem_s, c.tcrow_s, c.g, scale, c.dx);
         } else if (LIN == 1) {
             c.kry_iters += krylov_solve<NW, GROUND>(c, c.pm, c.H, c.g, scale, c.lin_tol, c.lin_maxit);
         } else if (NW == 1) {

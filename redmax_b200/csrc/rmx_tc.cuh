@@ -77,6 +77,8 @@ __device__ __forceinline__ void eval_columns_tc(Ctx2& c, double sq, double sqd, 
     __syncwarp();
     const int nT = (n + 7) >> 3;
     const bool chain = c.is_chain != 0;
+    const int* __restrict__ idxs = c.tcidx_s;
+    __builtin_assume(__isShared(idxs));
     // rows >= n of W / RZ are never written: whatever is there only reaches C rows / columns >= n, which are not stored
     for (int I = 0; I < nT; ++I) {
         const int k = 8 * I + g;  // row joint of this lane's A fragments and C elements
@@ -86,8 +88,11 @@ __device__ __forceinline__ void eval_columns_tc(Ctx2& c, double sq, double sqd, 
         for (int ks = 0; ks < KS1; ++ks) a1[ks] = (4 * ks + 3 < NL || 4 * ks + t4 < NL) ? wk[4 * ks] : 0.0;
         a2[0] = wk[NL];
         a2[1] = (t4 < 2) ? wk[NL + 4] : 0.0;
-        const int2 iek = (k < n) ? c.ie_s[k] : make_int2(-1, 0);
-        double* orow = out + iek.x;
+        // tree relation of row joint k with every column joint, and its reduced index (no row if fixed or k >= n)
+        const int idxk = (k < n) ? idxs[k] : -1;
+        const unsigned subk = (idxk >= 0) ? c.tcsub_s[k] : 0u;
+        const unsigned anck = (idxk >= 0) ? c.tcanc_s[k] : 0u;
+        double* orow = out + idxk;
         for (int J = 0; J < nT; ++J) {
             // serial chain: a tile strictly above the diagonal holds ancestor entries only, strictly below subtree entries only
             const bool need_sub = !chain || I >= J;
@@ -107,27 +112,20 @@ __device__ __forceinline__ void eval_columns_tc(Ctx2& c, double sq, double sqd, 
                 dmma884(z0, z1, a2[0], b0);
                 dmma884(z0, z1, a2[1], b1);
             }
-            const int i0 = 8 * J + 2 * t4;  // column joints i0, i0+1 of this lane's C elements
-            if (k < n && iek.x >= 0) {
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int i = i0 + e;
-                    if (i < n) {
-                        const int2 iei = c.ie_s[i];
-                        if (iei.x >= 0) {
-                            double v = 0.0;
-                            if (i <= k && k < iei.y)
-                                v = e ? s1 : s0;  // k in sub(i):  L_k . Rt_i
-                            else if (k < i && i < iek.y)
-                                v = e ? z1 : z0;  // k a proper ancestor of i:  s_k . Z_i
-                            if (k == i) v += -cc * (sq * c.sp2[iei.x] + sqd * c.sp1[iei.x]);  // Kr, Dr of Joint.m:470-481
-                            orow[iei.x * LD] = scale * v;
-                        }
-                    }
-                }
+            const int i0 = 8 * J + 2 * t4;  // column joints i0, i0+1 of this lane's C elements (tcidx_s has 32 entries)
+            const int2 ix = *reinterpret_cast<const int2*>(idxs + i0);
+            const unsigned sb = subk >> i0, ab = anck >> i0;
+            const double v0 = (sb & 1u) ? s0 : ((ab & 1u) ? z0 : 0.0);  // k in sub(i): L_k . Rt_i ; k proper ancestor of i: s_k . Z_i
+            const double v1 = (sb & 2u) ? s1 : ((ab & 2u) ? z1 : 0.0);
+            if (idxk >= 0) {
+                if (i0 < n && ix.x >= 0) orow[ix.x * LD] = scale * v0;
+                if (i0 + 1 < n && ix.y >= 0) orow[ix.y * LD] = scale * v1;
             }
         }
     }
+    __syncwarp();
+    // diagonal: joint stiffness / damping / limit terms Kr, Dr (Joint.m:470-481)
+    if (myidx >= 0) out[myidx * (LD + 1)] += scale * (-cc * (sq * c.sp2[myidx] + sqd * c.sp1[myidx]));
     // identity padding up to a multiple of 8 (the blocked LU runs whole panels and whole tiles)
     const int np8 = (nr + 7) & ~7;
     for (int col = nr; col < np8; ++col) out[col * LD + lane] = (lane == col) ? 1.0 : 0.0;
@@ -139,10 +137,11 @@ __device__ __forceinline__ void eval_columns_tc(Ctx2& c, double sq, double sqd, 
 // ---------------------------------------------------------------------------------------------
 // lu_solve_warp_tc: dx = scale * H \ rhs for one warp, nr <= 32.  H: column-major, leading dimension 33, padded with an
 // identity block to np8 = 8*ceil(nr/8) rows and columns, in shared memory; overwritten by its factors (rows stay where they
-// are: row perm[k] is the k-th pivot row, unit-lower multipliers left of the diagonal position).  perm, rem: int[32] shared.
+// are: row perm[k] is the k-th pivot row, unit-lower multipliers left of the diagonal position).  perm, rem: int[32] shared;
+// rowbuf: 2 x 5 double2 shared (pivot-row broadcast inside a panel).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void lu_solve_warp_tc(int nr, double* H, int* perm, int* rem, const double* rhs, double scale,
-                                                 double* dx) {
+__device__ __forceinline__ void lu_solve_warp_tc(int nr, double* H, int* perm, int* rem, double2* rowbuf, const double* rhs,
+                                                 double scale, double* dx) {
     constexpr int LD = TC_LD;
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -150,6 +149,7 @@ __device__ __forceinline__ void lu_solve_warp_tc(int nr, double* H, int* perm, i
     __builtin_assume(__isShared(H));
     __builtin_assume(__isShared(perm));
     __builtin_assume(__isShared(rem));
+    __builtin_assume(__isShared(rowbuf));
     __builtin_assume(__isShared(rhs));
     __builtin_assume(__isShared(dx));
     const int NP = (nr + 7) >> 3;
@@ -194,17 +194,30 @@ __device__ __forceinline__ void lu_solve_warp_tc(int nr, double* H, int* perm, i
                 mypos = k;
             }
             if (lane == k) perm[k] = src;
-            const double piv = __shfl_sync(FULL, a[i], src);
+            // the pivot lane publishes its panel row (entries i.. as 128-bit pairs) and right-hand side; two alternating buffers,
+            // so one __syncwarp per pivot step orders both the read-after-write and the next write-after-read
+            double2* buf = rowbuf + 5 * (i & 1);
+            if (lane == src) {
+#pragma unroll
+                for (int j = i / 2; j < 4; ++j) buf[j] = make_double2(a[2 * j], a[2 * j + 1]);
+                buf[4] = make_double2(b, 0.0);
+            }
+            __syncwarp();
+            double2 u2[4];
+#pragma unroll
+            for (int j = i / 2; j < 4; ++j) u2[j] = buf[j];
+            const double ub = buf[4].x;
+            const double piv = (i & 1) ? u2[i / 2].y : u2[i / 2].x;
             const double rp = __drcp_rn(piv);  // == 1.0 / piv, correctly rounded
             rdiag = (lane == src) ? rp : rdiag;
-            const double l = done ? 0.0 : a[i] * rp;
+            const double l = done ? 0.0 : a[i] * rp;  // l == 0 for rows that are already pivots
             a[i] = done ? a[i] : l;
+            if (!(i & 1)) a[i + 1] = fma(-l, u2[i / 2].y, a[i + 1]);
 #pragma unroll
-            for (int j = i + 1; j < 8; ++j) {
-                const double u = __shfl_sync(FULL, a[j], src);
-                a[j] = fma(-l, u, a[j]);  // l == 0 for rows that are already pivots
+            for (int j = i / 2 + 1; j < 4; ++j) {
+                a[2 * j] = fma(-l, u2[j].x, a[2 * j]);
+                a[2 * j + 1] = fma(-l, u2[j].y, a[2 * j + 1]);
             }
-            const double ub = __shfl_sync(FULL, b, src);
             b = fma(-l, ub, b);
         }
 #pragma unroll
