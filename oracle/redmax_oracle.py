@@ -686,6 +686,85 @@ class ForceNull(Force):
     pass
 
 
+class ForcePointPoint(Force):
+    """ForcePointPoint.m -- linear zero-rest-length spring/damper between two body points (a body may be None = world)."""
+
+    def __init__(self, body1, x_1, body2, x_2):
+        """ForcePointPoint.m:15"""
+        self.body1 = body1
+        self.body2 = body2
+        self.x_1 = np.asarray(x_1, dtype=float).reshape(3)
+        self.x_2 = np.asarray(x_2, dtype=float).reshape(3)
+        self.stiffness = 1.0
+        self.damping = 0.0
+
+    def setStiffness(self, stiffness):
+        self.stiffness = stiffness
+
+    def setDamping(self, damping):
+        self.damping = damping
+
+    def _point(self, body, xl):
+        """world position / velocity of a body point, local velocity, R, p, Gamma (ForcePointPoint.m:50-73)"""
+        if body is None:
+            return xl, np.zeros(3), None, None, None, None
+        E = body.E_wi
+        R = E[0:3, 0:3]
+        p = E[0:3, 3]
+        G = se3_Gamma(xl)
+        vl = G @ body.phi
+        return R @ xl + p, R @ vl, vl, R, p, G
+
+    def computeValues_(self, fr, fm, Kr=None, Km=None, Dr=None, Dm=None):
+        """ForcePointPoint.m:48-113"""
+        xw1, vw1, vl1, R1, p1, G1 = self._point(self.body1, self.x_1)
+        xw2, vw2, vl2, R2, p2, G2 = self._point(self.body2, self.x_2)
+        dx = xw2 - xw1
+        dv = vw2 - vw1
+        I = np.eye(3)
+        Z = np.zeros((3, 3))
+        ks = self.stiffness
+        kd = self.damping
+        f = ks * dx + kd * dv
+        b1, b2 = self.body1 is not None, self.body2 is not None
+        if b1:
+            idx1 = self.body1.idxM
+            fm[idx1] += G1.T @ (R1.T @ f)
+        if b2:
+            idx2 = self.body2.idxM
+            fm[idx2] -= G2.T @ (R2.T @ f)
+        if Km is None:
+            return
+        if b1:
+            i11 = np.ix_(idx1, idx1)
+            Km[i11] += ks * (G1.T @ np.hstack([se3_brac(R1.T @ (xw2 - p1)), -I]))
+            Km[i11] += kd * (G1.T @ np.hstack([se3_brac(R1.T @ vw2), Z]))
+            Dm[i11] -= kd * (G1.T @ G1)
+        if b2:
+            i22 = np.ix_(idx2, idx2)
+            Km[i22] += ks * (G2.T @ np.hstack([se3_brac(R2.T @ (xw1 - p2)), -I]))
+            Km[i22] += kd * (G2.T @ np.hstack([se3_brac(R2.T @ vw1), Z]))
+            Dm[i22] -= kd * (G2.T @ G2)
+        if b1 and b2:
+            i12 = np.ix_(idx1, idx2)
+            i21 = np.ix_(idx2, idx1)
+            Km[i12] += ks * (G1.T @ R1.T @ R2 @ np.hstack([-se3_brac(self.x_2), I]))
+            Km[i21] += ks * (G2.T @ R2.T @ R1 @ np.hstack([-se3_brac(self.x_1), I]))
+            Km[i12] -= kd * (G1.T @ R1.T @ R2 @ np.hstack([se3_brac(vl2), Z]))
+            Km[i21] -= kd * (G2.T @ R2.T @ R1 @ np.hstack([se3_brac(vl1), Z]))
+            Dm[i12] += kd * (G1.T @ R1.T @ R2 @ G2)
+            Dm[i21] += kd * (G2.T @ R2.T @ R1 @ G1)
+
+    def computeEnergy_(self, V):
+        """ForcePointPoint.m:116-132"""
+        E1 = np.eye(4) if self.body1 is None else self.body1.E_wi
+        E2 = np.eye(4) if self.body2 is None else self.body2.E_wi
+        x1w = E1[0:3, :] @ np.append(self.x_1, 1.0)
+        x2w = E2[0:3, :] @ np.append(self.x_2, 1.0)
+        d = x2w - x1w
+        return V + 0.5 * self.stiffness * (d @ d)
+
+
 _CORNERS = np.array([
     [-1, -1, -1, 1],
     [-1, -1, 1, 1],

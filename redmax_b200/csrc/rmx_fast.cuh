@@ -79,15 +79,36 @@ __host__ __device__ inline size_t soa_doubles(int n, int nr, bool ground, bool k
     return (d + 1) & ~(size_t)1;
 }
 
-// tensor-core path extras (doubles): idx[32] + submask[32] + ancmask[32] ints, two 10-double pivot-row buffers (16B aligned)
-constexpr int TC_TABLES = 48 + 24;
+// Static shared-memory layout of the tensor-core forward kernels (capacity n = nr = 32 whatever the scene): every vector and
+// table sits at a compile-time offset from the block's base, so no pointer lives in a register and no address is computed.
+template <bool GROUND>
+struct TcLayout {
+    typedef Fld<GROUND, false> F;
+    static constexpr int CAP = 32, NS = 33, LD = 33;
+    static constexpr int W_OFF = 0;                   // W  [32][NW_]  rows [L_k ; s_k]
+    static constexpr int RZ_OFF = CAP * F::NW_;       // RZ [32][NW_]  rows [Rt_i ; Z_i]
+    static constexpr int H_OFF = 2 * CAP * F::NW_;    // H  [32][33]   column-major, identity padded to whole tiles
+    static constexpr int SOA_FIELDS = NS * F::TOTAL;  // the SoA block of eval_base2 (overlaid by W, RZ, H during assembly + LU)
+    static constexpr int SOA = ((SOA_FIELDS > H_OFF + CAP * LD ? SOA_FIELDS : H_OFF + CAP * LD) + 1) & ~1;
+    static constexpr int NV = 12;                     // q qd dq g dx tau hq0 hqd0 hq1 hqd1 sp1 sp2 (x0, sp0 are unused)
+    static constexpr int VEC = SOA;                   // NV vectors of 32
+    static constexpr int RED = VEC + NV * CAP;        // 16 + 8 reduction scratch
+    static constexpr int ROWBUF = RED + 24;           // 2 x 5 double2 pivot-row buffers (16B aligned: all terms even)
+    static constexpr int IE = ROWBUF + 20;            // int2 ie_s[32]
+    static constexpr int PAR = IE + CAP;              // int par_s[32]
+    static constexpr int REM = PAR + CAP / 2;         // int rem_s[32]
+    static constexpr int TIDX = REM + CAP / 2;        // int tcidx_s[32]
+    static constexpr int TSUB = TIDX + CAP / 2;       // unsigned tcsub_s[32]
+    static constexpr int TANC = TSUB + CAP / 2;       // unsigned tcanc_s[32]
+    static constexpr int TOTAL = (TANC + CAP / 2 + 1) & ~1;
+};
 constexpr int LUBUF = 2 * (32 / 2 + 1) * 2;  // doubles: two pivot-row buffers of the warp LU (lu_solve_warp_sm), 16B aligned
 
 __host__ __device__ inline size_t smem_doubles2(int n, int nr, bool ground, bool keep) {
-    size_t d = soa_doubles(n, nr, ground, keep) + (tc_layout(n, nr, keep) ? 0 : LUBUF) + (size_t)NVEC * nr + 16 + 8;
+    if (tc_layout(n, nr, keep)) return ground ? TcLayout<true>::TOTAL : TcLayout<false>::TOTAL;
+    size_t d = soa_doubles(n, nr, ground, keep) + LUBUF + (size_t)NVEC * nr + 16 + 8;
     if (!h_aliased(n, nr, ground, keep)) d += (size_t)nr * h_ld2(n, nr, keep);
     d += (size_t)(3 * n + 1) / 2 + 1 + 16;  // int tables {idx,end}/parent, rem[32]
-    if (tc_layout(n, nr, keep)) d += TC_TABLES;
     return (d + 1) & ~(size_t)1;
 }
 
@@ -115,7 +136,7 @@ __device__ __forceinline__ void ctx2_carve(Ctx2& c, double* sm, int n, int nr, b
     c.sa = p;
     p += soa_doubles(n, nr, ground, keep);  // even number of doubles: p stays 16B aligned
     c.lubuf = reinterpret_cast<double2*>(p);
-    if (!tc_layout(n, nr, keep)) p += LUBUF;  // the tensor-core LU keeps no row buffers
+    p += LUBUF;
     c.rec1 = nullptr;
     c.rec2 = nullptr;
     c.KD = nullptr;
@@ -144,23 +165,51 @@ __device__ __forceinline__ void ctx2_carve(Ctx2& c, double* sm, int n, int nr, b
     c.tcsub_s = nullptr;
     c.tcanc_s = nullptr;
     c.tcrow_s = nullptr;
-    if (tc_layout(n, nr, keep)) {
-        p = (double*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
-        c.tcrow_s = reinterpret_cast<double2*>(p);
-        p += 20;
-        c.tcidx_s = reinterpret_cast<int*>(p);
-        c.tcsub_s = reinterpret_cast<unsigned*>(p) + 32;
-        c.tcanc_s = reinterpret_cast<unsigned*>(p) + 64;
-        p += 48;
-    }
-    if (tc_layout(n, nr, keep)) {
-        c.H = c.sa + tc_h_offset(n, ground);
-    } else if (h_aliased(n, nr, ground, keep)) {
+    if (h_aliased(n, nr, ground, keep)) {
         c.H = c.sa + (size_t)(ground ? Fld<true, false>::HALIAS : Fld<false, false>::HALIAS) * c.NS;
     } else {
         p = (double*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
         c.H = p;
     }
+}
+
+// Tensor-core forward kernels: the static layout above (nothing depends on n or nr).
+template <bool GROUND>
+__device__ __forceinline__ void ctx2_carve_tc(Ctx2& c, double* sm, int n, int nr) {
+    typedef TcLayout<GROUND> T;
+    c.n = n;
+    c.nr = nr;
+    c.ld = T::LD;
+    c.NS = T::NS;
+    c.sa = sm;
+    c.lubuf = nullptr;
+    c.rec1 = nullptr;
+    c.rec2 = nullptr;
+    c.KD = nullptr;
+    double* v = sm + T::VEC;
+    c.q = v;
+    c.qd = v + 1 * T::CAP;
+    c.dq = v + 2 * T::CAP;
+    c.g = v + 3 * T::CAP;
+    c.dx = v + 4 * T::CAP;
+    c.x0 = nullptr;
+    c.sp0 = nullptr;
+    c.tau = v + 5 * T::CAP;
+    c.hq0 = v + 6 * T::CAP;
+    c.hqd0 = v + 7 * T::CAP;
+    c.hq1 = v + 8 * T::CAP;
+    c.hqd1 = v + 9 * T::CAP;
+    c.sp1 = v + 10 * T::CAP;
+    c.sp2 = v + 11 * T::CAP;
+    c.red = sm + T::RED;
+    c.tcrow_s = reinterpret_cast<double2*>(sm + T::ROWBUF);
+    c.ie_s = reinterpret_cast<int2*>(sm + T::IE);
+    c.par_s = reinterpret_cast<int*>(sm + T::PAR);
+    c.rem_s = reinterpret_cast<int*>(sm + T::REM);
+    c.tcidx_s = reinterpret_cast<int*>(sm + T::TIDX);
+    c.tcsub_s = reinterpret_cast<unsigned*>(sm + T::TSUB);
+    c.tcanc_s = reinterpret_cast<unsigned*>(sm + T::TANC);
+    c.H = sm + T::H_OFF;
 }
 
 #define SA(f, k, j) c.sa[(size_t)((f) + (k)) * NS + (j)]

@@ -115,7 +115,10 @@ struct Eval<2, NW, GROUND, KEEP, LIN> {
     // one-warp forward kernels assemble and factor the Newton matrix on the FP64 tensor cores (rmx_tc.cuh)
     static constexpr bool TC = (NW == 1 && !KEEP && LIN == 0);
     static __device__ __forceinline__ void setup(C& c, double* sm, const DevScene& sc, const StepOpts& op) {
-        ctx2_carve(c, sm, sc.n, sc.nr, GROUND, KEEP);
+        if (TC)
+            ctx2_carve_tc<GROUND>(c, sm, sc.n, sc.nr);
+        else
+            ctx2_carve(c, sm, sc.n, sc.nr, GROUND, KEEP);
         c.lin_tol = op.lin_tol;
         c.lin_maxit = op.lin_maxit;
         c.kry_iters = 0;
@@ -341,15 +344,17 @@ __device__ __forceinline__ int newton_adjoint(typename E::C& c, const StepOpts& 
 // Forward rollout kernel: simLoop of driverRedMaxBDF1.m:57-91 / driverRedMaxBDF2.m:57-125 (ADJ = false) and of
 // driverRedMaxAdjointBDF1.m:65-102 / driverRedMaxAdjointBDF2.m:65-136 (ADJ = true), one block per rollout.
 // ---------------------------------------------------------------------------------------------
-#ifndef RMX_MINB_FWD
-// resident blocks per SM asked of ptxas for the one-warp forward kernel (register cap 65536/(32*MINB)).  Measured
-// (profiles/r01_ab_lu_occupancy.log): 10 blocks/SM at 168 registers spills ~500 B per thread and is 8-12 % slower than
-// 8 blocks/SM at 230 registers without spills, so the cap stays off.
-#define RMX_MINB_FWD 1
+// Register budget of the one-warp tensor-core forward kernel.  Measured on B200 (profiles/r01_residency_probe.log,
+// r01_regcap_ab.log): the kernel is latency-bound per warp -- time per block is almost flat in the number of resident blocks
+// (59.7 us per rollout-step alone on an SM, 71.4 us with 8 resident) -- but capping registers to fit 10 blocks per SM
+// (200 registers, ~400 B of spills) slows every block by 27 % and loses more than the third wave gains (34.1 vs 27.2 ms), and
+// 184 registers is worse still.  So: no cap (255 registers, 8 blocks per SM).
+#ifndef RMX_MAXNREG_FWD
+#define RMX_MAXNREG_FWD 255
 #endif
+#define RMX_FWD_BOUNDS __maxnreg__((NW == 1 && !ADJ && LIN == 0 && IMPL == 2) ? RMX_MAXNREG_FWD : 255)
 template <int NW, bool GROUND, bool ADJ, int IMPL, int LIN>
-__global__ void __launch_bounds__(32 * NW, (NW == 1 && !ADJ && !GROUND && LIN == 0 && IMPL == 2) ? RMX_MINB_FWD : 1)
-rollout_fwd_kernel(RolloutArgs a) {
+__global__ void RMX_FWD_BOUNDS rollout_fwd_kernel(RolloutArgs a) {
     typedef Eval<IMPL, NW, GROUND, ADJ || LIN == 1, LIN> E;
     extern __shared__ double2 smem_raw[];
     double* sm = reinterpret_cast<double*>(smem_raw);

@@ -46,7 +46,7 @@ __device__ __forceinline__ void eval_columns_tc(Ctx2& c, double sq, double sqd, 
     __builtin_assume(__isShared(out));
     const int myidx = (lane < n) ? c.ie_s[lane].x : -1;
     double* __restrict__ Wb = c.sa;
-    double* __restrict__ RZb = c.sa + n * NWD;
+    double* __restrict__ RZb = c.sa + TcLayout<GROUND>::RZ_OFF;
     {
         double Rt[NL], Z[6], L[NL], s[6];
         columns_joint<1, GROUND, false>(c, lane, myidx, sq, sqd, sd, L, s, Rt, Z);

@@ -205,6 +205,33 @@ def scenesRedMax(sceneID, api=None):
                 j.q[1] = math.pi / 8
             scene.bodies.append(b)
             scene.joints.append(j)
+    elif sceneID == 10:  # :261
+        scene.name = 'Loop'
+        scene.Hexpected[:] = [1.2376477982839792e+03, 4.1146190850293169e+03]
+        bs = [api.BodyCuboid(density, [20, 1, 1]), api.BodyCuboid(density, [1, 1, 10]), api.BodyCuboid(density, [1, 1, 10]),
+              api.BodyCuboid(density, [20, 1, 1]), api.BodyCuboid(density, [1, 1, 10])]
+        j1 = api.JointFixed(None, bs[0])
+        j2 = api.JointRevolute(j1, bs[1], [0, 1, 0])
+        j3 = api.JointRevolute(j1, bs[2], [0, 1, 0])
+        j4 = api.JointRevolute(j2, bs[3], [0, 1, 0])
+        j5 = api.JointRevolute(j4, bs[4], [0, 1, 0])
+        bs[0].setBodyTransform(np.eye(4))
+        bs[1].setBodyTransform(_trans([0, 0, -5]))
+        bs[2].setBodyTransform(_trans([0, 0, -5]))
+        bs[3].setBodyTransform(_trans([10, 0, 0]))
+        bs[4].setBodyTransform(_trans([0, 0, -5]))
+        j1.setJointTransform(np.eye(4))
+        j2.setJointTransform(_trans([-10, 0, 0]))
+        j3.setJointTransform(_trans([10, 0, 0]))
+        j4.setJointTransform(_trans([0, 0, -10]))
+        j5.setJointTransform(_trans([10, 0, 0]))
+        f = api.ForcePointPoint(bs[2], [0, 0, -5], bs[3], [10, 0, 0])
+        f.setStiffness(1e7)
+        f.setDamping(0)
+        j5.qdot[0] = 5
+        scene.bodies = bs
+        scene.joints = [j1, j2, j3, j4, j5]
+        scene.forces = [f]
     elif sceneID == 14:  # :371
         scene.name = 'Joint limits'
         scene.Hexpected[:] = [-2.5928305306546572e+04, -1.8476279319765570e+04]
