@@ -66,6 +66,7 @@ extern "C" {
 #define RMX_ST_MAXITER 2   /* 'Newton did not converge'    (iter >= iterMax) in some step */
 #define RMX_ST_LSFAIL 4    /* line search exhausted iterLsMax halvings in some step (silent in reference) */
 #define RMX_ST_NAN 8       /* non-finite state produced */
+#define RMX_ST_SCHED 16    /* internal: a load-balanced rollout never received its first part (should not happen) */
 
 /* tau layout for rmx_rollout */
 #define RMX_TAU_NONE 0     /* tau == NULL: joint.tau = 0 */

@@ -38,13 +38,24 @@ struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
 };
+// Load-balancing plan of a forward launch (see RolloutArgs::seg): cached per device for the last (B, nsteps, slots)
+struct SchedPlan {
+    long long B = -1;
+    int nsteps = -1;
+    long long slots = -1;
+    std::vector<int4> seg;
+    std::vector<int> off;
+};
+
 struct DevCopy {
+    SchedPlan plan;
     JointConst* jc = nullptr;
     int* ends = nullptr;
     int* anc = nullptr;
     unsigned long long* kry = nullptr;  // Krylov iteration counter
     cudaStream_t stream = nullptr;
     DevBuf buf[16];
+    void* plan_dev = nullptr;  // device copy of `plan` currently in buf[13]/buf[14]
 };
 
 struct rmx_scene {
@@ -464,12 +475,78 @@ static int set_smem(K kernel, size_t bytes) {
     return RMX_OK;
 }
 
+
+static bool sched_enabled() {
+    const char* e = std::getenv("RMX_SCHED");  // developer switch: RMX_SCHED=0 launches one block per rollout
+    return !(e && e[0] == '0');
+}
+
+// McNaughton wrap-around schedule of B rollouts x nsteps steps over `slots` co-resident blocks: every block gets
+// T = ceil(B nsteps / slots) steps; a rollout that does not fit the rest of a block's quota is cut there -- its LAST steps fill
+// the tail of that block (and wait), its FIRST steps open the next block's list (and signal).  nsteps <= T, so the two
+// parts never overlap in time.
+static void build_plan(SchedPlan& p, long long B, int nsteps, long long slots) {
+    p.B = B;
+    p.nsteps = nsteps;
+    p.slots = slots;
+    p.seg.clear();
+    p.off.assign((size_t)slots + 1, 0);
+    const long long T = (B * nsteps + slots - 1) / slots;
+    long long m = 0, t = 0;
+    for (long long b = 0; b < B; ++b) {
+        if (t + nsteps <= T) {
+            p.seg.push_back(make_int4((int)b, 0, nsteps, 0));
+            t += nsteps;
+            if (t == T && b + 1 < B) {
+                p.off[++m] = (int)p.seg.size();
+                t = 0;
+            }
+        } else {
+            const int d = (int)(T - t), first = nsteps - d;
+            p.seg.push_back(make_int4((int)b, first, nsteps, 1));
+            p.off[++m] = (int)p.seg.size();
+            p.seg.push_back(make_int4((int)b, 0, first, 2));
+            t = first;
+        }
+    }
+    for (long long k = m + 1; k <= slots; ++k) p.off[k] = (int)p.seg.size();
+}
+
 template <int NW, bool GROUND, bool ADJ, int IMPL, int LIN = 0>
-static int launch_fwd_t(const RolloutArgs& a, size_t smem, cudaStream_t st) {
-    int rc = set_smem(rollout_fwd_kernel<NW, GROUND, ADJ, IMPL, LIN>, smem);
+static int launch_fwd_t(const RolloutArgs& a0, size_t smem, cudaStream_t st, DevCopy* dc = nullptr) {
+    auto kernel = rollout_fwd_kernel<NW, GROUND, ADJ, IMPL, LIN>;
+    int rc = set_smem(kernel, smem);
     if (rc) return rc;
-    const long long grid = a.B;
-    rollout_fwd_kernel<NW, GROUND, ADJ, IMPL, LIN><<<(unsigned)grid, 32 * NW, smem, st>>>(a);
+    RolloutArgs a = a0;
+    long long grid = a.B;
+    if (!ADJ && LIN == 0 && dc && a.qd_out && a.op.nsteps >= 2 && a.B < (1ll << 30) && sched_enabled()) {
+        int nb = 0, dev = 0, sms = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, 32 * NW, smem));
+        CUDA_TRY(cudaGetDevice(&dev));
+        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const long long slots = (long long)nb * sms;
+        if (slots > 0 && a.B > slots && a.B % slots != 0) {
+            SchedPlan& p = dc->plan;
+            const bool fresh = !(p.B == a.B && p.nsteps == a.op.nsteps && p.slots == slots);
+            if (fresh) build_plan(p, a.B, a.op.nsteps, slots);
+            const size_t sb = p.seg.size() * sizeof(int4), ob = p.off.size() * sizeof(int), fb = (size_t)a.B * sizeof(int);
+            if ((rc = dev_reserve(dc->buf[13], sb)) || (rc = dev_reserve(dc->buf[14], ob)) || (rc = dev_reserve(dc->buf[15], fb)))
+                return rc;
+            if (fresh || dc->plan_dev != dc->buf[13].p) {
+                CUDA_TRY(cudaMemcpyAsync(dc->buf[13].p, p.seg.data(), sb, cudaMemcpyHostToDevice, st));
+                CUDA_TRY(cudaMemcpyAsync(dc->buf[14].p, p.off.data(), ob, cudaMemcpyHostToDevice, st));
+                dc->plan_dev = dc->buf[13].p;
+            }
+            CUDA_TRY(cudaMemsetAsync(dc->buf[15].p, 0, fb, st));
+            CUDA_TRY(cudaMemsetAsync(a.status, 0, (size_t)a.B * sizeof(int), st));
+            if (a.iters) CUDA_TRY(cudaMemsetAsync(a.iters, 0, 2 * (size_t)a.B * sizeof(int), st));
+            a.seg = (const int4*)dc->buf[13].p;
+            a.seg_off = (const int*)dc->buf[14].p;
+            a.flags = (int*)dc->buf[15].p;
+            grid = slots;
+        }
+    }
+    kernel<<<(unsigned)grid, 32 * NW, smem, st>>>(a);
     CUDA_TRY(cudaGetLastError());
     return RMX_OK;
 }
@@ -486,18 +563,18 @@ static int launch_fwd_pcg(const rmx_scene* s, const RolloutArgs& a, cudaStream_t
 }
 
 template <bool ADJ>
-static int launch_fwd(const rmx_scene* s, const RolloutArgs& a, cudaStream_t st) {
+static int launch_fwd(const rmx_scene* s, const RolloutArgs& a, cudaStream_t st, DevCopy* dc = nullptr) {
     const int nw = warps_for(s);
     const bool g = s->has_ground != 0;
     const size_t smem = (scene_smem_doubles(s, ADJ) + (ADJ ? 6 * (size_t)s->nr : 0)) * sizeof(double);
     if (smem > 227 * 1024) return fail(RMX_ELIMIT, "scene does not fit the 227 KB shared memory of one SM");
     if (s->impl == 2) {
-        if (nw == 1) return g ? launch_fwd_t<1, true, ADJ, 2>(a, smem, st) : launch_fwd_t<1, false, ADJ, 2>(a, smem, st);
-        return g ? launch_fwd_t<2, true, ADJ, 2>(a, smem, st) : launch_fwd_t<2, false, ADJ, 2>(a, smem, st);
+        if (nw == 1) return g ? launch_fwd_t<1, true, ADJ, 2>(a, smem, st, dc) : launch_fwd_t<1, false, ADJ, 2>(a, smem, st, dc);
+        return g ? launch_fwd_t<2, true, ADJ, 2>(a, smem, st, dc) : launch_fwd_t<2, false, ADJ, 2>(a, smem, st, dc);
     }
-    if (nw == 1) return g ? launch_fwd_t<1, true, ADJ, 1>(a, smem, st) : launch_fwd_t<1, false, ADJ, 1>(a, smem, st);
-    if (nw == 2) return g ? launch_fwd_t<2, true, ADJ, 1>(a, smem, st) : launch_fwd_t<2, false, ADJ, 1>(a, smem, st);
-    return g ? launch_fwd_t<4, true, ADJ, 1>(a, smem, st) : launch_fwd_t<4, false, ADJ, 1>(a, smem, st);
+    if (nw == 1) return g ? launch_fwd_t<1, true, ADJ, 1>(a, smem, st, dc) : launch_fwd_t<1, false, ADJ, 1>(a, smem, st, dc);
+    if (nw == 2) return g ? launch_fwd_t<2, true, ADJ, 1>(a, smem, st, dc) : launch_fwd_t<2, false, ADJ, 1>(a, smem, st, dc);
+    return g ? launch_fwd_t<4, true, ADJ, 1>(a, smem, st, dc) : launch_fwd_t<4, false, ADJ, 1>(a, smem, st, dc);
 }
 
 extern "C" int rmx_rollout_dev(rmx_scene* s, const rmx_opts* o, int64_t B, const double* q0, const double* qdot0,
@@ -533,7 +610,7 @@ extern "C" int rmx_rollout_dev(rmx_scene* s, const rmx_opts* o, int64_t B, const
         if (!seen) s->kry_devs.push_back(dev);
         return launch_fwd_pcg(s, a, (cudaStream_t)cuda_stream);
     }
-    return launch_fwd<false>(s, a, (cudaStream_t)cuda_stream);
+    return launch_fwd<false>(s, a, (cudaStream_t)cuda_stream, dc);
 }
 
 // Host-pointer entry: shards the batch contiguously over o->ngpus devices (no communication during the rollout),

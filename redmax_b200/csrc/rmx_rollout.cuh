@@ -49,6 +49,13 @@ struct RolloutArgs {
     TapeArgs tape;
     TaskArgs task;
     unsigned long long* kry_total;  // total Krylov iterations of the launch (LIN == 1) or null
+    // Segment schedule (forward kernels, optional): block s runs segments seg[seg_off[s] .. seg_off[s+1]), each
+    // {rollout, first step, end step, bit0: wait for flags[rollout] / bit1: set it when done}.  A rollout is cut at most once,
+    // its first part at the head of one block's list, its second part at the tail of the previous block's list (McNaughton's
+    // wrap-around rule), so all blocks finish together instead of leaving a partial last wave.  Null: one block per rollout.
+    const int4* seg;
+    const int* seg_off;
+    int* flags;
 };
 
 __device__ __forceinline__ int krylov_count(const Ctx&) { return 0; }
@@ -368,22 +375,60 @@ __global__ void RMX_FWD_BOUNDS rollout_fwd_kernel(RolloutArgs a) {
     const double ah = __dmul_rn(SDIRK_A_CONST, h);
     const double bh = __dmul_rn(__dsub_rn(1.0, SDIRK_A_CONST), h);
 
-    for (long long b = blockIdx.x; b < a.B; b += gridDim.x) {
+    constexpr bool CAN_SCHED = !ADJ && LIN == 0;
+    const bool sched = CAN_SCHED && a.seg != nullptr;
+    long long it = sched ? (long long)a.seg_off[blockIdx.x] : (long long)blockIdx.x;
+    const long long it_end = sched ? (long long)a.seg_off[blockIdx.x + 1] : a.B;
+    const long long it_step = sched ? 1 : (long long)gridDim.x;
+    for (; it < it_end; it += it_step) {
+        long long b = it;
+        int k_begin = 0, k_end = op.nsteps, seg_flags = 0;
+        if (sched) {
+            const int4 sg = __ldg(a.seg + it);
+            b = sg.x;
+            k_begin = sg.y;
+            k_end = sg.z;
+            seg_flags = sg.w;
+        }
         double qc = 0.0, qdc = 0.0;  // current state of dof t (joint.q / joint.qdot)
         double q0t = 0.0, qd0t = 0.0, q1t = 0.0, qdat = 0.0;
+        int status = 0, n_iter = 0, n_ls = 0;
+        if (CAN_SCHED && (seg_flags & 1)) {
+            // second part of a cut rollout: wait until the block that runs the first part has published it (bounded spin: a
+            // lost signal becomes a status bit, never a hang), then resume from the trajectory already in global memory
+            if (t == 0) {
+                unsigned spins = 0;
+                while (atomicAdd(a.flags + b, 0) == 0 && ++spins < (1u << 26)) __nanosleep(200);
+                if (spins >= (1u << 26)) status |= 16;
+            }
+            bsync<NW>();
+            __threadfence();
+        }
         if (t < nr) {
-            qc = a.q0[b * nr + t];
-            qdc = a.qd0[b * nr + t];
+            if (CAN_SCHED && k_begin > 0) {
+                const size_t o1 = ((size_t)b * op.nsteps + (k_begin - 1)) * nr + t;
+                qc = __ldcg(a.q_out + o1);
+                qdc = __ldcg(a.qd_out + o1);
+                if (k_begin > 1) {  // BDF2 history: the state two steps back
+                    c.hq1[t] = __ldcg(a.q_out + o1 - nr);
+                    c.hqd1[t] = __ldcg(a.qd_out + o1 - nr);
+                } else {            // after the SDIRK2 first step the history is the initial state (driverRedMaxBDF2.m:86-91)
+                    c.hq1[t] = a.q0[b * nr + t];
+                    c.hqd1[t] = a.qd0[b * nr + t];
+                }
+            } else {
+                qc = a.q0[b * nr + t];
+                qdc = a.qd0[b * nr + t];
+                c.hq1[t] = qc;
+                c.hqd1[t] = qdc;
+            }
             if (ADJ)  // task.applyStep: joints{i}.tau = pscale*p(idxR)   (TaskBDF1PointPos.m:58-64)
                 c.tau[t] = __dmul_rn(a.task.pscale, a.task.p[b * nr + t]);
             else
                 c.tau[t] = (op.tau_mode == 1) ? a.tau[b * nr + t] : 0.0;
-            c.hq1[t] = qc;
-            c.hqd1[t] = qdc;
         }
-        int status = 0, n_iter = 0, n_ls = 0;
         double tcur = 0.0, Pacc = 0.0;  // scene.t (Scene.m:122), task.P
-        for (int k = 0; k < op.nsteps; ++k) {
+        for (int k = k_begin; k < k_end; ++k) {
             if (!ADJ && op.tau_mode == 2 && t < nr) c.tau[t] = a.tau[((size_t)b * op.nsteps + k) * nr + t];
             // scene.t after this step; TaskBDF1PointPos.calcStep samples the objective when |t_target - t| < 1e-6
             const double tnext = __dadd_rn(tcur, h);
@@ -487,11 +532,24 @@ __global__ void RMX_FWD_BOUNDS rollout_fwd_kernel(RolloutArgs a) {
         double bad = (t < nr && !(isfinite(qc) && isfinite(qdc))) ? 1.0 : 0.0;
         bad = block_sum<NW>(bad, c.red);
         if (bad > 0.0) status |= 8;
+        if (CAN_SCHED && (seg_flags & 2)) {  // first part of a cut rollout: publish the trajectory written so far
+            __threadfence();
+            bsync<NW>();
+            if (t == 0) atomicExch(a.flags + b, 1);
+        }
         if (t == 0) {
-            a.status[b] = status;
-            if (a.iters) {
-                a.iters[2 * b] = n_iter;
-                a.iters[2 * b + 1] = n_ls;
+            if (sched) {  // a rollout may arrive in two parts: accumulate (status / iters are zeroed before the launch)
+                if (status) atomicOr(a.status + b, status);
+                if (a.iters) {
+                    atomicAdd(a.iters + 2 * b, n_iter);
+                    atomicAdd(a.iters + 2 * b + 1, n_ls);
+                }
+            } else {
+                a.status[b] = status;
+                if (a.iters) {
+                    a.iters[2 * b] = n_iter;
+                    a.iters[2 * b + 1] = n_ls;
+                }
             }
             if (ADJ) a.task.P[b] = Pacc;  // objective part; the regulariser is added by the backward kernel
             if (LIN == 1 && IMPL == 2 && a.kry_total) {

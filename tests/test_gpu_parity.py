@@ -229,3 +229,23 @@ def test_newton_system_through_the_rollout_path(rb, oracle, name, mk):
         back = np.linalg.norm(H @ out['dx'] + g) / (np.linalg.norm(H, 2) * np.linalg.norm(out['dx']) + np.linalg.norm(g))
         assert back < 1e-14, back
         assert rel_err(out['dx'], dx) < 1e-12 * max(10.0, np.linalg.cond(H)), (rel_err(out['dx'], dx), np.linalg.cond(H))
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize('scheme', [1, 2])
+def test_load_balanced_schedule_is_bitwise_identical(rb, scheme):
+    """More rollouts than co-resident blocks, and not a multiple of them: the launch cuts rollouts across blocks (McNaughton
+    wrap-around schedule, second part resumes from the trajectory in global memory).  Every trajectory, status and iteration
+    count must equal the one-block-per-rollout launches bit for bit."""
+    sg = rb.chain_scene(8, nsteps=9, h=1e-3)
+    sg.init()
+    B = 3001
+    q0, qd0 = rb.synthetic_inputs(sg, B, seed=99)
+    out = sg.rollout(q0, qd0, scheme=scheme)
+    assert (out['status'] == 0).all()
+    for lo in range(0, B, 500):  # 500 rollouts fit the resident blocks: plain launches
+        ref = sg.rollout(q0[lo:lo + 500], qd0[lo:lo + 500], scheme=scheme)
+        np.testing.assert_array_equal(out['q'][lo:lo + 500], ref['q'])
+        np.testing.assert_array_equal(out['qdot'][lo:lo + 500], ref['qdot'])
+        np.testing.assert_array_equal(out['iters'][lo:lo + 500], ref['iters'])
+        np.testing.assert_array_equal(out['status'][lo:lo + 500], ref['status'])
