@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RMX_VERSION 102
+#define RMX_VERSION 103
 
 /* error codes */
 #define RMX_OK 0
@@ -50,6 +50,7 @@ extern "C" {
 #define RMX_JOINT_FREE2D 5        /* JointFree2D.m         [3] translation x, y then rotation about z */
 #define RMX_JOINT_UNIVERSAL 6     /* JointUniversal.m      [2] rotation about x then y */
 #define RMX_MAX_JOINT_DOF 3
+#define RMX_MAX_POINTFORCE 8
 
 /* integrators (driverRedMaxBDF1.m, driverRedMaxBDF2.m) */
 #define RMX_SCHEME_BDF1 1
@@ -75,7 +76,8 @@ extern "C" {
 
 /*
  * Flattened +redmax scene (what scenesRedMax.m builds with redmax.Scene / BodyCuboid / JointRevolute / JointFixed /
- * JointPrismatic / JointPlanar / JointTranslational / JointFree2D / JointUniversal / ForceGroundCuboid after
+ * JointPrismatic / JointPlanar / JointTranslational / JointFree2D / JointUniversal / ForceGroundCuboid /
+ * ForcePointPoint after
  * scene.init(), Scene.m:59-119).  All pointers are host pointers and are
  * copied by rmx_scene_create.
  */
@@ -107,6 +109,13 @@ typedef struct rmx_scene_desc {
     const double* ground_kt; /* [nground] tangential stiffness */
     const double* ground_kd; /* [nground] damping                      (ForceGroundCuboid.m:40) */
     const double* ground_mu; /* [nground] friction coefficient         (ForceGroundCuboid.m:45) */
+    int32_t npointforce;     /* number of ForcePointPoint forces (at most RMX_MAX_POINTFORCE) */
+    const int32_t* pf_body1; /* [npointforce] body (== joint) index or -1 for the world (ForcePointPoint.m:15) */
+    const int32_t* pf_body2; /* [npointforce] */
+    const double* pf_x1;     /* [3*npointforce] application point in body-1 (or world) coordinates */
+    const double* pf_x2;     /* [3*npointforce] */
+    const double* pf_ks;     /* [npointforce] stiffness (ForcePointPoint.m:37) */
+    const double* pf_kd;     /* [npointforce] damping   (ForcePointPoint.m:42) */
 } rmx_scene_desc;
 
 /* Solver constants hard-coded in the reference's newton() (driverRedMaxBDF1.m:95-98;

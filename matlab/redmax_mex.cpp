@@ -96,6 +96,19 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         sd.qLimK = mxGetDoubles(field(d, "qLimK"));
         sd.qLimD = mxGetDoubles(field(d, "qLimD"));
         std::memcpy(sd.grav, mxGetDoubles(field(d, "grav")), 3 * sizeof(double));
+        std::vector<int32_t> pfb1, pfb2;
+        const mxArray* pf1 = field(d, "pf_body1", false);
+        if (pf1 && mxGetNumberOfElements(pf1) > 0) {
+            pfb1 = to_i32(pf1);
+            pfb2 = to_i32(field(d, "pf_body2"));
+            sd.npointforce = (int32_t)pfb1.size();
+            sd.pf_body1 = pfb1.data();
+            sd.pf_body2 = pfb2.data();
+            sd.pf_x1 = mxGetDoubles(field(d, "pf_x1"));  // 3 x npointforce
+            sd.pf_x2 = mxGetDoubles(field(d, "pf_x2"));
+            sd.pf_ks = mxGetDoubles(field(d, "pf_ks"));
+            sd.pf_kd = mxGetDoubles(field(d, "pf_kd"));
+        }
         const mxArray* gb = field(d, "ground_body", false);
         if (gb && mxGetNumberOfElements(gb) > 0) {
             gbody = to_i32(gb);

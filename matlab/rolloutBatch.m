@@ -51,14 +51,28 @@ for i = 1 : n
 end
 d.grav = scene.grav;
 gb = []; gE = zeros(4,4,0); kn = []; kt = []; kd = []; mu = [];
+pb1 = []; pb2 = []; px1 = zeros(3,0); px2 = zeros(3,0); pks = []; pkd = [];
 for i = 1 : length(scene.forces)
 	f = scene.forces{i};
 	if isa(f,'redmax.ForceGroundCuboid')
 		gb(end+1) = find(cellfun(@(x) x == f.cuboid, scene.bodies)) - 1; %#ok<AGROW>
 		gE(:,:,end+1) = f.E; kn(end+1) = f.kn; kt(end+1) = f.kt; kd(end+1) = f.kd; mu(end+1) = f.mu; %#ok<AGROW>
+	elseif isa(f,'redmax.ForcePointPoint')
+		pb1(end+1) = bodyIndex(scene,f.body1); pb2(end+1) = bodyIndex(scene,f.body2); %#ok<AGROW>
+		px1(:,end+1) = f.x_1; px2(:,end+1) = f.x_2; pks(end+1) = f.stiffness; pkd(end+1) = f.damping; %#ok<AGROW>
 	elseif ~isa(f,'redmax.ForceNull')
-		error('only ForceGroundCuboid is on the GPU hot path');
+		error('only ForceGroundCuboid and ForcePointPoint are on the GPU hot path');
 	end
 end
+d.pf_body1 = pb1; d.pf_body2 = pb2; d.pf_x1 = px1; d.pf_x2 = px2; d.pf_ks = pks; d.pf_kd = pkd;
 d.ground_body = gb; d.ground_E = gE; d.ground_kn = kn; d.ground_kt = kt; d.ground_kd = kd; d.ground_mu = mu;
+end
+
+function i = bodyIndex(scene,body)
+% 0-based body index, -1 for the world (empty body)
+if isempty(body)
+	i = -1;
+else
+	i = find(cellfun(@(x) x == body, scene.bodies)) - 1;
+end
 end

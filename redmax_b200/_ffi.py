@@ -51,6 +51,8 @@ class rmx_scene_desc(C.Structure):
         ('nground', C.c_int32),
         ('ground_body', _pi), ('ground_E', _pd),
         ('ground_kn', _pd), ('ground_kt', _pd), ('ground_kd', _pd), ('ground_mu', _pd),
+        ('npointforce', C.c_int32),
+        ('pf_body1', _pi), ('pf_body2', _pi), ('pf_x1', _pd), ('pf_x2', _pd), ('pf_ks', _pd), ('pf_kd', _pd),
     ]
 
 

@@ -231,6 +231,24 @@ __global__ void __launch_bounds__(32 * NW) energies_kernel(EnergyArgs a) {
                 }
             }
         }
+        if (GROUND && t < c.npf) {  // ForcePointPoint.computeEnergy_ (ForcePointPoint.m:116-132): V += ks/2 |x2_w - x1_w|^2
+            const PointForce& P = c.pf[t];
+            double xw[2][3];
+#pragma unroll
+            for (int sd = 0; sd < 2; ++sd) {
+                const double xl[3] = {P.x[sd][0], P.x[sd][1], P.x[sd][2]};
+                if (P.body[sd] >= 0) {
+                    double rb[12];
+                    E::body_frame(c, P.body[sd], rb, rb + 9);
+                    mat3_vec(rb, xl, xw[sd]);
+                    xw[sd][0] += rb[9]; xw[sd][1] += rb[10]; xw[sd][2] += rb[11];
+                } else {
+                    xw[sd][0] = xl[0]; xw[sd][1] = xl[1]; xw[sd][2] = xl[2];
+                }
+            }
+            const double d0 = xw[1][0] - xw[0][0], d1 = xw[1][1] - xw[0][1], d2 = xw[1][2] - xw[0][2];
+            V += 0.5 * P.ks * (d0 * d0 + d1 * d1 + d2 * d2);
+        }
         T = block_sum<NW>(T, c.red);
         V = block_sum<NW>(V, c.red);
         if (t == 0) {

@@ -52,6 +52,8 @@ struct DevCopy {
     JointConst* jc = nullptr;
     int* ends = nullptr;
     int* anc = nullptr;
+    PointForce* pf = nullptr;
+    int* pf_ep = nullptr;
     unsigned long long* kry = nullptr;  // Krylov iteration counter
     cudaStream_t stream = nullptr;
     DevBuf buf[16];
@@ -66,6 +68,8 @@ struct rmx_scene {
     std::vector<int> ends_list;
     std::vector<int> user2int;    // expanded (virtual) joint index -> internal (preorder) index
     std::vector<int> body2int;    // user joint/body index -> internal index of the virtual joint that carries the body
+    std::vector<PointForce> pf;   // ForcePointPoint forces (internal body indices)
+    std::vector<int> pf_ep;       // per-body endpoint lists (JointConst::pf_ptr / pf_cnt), entry = 2*force + side
     std::vector<int> anc;         // [nrounds][n] 2^r-th ancestors (internal indices) for the pointer-jumping scans
     int nrounds = 0;
     int impl = 2;                 // 1 = sweep kernels (rmx_device.cuh), 2 = composite kernels (rmx_fast.cuh)
@@ -368,6 +372,49 @@ extern "C" int rmx_scene_create(const rmx_scene_desc* d, rmx_scene** out) {
     }
     s->body2int.assign(n_user, -1);
     for (int j = 0; j < n_user; ++j) s->body2int[j] = s->user2int[x.body_of_user[j]];
+    // ForcePointPoint forces
+    if (d->npointforce < 0 || d->npointforce > RMX_MAX_POINTFORCE) {
+        delete s;
+        return fail(RMX_ELIMIT, "rmx_scene_create: at most RMX_MAX_POINTFORCE point forces");
+    }
+    if (d->npointforce > 0) {
+        if (!d->pf_body1 || !d->pf_body2 || !d->pf_x1 || !d->pf_x2 || !d->pf_ks || !d->pf_kd) {
+            delete s;
+            return fail(RMX_EINVAL, "rmx_scene_create: missing point-force array");
+        }
+        if (s->impl != 2) {
+            delete s;
+            return fail(RMX_ELIMIT, "rmx_scene_create: point forces need the composite kernels (at most 64 virtual joints)");
+        }
+        std::vector<std::vector<int>> ep(n);
+        for (int f = 0; f < d->npointforce; ++f) {
+            PointForce P;
+            const int ub[2] = {d->pf_body1[f], d->pf_body2[f]};
+            for (int sd = 0; sd < 2; ++sd) {
+                if (ub[sd] < -1 || ub[sd] >= n_user) {
+                    delete s;
+                    return fail(RMX_EINVAL, "rmx_scene_create: point-force body out of range");
+                }
+                P.body[sd] = ub[sd] < 0 ? -1 : s->body2int[ub[sd]];
+                const double* xs = (sd ? d->pf_x2 : d->pf_x1) + 3 * f;
+                for (int i = 0; i < 3; ++i) P.x[sd][i] = xs[i];
+                if (P.body[sd] >= 0) ep[P.body[sd]].push_back(2 * f + sd);
+            }
+            if (P.body[0] >= 0 && P.body[0] == P.body[1]) {
+                delete s;
+                return fail(RMX_EINVAL, "rmx_scene_create: a point force must connect two different bodies (or a body and the world)");
+            }
+            P.ks = d->pf_ks[f];
+            P.kd = d->pf_kd[f];
+            s->pf.push_back(P);
+        }
+        for (int k = 0; k < n; ++k) {
+            s->jc[k].pf_ptr = (int)s->pf_ep.size();
+            s->jc[k].pf_cnt = (int)ep[k].size();
+            for (int e : ep[k]) s->pf_ep.push_back(e);
+        }
+        s->has_ground = 1;  // external-force fields (AEXT / CEXT) of the composite kernels
+    }
     *out = s;
     return RMX_OK;
 }
@@ -381,6 +428,8 @@ extern "C" void rmx_scene_destroy(rmx_scene* s) {
         cudaFree(kv.second.jc);
         cudaFree(kv.second.ends);
         cudaFree(kv.second.anc);
+        cudaFree(kv.second.pf);
+        cudaFree(kv.second.pf_ep);
         cudaFree(kv.second.kry);
         for (auto& b : kv.second.buf) cudaFree(b.p);
         if (kv.second.stream) cudaStreamDestroy(kv.second.stream);
@@ -402,6 +451,14 @@ static int scene_on_device(rmx_scene* s, int dev, DevCopy** out) {
         CUDA_TRY(cudaMemcpy(dc.ends, s->ends_list.data(), sizeof(int) * s->ends_list.size(), cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMalloc(&dc.anc, sizeof(int) * s->anc.size()));
         CUDA_TRY(cudaMemcpy(dc.anc, s->anc.data(), sizeof(int) * s->anc.size(), cudaMemcpyHostToDevice));
+        if (!s->pf.empty()) {
+            CUDA_TRY(cudaMalloc(&dc.pf, sizeof(PointForce) * s->pf.size()));
+            CUDA_TRY(cudaMemcpy(dc.pf, s->pf.data(), sizeof(PointForce) * s->pf.size(), cudaMemcpyHostToDevice));
+            const size_t ne = s->pf_ep.empty() ? 1 : s->pf_ep.size();
+            CUDA_TRY(cudaMalloc(&dc.pf_ep, sizeof(int) * ne));
+            if (!s->pf_ep.empty())
+                CUDA_TRY(cudaMemcpy(dc.pf_ep, s->pf_ep.data(), sizeof(int) * s->pf_ep.size(), cudaMemcpyHostToDevice));
+        }
         CUDA_TRY(cudaMalloc(&dc.kry, sizeof(unsigned long long)));
         CUDA_TRY(cudaMemset(dc.kry, 0, sizeof(unsigned long long)));
         CUDA_TRY(cudaStreamCreateWithFlags(&dc.stream, cudaStreamNonBlocking));
@@ -432,6 +489,9 @@ static DevScene make_devscene(const rmx_scene* s, const DevCopy* dc) {
     ds.ends_list = dc->ends;
     ds.anc = dc->anc;
     ds.nrounds = s->nrounds;
+    ds.pf = dc->pf;
+    ds.pf_ep = dc->pf_ep;
+    ds.npf = (int)s->pf.size();
     return ds;
 }
 
@@ -444,7 +504,9 @@ static int warps_for(const rmx_scene* s) {
 
 static size_t scene_smem_doubles(const rmx_scene* s, bool keep = true) {
     const bool g = s->has_ground != 0;
-    return s->impl == 2 ? smem_doubles2(s->n, s->nr, g, keep) : smem_doubles(s->n, s->nr, g);
+    if (s->impl != 2) return smem_doubles(s->n, s->nr, g);
+    if (!s->pf.empty()) return pf_offset_doubles(s->n, s->nr, g, keep) + s->pf.size() * (size_t)PF_DOUBLES;
+    return smem_doubles2(s->n, s->nr, g, keep);
 }
 
 static int check_opts(const rmx_scene* s, const rmx_opts* o, StepOpts* so, int adjoint) {
@@ -556,7 +618,7 @@ static int launch_fwd_pcg(const rmx_scene* s, const RolloutArgs& a, cudaStream_t
     if (s->impl != 2) return fail(RMX_ELIMIT, "linsolve=PCG needs the composite kernels (n <= 64 joints)");
     const int nw = warps_for(s);
     const bool g = s->has_ground != 0;
-    const size_t smem = (smem_doubles2(s->n, s->nr, g, true) + pcg_doubles(s->n, s->nr)) * sizeof(double);
+    const size_t smem = (scene_smem_doubles(s, true) + pcg_doubles(s->n, s->nr)) * sizeof(double);
     if (smem > 227 * 1024) return fail(RMX_ELIMIT, "scene does not fit the 227 KB shared memory of one SM");
     if (nw == 1) return g ? launch_fwd_t<1, true, false, 2, 1>(a, smem, st) : launch_fwd_t<1, false, false, 2, 1>(a, smem, st);
     return g ? launch_fwd_t<2, true, false, 2, 1>(a, smem, st) : launch_fwd_t<2, false, false, 2, 1>(a, smem, st);

@@ -47,9 +47,22 @@ struct JointConst {
     int axsign;     // +1 / -1
     int has_ground;
     int prismatic;  // 1: Q = trans(axis q), S = [0; axis] (JointPrismatic.m:28-34); 0: revolute (or fixed if idx < 0)
+    int pf_ptr;     // CSR into DevScene.pf_ep: point-force endpoints attached to this body (entry = 2*force + side)
+    int pf_cnt;
     int ends_ptr;   // CSR into DevScene.ends_list: joints k whose subtree ends exactly at this index
     int ends_cnt;
 };
+
+// ForcePointPoint (matlab-diff/+redmax/ForcePointPoint.m): linear zero-rest-length spring / damper between two body points
+struct PointForce {
+    int body[2];      // internal joint index of body 1 / body 2, -1 = world
+    double x[2][3];   // application points in body (or world) coordinates
+    double ks, kd;
+};
+constexpr int PF_MAX = 8;        // point forces per scene (shared-memory scratch is sized for this)
+constexpr int PF_REC = 18;       // published per endpoint: R[9] p[3] phi[6]
+constexpr int PF_BLK = 72;       // per ordered pair: Aext_ab[36], Cext_ab[36] (world frame, row-major)
+constexpr int PF_DOUBLES = 2 * (PF_REC + PF_BLK);  // shared-memory doubles per point force
 
 struct DevScene {
     int n, nr;
@@ -60,6 +73,9 @@ struct DevScene {
     const int* ends_list;
     const int* anc;   // [nrounds][n] 2^r-th ancestor of joint j or -1 (pointer-jumping scans of the fast path)
     int nrounds;
+    const PointForce* pf;  // [npf]
+    const int* pf_ep;      // endpoint lists (see JointConst::pf_ptr)
+    int npf;
 };
 
 struct StepOpts {
@@ -244,6 +260,11 @@ struct Ctx {
     double* sp2;
     double* H;
     double* red;  // reduction scratch [16]
+    // point forces (composite kernels only)
+    const PointForce* __restrict__ pf;
+    const int* __restrict__ pf_ep;
+    int npf;
+    double* pf_s;  // [npf][PF_DOUBLES]: endpoint records, then cross blocks
     // stage coefficients
     int stage;
     double h;

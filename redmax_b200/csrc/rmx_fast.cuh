@@ -237,6 +237,188 @@ __device__ __forceinline__ void xtmx_store(double* sa, int NS, int fld, int j, c
 }
 
 // ---------------------------------------------------------------------------------------------
+// ForcePointPoint (ForcePointPoint.m:48-113) in the composite formulation (prototype: tools/proto_pointforce.py).
+// The force on "me" (a body point xl) from the other end is f = ks (xw_o - xw_me) + kd (vw_o - vw_me); its body-frame wrench and
+// the diagonal blocks Km_aa, Dm_aa go where ground contact goes (fb, K, D); the off-diagonal blocks are kept per ordered pair as
+// world-frame 6x6 matrices Aext_ab = -c X_a' Dm_ab X_b, Cext_ab = -c X_a' Km_ab X_b for the cross-term pass of the assembly.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pf_point(const double* R, const double* p, const double* phi, const double* xl, double* xw, double* vl,
+                                         double* vw) {
+    mat3_vec(R, xl, xw);
+    xw[0] += p[0]; xw[1] += p[1]; xw[2] += p[2];
+    cross3(phi, xl, vl);  // Gamma(xl) phi = w x xl + v
+    vl[0] += phi[3]; vl[1] += phi[4]; vl[2] += phi[5];
+    mat3_vec(R, vl, vw);
+}
+
+// dst (row-major 6x6) = scale * X_a' M X_o,  X = Ad(E^-1)
+__device__ __forceinline__ void xtmy_store(double* dst, const double* Ra, const double* pa, const double* Ro, const double* po,
+                                           const double* M, double scale) {
+#pragma unroll
+    for (int m = 0; m < 6; ++m) {
+        double e[6] = {0, 0, 0, 0, 0, 0}, xe[6], y[6], wv[6];
+        e[m] = 1.0;
+        xm_w2b(Ro, po, e, xe);
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            double acc = 0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) acc += M[6 * r + k] * xe[k];
+            y[r] = acc;
+        }
+        xf_b2w(Ra, pa, y, wv);
+#pragma unroll
+        for (int r = 0; r < 6; ++r) dst[6 * r + m] = scale * wv[r];
+    }
+}
+
+// rows 0..2 of the 6x6 block = [xl] M3x6, rows 3..5 = M3x6   (Gamma(xl)' M)
+__device__ __forceinline__ void pf_gammaT(const double* xl, const double* M36, double* out, bool accumulate) {
+#pragma unroll
+    for (int cI = 0; cI < 6; ++cI) {
+        const double m0 = M36[cI], m1 = M36[6 + cI], m2 = M36[12 + cI];
+        const double t0 = xl[1] * m2 - xl[2] * m1, t1 = xl[2] * m0 - xl[0] * m2, t2 = xl[0] * m1 - xl[1] * m0;
+        if (accumulate) {
+            out[cI] += t0; out[6 + cI] += t1; out[12 + cI] += t2;
+            out[18 + cI] += m0; out[24 + cI] += m1; out[30 + cI] += m2;
+        } else {
+            out[cI] = t0; out[6 + cI] = t1; out[12 + cI] = t2;
+            out[18 + cI] = m0; out[24 + cI] = m1; out[30 + cI] = m2;
+        }
+    }
+}
+
+// all point forces attached to body t: adds the body-frame wrench to fb and (K, D != null) the diagonal blocks to K, D; writes the
+// cross blocks of its ordered pairs to shared memory
+__device__ __noinline__ void pf_body(Ctx& c, const JointConst& J, const double* Rb, const double* pb, const double* phi, double* fb, double* K,
+                        double* D) {
+    const double* recs = c.pf_s;
+    double* blks = c.pf_s + (size_t)2 * c.npf * PF_REC;
+    for (int e = 0; e < J.pf_cnt; ++e) {
+        const int code = __ldg(c.pf_ep + J.pf_ptr + e);
+        const int f = code >> 1, sd = code & 1;
+        const PointForce& P = c.pf[f];
+        const int ob = P.body[1 - sd];
+        const double ks = P.ks, kd = P.kd;
+        double xl[3] = {P.x[sd][0], P.x[sd][1], P.x[sd][2]}, xo[3] = {P.x[1 - sd][0], P.x[1 - sd][1], P.x[1 - sd][2]};
+        double xw[3], vl[3], vw[3], xwo[3], vlo[3] = {0, 0, 0}, vwo[3] = {0, 0, 0};
+        pf_point(Rb, pb, phi, xl, xw, vl, vw);
+        double Ro[9], po[3];
+        if (ob >= 0) {
+            const double* r = recs + (size_t)(2 * f + (1 - sd)) * PF_REC;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) Ro[i] = r[i];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) po[i] = r[9 + i];
+            pf_point(Ro, po, r + 12, xo, xwo, vlo, vwo);
+        } else {
+            xwo[0] = xo[0]; xwo[1] = xo[1]; xwo[2] = xo[2];
+        }
+        double fme[3], y[3], t3[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) fme[i] = ks * (xwo[i] - xw[i]) + kd * (vwo[i] - vw[i]);
+        mat3T_vec(Rb, fme, y);
+        cross3(xl, y, t3);
+        fb[0] += t3[0]; fb[1] += t3[1]; fb[2] += t3[2];
+        fb[3] += y[0]; fb[4] += y[1]; fb[5] += y[2];
+        if (K == nullptr) continue;
+        // diagonal blocks: Km_aa = G'[ks [R'(xw_o - p)] + kd [R' vw_o], -ks I],  Dm_aa = -kd G'G,  G = Gamma(xl) = [-[xl], I]
+        {
+            double d3[3] = {xwo[0] - pb[0], xwo[1] - pb[1], xwo[2] - pb[2]}, a3[3], b3[3], A[9], B[9], M36[18];
+            mat3T_vec(Rb, d3, a3);
+            mat3T_vec(Rb, vwo, b3);
+            brac3(a3, A);
+            brac3(b3, B);
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int cI = 0; cI < 3; ++cI) {
+                    M36[6 * r + cI] = ks * A[3 * r + cI] + kd * B[3 * r + cI];
+                    M36[6 * r + 3 + cI] = (r == cI) ? -ks : 0.0;
+                }
+            pf_gammaT(xl, M36, K, true);
+            double X[9], G36[18];
+            brac3(xl, X);
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int cI = 0; cI < 3; ++cI) {
+                    G36[6 * r + cI] = kd * X[3 * r + cI];            // -kd * (-[xl])
+                    G36[6 * r + 3 + cI] = (r == cI) ? -kd : 0.0;
+                }
+            pf_gammaT(xl, G36, D, true);
+        }
+        // off-diagonal blocks (both ends on bodies): Km_ab = G_a' R_a'R_o (ks [-[xo], I] - kd [[vl_o], 0]),  Dm_ab = kd G_a' R_a'R_o G_o
+        if (ob >= 0) {
+            double Rao[9], XO[9], VO[9], Kin[18], Din[18], Kab[36], Dab[36];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int cI = 0; cI < 3; ++cI) Rao[3 * r + cI] = Rb[r] * Ro[cI] + Rb[3 + r] * Ro[3 + cI] + Rb[6 + r] * Ro[6 + cI];
+            brac3(xo, XO);
+            brac3(vlo, VO);
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int cI = 0; cI < 3; ++cI) {
+                    double kl = 0.0, dl = 0.0;
+#pragma unroll
+                    for (int m = 0; m < 3; ++m) {
+                        kl += Rao[3 * r + m] * (-ks * XO[3 * m + cI] - kd * VO[3 * m + cI]);
+                        dl += Rao[3 * r + m] * (-kd * XO[3 * m + cI]);
+                    }
+                    Kin[6 * r + cI] = kl;
+                    Kin[6 * r + 3 + cI] = ks * Rao[3 * r + cI];
+                    Din[6 * r + cI] = dl;
+                    Din[6 * r + 3 + cI] = kd * Rao[3 * r + cI];
+                }
+            pf_gammaT(xl, Kin, Kab, false);
+            pf_gammaT(xl, Din, Dab, false);
+            double* blk = blks + (size_t)(2 * f + sd) * PF_BLK;
+            xtmy_store(blk, Rb, pb, Ro, po, Dab, -c.c);
+            xtmy_store(blk + 36, Rb, pb, Ro, po, Kab, -c.c);
+        }
+    }
+}
+
+// Cross-term pass of the assembly: for every point force between two bodies and both orderings (a, b):
+//   out[k][i] += scale * s_k . (Aext_ab c1_i + Cext_ab (sq s_i))     for joints k in anc*(a), i in anc*(b).
+// Thread t owns column joint t; Wb: joint-major rows [L_k ; s_k] (stride NWD, s at offset NL).
+__device__ __forceinline__ void pf_cross_pass(Ctx2& c, int t, int myidx, const double* c1, const double* sqs, double scale, double* out,
+                                              int ld, const double* Wb, int NWD, int NL) {
+    const double* blks = c.pf_s + (size_t)2 * c.npf * PF_REC;
+    const int myend = (myidx >= 0) ? c.ie_s[t].y : 0;
+    for (int f = 0; f < c.npf; ++f) {
+        const int b0 = c.pf[f].body[0], b1 = c.pf[f].body[1];
+        if (b0 < 0 || b1 < 0) continue;  // uniform
+        for (int sd = 0; sd < 2; ++sd) {
+            const int a = sd ? b1 : b0, b = sd ? b0 : b1;
+            const bool mine = myidx >= 0 && t <= b && b < myend;
+            double y[6] = {0, 0, 0, 0, 0, 0};
+            if (mine) {
+                const double* A = blks + (size_t)(2 * f + sd) * PF_BLK;
+#pragma unroll
+                for (int r = 0; r < 6; ++r) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int m = 0; m < 6; ++m) acc += A[6 * r + m] * c1[m] + A[36 + 6 * r + m] * sqs[m];
+                    y[r] = acc;
+                }
+            }
+            for (int k = a; k >= 0; k = c.par_s[k]) {  // uniform walk up the ancestors of a
+                const int ik = c.ie_s[k].x;
+                if (ik < 0 || !mine) continue;
+                const double* sk = Wb + (size_t)k * NWD + NL;
+                double acc = 0.0;
+#pragma unroll
+                for (int m = 0; m < 6; ++m) acc += sk[m] * y[m];
+                out[(size_t)myidx * ld + ik] += scale * acc;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // eval_base2: residual g at iterate c.q (and, if deriv, the composite blocks eval_columns2 needs).
 // ---------------------------------------------------------------------------------------------
 template <int NW, bool GROUND, bool KEEP>
@@ -371,6 +553,27 @@ __device__ void eval_base2(Ctx2& c, bool deriv) {
         }
         bsync<NW>();
     }
+    // ---- point forces: every attached body publishes its frame and twist for the other end -------------------------
+    if (GROUND && c.npf > 0) {  // uniform
+        if (t < n && c.jc[t].pf_cnt > 0) {
+            const JointConst& J = c.jc[t];
+            double Rb[9], pb[3], phi[6];
+            mat3_mul(Rj, J.Rji, Rb);
+            mat3_vec(Rj, J.pji, pb);
+            pb[0] += pj[0]; pb[1] += pj[1]; pb[2] += pj[2];
+            xm_w2b(Rb, pb, Vj, phi);
+            for (int e = 0; e < J.pf_cnt; ++e) {
+                double* r = c.pf_s + (size_t)__ldg(c.pf_ep + J.pf_ptr + e) * PF_REC;
+#pragma unroll
+                for (int i = 0; i < 9; ++i) r[i] = Rb[i];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) r[9 + i] = pb[i];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) r[12 + i] = phi[i];
+            }
+        }
+        bsync<NW>();
+    }
     // ---- per body: frame, twist, wrench, and (deriv) the world-frame blocks ------------------------------------
     if (t < n) {
         const JointConst& J = c.jc[t];
@@ -391,16 +594,19 @@ __device__ void eval_base2(Ctx2& c, bool deriv) {
         mat3T_vec(Rb, gw, gb);
         fb[3] += m * gb[0]; fb[4] += m * gb[1]; fb[5] += m * gb[2];
         if (GROUND) {
-            if (J.has_ground) {
+            const bool hp = c.npf > 0 && J.pf_cnt > 0;
+            if (J.has_ground || hp) {
                 if (deriv) {
                     double K[36], D[36];
 #pragma unroll
                     for (int i = 0; i < 36; ++i) K[i] = D[i] = 0;
-                    ground_body<true>(J, Rb, pb, phi, fb, K, D);
+                    if (J.has_ground) ground_body<true>(J, Rb, pb, phi, fb, K, D);
+                    if (hp) pf_body(c, J, Rb, pb, phi, fb, K, D);
                     xtmx_store(c.sa, NS, F::AEXT, t, Rb, pb, D, -c.c);
                     xtmx_store(c.sa, NS, F::CEXT, t, Rb, pb, K, -c.c);
                 } else {
-                    ground_body<false>(J, Rb, pb, phi, fb, nullptr, nullptr);
+                    if (J.has_ground) ground_body<false>(J, Rb, pb, phi, fb, nullptr, nullptr);
+                    if (hp) pf_body(c, J, Rb, pb, phi, fb, nullptr, nullptr);
                 }
             } else if (deriv) {
                 for (int i = 0; i < 72; ++i) SA(F::AEXT, i, t) = 0.0;
@@ -704,6 +910,8 @@ __device__ void eval_columns2(Ctx2& c, double sq, double sqd, double sd, double 
             col[ie.x] = scale * (v + v2);
         }
     }
+    if (GROUND && c.npf > 0)  // off-diagonal blocks of the point forces (same thread owns the column: no barrier needed before)
+        pf_cross_pass(c, t, myidx, Rt + 6, Rt + 12, scale, out, ld, c.sa, F::NW_, F::NL);
     bsync<NW>();
 }
 

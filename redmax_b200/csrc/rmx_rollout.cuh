@@ -58,6 +58,12 @@ struct RolloutArgs {
     int* flags;
 };
 
+// Shared-memory scratch of the point forces sits behind everything any kernel variant places after the Newton matrix
+// (task Jacobian rows of the adjoint kernels, Krylov vectors), at the same offset for all of them.
+__host__ __device__ inline size_t pf_offset_doubles(int n, int nr, bool ground, bool keep) {
+    return smem_doubles2(n, nr, ground, keep) + 6 * (size_t)nr + pcg_doubles(n, nr);
+}
+
 __device__ __forceinline__ int krylov_count(const Ctx&) { return 0; }
 __device__ __forceinline__ void krylov_reset(Ctx&) {}
 
@@ -82,6 +88,10 @@ struct Eval<1, NW, GROUND, KEEP, LIN> {
     static __device__ __forceinline__ size_t extra_off(const C& c) { return (size_t)c.nr * c.ld; }
     static __device__ __forceinline__ void setup(C& c, double* sm, const DevScene& sc, const StepOpts&) {
         ctx_carve(c, sm, sc.n, sc.nr, GROUND);
+        c.pf = nullptr;  // the sweep kernels take no point forces (rmx_scene_create rejects the combination)
+        c.pf_ep = nullptr;
+        c.npf = 0;
+        c.pf_s = nullptr;
         c.jc = sc.jc;
         c.ends_list = sc.ends_list;
         c.gx = sc.grav[0];
@@ -138,6 +148,10 @@ struct Eval<2, NW, GROUND, KEEP, LIN> {
         c.is_chain = sc.is_chain;
         c.anc = sc.anc;
         c.nrounds = sc.nrounds;
+        c.pf = sc.pf;
+        c.pf_ep = sc.pf_ep;
+        c.npf = sc.npf;
+        c.pf_s = sm + pf_offset_doubles(sc.n, sc.nr, GROUND, KEEP);
         for (int j = threadIdx.x; j < sc.n; j += 32 * NW) {
             c.ie_s[j] = make_int2(sc.jc[j].idx, sc.jc[j].end);
             c.par_s[j] = sc.jc[j].parent;

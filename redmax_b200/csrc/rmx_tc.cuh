@@ -126,6 +126,10 @@ __device__ __forceinline__ void eval_columns_tc(Ctx2& c, double sq, double sqd, 
     __syncwarp();
     // diagonal: joint stiffness / damping / limit terms Kr, Dr (Joint.m:470-481)
     if (myidx >= 0) out[myidx * (LD + 1)] += scale * (-cc * (sq * c.sp2[myidx] + sqd * c.sp1[myidx]));
+    if (GROUND && c.npf > 0) {  // off-diagonal blocks of the point forces; RZ row = [c2 ; c1 ; sq s ; Z]
+        const double* rzl = RZb + lane * NWD;
+        pf_cross_pass(c, lane, myidx, rzl + 6, rzl + 12, scale, out, LD, Wb, NWD, NL);
+    }
     // identity padding up to a multiple of 8 (the blocked LU runs whole panels and whole tiles)
     const int np8 = (nr + 7) & ~7;
     for (int col = nr; col < np8; ++col) out[col * LD + lane] = (lane == col) ? 1.0 : 0.0;

@@ -207,6 +207,25 @@ class ForceGroundCuboid:
         self.mu = float(mu)
 
 
+class ForcePointPoint:
+    """+redmax/ForcePointPoint.m:15-45 -- linear zero-rest-length spring / damper between two body points; a body may be
+    None (the point is then fixed in the world)."""
+
+    def __init__(self, body1, x_1, body2, x_2):
+        self.body1 = body1
+        self.body2 = body2
+        self.x_1 = np.asarray(x_1, dtype=float).reshape(3)
+        self.x_2 = np.asarray(x_2, dtype=float).reshape(3)
+        self.stiffness = 1.0
+        self.damping = 0.0
+
+    def setStiffness(self, stiffness):
+        self.stiffness = float(stiffness)
+
+    def setDamping(self, damping):
+        self.damping = float(damping)
+
+
 class _TaskPointPos:
     """+redmax/TaskBDF1PointPos.m / TaskBDF2PointPos.m (parameters = constant joint torques, objective = a body
     point reaching a target at time t)."""
@@ -337,8 +356,18 @@ class Scene:
         d.qLimD = arr([j.qLimD for j in self.joints], f64)
         d.grav = (C.c_double * 3)(*[float(x) for x in self.grav])
         grounds = [f for f in self.forces if isinstance(f, ForceGroundCuboid)]
-        if len(grounds) != len(self.forces):
-            raise RmxError('only ForceGroundCuboid is on the GPU hot path (SURVEY.md section 8)')
+        points = [f for f in self.forces if isinstance(f, ForcePointPoint)]
+        if len(grounds) + len(points) != len(self.forces):
+            raise RmxError('only ForceGroundCuboid and ForcePointPoint are on the GPU hot path (SURVEY.md section 8)')
+        d.npointforce = len(points)
+        if points:
+            bidx = {id(j.body): i for i, j in enumerate(self.joints)}
+            d.pf_body1 = arr([(-1 if f.body1 is None else bidx[id(f.body1)]) for f in points], i32)
+            d.pf_body2 = arr([(-1 if f.body2 is None else bidx[id(f.body2)]) for f in points], i32)
+            d.pf_x1 = arr(np.concatenate([f.x_1 for f in points]), f64)
+            d.pf_x2 = arr(np.concatenate([f.x_2 for f in points]), f64)
+            d.pf_ks = arr([f.stiffness for f in points], f64)
+            d.pf_kd = arr([f.damping for f in points], f64)
         d.nground = len(grounds)
         if grounds:
             d.ground_body = arr([index[id(f.cuboid.joint)] for f in grounds], i32)
