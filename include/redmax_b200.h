@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RMX_VERSION 103
+#define RMX_VERSION 104
 
 /* error codes */
 #define RMX_OK 0
@@ -51,6 +51,10 @@ extern "C" {
 #define RMX_JOINT_UNIVERSAL 6     /* JointUniversal.m      [2] rotation about x then y */
 #define RMX_MAX_JOINT_DOF 3
 #define RMX_MAX_POINTFORCE 8
+
+/* two-point forces (pf_* arrays) */
+#define RMX_FORCE_POINTPOINT 0   /* ForcePointPoint.m: linear, zero rest length: f = ks dx + kd dv */
+#define RMX_FORCE_SPRINGDAMPER 1 /* ForceSpringDamper.m (ForceSpringGeneric.m): along the line, f = ks (l-L)/L + kd ldot/L */
 
 /* integrators (driverRedMaxBDF1.m, driverRedMaxBDF2.m) */
 #define RMX_SCHEME_BDF1 1
@@ -109,13 +113,16 @@ typedef struct rmx_scene_desc {
     const double* ground_kt; /* [nground] tangential stiffness */
     const double* ground_kd; /* [nground] damping                      (ForceGroundCuboid.m:40) */
     const double* ground_mu; /* [nground] friction coefficient         (ForceGroundCuboid.m:45) */
-    int32_t npointforce;     /* number of ForcePointPoint forces (at most RMX_MAX_POINTFORCE) */
+    int32_t npointforce;     /* number of ForcePointPoint / ForceSpringDamper forces (at most RMX_MAX_POINTFORCE) */
     const int32_t* pf_body1; /* [npointforce] body (== joint) index or -1 for the world (ForcePointPoint.m:15) */
     const int32_t* pf_body2; /* [npointforce] */
     const double* pf_x1;     /* [3*npointforce] application point in body-1 (or world) coordinates */
     const double* pf_x2;     /* [3*npointforce] */
     const double* pf_ks;     /* [npointforce] stiffness (ForcePointPoint.m:37) */
     const double* pf_kd;     /* [npointforce] damping   (ForcePointPoint.m:42) */
+    const int32_t* pf_kind;  /* [npointforce] RMX_FORCE_*; NULL = all RMX_FORCE_POINTPOINT */
+    const double* pf_L;      /* [npointforce] rest length of a spring-damper (ForceSpringDamper.m:31); <= 0 or NULL = the
+                                distance of the two points in the initial configuration (ForceSpringDamper.m:38-62) */
 } rmx_scene_desc;
 
 /* Solver constants hard-coded in the reference's newton() (driverRedMaxBDF1.m:95-98;

@@ -96,7 +96,7 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         sd.qLimK = mxGetDoubles(field(d, "qLimK"));
         sd.qLimD = mxGetDoubles(field(d, "qLimD"));
         std::memcpy(sd.grav, mxGetDoubles(field(d, "grav")), 3 * sizeof(double));
-        std::vector<int32_t> pfb1, pfb2;
+        std::vector<int32_t> pfb1, pfb2, pfkind;
         const mxArray* pf1 = field(d, "pf_body1", false);
         if (pf1 && mxGetNumberOfElements(pf1) > 0) {
             pfb1 = to_i32(pf1);
@@ -108,6 +108,9 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
             sd.pf_x2 = mxGetDoubles(field(d, "pf_x2"));
             sd.pf_ks = mxGetDoubles(field(d, "pf_ks"));
             sd.pf_kd = mxGetDoubles(field(d, "pf_kd"));
+            pfkind = to_i32(field(d, "pf_kind"));
+            sd.pf_kind = pfkind.data();
+            sd.pf_L = mxGetDoubles(field(d, "pf_L"));
         }
         const mxArray* gb = field(d, "ground_body", false);
         if (gb && mxGetNumberOfElements(gb) > 0) {

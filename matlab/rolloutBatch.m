@@ -51,20 +51,25 @@ for i = 1 : n
 end
 d.grav = scene.grav;
 gb = []; gE = zeros(4,4,0); kn = []; kt = []; kd = []; mu = [];
-pb1 = []; pb2 = []; px1 = zeros(3,0); px2 = zeros(3,0); pks = []; pkd = [];
+pb1 = []; pb2 = []; px1 = zeros(3,0); px2 = zeros(3,0); pks = []; pkd = []; pkind = []; pL = [];
 for i = 1 : length(scene.forces)
 	f = scene.forces{i};
 	if isa(f,'redmax.ForceGroundCuboid')
 		gb(end+1) = find(cellfun(@(x) x == f.cuboid, scene.bodies)) - 1; %#ok<AGROW>
 		gE(:,:,end+1) = f.E; kn(end+1) = f.kn; kt(end+1) = f.kt; kd(end+1) = f.kd; mu(end+1) = f.mu; %#ok<AGROW>
-	elseif isa(f,'redmax.ForcePointPoint')
+	elseif isa(f,'redmax.ForcePointPoint') || isa(f,'redmax.ForceSpringDamper')
 		pb1(end+1) = bodyIndex(scene,f.body1); pb2(end+1) = bodyIndex(scene,f.body2); %#ok<AGROW>
 		px1(:,end+1) = f.x_1; px2(:,end+1) = f.x_2; pks(end+1) = f.stiffness; pkd(end+1) = f.damping; %#ok<AGROW>
+		if isa(f,'redmax.ForceSpringDamper')
+			pkind(end+1) = 1; pL(end+1) = f.L; %#ok<AGROW> % L was set by scene.init() (ForceSpringDamper.m:38-62)
+		else
+			pkind(end+1) = 0; pL(end+1) = 0; %#ok<AGROW>
+		end
 	elseif ~isa(f,'redmax.ForceNull')
-		error('only ForceGroundCuboid and ForcePointPoint are on the GPU hot path');
+		error('only ForceGroundCuboid, ForcePointPoint and ForceSpringDamper are on the GPU hot path');
 	end
 end
-d.pf_body1 = pb1; d.pf_body2 = pb2; d.pf_x1 = px1; d.pf_x2 = px2; d.pf_ks = pks; d.pf_kd = pkd;
+d.pf_body1 = pb1; d.pf_body2 = pb2; d.pf_x1 = px1; d.pf_x2 = px2; d.pf_ks = pks; d.pf_kd = pkd; d.pf_kind = pkind; d.pf_L = pL;
 d.ground_body = gb; d.ground_E = gE; d.ground_kn = kn; d.ground_kt = kt; d.ground_kd = kd; d.ground_mu = mu;
 end
 

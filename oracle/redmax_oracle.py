@@ -686,6 +686,142 @@ class ForceNull(Force):
     pass
 
 
+class ForceSpringGeneric(Force):
+    """ForceSpringGeneric.m -- generic spring along the line between two body points (a body may be None = world)."""
+
+    def __init__(self, body1, x_1, body2, x_2):
+        """ForceSpringGeneric.m:15"""
+        self.body1 = body1
+        self.body2 = body2
+        self.x_1 = np.asarray(x_1, dtype=float).reshape(3)
+        self.x_2 = np.asarray(x_2, dtype=float).reshape(3)
+
+    def _state(self):
+        """ForceSpringGeneric.m:37-66"""
+        E1 = np.eye(4) if self.body1 is None else self.body1.E_wi
+        E2 = np.eye(4) if self.body2 is None else self.body2.E_wi
+        phi1 = np.zeros(6) if self.body1 is None else self.body1.phi
+        phi2 = np.zeros(6) if self.body2 is None else self.body2.phi
+        G1 = se3_Gamma(self.x_1)
+        G2 = se3_Gamma(self.x_2)
+        R1, R2, p1, p2 = E1[0:3, 0:3], E2[0:3, 0:3], E1[0:3, 3], E2[0:3, 3]
+        xw1 = R1 @ self.x_1 + p1
+        xw2 = R2 @ self.x_2 + p2
+        vw1 = R1 @ (G1 @ phi1)
+        vw2 = R2 @ (G2 @ phi2)
+        dx = xw2 - xw1
+        l = np.linalg.norm(dx)
+        dv = vw2 - vw1
+        ldot = (dx @ dv) / l
+        return R1, R2, p1, p2, G1, G2, phi1, phi2, xw1, xw2, dx, l, dv, ldot
+
+    def computeValues_(self, fr, fm, Kr=None, Km=None, Dr=None, Dm=None):
+        """ForceSpringGeneric.m:35-143"""
+        R1, R2, p1, p2, G1, G2, phi1, phi2, xw1, xw2, dx, l, dv, ldot = self._state()
+        xl1, xl2 = self.x_1, self.x_2
+        _, fs, dfsdl, dfsdldot = self.computeSpringForce(l, ldot)
+        fx_1 = G1.T @ (R1.T @ dx)
+        fx_2 = -G2.T @ (R2.T @ dx)
+        fx = np.concatenate([fx_1, fx_2])
+        f = (fs / l) * fx
+        b1, b2 = self.body1 is not None, self.body2 is not None
+        if b1:
+            fm[self.body1.idxM] += f[0:6]
+        if b2:
+            fm[self.body2.idxM] += f[6:12]
+        if Km is None:
+            return
+        I = np.eye(3)
+        A = np.hstack([-R1 @ G1, R2 @ G2])  # 3 x 12
+        dldq = (dx / l) @ A
+        dldotdq = (((dx @ dx) * I - np.outer(dx, dx)) / l ** 3 @ dv) @ A
+        for ax in range(3):  # rotation columns of body 1 and body 2 (ForceSpringGeneric.m:88-90)
+            e = np.zeros(3)
+            e[ax] = 1.0
+            eb = se3_brac(e)
+            dldotdq[ax] += (dx / l) @ (-R1 @ eb @ (G1 @ phi1))
+            dldotdq[6 + ax] += (dx / l) @ (R2 @ eb @ (G2 @ phi2))
+        dfsdq = dfsdl * dldq + dfsdldot * dldotdq
+        K1 = np.outer(fx, dfsdq / l - fs / l ** 2 * dldq)
+        K2 = np.zeros((12, 12))
+        x1b = se3_brac(xl1)
+        x2b = se3_brac(xl2)
+        R2R1 = R2.T @ R1
+        R1R2 = R2R1.T
+        K2[3:6, 0:3] = se3_brac(R1.T @ (p1 - xw2))
+        K2[0:3, 0:3] = x1b @ K2[3:6, 0:3]
+        K2[9:12, 0:3] = R2R1 @ x1b
+        K2[6:9, 0:3] = x2b @ K2[9:12, 0:3]
+        K2[3:6, 3:6] = I
+        K2[0:3, 3:6] = x1b
+        K2[9:12, 3:6] = -R2R1
+        K2[6:9, 3:6] = x2b @ K2[9:12, 3:6]
+        K2[3:6, 6:9] = R1R2 @ x2b
+        K2[0:3, 6:9] = x1b @ K2[3:6, 6:9]
+        K2[9:12, 6:9] = se3_brac(R2.T @ (p2 - xw1))
+        K2[6:9, 6:9] = x2b @ K2[9:12, 6:9]
+        K2[3:6, 9:12] = -R1R2
+        K2[0:3, 9:12] = x1b @ K2[3:6, 9:12]
+        K2[9:12, 9:12] = I
+        K2[6:9, 9:12] = x2b
+        K2 = -(fs / l) * K2
+        K = K1 + K2
+        d_w = dfsdldot * dx / l ** 2
+        D = -np.outer(fx, np.concatenate([d_w @ R1 @ G1, -(d_w @ R2 @ G2)]))
+        if b1:
+            i1 = self.body1.idxM
+            Km[np.ix_(i1, i1)] += K[0:6, 0:6]
+            Dm[np.ix_(i1, i1)] += D[0:6, 0:6]
+        if b2:
+            i2 = self.body2.idxM
+            Km[np.ix_(i2, i2)] += K[6:12, 6:12]
+            Dm[np.ix_(i2, i2)] += D[6:12, 6:12]
+        if b1 and b2:
+            Km[np.ix_(i1, i2)] += K[0:6, 6:12]
+            Km[np.ix_(i2, i1)] += K[6:12, 0:6]
+            Dm[np.ix_(i1, i2)] += D[0:6, 6:12]
+            Dm[np.ix_(i2, i1)] += D[6:12, 0:6]
+
+    def computeEnergy_(self, V):
+        """ForceSpringGeneric.m:146-177"""
+        st = self._state()
+        return V + self.computeSpringForce(st[11], st[13])[0]
+
+
+class ForceSpringDamper(ForceSpringGeneric):
+    """ForceSpringDamper.m -- damped spring with rest length L (taken from the initial configuration unless set)."""
+
+    def __init__(self, body1, x_1, body2, x_2):
+        super().__init__(body1, x_1, body2, x_2)
+        self.stiffness = 1.0
+        self.damping = 1.0
+        self.L = 0.0
+
+    def setStiffness(self, stiffness):
+        self.stiffness = stiffness
+
+    def setDamping(self, damping):
+        self.damping = damping
+
+    def setRetLength(self, L):
+        """ForceSpringDamper.m:31 (sic)"""
+        self.L = L
+
+    def init_(self):
+        """ForceSpringDamper.m:38-62"""
+        if self.L > 0:
+            return
+        self.L = self._state()[11]
+
+    def computeSpringForce(self, l, ldot):
+        """ForceSpringDamper.m:65-72: positive force contracts the spring"""
+        strain = (l - self.L) / self.L
+        dstrain = ldot / self.L
+        V = (self.stiffness / 2) * strain ** 2 * self.L
+        f = self.stiffness * strain + self.damping * dstrain
+        return V, f, self.stiffness / self.L, self.damping / self.L
+
+
 class ForcePointPoint(Force):
     """ForcePointPoint.m -- linear zero-rest-length spring/damper between two body points (a body may be None = world)."""
 

@@ -24,6 +24,8 @@ RMX_JOINT_TRANSLATIONAL = 4
 RMX_JOINT_FREE2D = 5
 RMX_JOINT_UNIVERSAL = 6
 RMX_MAX_JOINT_DOF = 3
+RMX_FORCE_POINTPOINT = 0
+RMX_FORCE_SPRINGDAMPER = 1
 RMX_SCHEME_BDF1 = 1
 RMX_SCHEME_BDF2 = 2
 RMX_LINSOLVE_LU = 0
@@ -53,6 +55,7 @@ class rmx_scene_desc(C.Structure):
         ('ground_kn', _pd), ('ground_kt', _pd), ('ground_kd', _pd), ('ground_mu', _pd),
         ('npointforce', C.c_int32),
         ('pf_body1', _pi), ('pf_body2', _pi), ('pf_x1', _pd), ('pf_x2', _pd), ('pf_ks', _pd), ('pf_kd', _pd),
+        ('pf_kind', _pi), ('pf_L', _pd),
     ]
 
 

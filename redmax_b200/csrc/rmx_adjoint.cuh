@@ -247,7 +247,13 @@ __global__ void __launch_bounds__(32 * NW) energies_kernel(EnergyArgs a) {
                 }
             }
             const double d0 = xw[1][0] - xw[0][0], d1 = xw[1][1] - xw[0][1], d2 = xw[1][2] - xw[0][2];
-            V += 0.5 * P.ks * (d0 * d0 + d1 * d1 + d2 * d2);
+            const double l2 = d0 * d0 + d1 * d1 + d2 * d2;
+            if (P.kind == 1) {  // ForceSpringDamper.computeSpringForce: V = ks/2 strain^2 L
+                const double strain = (sqrt(l2) - P.L) / P.L;
+                V += 0.5 * P.ks * strain * strain * P.L;
+            } else {
+                V += 0.5 * P.ks * l2;
+            }
         }
         T = block_sum<NW>(T, c.red);
         V = block_sum<NW>(V, c.red);

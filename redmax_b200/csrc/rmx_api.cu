@@ -185,6 +185,72 @@ static void expand_scene(const rmx_scene_desc* d, const std::vector<int>& base, 
     }
 }
 
+// Host forward kinematics at the initial configuration (what Scene.init's update() leaves in body.E_wi, Scene.m:93): only
+// needed for quantities the reference derives from it at init time -- the rest length of ForceSpringDamper
+// (ForceSpringDamper.m:38-62).  jc: internal (preorder) joints; out: world frame of every body, R row-major and p.
+static void host_aa_to_mat(const JointConst& J, double angle, double* R) {
+    if (J.axtype != 0 && J.axsign < 0) angle = -angle;
+    const double sn = std::sin(angle), cs = std::cos(angle);
+    const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    std::memcpy(R, I, sizeof(I));
+    if (J.axtype == 3) {
+        R[0] = cs; R[1] = -sn; R[3] = sn; R[4] = cs;
+    } else if (J.axtype == 1) {
+        R[4] = cs; R[5] = -sn; R[7] = sn; R[8] = cs;
+    } else if (J.axtype == 2) {
+        R[0] = cs; R[2] = sn; R[6] = -sn; R[8] = cs;
+    } else {
+        const double ax = J.axn[0], ay = J.axn[1], az = J.axn[2], t = 1.0 - cs;
+        const double xz = ax * az, xy = ax * ay, yz = ay * az;
+        R[0] = t * ax * ax + cs; R[1] = t * xy - sn * az; R[2] = t * xz + sn * ay;
+        R[3] = t * xy + sn * az; R[4] = t * ay * ay + cs; R[5] = t * yz - sn * ax;
+        R[6] = t * xz - sn * ay; R[7] = t * yz + sn * ax; R[8] = t * az * az + cs;
+    }
+}
+static void h_mul(const double* A, const double* B, double* C) {
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+}
+static void h_mv(const double* A, const double* x, double* y) {
+    for (int i = 0; i < 3; ++i) y[i] = A[3 * i] * x[0] + A[3 * i + 1] * x[1] + A[3 * i + 2] * x[2];
+}
+static void host_body_frames(const std::vector<JointConst>& jc, std::vector<double>& Rb, std::vector<double>& pb) {
+    const int n = (int)jc.size();
+    std::vector<double> Rw(9 * n), pw(3 * n);
+    Rb.assign(9 * n, 0.0);
+    pb.assign(3 * n, 0.0);
+    for (int k = 0; k < n; ++k) {
+        const JointConst& J = jc[k];
+        double Rl[9], pl[3] = {J.p0[0], J.p0[1], J.p0[2]};
+        if (J.idx >= 0 && !J.prismatic) {
+            double Rq[9];
+            host_aa_to_mat(J, J.qRest, Rq);
+            h_mul(J.R0, Rq, Rl);
+        } else {
+            std::memcpy(Rl, J.R0, sizeof(Rl));
+            if (J.idx >= 0) {
+                const double aq[3] = {J.axis[0] * J.qRest, J.axis[1] * J.qRest, J.axis[2] * J.qRest};
+                double t3[3];
+                h_mv(J.R0, aq, t3);
+                for (int i = 0; i < 3; ++i) pl[i] += t3[i];
+            }
+        }
+        if (J.parent < 0) {
+            std::memcpy(&Rw[9 * k], Rl, sizeof(Rl));
+            std::memcpy(&pw[3 * k], pl, sizeof(pl));
+        } else {
+            double t3[3];
+            h_mul(&Rw[9 * J.parent], Rl, &Rw[9 * k]);
+            h_mv(&Rw[9 * J.parent], pl, t3);
+            for (int i = 0; i < 3; ++i) pw[3 * k + i] = pw[3 * J.parent + i] + t3[i];
+        }
+        double t3[3];
+        h_mul(&Rw[9 * k], J.Rji, &Rb[9 * k]);
+        h_mv(&Rw[9 * k], J.pji, t3);
+        for (int i = 0; i < 3; ++i) pb[3 * k + i] = pw[3 * k + i] + t3[i];
+    }
+}
+
 extern "C" int rmx_scene_create(const rmx_scene_desc* d, rmx_scene** out) {
     if (!d || !out) return fail(RMX_EINVAL, "rmx_scene_create: null argument");
     *out = nullptr;
@@ -406,7 +472,40 @@ extern "C" int rmx_scene_create(const rmx_scene_desc* d, rmx_scene** out) {
             }
             P.ks = d->pf_ks[f];
             P.kd = d->pf_kd[f];
+            P.kind = d->pf_kind ? d->pf_kind[f] : RMX_FORCE_POINTPOINT;
+            P.L = (d->pf_L && P.kind == RMX_FORCE_SPRINGDAMPER) ? d->pf_L[f] : 0.0;
+            P.pad_ = 0;
+            if (P.kind != RMX_FORCE_POINTPOINT && P.kind != RMX_FORCE_SPRINGDAMPER) {
+                delete s;
+                return fail(RMX_EINVAL, "rmx_scene_create: unknown point-force kind");
+            }
             s->pf.push_back(P);
+        }
+        {   // rest lengths not given: distance of the two points in the initial configuration (ForceSpringDamper.m:38-62)
+            std::vector<double> Rb, pb;
+            bool have = false;
+            for (PointForce& P : s->pf) {
+                if (P.kind != RMX_FORCE_SPRINGDAMPER || P.L > 0) continue;
+                if (!have) {
+                    host_body_frames(s->jc, Rb, pb);
+                    have = true;
+                }
+                double xw[2][3];
+                for (int sd = 0; sd < 2; ++sd) {
+                    if (P.body[sd] >= 0) {
+                        h_mv(&Rb[9 * P.body[sd]], P.x[sd], xw[sd]);
+                        for (int i = 0; i < 3; ++i) xw[sd][i] += pb[3 * P.body[sd] + i];
+                    } else {
+                        for (int i = 0; i < 3; ++i) xw[sd][i] = P.x[sd][i];
+                    }
+                }
+                const double d0 = xw[1][0] - xw[0][0], d1 = xw[1][1] - xw[0][1], d2 = xw[1][2] - xw[0][2];
+                P.L = std::sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+                if (!(P.L > 0)) {
+                    delete s;
+                    return fail(RMX_EINVAL, "rmx_scene_create: spring with zero rest length (use ForcePointPoint)");
+                }
+            }
         }
         for (int k = 0; k < n; ++k) {
             s->jc[k].pf_ptr = (int)s->pf_ep.size();

@@ -58,6 +58,9 @@ struct PointForce {
     int body[2];      // internal joint index of body 1 / body 2, -1 = world
     double x[2][3];   // application points in body (or world) coordinates
     double ks, kd;
+    double L;         // rest length (kind 1)
+    int kind;         // 0: ForcePointPoint (linear, zero rest length); 1: ForceSpringDamper (ForceSpringGeneric.m + ForceSpringDamper.m)
+    int pad_;
 };
 constexpr int PF_MAX = 8;        // point forces per scene (shared-memory scratch is sized for this)
 constexpr int PF_REC = 18;       // published per endpoint: R[9] p[3] phi[6]

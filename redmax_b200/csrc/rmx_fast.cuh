@@ -288,6 +288,170 @@ __device__ __forceinline__ void pf_gammaT(const double* xl, const double* M36, d
     }
 }
 
+// ForceSpringGeneric.computeValues_ (ForceSpringGeneric.m:35-143) with ForceSpringDamper.computeSpringForce
+// (ForceSpringDamper.m:65-72) for one end ("me" = side sd) of a spring: body-frame wrench f6, diagonal blocks Kown / Down and
+// off-diagonal blocks Kab / Dab (rows: me, columns: the other body), all 6x6 row-major, written out as the reference forms
+// its 12x12 K = K1 + K2 and D.  E[0], E[1] are the two ends in the reference's order (R p phi x); a world end has R = I, p = 0,
+// phi = 0.
+struct PfEnd {
+    double R[9], p[3], phi[6], x[3];
+};
+__device__ __noinline__ void pf_spring(const PfEnd* E, int sd, double ks, double kd, double L, double* f6, double* Kown, double* Down,
+                                       double* Kab, double* Dab, bool deriv) {
+    double xw[2][3], vl[2][3], vw[2][3];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) pf_point(E[e].R, E[e].p, E[e].phi, E[e].x, xw[e], vl[e], vw[e]);
+    double dx[3], dv[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        dx[i] = xw[1][i] - xw[0][i];
+        dv[i] = vw[1][i] - vw[0][i];
+    }
+    const double l2 = dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2];
+    const double l = sqrt(l2);
+    const double ldot = (dx[0] * dv[0] + dx[1] * dv[1] + dx[2] * dv[2]) / l;
+    const double strain = (l - L) / L, dstrain = ldot / L;
+    const double fs = ks * strain + kd * dstrain, dfsdl = ks / L, dfsdldot = kd / L;
+    // fx = [G1'R1'dx ; -G2'R2'dx]
+    double fx[12];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        double y[3], t3[3];
+        mat3T_vec(E[e].R, dx, y);
+        cross3(E[e].x, y, t3);
+        const double sg = e ? -1.0 : 1.0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            fx[6 * e + i] = sg * t3[i];
+            fx[6 * e + 3 + i] = sg * y[i];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) f6[i] = (fs / l) * fx[6 * sd + i];
+    if (!deriv) return;
+    // A = [-R1 G1, R2 G2] (3 x 12), G = [-[x], I]:  R G = [-R [x], R]
+    double A[36];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        double X[9], RX[9];
+        brac3(E[e].x, X);
+        mat3_mul(E[e].R, X, RX);
+        const double sg = e ? 1.0 : -1.0;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int cI = 0; cI < 3; ++cI) {
+                A[12 * r + 6 * e + cI] = -sg * RX[3 * r + cI];
+                A[12 * r + 6 * e + 3 + cI] = sg * E[e].R[3 * r + cI];
+            }
+    }
+    double dldq[12], dldotdq[12], w3[3];
+    {
+        // ((dx'dx I - dx dx') / l^3 dv)
+        const double dd = dx[0] * dv[0] + dx[1] * dv[1] + dx[2] * dv[2];
+        const double il3 = 1.0 / (l2 * l);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) w3[i] = (l2 * dv[i] - dx[i] * dd) * il3;
+    }
+#pragma unroll
+    for (int cI = 0; cI < 12; ++cI) {
+        dldq[cI] = (dx[0] * A[cI] + dx[1] * A[12 + cI] + dx[2] * A[24 + cI]) / l;
+        dldotdq[cI] = w3[0] * A[cI] + w3[1] * A[12 + cI] + w3[2] * A[24 + cI];
+    }
+    // rotation columns: dldotdq(ax) += dx'/l * (-R1 [e_ax] G1 phi1),  dldotdq(6+ax) += dx'/l * (R2 [e_ax] G2 phi2);  G phi = vl
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        double y[3];
+        mat3T_vec(E[e].R, dx, y);  // R' dx
+        // dx' R [e_ax] vl = (R'dx) . (e_ax x vl) = e_ax . (vl x R'dx)
+        double t3[3];
+        cross3(vl[e], y, t3);
+        const double sg = e ? 1.0 : -1.0;
+#pragma unroll
+        for (int ax = 0; ax < 3; ++ax) dldotdq[6 * e + ax] += sg * t3[ax] / l;
+    }
+    double dfsdq[12];
+#pragma unroll
+    for (int cI = 0; cI < 12; ++cI) dfsdq[cI] = dfsdl * dldq[cI] + dfsdldot * dldotdq[cI];
+    // K2 (12 x 12), ForceSpringGeneric.m:96-116: only the six rows of this end are kept
+    double K2[72];
+    for (int i = 0; i < 72; ++i) K2[i] = 0.0;
+    {
+        const double* R1 = E[0].R;
+        const double* R2 = E[1].R;
+        double x1b[9], x2b[9], R2R1[9], R1R2[9], B[9], T[9], d3[3], a3[3];
+        brac3(E[0].x, x1b);
+        brac3(E[1].x, x2b);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int cI = 0; cI < 3; ++cI) {
+                R2R1[3 * r + cI] = R2[r] * R1[cI] + R2[3 + r] * R1[3 + cI] + R2[6 + r] * R1[6 + cI];
+            }
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int cI = 0; cI < 3; ++cI) R1R2[3 * r + cI] = R2R1[3 * cI + r];
+        auto put = [&](int r0, int c0, const double* M, double sg) {
+            if (r0 / 6 != sd) return;
+            for (int r = 0; r < 3; ++r)
+                for (int cI = 0; cI < 3; ++cI) K2[12 * (r0 - 6 * sd + r) + c0 + cI] = sg * M[3 * r + cI];
+        };
+        const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        // column block 1:3
+        for (int i = 0; i < 3; ++i) d3[i] = E[0].p[i] - xw[1][i];
+        mat3T_vec(R1, d3, a3);
+        brac3(a3, B);             // K2(4:6,1:3) = [R1'(p1 - xw2)]
+        put(3, 0, B, 1.0);
+        mat3_mul(x1b, B, T);
+        put(0, 0, T, 1.0);        // K2(1:3,1:3) = x1b * K2(4:6,1:3)
+        mat3_mul(R2R1, x1b, B);
+        put(9, 0, B, 1.0);        // K2(10:12,1:3) = R2R1 x1b
+        mat3_mul(x2b, B, T);
+        put(6, 0, T, 1.0);        // K2(7:9,1:3) = x2b * K2(10:12,1:3)
+        // column block 4:6
+        put(3, 3, I3, 1.0);
+        put(0, 3, x1b, 1.0);
+        put(9, 3, R2R1, -1.0);
+        mat3_mul(x2b, R2R1, T);
+        put(6, 3, T, -1.0);
+        // column block 7:9
+        mat3_mul(R1R2, x2b, B);
+        put(3, 6, B, 1.0);
+        mat3_mul(x1b, B, T);
+        put(0, 6, T, 1.0);
+        for (int i = 0; i < 3; ++i) d3[i] = E[1].p[i] - xw[0][i];
+        mat3T_vec(R2, d3, a3);
+        brac3(a3, B);
+        put(9, 6, B, 1.0);
+        mat3_mul(x2b, B, T);
+        put(6, 6, T, 1.0);
+        // column block 10:12
+        put(3, 9, R1R2, -1.0);
+        mat3_mul(x1b, R1R2, T);
+        put(0, 9, T, -1.0);
+        put(9, 9, I3, 1.0);
+        put(6, 9, x2b, 1.0);
+    }
+    // D = -fx * [d_w'R1 G1, -d_w'R2 G2],  d_w = dfsdldot dx / l^2  ->  row vector dvec = -(d_w' A) (A = [-R1G1, R2G2])
+    double dvec[12];
+    {
+        const double sdw = dfsdldot / l2;
+#pragma unroll
+        for (int cI = 0; cI < 12; ++cI) dvec[cI] = -sdw * (dx[0] * A[cI] + dx[1] * A[12 + cI] + dx[2] * A[24 + cI]);
+    }
+    const int r0 = 6 * sd, co = 6 * sd, cx = 6 * (1 - sd);
+    const double fl = fs / l;
+    for (int r = 0; r < 6; ++r)
+        for (int cI = 0; cI < 6; ++cI) {
+            const double fr = fx[r0 + r];
+            Kown[6 * r + cI] = fr * (dfsdq[co + cI] / l - fs / l2 * dldq[co + cI]) - fl * K2[12 * r + co + cI];
+            Kab[6 * r + cI] = fr * (dfsdq[cx + cI] / l - fs / l2 * dldq[cx + cI]) - fl * K2[12 * r + cx + cI];
+            Down[6 * r + cI] = -fr * dvec[co + cI];
+            Dab[6 * r + cI] = -fr * dvec[cx + cI];
+        }
+}
+
 // all point forces attached to body t: adds the body-frame wrench to fb and (K, D != null) the diagonal blocks to K, D; writes the
 // cross blocks of its ordered pairs to shared memory
 __device__ __noinline__ void pf_body(Ctx& c, const JointConst& J, const double* Rb, const double* pb, const double* phi, double* fb, double* K,
@@ -313,6 +477,44 @@ __device__ __noinline__ void pf_body(Ctx& c, const JointConst& J, const double* 
             pf_point(Ro, po, r + 12, xo, xwo, vlo, vwo);
         } else {
             xwo[0] = xo[0]; xwo[1] = xo[1]; xwo[2] = xo[2];
+        }
+        if (P.kind == 1) {  // ForceSpringDamper
+            PfEnd E[2];
+            PfEnd& me = E[sd];
+            PfEnd& ot = E[1 - sd];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                me.R[i] = Rb[i];
+                ot.R[i] = (ob >= 0) ? Ro[i] : ((i % 4 == 0) ? 1.0 : 0.0);
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                me.p[i] = pb[i];
+                ot.p[i] = (ob >= 0) ? po[i] : 0.0;
+                me.x[i] = xl[i];
+                ot.x[i] = xo[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                me.phi[i] = phi[i];
+                ot.phi[i] = (ob >= 0) ? recs[(size_t)(2 * f + (1 - sd)) * PF_REC + 12 + i] : 0.0;
+            }
+            double f6[6], Ko[36], Do[36], Kab[36], Dab[36];
+            pf_spring(E, sd, ks, kd, P.L, f6, Ko, Do, Kab, Dab, K != nullptr);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) fb[i] += f6[i];
+            if (K != nullptr) {
+                for (int i = 0; i < 36; ++i) {
+                    K[i] += Ko[i];
+                    D[i] += Do[i];
+                }
+                if (ob >= 0) {
+                    double* blk = blks + (size_t)(2 * f + sd) * PF_BLK;
+                    xtmy_store(blk, Rb, pb, ot.R, ot.p, Dab, -c.c);
+                    xtmy_store(blk + 36, Rb, pb, ot.R, ot.p, Kab, -c.c);
+                }
+            }
+            continue;
         }
         double fme[3], y[3], t3[3];
 #pragma unroll

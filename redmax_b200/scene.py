@@ -211,6 +211,8 @@ class ForcePointPoint:
     """+redmax/ForcePointPoint.m:15-45 -- linear zero-rest-length spring / damper between two body points; a body may be
     None (the point is then fixed in the world)."""
 
+    kind = _ffi.RMX_FORCE_POINTPOINT
+
     def __init__(self, body1, x_1, body2, x_2):
         self.body1 = body1
         self.body2 = body2
@@ -224,6 +226,22 @@ class ForcePointPoint:
 
     def setDamping(self, damping):
         self.damping = float(damping)
+
+
+class ForceSpringDamper(ForcePointPoint):
+    """+redmax/ForceSpringDamper.m -- damped spring with rest length L along the line between two body points; L defaults to
+    the distance in the initial configuration (init_, ForceSpringDamper.m:38-62; computed by the library)."""
+    kind = _ffi.RMX_FORCE_SPRINGDAMPER
+
+    def __init__(self, body1, x_1, body2, x_2):
+        super().__init__(body1, x_1, body2, x_2)
+        self.stiffness = 1.0
+        self.damping = 1.0  # ForceSpringDamper.m:15
+        self.L = 0.0
+
+    def setRetLength(self, L):
+        """ForceSpringDamper.m:31 (sic)"""
+        self.L = float(L)
 
 
 class _TaskPointPos:
@@ -358,7 +376,8 @@ class Scene:
         grounds = [f for f in self.forces if isinstance(f, ForceGroundCuboid)]
         points = [f for f in self.forces if isinstance(f, ForcePointPoint)]
         if len(grounds) + len(points) != len(self.forces):
-            raise RmxError('only ForceGroundCuboid and ForcePointPoint are on the GPU hot path (SURVEY.md section 8)')
+            raise RmxError('only ForceGroundCuboid, ForcePointPoint and ForceSpringDamper are on the GPU hot path '
+                           '(SURVEY.md section 8)')
         d.npointforce = len(points)
         if points:
             bidx = {id(j.body): i for i, j in enumerate(self.joints)}
@@ -368,6 +387,8 @@ class Scene:
             d.pf_x2 = arr(np.concatenate([f.x_2 for f in points]), f64)
             d.pf_ks = arr([f.stiffness for f in points], f64)
             d.pf_kd = arr([f.damping for f in points], f64)
+            d.pf_kind = arr([f.kind for f in points], i32)
+            d.pf_L = arr([getattr(f, 'L', 0.0) for f in points], f64)
         d.nground = len(grounds)
         if grounds:
             d.ground_body = arr([index[id(f.cuboid.joint)] for f in grounds], i32)

@@ -232,6 +232,26 @@ def scenesRedMax(sceneID, api=None):
         scene.bodies = bs
         scene.joints = [j1, j2, j3, j4, j5]
         scene.forces = [f]
+    elif sceneID == 12:  # :312
+        scene.name = 'Spring-damper'
+        scene.Hexpected[:] = [-2.2145412057327565e+04, -8.9887693524038732e+03]
+        b1 = api.BodyCuboid(density, [10, 1, 1])
+        j1 = api.JointRevolute(None, b1, [0, 1, 0])
+        j1.setJointTransform(np.eye(4))
+        b1.setBodyTransform(_trans([5, 0, 0]))
+        b2 = api.BodyCuboid(density, [10, 1, 1])
+        j2 = api.JointRevolute(j1, b2, [0, 1, 0])
+        j2.setJointTransform(_trans([10, 0, 0]))
+        b2.setBodyTransform(_trans([5, 0, 0]))
+        f1 = api.ForceSpringDamper(None, [-5, 0, -5], b2, [0, 0, -2])
+        f1.setStiffness(1e6)
+        f1.setDamping(1e3)
+        f2 = api.ForceSpringDamper(b1, [0, 0, 2], b2, [0, 0, 2])
+        f2.setStiffness(1e6)
+        f2.setDamping(1e3)
+        scene.bodies = [b1, b2]
+        scene.joints = [j1, j2]
+        scene.forces = [f1, f2]
     elif sceneID == 14:  # :371
         scene.name = 'Joint limits'
         scene.Hexpected[:] = [-2.5928305306546572e+04, -1.8476279319765570e+04]

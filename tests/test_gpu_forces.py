@@ -86,3 +86,74 @@ def test_variant_rollouts_match_oracle(rb, oracle):
     so.update()
     To, Vo = so.computeEnergies()
     assert abs(V[0] - Vo) <= 1e-10 * max(1.0, abs(Vo)) and abs(T[0] - To) <= 1e-10 * max(1.0, abs(To))
+
+
+def spring_variant(api=None):
+    """scene 12 plus a rest-length-set spring between the two bodies' far ends and a world spring on body 1."""
+    import redmax_b200 as rb
+    api = api or rb
+    sc = rb.scenesRedMax(12, api=api)
+    f3 = api.ForceSpringDamper(sc.bodies[0], [-4, 0.3, 0.2], sc.bodies[1], [4, -0.2, 0.1])
+    f3.setStiffness(3e5)
+    f3.setDamping(2e3)
+    f3.setRetLength(17.0)
+    f4 = api.ForceSpringDamper(sc.bodies[0], [1, 0, -0.5], None, [2.0, 1.0, -9.0])
+    f4.setStiffness(2e5)
+    f4.setDamping(5e2)
+    sc.forces += [f3, f4]
+    sc.joints[0].q[0] = 0.2
+    sc.joints[1].q[0] = -0.3
+    return sc
+
+
+SPRING_CASES = [('scene12', lambda rb: (rb.scenesRedMax, (12,), {})), ('spring_variant', lambda rb: (spring_variant, (), {}))]
+
+
+@pytest.mark.parametrize('name,mk', SPRING_CASES, ids=[c[0] for c in SPRING_CASES])
+def test_spring_damper_eval_matches_oracle(rb, oracle, name, mk):
+    """ForceSpringDamper (ForceSpringGeneric.m:35-143): g, H, M, D and the Newton step through both assembly paths."""
+    factory, a, kw = mk(rb)
+    sg, so = both(rb, oracle, factory, *a, **kw)
+    rng = np.random.default_rng(78)
+    nr, h = sg.nr, sg.h
+    for trial in range(3):
+        q = sg.qInit + 0.3 * rng.uniform(-1, 1, nr)
+        q0 = q - 0.02 * rng.uniform(-1, 1, nr)
+        qdot0 = rng.uniform(-1, 1, nr)
+        g, H, M, D, f = oracle_eval(oracle, so, q, qdot0, q0, None)
+        args = (q, (q - q0) / h, q - q0 - h * qdot0, h * h, 1.0 / h)
+        out = sg.eval(*args)
+        for nm_, ref, tol in (('g', g, TOL_EVAL), ('H', H, TOL_EVAL), ('M', M, TOL_EVAL), ('f', f, 1e-9)):
+            assert rel_err(out[nm_], ref) < tol, (name, trial, nm_, rel_err(out[nm_], ref))
+        assert np.max(np.abs(out['D'] - D)) < 1e-10 * max(np.max(np.abs(D)), np.max(np.abs(M)))
+        nw = sg.eval_newton(*args)
+        assert rel_err(nw['H'], H) < TOL_EVAL
+        assert rel_err(nw['dx'], np.linalg.solve(H, -g)) < 1e-12 * max(10.0, np.linalg.cond(H))
+
+
+@pytest.mark.parametrize('itype', [1, 2])
+def test_scene12_golden_energy_and_trajectory(rb, oracle, itype):
+    sg, so = both(rb, oracle, rb.scenesRedMax, 12)
+    out = sg.rollout(scheme=itype)
+    assert out['status'].tolist() == [0]
+    T1, V1 = sg.energies(out['q'][0, -1], out['qdot'][0, -1])
+    _, V0 = sg.energies(sg.qInit, sg.qdotInit)
+    Hend = T1[0] + V1[0] - V0[0]
+    assert abs(Hend - sg.Hexpected[itype - 1]) <= 1e-2, (Hend, sg.Hexpected[itype - 1])
+    qs, _ = oracle.run_forward(so, itype, sg.qInit, sg.qdotInit)
+    assert rel_err(out['q'][0], qs) < TOL_Q, rel_err(out['q'][0], qs)
+
+
+def test_spring_variant_rollout_and_energy(rb, oracle):
+    sg, so = both(rb, oracle, spring_variant)
+    assert so.forces[0].L > 0 and so.forces[2].L == 17.0  # rest length from the initial configuration unless set
+    q0, qd0 = rb.synthetic_inputs(sg, 2, seed=32)
+    out = sg.rollout(q0, qd0, scheme=2, nsteps=60)
+    for b in range(2):
+        qs, _ = oracle.run_forward(so, 2, q0[b], qd0[b], nsteps=60)
+        assert rel_err(out['q'][b], qs) < TOL_Q, (b, rel_err(out['q'][b], qs))
+    T, V = sg.energies(q0[1], qd0[1])
+    so.setQ(q0[1], qd0[1])
+    so.update()
+    To, Vo = so.computeEnergies()
+    assert abs(V[0] - Vo) <= 1e-10 * max(1.0, abs(Vo)) and abs(T[0] - To) <= 1e-10 * max(1.0, abs(To))

@@ -20,6 +20,8 @@ PINS = {
     8: (-2.5276246935781084e+04, -1.3781281283808785e+03),
     # rank 2, first force with off-diagonal blocks: ForcePointPoint (scene 10 'Loop', scenesRedMax.m:264-265)
     10: (1.2376477982839792e+03, 4.1146190850293169e+03),
+    # ForceSpringDamper (scene 12 'Spring-damper', scenesRedMax.m:314-315)
+    12: (-2.2145412057327565e+04, -8.9887693524038732e+03),
 }
 
 
@@ -36,7 +38,7 @@ def test_hexpected(oracle, sid, itype):
     assert abs(H - PINS[sid][itype - 1]) < 1e-6
 
 
-@pytest.mark.parametrize('sid', [3, 4, 5, 6, 8, 10])
+@pytest.mark.parametrize('sid', [3, 4, 5, 6, 8, 10, 12])
 @pytest.mark.parametrize('itype', [1, 2])
 def test_hexpected_more_joint_types(oracle, sid, itype):
     """JointPrismatic / JointPlanar / JointTranslational / JointFree2D / JointUniversal restatements against the
