@@ -236,6 +236,27 @@ __device__ __forceinline__ void xtmx_store(double* sa, int NS, int fld, int j, c
     }
 }
 
+// same as xtmx_store, accumulating into the field
+__device__ __forceinline__ void xtmx_add(double* sa, int NS, int fld, int j, const double* R, const double* p, const double* M,
+                                         double scale) {
+#pragma unroll
+    for (int m = 0; m < 6; ++m) {
+        double e[6] = {0, 0, 0, 0, 0, 0}, xe[6], y[6], wv[6];
+        e[m] = 1.0;
+        xm_w2b(R, p, e, xe);
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            double acc = 0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) acc += M[6 * r + k] * xe[k];
+            y[r] = acc;
+        }
+        xf_b2w(R, p, y, wv);
+#pragma unroll
+        for (int r = 0; r < 6; ++r) sa[(size_t)(fld + 6 * r + m) * NS + j] += scale * wv[r];
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // ForcePointPoint (ForcePointPoint.m:48-113) in the composite formulation (prototype: tools/proto_pointforce.py).
 // The force on "me" (a body point xl) from the other end is f = ks (xw_o - xw_me) + kd (vw_o - vw_me); its body-frame wrench and
@@ -452,10 +473,17 @@ __device__ __noinline__ void pf_spring(const PfEnd* E, int sd, double ks, double
         }
 }
 
-// all point forces attached to body t: adds the body-frame wrench to fb and (K, D != null) the diagonal blocks to K, D; writes the
-// cross blocks of its ordered pairs to shared memory
-__device__ __noinline__ void pf_body(Ctx& c, const JointConst& J, const double* Rb, const double* pb, const double* phi, double* fb, double* K,
-                        double* D) {
+// all point forces attached to body t: returns their body-frame wrench in f6 and, if deriv, adds the diagonal blocks
+// -c X'DX, -c X'KX to the external-force fields aext / cext of joint t in the SoA block (after the caller has stored or zeroed
+// them) and writes the cross blocks of its ordered pairs to shared memory.  Kept out of line and off the caller's registers:
+// scenes without point forces must not pay for it.
+__device__ __noinline__ void pf_body(Ctx& c, const JointConst& J, const double* Rb, const double* pb, const double* phi, double* f6,
+                                     bool deriv, double* sa, int NS, int aext, int cext, int t) {
+    double fb[6] = {0, 0, 0, 0, 0, 0};
+    double Kacc[36], Dacc[36];
+    for (int i = 0; i < 36; ++i) Kacc[i] = Dacc[i] = 0.0;
+    double* K = deriv ? Kacc : nullptr;
+    double* D = deriv ? Dacc : nullptr;
     const double* recs = c.pf_s;
     double* blks = c.pf_s + (size_t)2 * c.npf * PF_REC;
     for (int e = 0; e < J.pf_cnt; ++e) {
@@ -580,6 +608,12 @@ __device__ __noinline__ void pf_body(Ctx& c, const JointConst& J, const double* 
             xtmy_store(blk, Rb, pb, Ro, po, Dab, -c.c);
             xtmy_store(blk + 36, Rb, pb, Ro, po, Kab, -c.c);
         }
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) f6[i] = fb[i];
+    if (deriv) {
+        xtmx_add(sa, NS, aext, t, Rb, pb, Dacc, -c.c);
+        xtmx_add(sa, NS, cext, t, Rb, pb, Kacc, -c.c);
     }
 }
 
@@ -796,22 +830,35 @@ __device__ void eval_base2(Ctx2& c, bool deriv) {
         mat3T_vec(Rb, gw, gb);
         fb[3] += m * gb[0]; fb[4] += m * gb[1]; fb[5] += m * gb[2];
         if (GROUND) {
-            const bool hp = c.npf > 0 && J.pf_cnt > 0;
-            if (J.has_ground || hp) {
+            // a cuboid whose lowest corner is clearly above the plane takes no part (ForceGroundCuboid.m:89-93 skips every
+            // corner with d > 0): lowest corner depth = n.(p - xg) - sum_i |n_b,i| hs_i
+            bool contact = false;
+            if (J.has_ground) {
+                double nb[3];
+                mat3T_vec(Rb, J.gng, nb);
+                const double dp = J.gng[0] * (pb[0] - J.gxg[0]) + J.gng[1] * (pb[1] - J.gxg[1]) + J.gng[2] * (pb[2] - J.gxg[2]);
+                const double reach = fabs(nb[0]) * J.hs[0] + fabs(nb[1]) * J.hs[1] + fabs(nb[2]) * J.hs[2];
+                contact = dp - reach <= 1e-12 * (fabs(dp) + reach);
+            }
+            if (contact) {
                 if (deriv) {
                     double K[36], D[36];
 #pragma unroll
                     for (int i = 0; i < 36; ++i) K[i] = D[i] = 0;
-                    if (J.has_ground) ground_body<true>(J, Rb, pb, phi, fb, K, D);
-                    if (hp) pf_body(c, J, Rb, pb, phi, fb, K, D);
+                    ground_body<true>(J, Rb, pb, phi, fb, K, D);
                     xtmx_store(c.sa, NS, F::AEXT, t, Rb, pb, D, -c.c);
                     xtmx_store(c.sa, NS, F::CEXT, t, Rb, pb, K, -c.c);
                 } else {
-                    if (J.has_ground) ground_body<false>(J, Rb, pb, phi, fb, nullptr, nullptr);
-                    if (hp) pf_body(c, J, Rb, pb, phi, fb, nullptr, nullptr);
+                    ground_body<false>(J, Rb, pb, phi, fb, nullptr, nullptr);
                 }
             } else if (deriv) {
                 for (int i = 0; i < 72; ++i) SA(F::AEXT, i, t) = 0.0;
+            }
+            if (c.npf > 0 && J.pf_cnt > 0) {
+                double f6[6];
+                pf_body(c, J, Rb, pb, phi, f6, deriv, c.sa, NS, F::AEXT, F::CEXT, t);
+#pragma unroll
+                for (int i = 0; i < 6; ++i) fb[i] += f6[i];
             }
         }
         double Fb[6], Fw[6];
