@@ -822,6 +822,167 @@ class ForceSpringDamper(ForceSpringGeneric):
         return V, f, self.stiffness / self.L, self.damping / self.L
 
 
+class ForceSpringMultiPointGeneric(Force):
+    """ForceSpringMultiPointGeneric.m -- generic spring routed along a sequence of body points (a body may be None = world)."""
+
+    def __init__(self):
+        self.bodies = []
+        self.xls = []
+
+    def addBodyPoint(self, body, xl):
+        """ForceSpringMultiPointGeneric.m:20"""
+        self.bodies.append(body)
+        self.xls.append(np.asarray(xl, dtype=float).reshape(3))
+
+    def _points(self):
+        """ForceSpringMultiPointGeneric.m:31-53"""
+        out = []
+        for body, xl in zip(self.bodies, self.xls):
+            E = np.eye(4) if body is None else body.E_wi
+            phi = np.zeros(6) if body is None else body.phi
+            G = se3_Gamma(xl)
+            R, p = E[0:3, 0:3], E[0:3, 3]
+            out.append(dict(R=R, p=p, G=G, phi=phi, xl=xl, xw=R @ xl + p, vw=R @ (G @ phi)))
+        return out
+
+    def _length(self, pts):
+        l = 0.0
+        ldot = 0.0
+        for k in range(len(pts) - 1):
+            dx = pts[k + 1]['xw'] - pts[k]['xw']
+            dv = pts[k + 1]['vw'] - pts[k]['vw']
+            dxlen = np.linalg.norm(dx)
+            l += dxlen
+            ldot += (dx @ dv) / dxlen
+        return l, ldot
+
+    def computeValues_(self, fr, fm, Kr=None, Km=None, Dr=None, Dm=None):
+        """ForceSpringMultiPointGeneric.m:29-190"""
+        pts = self._points()
+        npts = len(pts)
+        fn = np.zeros(6 * npts)
+        for k in range(npts - 1):
+            a, b = pts[k], pts[k + 1]
+            dx = b['xw'] - a['xw']
+            dxlen = np.linalg.norm(dx)
+            fx = np.concatenate([a['G'].T @ (a['R'].T @ dx), -(b['G'].T @ (b['R'].T @ dx))])
+            fn[6 * k:6 * k + 12] += fx / dxlen
+        l, ldot = self._length(pts)
+        _, fs, dfsdl, dfsdldot = self.computeSpringForce(l, ldot)
+        f = fs * fn
+        for k, body in enumerate(self.bodies):
+            if body is not None:
+                fm[body.idxM] += f[6 * k:6 * k + 6]
+        if Km is None:
+            return
+        I = np.eye(3)
+        Kn = np.zeros((6 * npts, 6 * npts))
+        dfsdq = np.zeros(6 * npts)
+        dfsdqdot = np.zeros(6 * npts)
+        for k in range(npts - 1):
+            a, b = pts[k], pts[k + 1]
+            sl = slice(6 * k, 6 * k + 12)
+            R1, R2, G1, G2 = a['R'], b['R'], a['G'], b['G']
+            dx = b['xw'] - a['xw']
+            dv = b['vw'] - a['vw']
+            dxlen = np.linalg.norm(dx)
+            dxnor = dx / dxlen
+            A = np.hstack([-R1 @ G1, R2 @ G2])
+            dldq = dxnor @ A
+            dldotdq = ((I - np.outer(dxnor, dxnor)) / dxlen @ dv) @ A
+            for ax in range(3):
+                e = np.zeros(3)
+                e[ax] = 1.0
+                eb = se3_brac(e)
+                dldotdq[ax] += dxnor @ (-R1 @ eb @ (G1 @ a['phi']))
+                dldotdq[6 + ax] += dxnor @ (R2 @ eb @ (G2 @ b['phi']))
+            dfsdq[sl] += dfsdl * dldq + dfsdldot * dldotdq
+            fx = np.concatenate([G1.T @ (R1.T @ dx), -(G2.T @ (R2.T @ dx))])
+            d = -dx / dxlen ** 3
+            K1 = np.outer(fx, np.concatenate([d @ R1 @ G1, -(d @ R2 @ G2)]))
+            K2 = np.zeros((12, 12))
+            x1b = se3_brac(a['xl'])
+            x2b = se3_brac(b['xl'])
+            R2R1 = R2.T @ R1
+            R1R2 = R2R1.T
+            K2[3:6, 0:3] = se3_brac(R1.T @ (a['p'] - b['xw']))
+            K2[0:3, 0:3] = x1b @ K2[3:6, 0:3]
+            K2[9:12, 0:3] = R2R1 @ x1b
+            K2[6:9, 0:3] = x2b @ K2[9:12, 0:3]
+            K2[3:6, 3:6] = I
+            K2[0:3, 3:6] = x1b
+            K2[9:12, 3:6] = -R2R1
+            K2[6:9, 3:6] = x2b @ K2[9:12, 3:6]
+            K2[3:6, 6:9] = R1R2 @ x2b
+            K2[0:3, 6:9] = x1b @ K2[3:6, 6:9]
+            K2[9:12, 6:9] = se3_brac(R2.T @ (b['p'] - a['xw']))
+            K2[6:9, 6:9] = x2b @ K2[9:12, 6:9]
+            K2[3:6, 9:12] = -R1R2
+            K2[0:3, 9:12] = x1b @ K2[3:6, 9:12]
+            K2[9:12, 9:12] = I
+            K2[6:9, 9:12] = x2b
+            Kn[sl, sl] += K1 + K2 / dxlen
+            d = dfsdldot * dxnor
+            dfsdqdot[6 * k:6 * k + 6] -= d @ R1 @ G1
+            dfsdqdot[6 * k + 6:6 * k + 12] += d @ R2 @ G2
+        K = np.outer(fn, dfsdq) - fs * Kn
+        D = np.outer(fn, dfsdqdot)
+        for k1, b1 in enumerate(self.bodies):
+            if b1 is None:
+                continue
+            s1 = slice(6 * k1, 6 * k1 + 6)
+            Km[np.ix_(b1.idxM, b1.idxM)] += K[s1, s1]
+            Dm[np.ix_(b1.idxM, b1.idxM)] += D[s1, s1]
+            for k2 in range(k1 + 1, npts):
+                b2 = self.bodies[k2]
+                if b2 is None:
+                    continue
+                s2 = slice(6 * k2, 6 * k2 + 6)
+                Km[np.ix_(b1.idxM, b2.idxM)] += K[s1, s2]
+                Km[np.ix_(b2.idxM, b1.idxM)] += K[s2, s1]
+                Dm[np.ix_(b1.idxM, b2.idxM)] += D[s1, s2]
+                Dm[np.ix_(b2.idxM, b1.idxM)] += D[s2, s1]
+
+    def computeEnergy_(self, V):
+        """ForceSpringMultiPointGeneric.m:193-232"""
+        l, ldot = self._length(self._points())
+        return V + self.computeSpringForce(l, ldot)[0]
+
+
+class ForceCable(ForceSpringMultiPointGeneric):
+    """ForceCable.m -- a cable routed through several points: pulls only when stretched beyond its rest length."""
+
+    def __init__(self):
+        super().__init__()
+        self.stiffness = 1.0
+        self.damping = 1.0
+        self.L = 0.0
+
+    def setStiffness(self, stiffness):
+        self.stiffness = stiffness
+
+    def setDamping(self, damping):
+        self.damping = damping
+
+    def setRetLength(self, L):
+        self.L = L
+
+    def init_(self):
+        """ForceCable.m:36-63"""
+        if self.L > 0:
+            return
+        self.L = self._length(self._points())[0]
+
+    def computeSpringForce(self, l, ldot):
+        """ForceCable.m:66-81"""
+        strain = (l - self.L) / self.L
+        dstrain = ldot / self.L
+        if strain > 0:
+            return ((self.stiffness / 2) * strain ** 2 * self.L, self.stiffness * strain + self.damping * dstrain,
+                    self.stiffness / self.L, self.damping / self.L)
+        return 0.0, 0.0, 0.0, 0.0
+
+
 class ForcePointPoint(Force):
     """ForcePointPoint.m -- linear zero-rest-length spring/damper between two body points (a body may be None = world)."""
 

@@ -252,6 +252,36 @@ def scenesRedMax(sceneID, api=None):
         scene.bodies = [b1, b2]
         scene.joints = [j1, j2]
         scene.forces = [f1, f2]
+    elif sceneID == 13:  # :340
+        scene.name = 'Cables'
+        scene.Hexpected[:] = [-3.1874892332895153e+04, -2.7872894793863266e+04]
+        b1 = api.BodyCuboid(density, [0.1, 0.1, 0.1])
+        j1 = api.JointFixed(None, b1)
+        b2 = api.BodyCuboid(density, [10, 1, 1])
+        j2 = api.JointRevolute(j1, b2, [0, 1, 0])
+        j2.setJointTransform(np.eye(4))
+        b2.setBodyTransform(_trans([5, 0, 0]))
+        j2.q[0] = math.pi / 2
+        b3 = api.BodyCuboid(density, [10, 1, 1])
+        j3 = api.JointRevolute(j2, b3, [0, 1, 0])
+        j3.setJointTransform(_trans([10, 0, 0]))
+        b3.setBodyTransform(_trans([5, 0, 0]))
+        j3.q[0] = -math.pi / 2
+        b4 = api.BodyCuboid(density, [1, 1, 1])
+        j4 = api.JointPrismatic(j1, b4, [1, 0, 0])
+        j4.setJointTransform(_trans([10, 0, 0]))
+        b4.setBodyTransform(np.eye(4))
+        j4.setStiffness(1e4)
+        j4.setDamping(1e3)
+        f = api.ForceCable()
+        f.setStiffness(1e6)
+        f.setDamping(1e3)
+        f.addBodyPoint(b4, [0, 0, 0])
+        f.addBodyPoint(b2, [-4, 0, 1])
+        f.addBodyPoint(b3, [-4, 0, 1])
+        scene.bodies = [b1, b2, b3, b4]
+        scene.joints = [j1, j2, j3, j4]
+        scene.forces = [f]
     elif sceneID == 14:  # :371
         scene.name = 'Joint limits'
         scene.Hexpected[:] = [-2.5928305306546572e+04, -1.8476279319765570e+04]
