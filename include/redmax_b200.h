@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RMX_VERSION 104
+#define RMX_VERSION 105
 
 /* error codes */
 #define RMX_OK 0
@@ -51,10 +51,13 @@ extern "C" {
 #define RMX_JOINT_UNIVERSAL 6     /* JointUniversal.m      [2] rotation about x then y */
 #define RMX_MAX_JOINT_DOF 3
 #define RMX_MAX_POINTFORCE 8
+#define RMX_MAX_CABLE_POINTS 4
 
 /* two-point forces (pf_* arrays) */
 #define RMX_FORCE_POINTPOINT 0   /* ForcePointPoint.m: linear, zero rest length: f = ks dx + kd dv */
 #define RMX_FORCE_SPRINGDAMPER 1 /* ForceSpringDamper.m (ForceSpringGeneric.m): along the line, f = ks (l-L)/L + kd ldot/L */
+#define RMX_FORCE_CABLE 2        /* ForceCable.m (ForceSpringMultiPointGeneric.m): routed through cable_* points, pulls only when
+                                    stretched; not a pf_kind value -- cables are described by the cable_* arrays */
 
 /* integrators (driverRedMaxBDF1.m, driverRedMaxBDF2.m) */
 #define RMX_SCHEME_BDF1 1
@@ -81,7 +84,7 @@ extern "C" {
 /*
  * Flattened +redmax scene (what scenesRedMax.m builds with redmax.Scene / BodyCuboid / JointRevolute / JointFixed /
  * JointPrismatic / JointPlanar / JointTranslational / JointFree2D / JointUniversal / ForceGroundCuboid /
- * ForcePointPoint after
+ * ForcePointPoint / ForceSpringDamper / ForceCable after
  * scene.init(), Scene.m:59-119).  All pointers are host pointers and are
  * copied by rmx_scene_create.
  */
@@ -123,6 +126,13 @@ typedef struct rmx_scene_desc {
     const int32_t* pf_kind;  /* [npointforce] RMX_FORCE_*; NULL = all RMX_FORCE_POINTPOINT */
     const double* pf_L;      /* [npointforce] rest length of a spring-damper (ForceSpringDamper.m:31); <= 0 or NULL = the
                                 distance of the two points in the initial configuration (ForceSpringDamper.m:38-62) */
+    int32_t ncable;          /* number of ForceCable forces; npointforce + ncable <= RMX_MAX_POINTFORCE */
+    const int32_t* cable_npts; /* [ncable] points per cable, 2 .. RMX_MAX_CABLE_POINTS (ForceSpringMultiPointGeneric.addBodyPoint) */
+    const int32_t* cable_body; /* [RMX_MAX_CABLE_POINTS*ncable] body index of each point or -1 for the world */
+    const double* cable_x;   /* [3*RMX_MAX_CABLE_POINTS*ncable] the points in body (or world) coordinates */
+    const double* cable_ks;  /* [ncable] ForceCable.m:20 */
+    const double* cable_kd;  /* [ncable] ForceCable.m:25 */
+    const double* cable_L;   /* [ncable] rest length (ForceCable.m:30); <= 0 or NULL = routed length in the initial configuration */
 } rmx_scene_desc;
 
 /* Solver constants hard-coded in the reference's newton() (driverRedMaxBDF1.m:95-98;

@@ -112,6 +112,19 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
             sd.pf_kind = pfkind.data();
             sd.pf_L = mxGetDoubles(field(d, "pf_L"));
         }
+        std::vector<int32_t> cnpts, cbody;
+        const mxArray* cn = field(d, "cable_npts", false);
+        if (cn && mxGetNumberOfElements(cn) > 0) {
+            cnpts = to_i32(cn);
+            cbody = to_i32(field(d, "cable_body"));  // RMX_MAX_CABLE_POINTS x ncable
+            sd.ncable = (int32_t)cnpts.size();
+            sd.cable_npts = cnpts.data();
+            sd.cable_body = cbody.data();
+            sd.cable_x = mxGetDoubles(field(d, "cable_x"));  // 3 x RMX_MAX_CABLE_POINTS x ncable
+            sd.cable_ks = mxGetDoubles(field(d, "cable_ks"));
+            sd.cable_kd = mxGetDoubles(field(d, "cable_kd"));
+            sd.cable_L = mxGetDoubles(field(d, "cable_L"));
+        }
         const mxArray* gb = field(d, "ground_body", false);
         if (gb && mxGetNumberOfElements(gb) > 0) {
             gbody = to_i32(gb);

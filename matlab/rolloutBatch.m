@@ -52,6 +52,7 @@ end
 d.grav = scene.grav;
 gb = []; gE = zeros(4,4,0); kn = []; kt = []; kd = []; mu = [];
 pb1 = []; pb2 = []; px1 = zeros(3,0); px2 = zeros(3,0); pks = []; pkd = []; pkind = []; pL = [];
+cn = []; cb = zeros(4,0); cx = zeros(3,4,0); cks = []; ckd = []; cL = []; % RMX_MAX_CABLE_POINTS = 4
 for i = 1 : length(scene.forces)
 	f = scene.forces{i};
 	if isa(f,'redmax.ForceGroundCuboid')
@@ -65,11 +66,19 @@ for i = 1 : length(scene.forces)
 		else
 			pkind(end+1) = 0; pL(end+1) = 0; %#ok<AGROW>
 		end
+	elseif isa(f,'redmax.ForceCable')
+		np = length(f.bodies);
+		cn(end+1) = np; cb(:,end+1) = -1; cx(:,:,end+1) = 0; %#ok<AGROW>
+		for k = 1 : np
+			cb(k,end) = bodyIndex(scene,f.bodies{k}); cx(:,k,end) = f.xls{k};
+		end
+		cks(end+1) = f.stiffness; ckd(end+1) = f.damping; cL(end+1) = f.L; %#ok<AGROW>
 	elseif ~isa(f,'redmax.ForceNull')
-		error('only ForceGroundCuboid, ForcePointPoint and ForceSpringDamper are on the GPU hot path');
+		error('only ForceGroundCuboid, ForcePointPoint, ForceSpringDamper and ForceCable are on the GPU hot path');
 	end
 end
 d.pf_body1 = pb1; d.pf_body2 = pb2; d.pf_x1 = px1; d.pf_x2 = px2; d.pf_ks = pks; d.pf_kd = pkd; d.pf_kind = pkind; d.pf_L = pL;
+d.cable_npts = cn; d.cable_body = cb; d.cable_x = cx; d.cable_ks = cks; d.cable_kd = ckd; d.cable_L = cL;
 d.ground_body = gb; d.ground_E = gE; d.ground_kn = kn; d.ground_kt = kt; d.ground_kd = kd; d.ground_mu = mu;
 end
 

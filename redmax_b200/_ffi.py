@@ -26,6 +26,7 @@ RMX_JOINT_UNIVERSAL = 6
 RMX_MAX_JOINT_DOF = 3
 RMX_FORCE_POINTPOINT = 0
 RMX_FORCE_SPRINGDAMPER = 1
+RMX_MAX_CABLE_POINTS = 4
 RMX_SCHEME_BDF1 = 1
 RMX_SCHEME_BDF2 = 2
 RMX_LINSOLVE_LU = 0
@@ -56,6 +57,8 @@ class rmx_scene_desc(C.Structure):
         ('npointforce', C.c_int32),
         ('pf_body1', _pi), ('pf_body2', _pi), ('pf_x1', _pd), ('pf_x2', _pd), ('pf_ks', _pd), ('pf_kd', _pd),
         ('pf_kind', _pi), ('pf_L', _pd),
+        ('ncable', C.c_int32),
+        ('cable_npts', _pi), ('cable_body', _pi), ('cable_x', _pd), ('cable_ks', _pd), ('cable_kd', _pd), ('cable_L', _pd),
     ]
 
 

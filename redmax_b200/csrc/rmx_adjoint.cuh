@@ -231,28 +231,32 @@ __global__ void __launch_bounds__(32 * NW) energies_kernel(EnergyArgs a) {
                 }
             }
         }
-        if (GROUND && t < c.npf) {  // ForcePointPoint.computeEnergy_ (ForcePointPoint.m:116-132): V += ks/2 |x2_w - x1_w|^2
+        if (GROUND && t < c.npf) {  // Force*.computeEnergy_ (ForcePointPoint.m:116, ForceSpringGeneric.m:146, ForceSpringMultiPointGeneric.m:193)
             const PointForce& P = c.pf[t];
-            double xw[2][3];
-#pragma unroll
-            for (int sd = 0; sd < 2; ++sd) {
-                const double xl[3] = {P.x[sd][0], P.x[sd][1], P.x[sd][2]};
-                if (P.body[sd] >= 0) {
+            double xprev[3] = {0, 0, 0}, len = 0.0, l2 = 0.0;
+            for (int k = 0; k < P.npts; ++k) {
+                const double xl[3] = {P.x[k][0], P.x[k][1], P.x[k][2]};
+                double xw[3];
+                if (P.body[k] >= 0) {
                     double rb[12];
-                    E::body_frame(c, P.body[sd], rb, rb + 9);
-                    mat3_vec(rb, xl, xw[sd]);
-                    xw[sd][0] += rb[9]; xw[sd][1] += rb[10]; xw[sd][2] += rb[11];
+                    E::body_frame(c, P.body[k], rb, rb + 9);
+                    mat3_vec(rb, xl, xw);
+                    xw[0] += rb[9]; xw[1] += rb[10]; xw[2] += rb[11];
                 } else {
-                    xw[sd][0] = xl[0]; xw[sd][1] = xl[1]; xw[sd][2] = xl[2];
+                    xw[0] = xl[0]; xw[1] = xl[1]; xw[2] = xl[2];
                 }
+                if (k > 0) {
+                    const double d0 = xw[0] - xprev[0], d1 = xw[1] - xprev[1], d2 = xw[2] - xprev[2];
+                    l2 = d0 * d0 + d1 * d1 + d2 * d2;
+                    len += sqrt(l2);
+                }
+                xprev[0] = xw[0]; xprev[1] = xw[1]; xprev[2] = xw[2];
             }
-            const double d0 = xw[1][0] - xw[0][0], d1 = xw[1][1] - xw[0][1], d2 = xw[1][2] - xw[0][2];
-            const double l2 = d0 * d0 + d1 * d1 + d2 * d2;
-            if (P.kind == 1) {  // ForceSpringDamper.computeSpringForce: V = ks/2 strain^2 L
-                const double strain = (sqrt(l2) - P.L) / P.L;
-                V += 0.5 * P.ks * strain * strain * P.L;
+            if (P.kind == 0) {
+                V += 0.5 * P.ks * l2;  // zero rest length, linear
             } else {
-                V += 0.5 * P.ks * l2;
+                const double strain = (len - P.L) / P.L;  // spring-damper; cable: only when stretched (ForceCable.m:70)
+                if (P.kind == 1 || strain > 0) V += 0.5 * P.ks * strain * strain * P.L;
             }
         }
         T = block_sum<NW>(T, c.red);

@@ -69,7 +69,8 @@ struct rmx_scene {
     std::vector<int> user2int;    // expanded (virtual) joint index -> internal (preorder) index
     std::vector<int> body2int;    // user joint/body index -> internal index of the virtual joint that carries the body
     std::vector<PointForce> pf;   // ForcePointPoint forces (internal body indices)
-    std::vector<int> pf_ep;       // per-body endpoint lists (JointConst::pf_ptr / pf_cnt), entry = 2*force + side
+    std::vector<int> pf_ep;       // per-body attachment lists (JointConst::pf_ptr / pf_cnt), entry = PF_MAXPTS*force + attachment
+    int pf_doubles = 0;           // shared-memory scratch of the forces (attachment records + cross blocks)
     std::vector<int> anc;         // [nrounds][n] 2^r-th ancestors (internal indices) for the pointer-jumping scans
     int nrounds = 0;
     int impl = 2;                 // 1 = sweep kernels (rmx_device.cuh), 2 = composite kernels (rmx_fast.cuh)
@@ -438,75 +439,115 @@ extern "C" int rmx_scene_create(const rmx_scene_desc* d, rmx_scene** out) {
     }
     s->body2int.assign(n_user, -1);
     for (int j = 0; j < n_user; ++j) s->body2int[j] = s->user2int[x.body_of_user[j]];
-    // ForcePointPoint forces
-    if (d->npointforce < 0 || d->npointforce > RMX_MAX_POINTFORCE) {
+    // forces between body points: ForcePointPoint / ForceSpringDamper (pf_*) and ForceCable (cable_*)
+    const int nforce = (d->npointforce > 0 ? d->npointforce : 0) + (d->ncable > 0 ? d->ncable : 0);
+    if (d->npointforce < 0 || d->ncable < 0 || nforce > RMX_MAX_POINTFORCE) {
         delete s;
-        return fail(RMX_ELIMIT, "rmx_scene_create: at most RMX_MAX_POINTFORCE point forces");
+        return fail(RMX_ELIMIT, "rmx_scene_create: at most RMX_MAX_POINTFORCE point forces and cables");
     }
-    if (d->npointforce > 0) {
-        if (!d->pf_body1 || !d->pf_body2 || !d->pf_x1 || !d->pf_x2 || !d->pf_ks || !d->pf_kd) {
+    if (nforce > 0) {
+        if ((d->npointforce > 0 && (!d->pf_body1 || !d->pf_body2 || !d->pf_x1 || !d->pf_x2 || !d->pf_ks || !d->pf_kd)) ||
+            (d->ncable > 0 && (!d->cable_npts || !d->cable_body || !d->cable_x || !d->cable_ks || !d->cable_kd))) {
             delete s;
-            return fail(RMX_EINVAL, "rmx_scene_create: missing point-force array");
+            return fail(RMX_EINVAL, "rmx_scene_create: missing point-force / cable array");
         }
         if (s->impl != 2) {
             delete s;
             return fail(RMX_ELIMIT, "rmx_scene_create: point forces need the composite kernels (at most 64 virtual joints)");
         }
-        std::vector<std::vector<int>> ep(n);
-        for (int f = 0; f < d->npointforce; ++f) {
+        static_assert(RMX_MAX_CABLE_POINTS == PF_MAXPTS, "cable capacity");
+        for (int f = 0; f < nforce; ++f) {
             PointForce P;
-            const int ub[2] = {d->pf_body1[f], d->pf_body2[f]};
-            for (int sd = 0; sd < 2; ++sd) {
-                if (ub[sd] < -1 || ub[sd] >= n_user) {
+            std::memset(&P, 0, sizeof(P));
+            int ub[PF_MAXPTS] = {-1, -1, -1, -1};
+            if (f < d->npointforce) {
+                P.kind = d->pf_kind ? d->pf_kind[f] : RMX_FORCE_POINTPOINT;
+                if (P.kind != RMX_FORCE_POINTPOINT && P.kind != RMX_FORCE_SPRINGDAMPER) {
+                    delete s;
+                    return fail(RMX_EINVAL, "rmx_scene_create: unknown point-force kind");
+                }
+                P.npts = 2;
+                ub[0] = d->pf_body1[f];
+                ub[1] = d->pf_body2[f];
+                for (int i = 0; i < 3; ++i) {
+                    P.x[0][i] = d->pf_x1[3 * f + i];
+                    P.x[1][i] = d->pf_x2[3 * f + i];
+                }
+                P.ks = d->pf_ks[f];
+                P.kd = d->pf_kd[f];
+                P.L = (d->pf_L && P.kind == RMX_FORCE_SPRINGDAMPER) ? d->pf_L[f] : 0.0;
+            } else {
+                const int cI = f - d->npointforce;
+                P.kind = RMX_FORCE_CABLE;
+                P.npts = d->cable_npts[cI];
+                if (P.npts < 2 || P.npts > PF_MAXPTS) {
+                    delete s;
+                    return fail(RMX_ELIMIT, "rmx_scene_create: a cable has 2 .. RMX_MAX_CABLE_POINTS points");
+                }
+                for (int k = 0; k < P.npts; ++k) {
+                    ub[k] = d->cable_body[PF_MAXPTS * cI + k];
+                    for (int i = 0; i < 3; ++i) P.x[k][i] = d->cable_x[3 * (PF_MAXPTS * cI + k) + i];
+                }
+                P.ks = d->cable_ks[cI];
+                P.kd = d->cable_kd[cI];
+                P.L = d->cable_L ? d->cable_L[cI] : 0.0;
+            }
+            for (int k = 0; k < P.npts; ++k) {
+                if (ub[k] < -1 || ub[k] >= n_user) {
                     delete s;
                     return fail(RMX_EINVAL, "rmx_scene_create: point-force body out of range");
                 }
-                P.body[sd] = ub[sd] < 0 ? -1 : s->body2int[ub[sd]];
-                const double* xs = (sd ? d->pf_x2 : d->pf_x1) + 3 * f;
-                for (int i = 0; i < 3; ++i) P.x[sd][i] = xs[i];
-                if (P.body[sd] >= 0) ep[P.body[sd]].push_back(2 * f + sd);
-            }
-            if (P.body[0] >= 0 && P.body[0] == P.body[1]) {
-                delete s;
-                return fail(RMX_EINVAL, "rmx_scene_create: a point force must connect two different bodies (or a body and the world)");
-            }
-            P.ks = d->pf_ks[f];
-            P.kd = d->pf_kd[f];
-            P.kind = d->pf_kind ? d->pf_kind[f] : RMX_FORCE_POINTPOINT;
-            P.L = (d->pf_L && P.kind == RMX_FORCE_SPRINGDAMPER) ? d->pf_L[f] : 0.0;
-            P.pad_ = 0;
-            if (P.kind != RMX_FORCE_POINTPOINT && P.kind != RMX_FORCE_SPRINGDAMPER) {
-                delete s;
-                return fail(RMX_EINVAL, "rmx_scene_create: unknown point-force kind");
+                P.body[k] = ub[k] < 0 ? -1 : s->body2int[ub[k]];
+                for (int k2 = 0; k2 < k; ++k2)
+                    if (P.body[k] >= 0 && P.body[k] == P.body[k2]) {
+                        delete s;
+                        return fail(RMX_EINVAL, "rmx_scene_create: the points of a force must lie on different bodies (or the world)");
+                    }
             }
             s->pf.push_back(P);
         }
-        {   // rest lengths not given: distance of the two points in the initial configuration (ForceSpringDamper.m:38-62)
-            std::vector<double> Rb, pb;
-            bool have = false;
-            for (PointForce& P : s->pf) {
-                if (P.kind != RMX_FORCE_SPRINGDAMPER || P.L > 0) continue;
-                if (!have) {
-                    host_body_frames(s->jc, Rb, pb);
-                    have = true;
+        // shared-memory scratch offsets, attachment lists, rest lengths
+        std::vector<std::vector<int>> ep(n);
+        std::vector<double> Rb, pb;
+        bool have = false;
+        int off = 0;
+        for (int f = 0; f < nforce; ++f) {
+            PointForce& P = s->pf[f];
+            P.rec_off = off;
+            off += P.npts * PF_REC;
+            P.blk_off = off;
+            off += P.npts * P.npts * PF_BLK;
+            for (int k = 0; k < P.npts; ++k)
+                if (P.body[k] >= 0) ep[P.body[k]].push_back(PF_MAXPTS * f + k);
+            if (P.kind == RMX_FORCE_POINTPOINT || P.L > 0) continue;
+            // rest length not given: (routed) distance of the points in the initial configuration
+            // (ForceSpringDamper.m:38-62, ForceCable.m:36-63)
+            if (!have) {
+                host_body_frames(s->jc, Rb, pb);
+                have = true;
+            }
+            double prev[3] = {0, 0, 0};
+            P.L = 0.0;
+            for (int k = 0; k < P.npts; ++k) {
+                double xw[3];
+                if (P.body[k] >= 0) {
+                    h_mv(&Rb[9 * P.body[k]], P.x[k], xw);
+                    for (int i = 0; i < 3; ++i) xw[i] += pb[3 * P.body[k] + i];
+                } else {
+                    for (int i = 0; i < 3; ++i) xw[i] = P.x[k][i];
                 }
-                double xw[2][3];
-                for (int sd = 0; sd < 2; ++sd) {
-                    if (P.body[sd] >= 0) {
-                        h_mv(&Rb[9 * P.body[sd]], P.x[sd], xw[sd]);
-                        for (int i = 0; i < 3; ++i) xw[sd][i] += pb[3 * P.body[sd] + i];
-                    } else {
-                        for (int i = 0; i < 3; ++i) xw[sd][i] = P.x[sd][i];
-                    }
+                if (k > 0) {
+                    const double d0 = xw[0] - prev[0], d1 = xw[1] - prev[1], d2 = xw[2] - prev[2];
+                    P.L += std::sqrt(d0 * d0 + d1 * d1 + d2 * d2);
                 }
-                const double d0 = xw[1][0] - xw[0][0], d1 = xw[1][1] - xw[0][1], d2 = xw[1][2] - xw[0][2];
-                P.L = std::sqrt(d0 * d0 + d1 * d1 + d2 * d2);
-                if (!(P.L > 0)) {
-                    delete s;
-                    return fail(RMX_EINVAL, "rmx_scene_create: spring with zero rest length (use ForcePointPoint)");
-                }
+                for (int i = 0; i < 3; ++i) prev[i] = xw[i];
+            }
+            if (!(P.L > 0)) {
+                delete s;
+                return fail(RMX_EINVAL, "rmx_scene_create: spring / cable with zero rest length");
             }
         }
+        s->pf_doubles = off;
         for (int k = 0; k < n; ++k) {
             s->jc[k].pf_ptr = (int)s->pf_ep.size();
             s->jc[k].pf_cnt = (int)ep[k].size();
@@ -604,7 +645,7 @@ static int warps_for(const rmx_scene* s) {
 static size_t scene_smem_doubles(const rmx_scene* s, bool keep = true) {
     const bool g = s->has_ground != 0;
     if (s->impl != 2) return smem_doubles(s->n, s->nr, g);
-    if (!s->pf.empty()) return pf_offset_doubles(s->n, s->nr, g, keep) + s->pf.size() * (size_t)PF_DOUBLES;
+    if (!s->pf.empty()) return pf_offset_doubles(s->n, s->nr, g, keep) + (size_t)s->pf_doubles;
     return smem_doubles2(s->n, s->nr, g, keep);
 }
 

@@ -47,25 +47,29 @@ struct JointConst {
     int axsign;     // +1 / -1
     int has_ground;
     int prismatic;  // 1: Q = trans(axis q), S = [0; axis] (JointPrismatic.m:28-34); 0: revolute (or fixed if idx < 0)
-    int pf_ptr;     // CSR into DevScene.pf_ep: point-force endpoints attached to this body (entry = 2*force + side)
+    int pf_ptr;     // CSR into DevScene.pf_ep: force attachments on this body (entry = PF_MAXPTS*force + attachment)
     int pf_cnt;
     int ends_ptr;   // CSR into DevScene.ends_list: joints k whose subtree ends exactly at this index
     int ends_cnt;
 };
 
-// ForcePointPoint (matlab-diff/+redmax/ForcePointPoint.m): linear zero-rest-length spring / damper between two body points
+// Forces between body points (matlab-diff/+redmax): ForcePointPoint.m (linear, zero rest length), ForceSpringDamper.m
+// (ForceSpringGeneric.m, along the line, rest length L) and ForceCable.m (ForceSpringMultiPointGeneric.m, routed through
+// up to PF_MAXPTS points, pulls only when stretched)
+constexpr int PF_MAXPTS = 4;
 struct PointForce {
-    int body[2];      // internal joint index of body 1 / body 2, -1 = world
-    double x[2][3];   // application points in body (or world) coordinates
+    int kind;                  // 0 point-point, 1 spring-damper, 2 cable
+    int npts;                  // 2, or the number of cable points
+    int body[PF_MAXPTS];       // internal joint index of each attachment's body, -1 = world
+    double x[PF_MAXPTS][3];    // application points in body (or world) coordinates
     double ks, kd;
-    double L;         // rest length (kind 1)
-    int kind;         // 0: ForcePointPoint (linear, zero rest length); 1: ForceSpringDamper (ForceSpringGeneric.m + ForceSpringDamper.m)
-    int pad_;
+    double L;                  // rest length (kinds 1, 2)
+    int rec_off;               // offset (doubles) into the shared-memory scratch of this force's attachment records [npts][PF_REC]
+    int blk_off;               // ... and of its cross blocks: ordered pair (k, k2) at blk_off + (k npts + k2) PF_BLK
 };
-constexpr int PF_MAX = 8;        // point forces per scene (shared-memory scratch is sized for this)
-constexpr int PF_REC = 18;       // published per endpoint: R[9] p[3] phi[6]
+constexpr int PF_MAX = 8;        // forces per scene
+constexpr int PF_REC = 18;       // published per attachment: R[9] p[3] phi[6]
 constexpr int PF_BLK = 72;       // per ordered pair: Aext_ab[36], Cext_ab[36] (world frame, row-major)
-constexpr int PF_DOUBLES = 2 * (PF_REC + PF_BLK);  // shared-memory doubles per point force
 
 struct DevScene {
     int n, nr;
@@ -267,7 +271,7 @@ struct Ctx {
     const PointForce* __restrict__ pf;
     const int* __restrict__ pf_ep;
     int npf;
-    double* pf_s;  // [npf][PF_DOUBLES]: endpoint records, then cross blocks
+    double* pf_s;  // attachment records and cross blocks (PointForce::rec_off / blk_off)
     // stage coefficients
     int stage;
     double h;

@@ -473,6 +473,216 @@ __device__ __noinline__ void pf_spring(const PfEnd* E, int sd, double ks, double
         }
 }
 
+// One segment (point a -> point b) of a multi-point spring, ForceSpringMultiPointGeneric.m:58-81 and :103-170: length, length
+// rate, the normalised generalised force fxn = [G1'R1'dx ; -G2'R2'dx] / |dx|, the gradients dldq, dldotdq (1 x 12), the
+// damping row dqd = [-dxnor'R1G1, dxnor'R2G2], and -- for the end `side` (0: a, 1: b, < 0: none) -- the six rows of the
+// normalised-vector stiffness K1 + K2/|dx| (6 x 12 row-major in Knr).
+__device__ __noinline__ void pf_segment(const PfEnd& Ea, const PfEnd& Eb, int side, bool deriv, double* dxlen_out, double* ldot_out,
+                                        double* fxn, double* dldq, double* dldotdq, double* dqd, double* Knr) {
+    const PfEnd* E[2] = {&Ea, &Eb};
+    double xw[2][3], vl[2][3], vw[2][3];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) pf_point(E[e]->R, E[e]->p, E[e]->phi, E[e]->x, xw[e], vl[e], vw[e]);
+    double dx[3], dv[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        dx[i] = xw[1][i] - xw[0][i];
+        dv[i] = vw[1][i] - vw[0][i];
+    }
+    const double l2 = dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2];
+    const double l = sqrt(l2);
+    *dxlen_out = l;
+    *ldot_out = (dx[0] * dv[0] + dx[1] * dv[1] + dx[2] * dv[2]) / l;
+    double fx[12];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        double y[3], t3[3];
+        mat3T_vec(E[e]->R, dx, y);
+        cross3(E[e]->x, y, t3);
+        const double sg = e ? -1.0 : 1.0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            fx[6 * e + i] = sg * t3[i];
+            fx[6 * e + 3 + i] = sg * y[i];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) fxn[i] = fx[i] / l;
+    if (!deriv) return;
+    double A[36];  // [-R1 G1, R2 G2]
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        double X[9], RX[9];
+        brac3(E[e]->x, X);
+        mat3_mul(E[e]->R, X, RX);
+        const double sg = e ? 1.0 : -1.0;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int cI = 0; cI < 3; ++cI) {
+                A[12 * r + 6 * e + cI] = -sg * RX[3 * r + cI];
+                A[12 * r + 6 * e + 3 + cI] = sg * E[e]->R[3 * r + cI];
+            }
+    }
+    double w3[3];
+    {
+        const double dd = dx[0] * dv[0] + dx[1] * dv[1] + dx[2] * dv[2];
+        const double il3 = 1.0 / (l2 * l);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) w3[i] = (l2 * dv[i] - dx[i] * dd) * il3;  // (I - n n')/|dx| dv
+    }
+    double dxA[12];  // dx' A
+#pragma unroll
+    for (int cI = 0; cI < 12; ++cI) {
+        dxA[cI] = dx[0] * A[cI] + dx[1] * A[12 + cI] + dx[2] * A[24 + cI];
+        dldq[cI] = dxA[cI] / l;
+        dldotdq[cI] = w3[0] * A[cI] + w3[1] * A[12 + cI] + w3[2] * A[24 + cI];
+        dqd[cI] = dxA[cI] / l;  // [-n'R1G1, n'R2G2] = n'A
+    }
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        double y[3], t3[3];
+        mat3T_vec(E[e]->R, dx, y);
+        cross3(vl[e], y, t3);
+        const double sg = e ? 1.0 : -1.0;
+#pragma unroll
+        for (int ax = 0; ax < 3; ++ax) dldotdq[6 * e + ax] += sg * t3[ax] / l;
+    }
+    if (side < 0) return;
+    // K1 = fx [d'R1G1, -d'R2G2], d = -dx/|dx|^3  ->  K1 = fx (dx'A) / |dx|^3
+    const double il3 = 1.0 / (l2 * l);
+    for (int i = 0; i < 72; ++i) Knr[i] = 0.0;
+    {
+        const double* R1 = Ea.R;
+        const double* R2 = Eb.R;
+        double x1b[9], x2b[9], R2R1[9], R1R2[9], B[9], T[9], d3[3], a3[3];
+        brac3(Ea.x, x1b);
+        brac3(Eb.x, x2b);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int cI = 0; cI < 3; ++cI) R2R1[3 * r + cI] = R2[r] * R1[cI] + R2[3 + r] * R1[3 + cI] + R2[6 + r] * R1[6 + cI];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int cI = 0; cI < 3; ++cI) R1R2[3 * r + cI] = R2R1[3 * cI + r];
+        auto put = [&](int r0, int c0, const double* M, double sg) {
+            if (r0 / 6 != side) return;
+            for (int r = 0; r < 3; ++r)
+                for (int cI = 0; cI < 3; ++cI) Knr[12 * (r0 - 6 * side + r) + c0 + cI] = sg * M[3 * r + cI] / l;
+        };
+        const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        for (int i = 0; i < 3; ++i) d3[i] = Ea.p[i] - xw[1][i];
+        mat3T_vec(R1, d3, a3);
+        brac3(a3, B);
+        put(3, 0, B, 1.0);
+        mat3_mul(x1b, B, T);
+        put(0, 0, T, 1.0);
+        mat3_mul(R2R1, x1b, B);
+        put(9, 0, B, 1.0);
+        mat3_mul(x2b, B, T);
+        put(6, 0, T, 1.0);
+        put(3, 3, I3, 1.0);
+        put(0, 3, x1b, 1.0);
+        put(9, 3, R2R1, -1.0);
+        mat3_mul(x2b, R2R1, T);
+        put(6, 3, T, -1.0);
+        mat3_mul(R1R2, x2b, B);
+        put(3, 6, B, 1.0);
+        mat3_mul(x1b, B, T);
+        put(0, 6, T, 1.0);
+        for (int i = 0; i < 3; ++i) d3[i] = Eb.p[i] - xw[0][i];
+        mat3T_vec(R2, d3, a3);
+        brac3(a3, B);
+        put(9, 6, B, 1.0);
+        mat3_mul(x2b, B, T);
+        put(6, 6, T, 1.0);
+        put(3, 9, R1R2, -1.0);
+        mat3_mul(x1b, R1R2, T);
+        put(0, 9, T, -1.0);
+        put(9, 9, I3, 1.0);
+        put(6, 9, x2b, 1.0);
+    }
+    for (int r = 0; r < 6; ++r)
+        for (int cI = 0; cI < 12; ++cI) Knr[12 * r + cI] += fx[6 * side + r] * dxA[cI] * il3;
+}
+
+// ForceCable through attachment `me` of force P (ForceSpringMultiPointGeneric.m:29-190, ForceCable.m:66-81): adds this body's
+// wrench to fb and, if K != null, its diagonal blocks to K, D and writes its cross blocks K(me,k2), D(me,k2) (world frame) to
+// shared memory.  K = fn dfsdq - fs Kn, D = fn dfsdqdot.
+__device__ __noinline__ void pf_cable(Ctx& c, const PointForce& P, int me, const double* Rb, const double* pb, double* fb, double* K,
+                                      double* D) {
+    const int np = P.npts;
+    const double* recs = c.pf_s + P.rec_off;
+    PfEnd E[PF_MAXPTS];
+    for (int k = 0; k < np; ++k) {
+        const bool world = P.body[k] < 0;
+        const double* r = recs + (size_t)k * PF_REC;
+        for (int i = 0; i < 9; ++i) E[k].R[i] = world ? ((i % 4 == 0) ? 1.0 : 0.0) : r[i];
+        for (int i = 0; i < 3; ++i) {
+            E[k].p[i] = world ? 0.0 : r[9 + i];
+            E[k].x[i] = P.x[k][i];
+        }
+        for (int i = 0; i < 6; ++i) E[k].phi[i] = world ? 0.0 : r[12 + i];
+    }
+    const bool deriv = K != nullptr;
+    double fn[6] = {0, 0, 0, 0, 0, 0};
+    double dfl[6 * PF_MAXPTS], dfld[6 * PF_MAXPTS], dfd[6 * PF_MAXPTS];  // sums of dldq, dldotdq, dqd over the segments
+    double Knrow[6 * 6 * PF_MAXPTS];                                       // rows of Kn of this attachment
+    for (int i = 0; i < 6 * PF_MAXPTS; ++i) dfl[i] = dfld[i] = dfd[i] = 0.0;
+    for (int i = 0; i < 36 * PF_MAXPTS; ++i) Knrow[i] = 0.0;
+    double l = 0.0, ldot = 0.0;
+    for (int sI = 0; sI + 1 < np; ++sI) {
+        const int side = (me == sI) ? 0 : ((me == sI + 1) ? 1 : -1);
+        double dxlen, ld1, fxn[12], dldq[12], dldotdq[12], dqd[12], Knr[72];
+        pf_segment(E[sI], E[sI + 1], side, deriv, &dxlen, &ld1, fxn, dldq, dldotdq, dqd, Knr);
+        l += dxlen;
+        ldot += ld1;
+        if (side >= 0)
+            for (int i = 0; i < 6; ++i) fn[i] += fxn[6 * side + i];
+        if (deriv) {
+            for (int i = 0; i < 12; ++i) {
+                dfl[6 * sI + i] += dldq[i];
+                dfld[6 * sI + i] += dldotdq[i];
+                dfd[6 * sI + i] += dqd[i];
+            }
+            if (side >= 0)
+                for (int r = 0; r < 6; ++r)
+                    for (int i = 0; i < 12; ++i) Knrow[(6 * PF_MAXPTS) * r + 6 * sI + i] += Knr[12 * r + i];
+        }
+    }
+    // ForceCable.computeSpringForce: pulls only when stretched
+    const double strain = (l - P.L) / P.L, dstrain = ldot / P.L;
+    double fs = 0.0, dfsdl = 0.0, dfsdldot = 0.0;
+    if (strain > 0) {
+        fs = P.ks * strain + P.kd * dstrain;
+        dfsdl = P.ks / P.L;
+        dfsdldot = P.kd / P.L;
+    }
+    for (int i = 0; i < 6; ++i) fb[i] += fs * fn[i];
+    if (!deriv) return;
+    double* blks = c.pf_s + P.blk_off;
+    for (int k2 = 0; k2 < np; ++k2) {
+        double Kb[36], Db[36];
+        for (int r = 0; r < 6; ++r)
+            for (int i = 0; i < 6; ++i) {
+                const int col = 6 * k2 + i;
+                Kb[6 * r + i] = fn[r] * (dfsdl * dfl[col] + dfsdldot * dfld[col]) - fs * Knrow[(6 * PF_MAXPTS) * r + col];
+                Db[6 * r + i] = fn[r] * (dfsdldot * dfd[col]);
+            }
+        if (k2 == me) {
+            for (int i = 0; i < 36; ++i) {
+                K[i] += Kb[i];
+                D[i] += Db[i];
+            }
+        } else if (P.body[k2] >= 0) {
+            double* blk = blks + (size_t)(me * np + k2) * PF_BLK;
+            xtmy_store(blk, Rb, pb, E[k2].R, E[k2].p, Db, -c.c);
+            xtmy_store(blk + 36, Rb, pb, E[k2].R, E[k2].p, Kb, -c.c);
+        }
+    }
+}
+
 // all point forces attached to body t: returns their body-frame wrench in f6 and, if deriv, adds the diagonal blocks
 // -c X'DX, -c X'KX to the external-force fields aext / cext of joint t in the SoA block (after the caller has stored or zeroed
 // them) and writes the cross blocks of its ordered pairs to shared memory.  Kept out of line and off the caller's registers:
@@ -484,12 +694,16 @@ __device__ __noinline__ void pf_body(Ctx& c, const JointConst& J, const double* 
     for (int i = 0; i < 36; ++i) Kacc[i] = Dacc[i] = 0.0;
     double* K = deriv ? Kacc : nullptr;
     double* D = deriv ? Dacc : nullptr;
-    const double* recs = c.pf_s;
-    double* blks = c.pf_s + (size_t)2 * c.npf * PF_REC;
     for (int e = 0; e < J.pf_cnt; ++e) {
         const int code = __ldg(c.pf_ep + J.pf_ptr + e);
-        const int f = code >> 1, sd = code & 1;
+        const int f = code / PF_MAXPTS, sd = code % PF_MAXPTS;
         const PointForce& P = c.pf[f];
+        const double* recs = c.pf_s + P.rec_off;  // attachment k at recs + k PF_REC
+        double* blks = c.pf_s + P.blk_off;        // ordered pair (k, k2) at blks + (k npts + k2) PF_BLK
+        if (P.kind == 2) {  // ForceCable
+            pf_cable(c, P, sd, Rb, pb, fb, K, D);
+            continue;
+        }
         const int ob = P.body[1 - sd];
         const double ks = P.ks, kd = P.kd;
         double xl[3] = {P.x[sd][0], P.x[sd][1], P.x[sd][2]}, xo[3] = {P.x[1 - sd][0], P.x[1 - sd][1], P.x[1 - sd][2]};
@@ -497,7 +711,7 @@ __device__ __noinline__ void pf_body(Ctx& c, const JointConst& J, const double* 
         pf_point(Rb, pb, phi, xl, xw, vl, vw);
         double Ro[9], po[3];
         if (ob >= 0) {
-            const double* r = recs + (size_t)(2 * f + (1 - sd)) * PF_REC;
+            const double* r = recs + (size_t)(1 - sd) * PF_REC;
 #pragma unroll
             for (int i = 0; i < 9; ++i) Ro[i] = r[i];
 #pragma unroll
@@ -525,7 +739,7 @@ __device__ __noinline__ void pf_body(Ctx& c, const JointConst& J, const double* 
 #pragma unroll
             for (int i = 0; i < 6; ++i) {
                 me.phi[i] = phi[i];
-                ot.phi[i] = (ob >= 0) ? recs[(size_t)(2 * f + (1 - sd)) * PF_REC + 12 + i] : 0.0;
+                ot.phi[i] = (ob >= 0) ? recs[(size_t)(1 - sd) * PF_REC + 12 + i] : 0.0;
             }
             double f6[6], Ko[36], Do[36], Kab[36], Dab[36];
             pf_spring(E, sd, ks, kd, P.L, f6, Ko, Do, Kab, Dab, K != nullptr);
@@ -537,7 +751,7 @@ __device__ __noinline__ void pf_body(Ctx& c, const JointConst& J, const double* 
                     D[i] += Do[i];
                 }
                 if (ob >= 0) {
-                    double* blk = blks + (size_t)(2 * f + sd) * PF_BLK;
+                    double* blk = blks + (size_t)(sd * 2 + (1 - sd)) * PF_BLK;
                     xtmy_store(blk, Rb, pb, ot.R, ot.p, Dab, -c.c);
                     xtmy_store(blk + 36, Rb, pb, ot.R, ot.p, Kab, -c.c);
                 }
@@ -604,7 +818,7 @@ __device__ __noinline__ void pf_body(Ctx& c, const JointConst& J, const double* 
                 }
             pf_gammaT(xl, Kin, Kab, false);
             pf_gammaT(xl, Din, Dab, false);
-            double* blk = blks + (size_t)(2 * f + sd) * PF_BLK;
+            double* blk = blks + (size_t)(sd * 2 + (1 - sd)) * PF_BLK;
             xtmy_store(blk, Rb, pb, Ro, po, Dab, -c.c);
             xtmy_store(blk + 36, Rb, pb, Ro, po, Kab, -c.c);
         }
@@ -622,17 +836,18 @@ __device__ __noinline__ void pf_body(Ctx& c, const JointConst& J, const double* 
 // Thread t owns column joint t; Wb: joint-major rows [L_k ; s_k] (stride NWD, s at offset NL).
 __device__ __forceinline__ void pf_cross_pass(Ctx2& c, int t, int myidx, const double* c1, const double* sqs, double scale, double* out,
                                               int ld, const double* Wb, int NWD, int NL) {
-    const double* blks = c.pf_s + (size_t)2 * c.npf * PF_REC;
     const int myend = (myidx >= 0) ? c.ie_s[t].y : 0;
     for (int f = 0; f < c.npf; ++f) {
-        const int b0 = c.pf[f].body[0], b1 = c.pf[f].body[1];
-        if (b0 < 0 || b1 < 0) continue;  // uniform
-        for (int sd = 0; sd < 2; ++sd) {
-            const int a = sd ? b1 : b0, b = sd ? b0 : b1;
+        const PointForce& P = c.pf[f];
+        const int np = P.npts;
+        for (int pr = 0; pr < np * np; ++pr) {  // ordered pairs (k1, k2) of attachments on two bodies
+            const int k1 = pr / np, k2 = pr - k1 * np;
+            const int a = P.body[k1], b = P.body[k2];
+            if (k1 == k2 || a < 0 || b < 0) continue;  // uniform
             const bool mine = myidx >= 0 && t <= b && b < myend;
             double y[6] = {0, 0, 0, 0, 0, 0};
             if (mine) {
-                const double* A = blks + (size_t)(2 * f + sd) * PF_BLK;
+                const double* A = c.pf_s + P.blk_off + (size_t)pr * PF_BLK;
 #pragma unroll
                 for (int r = 0; r < 6; ++r) {
                     double acc = 0.0;
@@ -799,7 +1014,8 @@ __device__ void eval_base2(Ctx2& c, bool deriv) {
             pb[0] += pj[0]; pb[1] += pj[1]; pb[2] += pj[2];
             xm_w2b(Rb, pb, Vj, phi);
             for (int e = 0; e < J.pf_cnt; ++e) {
-                double* r = c.pf_s + (size_t)__ldg(c.pf_ep + J.pf_ptr + e) * PF_REC;
+                const int code = __ldg(c.pf_ep + J.pf_ptr + e);
+                double* r = c.pf_s + c.pf[code / PF_MAXPTS].rec_off + (code % PF_MAXPTS) * PF_REC;
 #pragma unroll
                 for (int i = 0; i < 9; ++i) r[i] = Rb[i];
 #pragma unroll

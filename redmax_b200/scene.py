@@ -244,6 +244,32 @@ class ForceSpringDamper(ForcePointPoint):
         self.L = float(L)
 
 
+class ForceCable:
+    """+redmax/ForceCable.m (ForceSpringMultiPointGeneric.m) -- a cable routed through up to four body points (a body may be
+    None = world); pulls only when stretched beyond its rest length L (default: routed length in the initial configuration)."""
+
+    def __init__(self):
+        self.bodies = []
+        self.xls = []
+        self.stiffness = 1.0
+        self.damping = 1.0
+        self.L = 0.0
+
+    def addBodyPoint(self, body, xl):
+        """ForceSpringMultiPointGeneric.m:20"""
+        self.bodies.append(body)
+        self.xls.append(np.asarray(xl, dtype=float).reshape(3))
+
+    def setStiffness(self, stiffness):
+        self.stiffness = float(stiffness)
+
+    def setDamping(self, damping):
+        self.damping = float(damping)
+
+    def setRetLength(self, L):
+        self.L = float(L)
+
+
 class _TaskPointPos:
     """+redmax/TaskBDF1PointPos.m / TaskBDF2PointPos.m (parameters = constant joint torques, objective = a body
     point reaching a target at time t)."""
@@ -375,12 +401,30 @@ class Scene:
         d.grav = (C.c_double * 3)(*[float(x) for x in self.grav])
         grounds = [f for f in self.forces if isinstance(f, ForceGroundCuboid)]
         points = [f for f in self.forces if isinstance(f, ForcePointPoint)]
-        if len(grounds) + len(points) != len(self.forces):
-            raise RmxError('only ForceGroundCuboid, ForcePointPoint and ForceSpringDamper are on the GPU hot path '
+        cables = [f for f in self.forces if isinstance(f, ForceCable)]
+        bidx = {id(j.body): i for i, j in enumerate(self.joints)}
+        d.ncable = len(cables)
+        if cables:
+            mp = _ffi.RMX_MAX_CABLE_POINTS
+            if any(not (2 <= len(f.bodies) <= mp) for f in cables):
+                raise RmxError('a cable has 2 .. %d points' % mp)
+            cb = -np.ones((len(cables), mp), dtype=np.int32)
+            cx = np.zeros((len(cables), mp, 3))
+            for i, f in enumerate(cables):
+                for k, (b, xl) in enumerate(zip(f.bodies, f.xls)):
+                    cb[i, k] = -1 if b is None else bidx[id(b)]
+                    cx[i, k] = xl
+            d.cable_npts = arr([len(f.bodies) for f in cables], i32)
+            d.cable_body = arr(cb, i32)
+            d.cable_x = arr(cx, f64)
+            d.cable_ks = arr([f.stiffness for f in cables], f64)
+            d.cable_kd = arr([f.damping for f in cables], f64)
+            d.cable_L = arr([f.L for f in cables], f64)
+        if len(grounds) + len(points) + len(cables) != len(self.forces):
+            raise RmxError('only ForceGroundCuboid, ForcePointPoint, ForceSpringDamper and ForceCable are on the GPU hot path '
                            '(SURVEY.md section 8)')
         d.npointforce = len(points)
         if points:
-            bidx = {id(j.body): i for i, j in enumerate(self.joints)}
             d.pf_body1 = arr([(-1 if f.body1 is None else bidx[id(f.body1)]) for f in points], i32)
             d.pf_body2 = arr([(-1 if f.body2 is None else bidx[id(f.body2)]) for f in points], i32)
             d.pf_x1 = arr(np.concatenate([f.x_1 for f in points]), f64)

@@ -7,7 +7,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-IN_SCOPE = [0, 1, 2, 3, 4, 5, 6, 8, 10, 12, 14]
+IN_SCOPE = [0, 1, 2, 3, 4, 5, 6, 8, 10, 12, 13, 14]
 
 
 @pytest.mark.parametrize('sid', IN_SCOPE)

@@ -157,3 +157,82 @@ def test_spring_variant_rollout_and_energy(rb, oracle):
     so.update()
     To, Vo = so.computeEnergies()
     assert abs(V[0] - Vo) <= 1e-10 * max(1.0, abs(Vo)) and abs(T[0] - To) <= 1e-10 * max(1.0, abs(To))
+
+
+def cable_variant(api=None):
+    """scene 13 with a second, world-anchored two-point cable and a four-point cable with a set rest length."""
+    import redmax_b200 as rb
+    api = api or rb
+    sc = rb.scenesRedMax(13, api=api)
+    f2 = api.ForceCable()
+    f2.setStiffness(4e5)
+    f2.setDamping(2e3)
+    f2.addBodyPoint(None, [12.0, 0.5, 6.0])
+    f2.addBodyPoint(sc.bodies[2], [3.0, 0.0, 0.5])
+    f3 = api.ForceCable()
+    f3.setStiffness(2e5)
+    f3.setDamping(1e3)
+    f3.setRetLength(20.0)
+    f3.addBodyPoint(sc.bodies[3], [0.2, 0.0, 0.3])
+    f3.addBodyPoint(sc.bodies[1], [2.0, 0.0, -0.5])
+    f3.addBodyPoint(sc.bodies[2], [1.0, 0.2, 0.5])
+    f3.addBodyPoint(None, [-3.0, 1.0, -14.0])
+    sc.forces += [f2, f3]
+    return sc
+
+
+CABLE_CASES = [('scene13', lambda rb: (rb.scenesRedMax, (13,), {})), ('cable_variant', lambda rb: (cable_variant, (), {}))]
+
+
+@pytest.mark.parametrize('name,mk', CABLE_CASES, ids=[c[0] for c in CABLE_CASES])
+def test_cable_eval_matches_oracle(rb, oracle, name, mk):
+    """ForceCable (ForceSpringMultiPointGeneric.m:29-190): taut and slack states, g, H, M, D and the Newton step."""
+    factory, a, kw = mk(rb)
+    sg, so = both(rb, oracle, factory, *a, **kw)
+    rng = np.random.default_rng(79)
+    nr, h = sg.nr, sg.h
+    taut = 0
+    for trial in range(6):
+        q = sg.qInit + 0.4 * rng.uniform(-1, 1, nr)
+        q0 = q - 0.02 * rng.uniform(-1, 1, nr)
+        qdot0 = rng.uniform(-1, 1, nr)
+        g, H, M, D, f = oracle_eval(oracle, so, q, qdot0, q0, None)
+        so.setQ(q, (q - q0) / h)
+        so.update()
+        pts = so.forces[0]._points()
+        taut += so.forces[0]._length(pts)[0] > so.forces[0].L
+        args = (q, (q - q0) / h, q - q0 - h * qdot0, h * h, 1.0 / h)
+        out = sg.eval(*args)
+        for nm_, ref, tol in (('g', g, TOL_EVAL), ('H', H, TOL_EVAL), ('M', M, TOL_EVAL), ('f', f, 1e-9)):
+            assert rel_err(out[nm_], ref) < tol, (name, trial, nm_, rel_err(out[nm_], ref))
+        assert np.max(np.abs(out['D'] - D)) < 1e-10 * max(np.max(np.abs(D)), np.max(np.abs(M)))
+        nw = sg.eval_newton(*args)
+        assert rel_err(nw['H'], H) < TOL_EVAL
+    assert 0 < taut < 6 or name != 'scene13', taut  # both branches of ForceCable.computeSpringForce were exercised
+
+
+@pytest.mark.parametrize('itype', [1, 2])
+def test_scene13_golden_energy_and_trajectory(rb, oracle, itype):
+    sg, so = both(rb, oracle, rb.scenesRedMax, 13)
+    out = sg.rollout(scheme=itype)
+    assert out['status'].tolist() == [0]
+    T1, V1 = sg.energies(out['q'][0, -1], out['qdot'][0, -1])
+    _, V0 = sg.energies(sg.qInit, sg.qdotInit)
+    Hend = T1[0] + V1[0] - V0[0]
+    assert abs(Hend - sg.Hexpected[itype - 1]) <= 1e-2, (Hend, sg.Hexpected[itype - 1])
+    qs, _ = oracle.run_forward(so, itype, sg.qInit, sg.qdotInit)
+    assert rel_err(out['q'][0], qs) < TOL_Q, rel_err(out['q'][0], qs)
+
+
+def test_cable_variant_rollout_and_energy(rb, oracle):
+    sg, so = both(rb, oracle, cable_variant)
+    q0, qd0 = rb.synthetic_inputs(sg, 2, seed=33)
+    out = sg.rollout(q0, qd0, scheme=1, nsteps=50)
+    for b in range(2):
+        qs, _ = oracle.run_forward(so, 1, q0[b], qd0[b], nsteps=50)
+        assert rel_err(out['q'][b], qs) < TOL_Q, (b, rel_err(out['q'][b], qs))
+    T, V = sg.energies(q0[1], qd0[1])
+    so.setQ(q0[1], qd0[1])
+    so.update()
+    To, Vo = so.computeEnergies()
+    assert abs(V[0] - Vo) <= 1e-10 * max(1.0, abs(Vo)) and abs(T[0] - To) <= 1e-10 * max(1.0, abs(To))

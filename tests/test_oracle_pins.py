@@ -22,6 +22,8 @@ PINS = {
     10: (1.2376477982839792e+03, 4.1146190850293169e+03),
     # ForceSpringDamper (scene 12 'Spring-damper', scenesRedMax.m:314-315)
     12: (-2.2145412057327565e+04, -8.9887693524038732e+03),
+    # ForceCable through a prismatic, a fixed and two revolute joints (scene 13 'Cables', scenesRedMax.m:342-343)
+    13: (-3.1874892332895153e+04, -2.7872894793863266e+04),
 }
 
 
@@ -38,7 +40,7 @@ def test_hexpected(oracle, sid, itype):
     assert abs(H - PINS[sid][itype - 1]) < 1e-6
 
 
-@pytest.mark.parametrize('sid', [3, 4, 5, 6, 8, 10, 12])
+@pytest.mark.parametrize('sid', [3, 4, 5, 6, 8, 10, 12, 13])
 @pytest.mark.parametrize('itype', [1, 2])
 def test_hexpected_more_joint_types(oracle, sid, itype):
     """JointPrismatic / JointPlanar / JointTranslational / JointFree2D / JointUniversal restatements against the
