@@ -217,6 +217,12 @@ int rmx_eval(rmx_scene* s, const double* q, const double* qdot, const double* dq
 int rmx_eval_newton(rmx_scene* s, const double* q, const double* qdot, const double* dqtmp, const double* tau,
                     double cK, double beta, double* H, double* dx);
 
+/* Test hook (host only): the load-balancing plan of a forward launch -- B rollouts x nsteps steps over `slots` co-resident
+ * blocks (McNaughton wrap-around: a rollout is cut at most once; its first part opens one block's list and signals, its second
+ * part closes the previous block's list and waits).  seg: 4 ints per segment {rollout, first step, end step, flags: 1 wait,
+ * 2 signal}; off: slots + 1 offsets.  Returns the number of segments or a negative RMX_E* code. */
+int rmx_debug_schedule(int64_t B, int32_t nsteps, int64_t slots, int32_t seg_capacity, int32_t* seg, int32_t* off);
+
 /* Scene.saveHistory energies (Scene.m:155-160; Joint.m:616, Body.m:167, ForceGroundCuboid.m:156) for B states:
  * T, V: B each. */
 int rmx_energies(rmx_scene* s, int64_t B, const double* q, const double* qdot, double* T, double* V);

@@ -1052,4 +1052,23 @@ extern "C" int rmx_eval_newton(rmx_scene* s, const double* q, const double* qdot
     return rc;
 }
 
+// Test hook (host only, no GPU needed): the load-balancing plan a forward launch of B rollouts x nsteps steps would use on
+// `slots` co-resident blocks.  seg: 4 ints per segment {rollout, first step, end step, flags (1 wait, 2 signal)}; off: slots+1.
+// Returns the number of segments (at most B + slots), or a negative error code if seg_capacity is too small.
+extern "C" int rmx_debug_schedule(int64_t B, int32_t nsteps, int64_t slots, int32_t seg_capacity, int32_t* seg, int32_t* off) {
+    if (B < 1 || nsteps < 1 || slots < 1 || !seg || !off) return fail(RMX_EINVAL, "rmx_debug_schedule: bad arguments");
+    if (B <= slots) return fail(RMX_EINVAL, "rmx_debug_schedule: B <= slots launches one block per rollout (no plan)");
+    SchedPlan p;
+    build_plan(p, B, nsteps, slots);
+    if ((int64_t)p.seg.size() > seg_capacity) return fail(RMX_EINVAL, "rmx_debug_schedule: seg_capacity too small");
+    for (size_t i = 0; i < p.seg.size(); ++i) {
+        seg[4 * i] = p.seg[i].x;
+        seg[4 * i + 1] = p.seg[i].y;
+        seg[4 * i + 2] = p.seg[i].z;
+        seg[4 * i + 3] = p.seg[i].w;
+    }
+    for (size_t i = 0; i < p.off.size(); ++i) off[i] = p.off[i];
+    return (int)p.seg.size();
+}
+
 #include "rmx_api_adjoint.inc"
