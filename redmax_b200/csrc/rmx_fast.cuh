@@ -125,6 +125,8 @@ struct Ctx2 : Ctx {
     double2* tcrow_s;     // [2][5] pivot-row buffers of the blocked LU
     const int* __restrict__ anc;  // [nrounds][n] ancestor tables (global)
     int nrounds;
+    int anc_r[6];  // this thread's 2^r-th ancestors (nrounds <= 6 for n <= 64), read once per kernel: the scans' rounds are
+                   // a dependent chain and must not wait for a global load each
 };
 
 __device__ __forceinline__ void ctx2_carve(Ctx2& c, double* sm, int n, int nr, bool ground, bool keep) {
@@ -912,8 +914,10 @@ __device__ void eval_base2(Ctx2& c, bool deriv) {
     }
     bsync<NW>();
     // ---- world frames: pointer-jumping prefix product  E_w,j = E_w,anc o E_(anc, j] -----------------------------
-    for (int r = 0; r < c.nrounds; ++r) {
-        const int a = (t < n) ? __ldg(c.anc + r * n + t) : -1;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        if (r >= c.nrounds) break;  // uniform
+        const int a = c.anc_r[r];
         if (a >= 0) {
             double Ra[9], pa[3], Rn[9], pn[3];
 #pragma unroll
@@ -960,8 +964,10 @@ __device__ void eval_base2(Ctx2& c, bool deriv) {
         }
     }
     bsync<NW>();
-    for (int r = 0; r < c.nrounds; ++r) {
-        const int a = (t < n) ? __ldg(c.anc + r * n + t) : -1;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        if (r >= c.nrounds) break;  // uniform
+        const int a = c.anc_r[r];
         if (a >= 0) {
 #pragma unroll
             for (int i = 0; i < 6; ++i) Vj[i] += SA(F::V, i, a);
@@ -991,8 +997,10 @@ __device__ void eval_base2(Ctx2& c, bool deriv) {
         for (int i = 0; i < 6; ++i) SA(F::U, i, t) = Uj[i];
     }
     bsync<NW>();
-    for (int r = 0; r < c.nrounds; ++r) {
-        const int a = (t < n) ? __ldg(c.anc + r * n + t) : -1;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        if (r >= c.nrounds) break;  // uniform
+        const int a = c.anc_r[r];
         if (a >= 0) {
 #pragma unroll
             for (int i = 0; i < 6; ++i) Uj[i] += SA(F::U, i, a);

@@ -148,6 +148,8 @@ struct Eval<2, NW, GROUND, KEEP, LIN> {
         c.is_chain = sc.is_chain;
         c.anc = sc.anc;
         c.nrounds = sc.nrounds;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) c.anc_r[r] = (r < sc.nrounds && (int)threadIdx.x < sc.n) ? __ldg(sc.anc + r * sc.n + threadIdx.x) : -1;
         c.pf = sc.pf;
         c.pf_ep = sc.pf_ep;
         c.npf = sc.npf;
