@@ -75,3 +75,66 @@ def test_compute_fails_loudly_without_gpu(rb):
     s.init()
     with pytest.raises(rb.RmxError):
         s.rollout()
+
+
+def _two_link(rb):
+    s = rb.Scene()
+    b1, b2 = rb.BodyCuboid(1, [4, 1, 1]), rb.BodyCuboid(1, [4, 1, 1])
+    j1 = rb.JointRevolute(None, b1, [0, 1, 0])
+    j2 = rb.JointRevolute(j1, b2, [0, 1, 0])
+    E = np.eye(4)
+    E[0, 3] = 4.0
+    j2.setJointTransform(E)
+    s.bodies = [b1, b2]
+    s.joints = [j1, j2]
+    return s, b1, b2
+
+
+def test_scene_create_validates_forces(rb):
+    """rmx_scene_create (host only): error behaviour for the two-point forces and cables."""
+    import pytest
+    s, b1, b2 = _two_link(rb)
+    s.forces = [rb.ForcePointPoint(b1, [0, 0, 0], b1, [1, 0, 0])]          # both points on one body
+    with pytest.raises(rb.RmxError):
+        s.init()
+    s, b1, b2 = _two_link(rb)
+    s.forces = [rb.ForcePointPoint(b1, [0, 0, 0], b2, [1, 0, 0]) for _ in range(9)]   # more than RMX_MAX_POINTFORCE
+    with pytest.raises(rb.RmxError):
+        s.init()
+    s, b1, b2 = _two_link(rb)
+    f = rb.ForceSpringDamper(b1, [2, 0, 0], b2, [-2, 0, 0])               # coincident points: zero rest length
+    s.forces = [f]
+    with pytest.raises(rb.RmxError):
+        s.init()
+    s, b1, b2 = _two_link(rb)
+    c = rb.ForceCable()
+    c.addBodyPoint(b1, [0, 0, 0])                                          # a cable needs at least two points
+    s.forces = [c]
+    with pytest.raises(rb.RmxError):
+        s.init()
+    s, b1, b2 = _two_link(rb)
+    c = rb.ForceCable()
+    c.addBodyPoint(None, [0, 0, 5])
+    c.addBodyPoint(b1, [1, 0, 0])
+    c.addBodyPoint(b2, [1, 0, 0])
+    f = rb.ForceSpringDamper(None, [0, 0, -3], b2, [2, 0, 0])
+    s.forces = [c, f, rb.ForcePointPoint(b1, [0, 0, 1], b2, [0, 0, 1])]
+    s.init()                                                               # a valid mix is accepted
+    assert s.nr == 2 and s.nm == 12
+
+
+def test_scene_create_accepts_every_hot_path_joint_type(rb):
+    s = rb.Scene()
+    bs = [rb.BodyCuboid(1, [1, 1, 1]) for _ in range(7)]
+    js = [rb.JointFixed(None, bs[0])]
+    js.append(rb.JointRevolute(js[0], bs[1], [0, 0, 1]))
+    js.append(rb.JointPrismatic(js[1], bs[2], [1, 0, 0]))
+    js.append(rb.JointPlanar(js[2], bs[3]))
+    js.append(rb.JointTranslational(js[3], bs[4]))
+    js.append(rb.JointFree2D(js[4], bs[5]))
+    js.append(rb.JointUniversal(js[5], bs[6]))
+    s.bodies, s.joints = bs, js
+    s.init()
+    assert s.nr == 0 + 1 + 1 + 2 + 3 + 3 + 2 and s.nm == 42
+    # leaf-to-root numbering with consecutive DOFs per joint (Scene.m:69-71, Joint.m:152)
+    assert js[-1].idxR.tolist() == [0, 1] and js[1].idxR.tolist() == [11]
