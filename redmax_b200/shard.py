@@ -33,10 +33,11 @@ def take_shard(array, world, rank):
     return array[lo:hi]
 
 
-def gather_trajectories(local, B=None, group=None):
+def gather_trajectories(local, B=None, group=None, out=None):
     """All-gather batch-leading trajectory shards (B_local x nsteps x nr) into the full (B x nsteps x nr) tensor on every
     rank.  Equal shards use one `all_gather_into_tensor` (a single NCCL all-gather over NVLink on the GPU box); ragged
-    shards (B not a multiple of the world size) are padded to the largest shard and trimmed after the gather."""
+    shards (B not a multiple of the world size) are padded to the largest shard and trimmed after the gather.  `out`: optional
+    preallocated (B x nsteps x nr) tensor for the equal-shard case (keeps the allocation out of a timed region)."""
     import torch
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()):
@@ -54,7 +55,8 @@ def gather_trajectories(local, B=None, group=None):
         raise ValueError('gather_trajectories: rank %d holds %d rollouts, partition says %d' % (rank, local.shape[0], sizes[rank]))
     local = local.contiguous()
     if len(set(sizes)) == 1:
-        out = local.new_empty((B,) + tuple(local.shape[1:]))
+        if out is None:
+            out = local.new_empty((B,) + tuple(local.shape[1:]))
         dist.all_gather_into_tensor(out, local, group=group)
         return out
     m = max(sizes)
