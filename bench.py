@@ -153,7 +153,8 @@ def workload_config(name, gpus):
     return {'workload': name, 'tree': '%d-link serial chain, all revolute' % w['n'], 'nr': w['n'],
             'scheme': 'BDF1' if w['scheme'] == 1 else 'SDIRK2+BDF2', 'h': w['h'], 'nsteps': w['nsteps'],
             'ground_friction': w['ground'], 'rollouts_per_gpu': w['B'], 'global_rollouts': w['B'] * gpus,
-            'parallelism': 'batch sharded over %d GPU(s), no data-path collective' % gpus,
+            'parallelism': 'batch sharded over %d GPU(s), no data-path collective; on each GPU the rollouts are load-balanced '
+                           'over the co-resident blocks (McNaughton schedule), one persistent launch' % gpus,
             'l2': 'flushed between timed iterations (256 MiB write); outputs per step (%.0f MB) exceed L2 as well'
                   % (2 * 8 * w['n'] * w['nsteps'] * w['B'] / 1e6),
             'seed': SEED}
