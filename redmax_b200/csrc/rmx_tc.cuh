@@ -76,7 +76,6 @@ __device__ __forceinline__ void eval_columns_tc(Ctx2& c, double sq, double sqd, 
     }
     __syncwarp();
     const int nT = (n + 7) >> 3;
-    const bool chain = c.is_chain != 0;
     const int* __restrict__ idxs = c.tcidx_s;
     __builtin_assume(__isShared(idxs));
     // rows >= n of W / RZ are never written: whatever is there only reaches C rows / columns >= n, which are not stored
@@ -93,25 +92,8 @@ __device__ __forceinline__ void eval_columns_tc(Ctx2& c, double sq, double sqd, 
         const unsigned subk = (idxk >= 0) ? c.tcsub_s[k] : 0u;
         const unsigned anck = (idxk >= 0) ? c.tcanc_s[k] : 0u;
         double* orow = out + idxk;
-        for (int J = 0; J < nT; ++J) {
-            // serial chain: a tile strictly above the diagonal holds ancestor entries only, strictly below subtree entries only
-            const bool need_sub = !chain || I >= J;
-            const bool need_anc = !chain || I <= J;
-            const double* rz = RZb + (8 * J + g) * NWD + t4;  // column joint 8J+g of this lane's B fragments
-            double s0 = 0.0, s1 = 0.0, z0 = 0.0, z1 = 0.0;
-            if (need_sub) {
-#pragma unroll
-                for (int ks = 0; ks < KS1; ++ks) {
-                    const double bf = (4 * ks + 3 < NL || 4 * ks + t4 < NL) ? rz[4 * ks] : 0.0;
-                    dmma884(s0, s1, a1[ks], bf);
-                }
-            }
-            if (need_anc) {
-                const double b0 = rz[NL];
-                const double b1 = (t4 < 2) ? rz[NL + 4] : 0.0;
-                dmma884(z0, z1, a2[0], b0);
-                dmma884(z0, z1, a2[1], b1);
-            }
+        // epilogue of one tile: pick subtree / ancestor / zero per entry (one bit test each) and store
+        auto store_tile = [&](int J, double s0, double s1, double z0, double z1) {
             const int i0 = 8 * J + 2 * t4;  // column joints i0, i0+1 of this lane's C elements (tcidx_s has 32 entries)
             const int2 ix = *reinterpret_cast<const int2*>(idxs + i0);
             const unsigned sb = subk >> i0, ab = anck >> i0;
@@ -121,6 +103,30 @@ __device__ __forceinline__ void eval_columns_tc(Ctx2& c, double sq, double sqd, 
                 if (i0 < n && ix.x >= 0) orow[ix.x * LD] = scale * v0;
                 if (i0 + 1 < n && ix.y >= 0) orow[ix.y * LD] = scale * v1;
             }
+        };
+        // two tiles of the row at a time: their DMMA chains (3 or 5 + 2 dependent instructions each, 26 cycles apart) interleave
+        for (int J = 0; J < nT; J += 2) {
+            const bool two = J + 1 < nT;  // warp-uniform
+            const double* rzA = RZb + (8 * J + g) * NWD + t4;  // column joint 8J+g of this lane's B fragments
+            const double* rzB = two ? rzA + 8 * NWD : rzA;
+            double sA0 = 0.0, sA1 = 0.0, zA0 = 0.0, zA1 = 0.0, sB0 = 0.0, sB1 = 0.0, zB0 = 0.0, zB1 = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < KS1; ++ks) {
+                const bool in = 4 * ks + 3 < NL || 4 * ks + t4 < NL;
+                const double bA = in ? rzA[4 * ks] : 0.0;
+                const double bB = in ? rzB[4 * ks] : 0.0;
+                dmma884(sA0, sA1, a1[ks], bA);
+                if (two) dmma884(sB0, sB1, a1[ks], bB);
+                if (ks < 2) {  // the ancestor part (k = 6, two steps) rides along
+                    const bool inz = ks == 0 || t4 < 2;
+                    const double cA = inz ? rzA[NL + 4 * ks] : 0.0;
+                    const double cB = inz ? rzB[NL + 4 * ks] : 0.0;
+                    dmma884(zA0, zA1, a2[ks], cA);
+                    if (two) dmma884(zB0, zB1, a2[ks], cB);
+                }
+            }
+            store_tile(J, sA0, sA1, zA0, zA1);
+            if (two) store_tile(J + 1, sB0, sB1, zB0, zB1);
         }
     }
     __syncwarp();
@@ -272,16 +278,25 @@ __device__ __forceinline__ void lu_solve_warp_tc(int nr, double* H, int* perm, i
             const double* Ub = H + (cJ + g) * LD;  // B fragments: U12[k-index][column cJ + g]
             const double bf0 = Ub[prt0], bf1 = Ub[prt1];
             double* Cc = H + (cJ + 2 * t4) * LD;   // C elements: columns cJ + 2 t4, + 1
+            double v0[3], v1[3];
 #pragma unroll
-            for (int I = 0; I < 3; ++I) {
+            for (int I = 0; I < 3; ++I)
                 if (I < nt) {
-                    double v0 = Cc[rI[I]], v1 = Cc[LD + rI[I]];
-                    dmma884(v0, v1, af0[I], bf0);
-                    dmma884(v0, v1, af1[I], bf1);
-                    Cc[rI[I]] = v0;
-                    Cc[LD + rI[I]] = v1;
+                    v0[I] = Cc[rI[I]];
+                    v1[I] = Cc[LD + rI[I]];
                 }
-            }
+#pragma unroll
+            for (int I = 0; I < 3; ++I)  // first k-step of every tile of this column, then the second: independent chains
+                if (I < nt) dmma884(v0[I], v1[I], af0[I], bf0);
+#pragma unroll
+            for (int I = 0; I < 3; ++I)
+                if (I < nt) dmma884(v0[I], v1[I], af1[I], bf1);
+#pragma unroll
+            for (int I = 0; I < 3; ++I)
+                if (I < nt) {
+                    Cc[rI[I]] = v0[I];
+                    Cc[LD + rI[I]] = v1[I];
+                }
         }
         __syncwarp();
     }
