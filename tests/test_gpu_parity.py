@@ -241,10 +241,12 @@ def test_load_balanced_schedule_is_bitwise_identical(rb, scheme):
     sg.init()
     B = 3001
     q0, qd0 = rb.synthetic_inputs(sg, B, seed=99)
-    out = sg.rollout(q0, qd0, scheme=scheme)
+    # per-step joint torques: the second part of a cut rollout must pick up its controls at the right step
+    tau = 50.0 * np.random.default_rng(5).uniform(-1, 1, (B, sg.nsteps, sg.nr))
+    out = sg.rollout(q0, qd0, tau=tau, scheme=scheme)
     assert (out['status'] == 0).all()
     for lo in range(0, B, 500):  # 500 rollouts fit the resident blocks: plain launches
-        ref = sg.rollout(q0[lo:lo + 500], qd0[lo:lo + 500], scheme=scheme)
+        ref = sg.rollout(q0[lo:lo + 500], qd0[lo:lo + 500], tau=tau[lo:lo + 500], scheme=scheme)
         np.testing.assert_array_equal(out['q'][lo:lo + 500], ref['q'])
         np.testing.assert_array_equal(out['qdot'][lo:lo + 500], ref['qdot'])
         np.testing.assert_array_equal(out['iters'][lo:lo + 500], ref['iters'])
