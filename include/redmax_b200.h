@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RMX_VERSION 105
+#define RMX_VERSION 106
 
 /* error codes */
 #define RMX_OK 0
@@ -226,6 +226,11 @@ int rmx_debug_schedule(int64_t B, int32_t nsteps, int64_t slots, int32_t seg_cap
 /* Scene.saveHistory energies (Scene.m:155-160; Joint.m:616, Body.m:167, ForceGroundCuboid.m:156) for B states:
  * T, V: B each. */
 int rmx_energies(rmx_scene* s, int64_t B, const double* q, const double* qdot, double* T, double* V);
+
+/* World frames of the bodies, body.E_wi after Joint.update / Body.update (Joint.m:382-434, Body.m:70-80), for B configurations:
+ * q is nr x B, E is 4 x 4 x nbodies x B (column-major 4x4 blocks, bodies in the scene's order).  What Scene.draw and the
+ * reference's trajectory export read. */
+int rmx_body_frames(rmx_scene* s, int64_t B, const double* q, double* E);
 
 #ifdef __cplusplus
 }

@@ -84,7 +84,7 @@ SYMBOLS = [
     'rmx_version', 'rmx_last_error', 'rmx_device_count', 'rmx_opts_default',
     'rmx_scene_create', 'rmx_scene_destroy', 'rmx_scene_nr', 'rmx_scene_nm',
     'rmx_rollout', 'rmx_rollout_dev', 'rmx_rollout_adjoint', 'rmx_rollout_adjoint_dev',
-    'rmx_adjoint_tape_bytes', 'rmx_eval', 'rmx_eval_newton', 'rmx_energies', 'rmx_linsolve_stats', 'rmx_debug_schedule',
+    'rmx_adjoint_tape_bytes', 'rmx_eval', 'rmx_eval_newton', 'rmx_energies', 'rmx_linsolve_stats', 'rmx_debug_schedule', 'rmx_body_frames',
 ]
 
 _lib = None
@@ -125,6 +125,7 @@ def lib():
     L.rmx_eval.argtypes = [vp, vp, vp, vp, vp, C.c_double, C.c_double, vp, vp, vp, vp, vp]
     L.rmx_eval_newton.argtypes = [vp, vp, vp, vp, vp, C.c_double, C.c_double, vp, vp]
     L.rmx_energies.argtypes = [vp, C.c_int64, vp, vp, vp, vp]
+    L.rmx_body_frames.argtypes = [vp, C.c_int64, vp, vp]
     L.rmx_debug_schedule.argtypes = [C.c_int64, C.c_int32, C.c_int64, C.c_int32, vp, vp]
     L.rmx_linsolve_stats.argtypes = [vp, C.POINTER(C.c_int64)]
     _lib = L

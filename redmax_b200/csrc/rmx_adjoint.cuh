@@ -170,6 +170,10 @@ struct EnergyArgs {
     const double* qd;
     double* T;
     double* V;
+    // optional (rmx_body_frames): world frames E_wi of the bodies, 4x4 column-major each, [B][nbody][16]
+    double* E_out;
+    const int* body_int;  // [nbody] internal joint index of each body
+    int nbody;
 };
 
 template <int NW, bool GROUND, int IMPL>
@@ -259,9 +263,23 @@ __global__ void __launch_bounds__(32 * NW) energies_kernel(EnergyArgs a) {
                 if (P.kind == 1 || strain > 0) V += 0.5 * P.ks * strain * strain * P.L;
             }
         }
+        if (a.E_out) {  // Body.update: E_wi = E_wj * E0_ji  (Body.m:70-80)
+            for (int j = t; j < a.nbody; j += 32 * NW) {
+                double rb[12];
+                E::body_frame(c, a.body_int[j], rb, rb + 9);
+                double* Eo = a.E_out + ((size_t)b * a.nbody + j) * 16;
+#pragma unroll
+                for (int col = 0; col < 3; ++col) {
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) Eo[4 * col + r] = rb[3 * r + col];
+                    Eo[4 * col + 3] = 0.0;
+                }
+                Eo[12] = rb[9]; Eo[13] = rb[10]; Eo[14] = rb[11]; Eo[15] = 1.0;
+            }
+        }
         T = block_sum<NW>(T, c.red);
         V = block_sum<NW>(V, c.red);
-        if (t == 0) {
+        if (t == 0 && a.T) {
             a.T[b] = T;
             a.V[b] = V;
         }

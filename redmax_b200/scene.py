@@ -617,6 +617,17 @@ class Scene:
                                      ptr(H), ptr(dx)), 'rmx_eval_newton')
         return dict(H=H.T.copy(), dx=dx)
 
+    def body_frames(self, q):
+        """World frames E_wi of all bodies (Body.update, Body.m:70-80) for B configurations q [B, nr] -> [B, nbodies, 4, 4]."""
+        L = self._require()
+        q = f64(q)
+        if q.ndim == 1:
+            q = q[None, :]
+        B = q.shape[0]
+        E = np.empty((B, len(self.bodies), 4, 4))
+        _ffi.check(L.rmx_body_frames(self._handle, B, ptr(q), ptr(E)), 'rmx_body_frames')
+        return np.ascontiguousarray(np.swapaxes(E, 2, 3))  # column-major 4x4 blocks -> [row, col]
+
     def energies(self, q, qdot):
         """T, V of Scene.saveHistory (Scene.m:155-160) for B states."""
         L = self._require()

@@ -20,3 +20,18 @@ def test_plot_energies_verdict(rb):
     sc2 = rb.scenesRedMax(-2)
     assert rb.plotEnergies(sc2, 1, 1.0, out) is None
     assert np.all(sc2.Hexpected == 0)
+
+
+def test_quaternion_of_rotation_roundtrip():
+    from redmax_b200 import export
+    rng = np.random.default_rng(3)
+    for _ in range(50):
+        A = rng.standard_normal((3, 3))
+        Q, _ = np.linalg.qr(A)
+        if np.linalg.det(Q) < 0:
+            Q[:, 0] = -Q[:, 0]
+        w, x, y, z = export.rotation_to_quaternion(Q)
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                      [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                      [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+        assert np.abs(R - Q).max() < 1e-12 and abs(w * w + x * x + y * y + z * z - 1) < 1e-12
