@@ -475,6 +475,23 @@ __device__ __noinline__ void pf_spring(const PfEnd* E, int sd, double ks, double
         }
 }
 
+// What the out-of-line force routines need of the kernel's context, handed BY VALUE together with the body frame: passing
+// `Ctx&` (or pointers to the caller's Rb / pb / phi) to a function that is not inlined makes those objects escape, the compiler
+// then keeps the whole context in local memory and addresses shared memory generically everywhere in the kernel -- measured on
+// the ground-contact variant as 1.3 GB of DRAM writes per launch and a 4.1-cycle long-scoreboard stall per issue.
+struct PfCtx {
+    const PointForce* pf;
+    const int* pf_ep;
+    double* pf_s;
+    double cK;
+};
+struct BodyFrame {
+    double R[9], p[3], phi[6];
+};
+struct Wrench6 {
+    double f[6];
+};
+
 // One segment (point a -> point b) of a multi-point spring, ForceSpringMultiPointGeneric.m:58-81 and :103-170: length, length
 // rate, the normalised generalised force fxn = [G1'R1'dx ; -G2'R2'dx] / |dx|, the gradients dldq, dldotdq (1 x 12), the
 // damping row dqd = [-dxnor'R1G1, dxnor'R2G2], and -- for the end `side` (0: a, 1: b, < 0: none) -- the six rows of the
@@ -612,7 +629,7 @@ __device__ __noinline__ void pf_segment(const PfEnd& Ea, const PfEnd& Eb, int si
 // ForceCable through attachment `me` of force P (ForceSpringMultiPointGeneric.m:29-190, ForceCable.m:66-81): adds this body's
 // wrench to fb and, if K != null, its diagonal blocks to K, D and writes its cross blocks K(me,k2), D(me,k2) (world frame) to
 // shared memory.  K = fn dfsdq - fs Kn, D = fn dfsdqdot.
-__device__ __noinline__ void pf_cable(Ctx& c, const PointForce& P, int me, const double* Rb, const double* pb, double* fb, double* K,
+__device__ __noinline__ void pf_cable(PfCtx c, const PointForce& P, int me, const double* Rb, const double* pb, double* fb, double* K,
                                       double* D) {
     const int np = P.npts;
     const double* recs = c.pf_s + P.rec_off;
@@ -679,8 +696,8 @@ __device__ __noinline__ void pf_cable(Ctx& c, const PointForce& P, int me, const
             }
         } else if (P.body[k2] >= 0) {
             double* blk = blks + (size_t)(me * np + k2) * PF_BLK;
-            xtmy_store(blk, Rb, pb, E[k2].R, E[k2].p, Db, -c.c);
-            xtmy_store(blk + 36, Rb, pb, E[k2].R, E[k2].p, Kb, -c.c);
+            xtmy_store(blk, Rb, pb, E[k2].R, E[k2].p, Db, -c.cK);
+            xtmy_store(blk + 36, Rb, pb, E[k2].R, E[k2].p, Kb, -c.cK);
         }
     }
 }
@@ -689,15 +706,18 @@ __device__ __noinline__ void pf_cable(Ctx& c, const PointForce& P, int me, const
 // -c X'DX, -c X'KX to the external-force fields aext / cext of joint t in the SoA block (after the caller has stored or zeroed
 // them) and writes the cross blocks of its ordered pairs to shared memory.  Kept out of line and off the caller's registers:
 // scenes without point forces must not pay for it.
-__device__ __noinline__ void pf_body(Ctx& c, const JointConst& J, const double* Rb, const double* pb, const double* phi, double* f6,
-                                     bool deriv, double* sa, int NS, int aext, int cext, int t) {
+__device__ __noinline__ Wrench6 pf_body(PfCtx c, int pf_ptr, int pf_cnt, BodyFrame B, bool deriv, double* sa, int NS, int aext,
+                                        int cext, int t) {
+    const double* Rb = B.R;
+    const double* pb = B.p;
+    const double* phi = B.phi;
     double fb[6] = {0, 0, 0, 0, 0, 0};
     double Kacc[36], Dacc[36];
     for (int i = 0; i < 36; ++i) Kacc[i] = Dacc[i] = 0.0;
     double* K = deriv ? Kacc : nullptr;
     double* D = deriv ? Dacc : nullptr;
-    for (int e = 0; e < J.pf_cnt; ++e) {
-        const int code = __ldg(c.pf_ep + J.pf_ptr + e);
+    for (int e = 0; e < pf_cnt; ++e) {
+        const int code = __ldg(c.pf_ep + pf_ptr + e);
         const int f = code / PF_MAXPTS, sd = code % PF_MAXPTS;
         const PointForce& P = c.pf[f];
         const double* recs = c.pf_s + P.rec_off;  // attachment k at recs + k PF_REC
@@ -754,8 +774,8 @@ __device__ __noinline__ void pf_body(Ctx& c, const JointConst& J, const double* 
                 }
                 if (ob >= 0) {
                     double* blk = blks + (size_t)(sd * 2 + (1 - sd)) * PF_BLK;
-                    xtmy_store(blk, Rb, pb, ot.R, ot.p, Dab, -c.c);
-                    xtmy_store(blk + 36, Rb, pb, ot.R, ot.p, Kab, -c.c);
+                    xtmy_store(blk, Rb, pb, ot.R, ot.p, Dab, -c.cK);
+                    xtmy_store(blk + 36, Rb, pb, ot.R, ot.p, Kab, -c.cK);
                 }
             }
             continue;
@@ -821,16 +841,18 @@ __device__ __noinline__ void pf_body(Ctx& c, const JointConst& J, const double* 
             pf_gammaT(xl, Kin, Kab, false);
             pf_gammaT(xl, Din, Dab, false);
             double* blk = blks + (size_t)(sd * 2 + (1 - sd)) * PF_BLK;
-            xtmy_store(blk, Rb, pb, Ro, po, Dab, -c.c);
-            xtmy_store(blk + 36, Rb, pb, Ro, po, Kab, -c.c);
+            xtmy_store(blk, Rb, pb, Ro, po, Dab, -c.cK);
+            xtmy_store(blk + 36, Rb, pb, Ro, po, Kab, -c.cK);
         }
     }
-#pragma unroll
-    for (int i = 0; i < 6; ++i) f6[i] = fb[i];
     if (deriv) {
-        xtmx_add(sa, NS, aext, t, Rb, pb, Dacc, -c.c);
-        xtmx_add(sa, NS, cext, t, Rb, pb, Kacc, -c.c);
+        xtmx_add(sa, NS, aext, t, Rb, pb, Dacc, -c.cK);
+        xtmx_add(sa, NS, cext, t, Rb, pb, Kacc, -c.cK);
     }
+    Wrench6 w;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) w.f[i] = fb[i];
+    return w;
 }
 
 // Cross-term pass of the assembly: for every point force between two bodies and both orderings (a, b):
@@ -1079,10 +1101,21 @@ __device__ void eval_base2(Ctx2& c, bool deriv) {
                 for (int i = 0; i < 72; ++i) SA(F::AEXT, i, t) = 0.0;
             }
             if (c.npf > 0 && J.pf_cnt > 0) {
-                double f6[6];
-                pf_body(c, J, Rb, pb, phi, f6, deriv, c.sa, NS, F::AEXT, F::CEXT, t);
+                PfCtx pc;
+                pc.pf = c.pf;
+                pc.pf_ep = c.pf_ep;
+                pc.pf_s = c.pf_s;
+                pc.cK = c.c;
+                BodyFrame B;
 #pragma unroll
-                for (int i = 0; i < 6; ++i) fb[i] += f6[i];
+                for (int i = 0; i < 9; ++i) B.R[i] = Rb[i];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) B.p[i] = pb[i];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) B.phi[i] = phi[i];
+                const Wrench6 w = pf_body(pc, J.pf_ptr, J.pf_cnt, B, deriv, c.sa, NS, F::AEXT, F::CEXT, t);
+#pragma unroll
+                for (int i = 0; i < 6; ++i) fb[i] += w.f[i];
             }
         }
         double Fb[6], Fw[6];
