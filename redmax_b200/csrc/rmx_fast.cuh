@@ -125,6 +125,7 @@ struct Ctx2 : Ctx {
     double2* tcrow_s;     // [2][5] pivot-row buffers of the blocked LU
     const int* __restrict__ anc;  // [nrounds][n] ancestor tables (global)
     int nrounds;
+    int anyext;    // external-force variants: some body of this rollout has contact / an attached force in the current evaluation
     int anc_r[6];  // this thread's 2^r-th ancestors (nrounds <= 6 for n <= 64), read once per kernel: the scans' rounds are
                    // a dependent chain and must not wait for a global load each
 };
@@ -1057,6 +1058,7 @@ __device__ void eval_base2(Ctx2& c, bool deriv) {
         bsync<NW>();
     }
     // ---- per body: frame, twist, wrench, and (deriv) the world-frame blocks ------------------------------------
+    bool myext = false;  // this body has ground contact or an attached force in this evaluation
     if (t < n) {
         const JointConst& J = c.jc[t];
         double Rb[9], pb[3];
@@ -1086,6 +1088,7 @@ __device__ void eval_base2(Ctx2& c, bool deriv) {
                 const double reach = fabs(nb[0]) * J.hs[0] + fabs(nb[1]) * J.hs[1] + fabs(nb[2]) * J.hs[2];
                 contact = dp - reach <= 1e-12 * (fabs(dp) + reach);
             }
+            myext = contact || (c.npf > 0 && J.pf_cnt > 0);
             if (contact) {
                 if (deriv) {
                     double K[36], D[36];
@@ -1174,10 +1177,16 @@ __device__ void eval_base2(Ctx2& c, bool deriv) {
             for (int i = 0; i < 3; ++i) SA(F::MV, i, t) = m * vc[i];
         }
     }
+    if (GROUND) {  // free flight: the 72 external-block components are all zero and are neither summed nor used
+        if (NW == 1)
+            c.anyext = __any_sync(0xffffffffu, myext);
+        else
+            c.anyext = __syncthreads_or(myext);
+    }
     bsync<NW>();
     // ---- composite sums, leaves -> root (one thread per component) ---------------------------------------------
     {
-        const int ncomp = deriv ? F::NCOMP : 6;
+        const int ncomp = deriv ? ((GROUND && !c.anyext) ? 28 : F::NCOMP) : 6;
         for (int comp = t; comp < ncomp; comp += NT) {
             double* col = c.sa + (size_t)(F::CF + comp) * NS;
             if (c.is_chain) {
@@ -1328,7 +1337,7 @@ __device__ __forceinline__ void columns_joint(Ctx2& c, int t, int myidx, double 
                 }
             }
         }
-        if (GROUND) {
+        if (GROUND && c.anyext) {
             // dense external blocks: b += Aext' s ; e += Cext' s ; Z += Aext c1 + sq Cext s
 #pragma unroll
             for (int r = 0; r < 6; ++r) {
