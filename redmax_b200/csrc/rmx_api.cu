@@ -779,9 +779,9 @@ static int launch_fwd(const rmx_scene* s, const RolloutArgs& a, cudaStream_t st,
     return g ? launch_fwd_t<4, true, ADJ, 1>(a, smem, st, dc) : launch_fwd_t<4, false, ADJ, 1>(a, smem, st, dc);
 }
 
-extern "C" int rmx_rollout_dev(rmx_scene* s, const rmx_opts* o, int64_t B, const double* q0, const double* qdot0,
-                               const double* tau, double* q_out, double* qdot_out, int32_t* status, int32_t* iters,
-                               void* cuda_stream) {
+static int rollout_dev_impl(rmx_scene* s, const rmx_opts* o, int64_t B, const double* q0, const double* qdot0,
+                            const double* tau, double* q_out, double* qdot_out, int32_t* status, int32_t* iters,
+                            void* cuda_stream, double* q_host, double* qdot_host) {
     StepOpts so;
     int rc = check_opts(s, o, &so, 0);
     if (rc) return rc;
@@ -804,6 +804,8 @@ extern "C" int rmx_rollout_dev(rmx_scene* s, const rmx_opts* o, int64_t B, const
     a.qd_out = qdot_out;
     a.status = status;
     a.iters = iters;
+    a.q_host = q_host;
+    a.qd_host = qdot_host;
     if (o->linsolve == RMX_LINSOLVE_PCG) {
         CUDA_TRY(cudaMemsetAsync(dc->kry, 0, sizeof(unsigned long long), (cudaStream_t)cuda_stream));
         a.kry_total = dc->kry;
@@ -813,6 +815,26 @@ extern "C" int rmx_rollout_dev(rmx_scene* s, const rmx_opts* o, int64_t B, const
         return launch_fwd_pcg(s, a, (cudaStream_t)cuda_stream);
     }
     return launch_fwd<false>(s, a, (cudaStream_t)cuda_stream, dc);
+}
+
+extern "C" int rmx_rollout_dev(rmx_scene* s, const rmx_opts* o, int64_t B, const double* q0, const double* qdot0,
+                               const double* tau, double* q_out, double* qdot_out, int32_t* status, int32_t* iters,
+                               void* cuda_stream) {
+    return rollout_dev_impl(s, o, B, q0, qdot0, tau, q_out, qdot_out, status, iters, cuda_stream, nullptr, nullptr);
+}
+
+// Device pointer of a caller's host buffer if the running kernel can store to it directly: page-locked memory
+// (cudaHostAlloc / cudaHostRegister; mapped on every device under unified addressing).  Null for pageable memory.
+// RMX_ZEROCOPY=0 (developer switch) forces the staged device-to-host copy.
+static double* mapped_host_ptr(double* p) {
+    const char* e = std::getenv("RMX_ZEROCOPY");
+    if (!p || (e && e[0] == '0')) return nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return at.type == cudaMemoryTypeHost ? (double*)at.devicePointer : nullptr;
 }
 
 // Host-pointer entry: shards the batch contiguously over o->ngpus devices (no communication during the rollout),
@@ -855,12 +877,16 @@ extern "C" int rmx_rollout(rmx_scene* s, const rmx_opts* o, int64_t B, const dou
         CUDA_TRY(cudaMemcpyAsync(dc->buf[0].p, q0 + b0 * nr, sz[0], cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(dc->buf[1].p, qdot0 + b0 * nr, sz[1], cudaMemcpyHostToDevice, st));
         if (tau) CUDA_TRY(cudaMemcpyAsync(dc->buf[2].p, tau + b0 * tau_per, sz[2], cudaMemcpyHostToDevice, st));
-        ret = rmx_rollout_dev(s, &o1, nb, (double*)dc->buf[0].p, (double*)dc->buf[1].p, tau ? (double*)dc->buf[2].p : nullptr,
-                              (double*)dc->buf[3].p, qdot_out ? (double*)dc->buf[4].p : nullptr, (int*)dc->buf[5].p,
-                              iters ? (int*)dc->buf[6].p : nullptr, st);
+        // Page-locked output buffers are written by the kernel itself while it runs (mirrored stores over PCIe, hidden
+        // behind the rollout); pageable ones get the staged copy after it.
+        double* qh = mapped_host_ptr(q_out + b0 * per);
+        double* qdh = qdot_out ? mapped_host_ptr(qdot_out + b0 * per) : nullptr;
+        ret = rollout_dev_impl(s, &o1, nb, (double*)dc->buf[0].p, (double*)dc->buf[1].p, tau ? (double*)dc->buf[2].p : nullptr,
+                               (double*)dc->buf[3].p, qdot_out ? (double*)dc->buf[4].p : nullptr, (int*)dc->buf[5].p,
+                               iters ? (int*)dc->buf[6].p : nullptr, st, qh, qdh);
         if (ret) break;
-        CUDA_TRY(cudaMemcpyAsync(q_out + b0 * per, dc->buf[3].p, sz[3], cudaMemcpyDeviceToHost, st));
-        if (qdot_out) CUDA_TRY(cudaMemcpyAsync(qdot_out + b0 * per, dc->buf[4].p, sz[4], cudaMemcpyDeviceToHost, st));
+        if (!qh) CUDA_TRY(cudaMemcpyAsync(q_out + b0 * per, dc->buf[3].p, sz[3], cudaMemcpyDeviceToHost, st));
+        if (qdot_out && !qdh) CUDA_TRY(cudaMemcpyAsync(qdot_out + b0 * per, dc->buf[4].p, sz[4], cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaMemcpyAsync(status + b0, dc->buf[5].p, sz[5], cudaMemcpyDeviceToHost, st));
         if (iters) CUDA_TRY(cudaMemcpyAsync(iters + 2 * b0, dc->buf[6].p, sz[6], cudaMemcpyDeviceToHost, st));
     }

@@ -56,6 +56,11 @@ struct RolloutArgs {
     const int4* seg;
     const int* seg_off;
     int* flags;
+    // Optional mirrors of q_out / qd_out in mapped pinned HOST memory (device pointers of the caller's buffers): every step
+    // is stored to both, so the trajectories cross PCIe while the rollout is still running and the host-pointer entry needs
+    // no device-to-host copy afterwards.  The device copies stay the ones a cut rollout resumes from.  Null: not mirrored.
+    double* q_host;
+    double* qd_host;
 };
 
 // Shared-memory scratch of the point forces sits behind everything any kernel variant places after the Newton matrix
@@ -514,6 +519,8 @@ __global__ void RMX_FWD_BOUNDS rollout_fwd_kernel(RolloutArgs a) {
                 const size_t o = ((size_t)b * op.nsteps + k) * nr + t;
                 if (a.q_out) a.q_out[o] = qc;
                 if (a.qd_out) a.qd_out[o] = qdc;
+                if (a.q_host) __stcs(a.q_host + o, qc);
+                if (a.qd_host) __stcs(a.qd_host + o, qdc);
             }
             if (ADJ) {
                 // task.calcStep (TaskBDF1PointPos.m:67-107): objective and dP/dq_k at the stored (final) q, with the

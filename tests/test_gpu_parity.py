@@ -233,6 +233,32 @@ def test_newton_system_through_the_rollout_path(rb, oracle, name, mk):
 
 @pytest.mark.timeout(300)
 @pytest.mark.parametrize('scheme', [1, 2])
+def test_page_locked_outputs_are_written_by_the_kernel_and_bitwise_identical(rb, scheme):
+    """rmx_rollout with page-locked q_out / qdot_out: the kernel mirrors every step into the mapped host buffers (no
+    device-to-host copy of the trajectories afterwards).  Must equal the staged copy into pageable buffers bit for bit, also
+    for a batch the launch cuts across blocks, and with only q_out page-locked."""
+    import torch
+    sg = rb.chain_scene(8, nsteps=9, h=1e-3)
+    sg.init()
+    B = 3001
+    q0, qd0 = rb.synthetic_inputs(sg, B, seed=77)
+    ref = sg.rollout(q0, qd0, scheme=scheme)  # pageable numpy buffers: staged copy
+    hq = torch.full((B, sg.nsteps, sg.nr), float('nan'), dtype=torch.float64).pin_memory()
+    hqd = torch.full((B, sg.nsteps, sg.nr), float('nan'), dtype=torch.float64).pin_memory()
+    out = sg.rollout_into(q0, qd0, hq.numpy(), hqd.numpy(), scheme=scheme)
+    np.testing.assert_array_equal(hq.numpy(), ref['q'])
+    np.testing.assert_array_equal(hqd.numpy(), ref['qdot'])
+    np.testing.assert_array_equal(out['status'], ref['status'])
+    np.testing.assert_array_equal(out['iters'], ref['iters'])
+    hq.fill_(float('nan'))
+    qd_pageable = np.full((B, sg.nsteps, sg.nr), np.nan)
+    sg.rollout_into(q0, qd0, hq.numpy(), qd_pageable, scheme=scheme)
+    np.testing.assert_array_equal(hq.numpy(), ref['q'])
+    np.testing.assert_array_equal(qd_pageable, ref['qdot'])
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize('scheme', [1, 2])
 def test_load_balanced_schedule_is_bitwise_identical(rb, scheme):
     """More rollouts than co-resident blocks, and not a multiple of them: the launch cuts rollouts across blocks (McNaughton
     wrap-around schedule, second part resumes from the trajectory in global memory).  Every trajectory, status and iteration
