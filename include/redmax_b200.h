@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RMX_VERSION 106
+#define RMX_VERSION 107
 
 /* error codes */
 #define RMX_OK 0
@@ -49,7 +49,12 @@ extern "C" {
 #define RMX_JOINT_TRANSLATIONAL 4 /* JointTranslational.m  [3] translation x, y, z */
 #define RMX_JOINT_FREE2D 5        /* JointFree2D.m         [3] translation x, y then rotation about z */
 #define RMX_JOINT_UNIVERSAL 6     /* JointUniversal.m      [2] rotation about x then y */
-#define RMX_MAX_JOINT_DOF 3
+#define RMX_JOINT_SPHERICAL 7     /* JointSpherical.m      [3] Euler angles in the reference's initial chart XYZ: R = X(q1) Y(q2) Z(q3)
+                                     (JointSpherical.m:33,1086).  The chart is fixed: where the reference would re-parameterise
+                                     (|det T| = |cos q2| <= 0.5 after a step, JointSpherical.m:63-67) the rollout sets RMX_ST_CHART
+                                     and carries on in chart XYZ */
+#define RMX_JOINT_FREE3D 8        /* JointFree3D.m         [6] translation x, y, z (q1..q3) then a spherical joint (q4..q6) */
+#define RMX_MAX_JOINT_DOF 6
 #define RMX_MAX_POINTFORCE 8
 #define RMX_MAX_CABLE_POINTS 4
 
@@ -75,6 +80,9 @@ extern "C" {
 #define RMX_ST_LSFAIL 4    /* line search exhausted iterLsMax halvings in some step (silent in reference) */
 #define RMX_ST_NAN 8       /* non-finite state produced */
 #define RMX_ST_SCHED 16    /* internal: a load-balanced rollout never received its first part (should not happen) */
+#define RMX_ST_CHART 32    /* a spherical / Free3D joint left the well-conditioned part of its Euler chart after some step
+                              (|cos q2| <= 0.5): driverRedMaxBDF2 would switch charts there (JointSpherical.m:63-103);
+                              driverRedMaxBDF1 and JointFree3D stop with an error at that point (chart1 is never set) */
 
 /* tau layout for rmx_rollout */
 #define RMX_TAU_NONE 0     /* tau == NULL: joint.tau = 0 */
@@ -83,7 +91,8 @@ extern "C" {
 
 /*
  * Flattened +redmax scene (what scenesRedMax.m builds with redmax.Scene / BodyCuboid / JointRevolute / JointFixed /
- * JointPrismatic / JointPlanar / JointTranslational / JointFree2D / JointUniversal / ForceGroundCuboid /
+ * JointPrismatic / JointPlanar / JointTranslational / JointFree2D / JointUniversal / JointSpherical / JointFree3D /
+ * ForceGroundCuboid /
  * ForcePointPoint / ForceSpringDamper / ForceCable after
  * scene.init(), Scene.m:59-119).  All pointers are host pointers and are
  * copied by rmx_scene_create.

@@ -18,7 +18,7 @@ n = length(scene.joints);
 d.parent = zeros(1,n); d.jtype = zeros(1,n);
 d.E0_pj = zeros(4,4,n); d.E0_ji = zeros(4,4,n); d.axis = zeros(3,n); d.I_i = zeros(6,n); d.sides = zeros(3,n);
 d.axis2 = repmat([0;1;0],1,n);
-d.stiffness = zeros(1,n); d.damping = zeros(1,n); d.qRest = zeros(3,n); % RMX_MAX_JOINT_DOF x n
+d.stiffness = zeros(1,n); d.damping = zeros(1,n); d.qRest = zeros(6,n); % RMX_MAX_JOINT_DOF x n
 d.qLimL = zeros(1,n); d.qLimU = zeros(1,n); d.qLimK = zeros(1,n); d.qLimD = zeros(1,n);
 for i = 1 : n
 	j = scene.joints{i};
@@ -42,6 +42,13 @@ for i = 1 : n
 		d.jtype(i) = 5;
 	elseif isa(j,'redmax.JointUniversal')
 		d.jtype(i) = 6;
+	elseif isa(j,'redmax.JointSpherical')
+		% fixed chart XYZ (the constructor's default, JointSpherical.m:33); status bit 32 marks rollouts that would re-parameterise
+		assert(j.chart == redmax.JointSpherical.CHART_XYZ);
+		d.jtype(i) = 7;
+	elseif isa(j,'redmax.JointFree3D')
+		assert(j.joint2.chart == redmax.JointSpherical.CHART_XYZ);
+		d.jtype(i) = 8;
 	else
 		error('joint type %s is not on the GPU hot path',class(j));
 	end

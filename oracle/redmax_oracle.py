@@ -14,6 +14,8 @@ traversal replaced by a loop over the same list order), these reference files (p
     +redmax/JointRevolute.m   -> JointRevolute.update_:29
     +redmax/JointFixed.m      -> JointFixed
     +redmax/JointFree2D.m     -> JointFree2D.update_:20 (only to reach the scene-11 ground-contact pin)
+    +redmax/JointSpherical.m  -> JointSpherical (update_:106, reparam_:63), euler_chart (getEuler:154 + the twelve generated
+                                 chart bodies), euler_chart_inv (getEulerInv:186 + :1809-1964); JointFree3D.m -> JointFree3D
     +redmax/Body.m            -> Body (update:70, computeMassGrav:83, computeEnergies:167)
     +redmax/BodyCuboid.m      -> BodyCuboid.computeInertia_:16
     +redmax/Force.m, ForceNull.m, ForceGroundCuboid.m:54-183
@@ -22,11 +24,12 @@ traversal replaced by a loop over the same list order), these reference files (p
     driverRedMaxBDF2.m        -> sim_loop_bdf2, eval_sdirk2a/b, eval_bdf2
     driverRedMaxAdjointBDF1.m, driverRedMaxAdjointBDF2.m -> newton_adjoint, sim_loop_adjoint_bdf1/2
     +redmax/TaskBDF1.m, TaskBDF2.m, TaskBDF1PointPos.m, TaskBDF2PointPos.m
-    scenesRedMax.m            -> scenes(sceneID) for IDs -2,-1,0,1,2,11,14,100,101
+    scenesRedMax.m            -> scenes(sceneID) for IDs -2,-1,0,1,2,11,14,100,101 (3-10, 12, 13 through redmax_b200/scenes.py)
 
 Pinning: `tests/test_oracle_pins.py` checks this oracle against every golden end-of-run energy
 `Hexpected(BDF1/BDF2)` the reference holds for the in-scope joint/force types (scenes 0,1,2,14 and the
-Free2D+ground scene 11, scenesRedMax.m:54,82,108,292,373; tolerance |dH|<=1e-2 as Scene.m:172).  The adjoint
+Free2D+ground scene 11, scenesRedMax.m:54,82,108,292,373; tolerance |dH|<=1e-2 as Scene.m:172; likewise scenes 3-10, 12, 13,
+among them the Euler-chart joints of scenes 7 and 9 -- scene 7 under BDF2 switches charts twice, XYZ -> XYX -> YXZ).  The adjoint
 scenes 100/101 carry no expected value in the reference ("parity unpinned" for P/dPdp by golden numbers);
 they are pinned by the reference's own finite-difference recipe (driverRedMaxAdjointBDF1.m:47-61).
 
@@ -355,6 +358,19 @@ class Joint:
     def update_(self, deriv):
         pass
 
+    def reparam_(self):
+        """Joint.m:790 -- subclasses may re-parameterise q, qdot (Euler-chart joints); True if they did"""
+        return False
+
+    def resetChart_(self):
+        """test aid, see Scene.reset"""
+
+    def setAux0_(self):
+        """Joint.m:795"""
+
+    def setAux1_(self):
+        """Joint.m:800"""
+
     def computeForce(self, fr, Kr=None, Dr=None):
         """Joint.m:437 (one joint)"""
         rows = self.idxR
@@ -666,6 +682,239 @@ class JointFree2D(Joint):
             self.dAdotdq[0:3, 0:3, 2] = dRdotdq
             self.dAdotdq[3:6, 3:6, 2] = dRdotdq
             self.dAdotdq[3:6, 0:3, 2] = pdotbrac @ dRdq + pbrac @ dRdotdq
+
+
+# Euler charts of JointSpherical.m:5-16, in the reference's numbering 1..12: the three rotation axes (0=X, 1=Y, 2=Z) of
+# R = R_a(q1) R_b(q2) R_c(q3).
+EULER_CHARTS = {1: (0, 1, 0), 2: (0, 2, 0), 3: (1, 2, 1), 4: (1, 0, 1), 5: (2, 0, 2), 6: (2, 1, 2),
+                7: (0, 1, 2), 8: (0, 2, 1), 9: (1, 2, 0), 10: (1, 0, 2), 11: (2, 0, 1), 12: (2, 1, 0)}
+EULER_CHART_NAMES = {k: ''.join('XYZ'[i] for i in v) for k, v in EULER_CHARTS.items()}
+CHART_XYZ = 7
+
+
+def _axis_rot(axis, angle):
+    e = np.zeros(3)
+    e[axis] = 1.0
+    return se3_aaToMat(e, angle)
+
+
+def euler_chart(chart, q, qdot):
+    """JointSpherical.getEuler (JointSpherical.m:154-183 and the generated per-chart bodies :342-1806), restated from the
+    definition the generated closed forms implement instead of term by term: R = R_a(q1) R_b(q2) R_c(q3),
+    body angular velocity omega = T qdot with T = [(R_b R_c)' e_a, R_c' e_b, e_c], and their analytic first / second
+    derivatives.  Checked against the reference's own entries for chart XYZ (R at JointSpherical.m:1162) and, for all
+    twelve charts, by finite differences (tests/test_oracle_pins.py).
+    Returns R, dRdq[3,3,3], Rdot, dRdotdq, T, detT, dTdq, Tdot, dTdotdq (third index = derivative direction)."""
+    a, b, c = EULER_CHARTS[chart]
+    E = [np.zeros(3), np.zeros(3), np.zeros(3)]
+    E[0][a] = E[1][b] = E[2][c] = 1.0
+    br = [se3_brac(E[0]), se3_brac(E[1]), se3_brac(E[2])]
+    Rs = [_axis_rot(a, q[0]), _axis_rot(b, q[1]), _axis_rot(c, q[2])]
+
+    def prod(ins):
+        # R_a [a]^i0 R_b [b]^i1 R_c [c]^i2
+        M = np.eye(3)
+        for k in range(3):
+            M = M @ Rs[k]
+            for _ in range(ins[k]):
+                M = M @ br[k]
+        return M
+
+    R = prod((0, 0, 0))
+    dRdq = np.zeros((3, 3, 3))
+    d2R = np.zeros((3, 3, 3, 3))
+    for i in range(3):
+        ins = [0, 0, 0]
+        ins[i] = 1
+        dRdq[:, :, i] = prod(ins)
+        for j in range(3):
+            ins2 = list(ins)
+            ins2[j] += 1
+            d2R[:, :, i, j] = prod(ins2)
+    Rdot = dRdq @ qdot
+    dRdotdq = d2R @ qdot  # d(Rdot)/dq_i = sum_j d2R/dq_i dq_j qdot_j
+    # T and its derivatives: column 0 = R_c' R_b' e_a, column 1 = R_c' e_b, column 2 = e_c;  d(R')/dq = -[e] R'
+    RbT, RcT = Rs[1].T, Rs[2].T
+    T = np.column_stack([RcT @ RbT @ E[0], RcT @ E[1], E[2]])
+    dTdq = np.zeros((3, 3, 3))
+    d2T = np.zeros((3, 3, 3, 3))
+    dTdq[:, 0, 1] = -RcT @ br[1] @ RbT @ E[0]
+    dTdq[:, 0, 2] = -br[2] @ RcT @ RbT @ E[0]
+    dTdq[:, 1, 2] = -br[2] @ RcT @ E[1]
+    d2T[:, 0, 1, 1] = RcT @ br[1] @ br[1] @ RbT @ E[0]
+    d2T[:, 0, 1, 2] = d2T[:, 0, 2, 1] = br[2] @ RcT @ br[1] @ RbT @ E[0]
+    d2T[:, 0, 2, 2] = br[2] @ br[2] @ RcT @ RbT @ E[0]
+    d2T[:, 1, 2, 2] = br[2] @ br[2] @ RcT @ E[1]
+    Tdot = dTdq @ qdot
+    dTdotdq = d2T @ qdot
+    detT = float(np.linalg.det(T))
+    return R, dRdq, Rdot, dRdotdq, T, detT, dTdq, Tdot, dTdotdq
+
+
+def euler_chart_inv(chart, R):
+    """JointSpherical.getEulerInv (JointSpherical.m:186-214, per-chart bodies :1809-1964): the twelve closed forms share
+    one pattern in terms of the axes (a, b, c) and the parity eps of (a, b, third axis); gimbal lock returns NaNs."""
+    a, b, c3 = EULER_CHARTS[chart]
+    if a == c3:  # proper Euler a-b-a: q2 = acos(R_aa) in (0, pi)
+        c = 3 - a - b
+        eps = 1.0 if (b - a) % 3 == 1 else -1.0
+        raa = R[a, a]
+        if not (-1.0 < raa < 1.0):
+            return np.full(3, np.nan)
+        return np.array([math.atan2(R[b, a], -eps * R[c, a]), math.acos(raa), math.atan2(R[a, b], eps * R[a, c])])
+    c = c3  # Tait-Bryan a-b-c: q2 = asin(eps R_ac) in (-pi/2, pi/2)
+    eps = 1.0 if (b - a) % 3 == 1 else -1.0
+    rac = R[a, c]
+    if not (-1.0 < rac < 1.0):
+        return np.full(3, np.nan)
+    return np.array([math.atan2(-eps * R[b, c], R[c, c]), math.asin(eps * rac), math.atan2(-eps * R[a, b], R[a, a])])
+
+
+class JointSpherical(Joint):
+    """JointSpherical.m -- ball joint in Euler angles with twelve coordinate charts and re-parameterisation."""
+
+    def __init__(self, parent, body):
+        """JointSpherical.m:30"""
+        super().__init__(parent, body, 3)
+        self.chart = CHART_XYZ
+        self.chart0 = None
+        self.chart1 = None
+        self.switches = []  # (old chart, new chart) of every re-parameterisation, for the tests
+
+    def setAux0_(self):
+        """JointSpherical.m:53"""
+        self.chart0 = self.chart
+
+    def setAux1_(self):
+        """JointSpherical.m:58"""
+        self.chart1 = self.chart
+
+    def reparam_(self):
+        """JointSpherical.m:63-103"""
+        R, _, _, _, Told, detTold, _, _, _ = euler_chart(self.chart, self.q, self.qdot)
+        if abs(detTold) > 0.5:
+            return False
+        if self.chart1 is None:
+            # the reference reaches getEuler with an empty chart1 here (BDF1 never calls setQ1; JointFree3D never forwards
+            # setAux1_ to its inner joint) and stops with an unassigned-output error
+            raise RuntimeError('JointSpherical.reparam_: chart1 unset (the reference errors at JointSpherical.m:73)')
+        z = np.zeros(3)
+        R1 = euler_chart(self.chart1, self.q1, z)[0]
+        detTs = np.zeros((2, 12))
+        for k in range(1, 13):
+            qk = euler_chart_inv(k, R)
+            detTs[0, k - 1] = euler_chart(k, qk, z)[5] if np.isfinite(qk).all() else np.nan
+            q1k = euler_chart_inv(k, R1)
+            detTs[1, k - 1] = euler_chart(k, q1k, z)[5] if np.isfinite(q1k).all() else np.nan
+        detTs[np.isnan(detTs)] = 0.0
+        old = self.chart
+        self.chart = int(np.argmax(np.min(np.abs(detTs), axis=0))) + 1  # first maximum, as MATLAB's max
+        self.switches.append((old, self.chart))
+        self.q = euler_chart_inv(self.chart, R)
+        Tnew = euler_chart(self.chart, self.q, z)[4]
+        self.qdot = np.linalg.solve(Tnew, Told @ self.qdot)
+        Told1 = euler_chart(self.chart1, self.q1, z)[4]
+        self.chart1 = self.chart
+        self.q1 = euler_chart_inv(self.chart1, R1)
+        Tnew1 = euler_chart(self.chart1, self.q1, z)[4]
+        self.qdot1 = np.linalg.solve(Tnew1, Told1 @ self.qdot1)
+        return True
+
+    def resetChart_(self):
+        self.chart = CHART_XYZ
+        self.chart0 = self.chart1 = None
+        self.switches = []
+
+    def update_(self, deriv):
+        """JointSpherical.m:106-130"""
+        R, dRdq, Rdot, dRdotdq, T, _, dTdq, Tdot, dTdotdq = euler_chart(self.chart, self.q, self.qdot)
+        self.Q[0:3, 0:3] = R
+        self.A[0:3, 0:3] = R
+        self.A[3:6, 3:6] = R
+        self.Adot[0:3, 0:3] = Rdot
+        self.Adot[3:6, 3:6] = Rdot
+        self.S[0:3, 0:3] = T
+        self.Sdot[0:3, 0:3] = Tdot
+        if deriv:
+            for k in range(3):
+                self.dAdq[0:3, 0:3, k] = dRdq[:, :, k]
+                self.dAdq[3:6, 3:6, k] = dRdq[:, :, k]
+                self.dAdotdq[0:3, 0:3, k] = dRdotdq[:, :, k]
+                self.dAdotdq[3:6, 3:6, k] = dRdotdq[:, :, k]
+                self.dSdq[0:3, :, k] = dTdq[:, :, k]
+                self.dSdotdq[0:3, :, k] = dTdotdq[:, :, k]
+
+
+class _InnerBody:
+    """stand-in for the body handle JointFree3D passes to its two inner joints (they never touch it)"""
+    joint = None
+
+
+class JointFree3D(Joint):
+    """JointFree3D.m -- free joint composed of a translational joint (q(1:3) = p) and a spherical joint (q(4:6))."""
+
+    def __init__(self, parent, body):
+        """JointFree3D.m:16-21"""
+        super().__init__(parent, body, 6)
+        self.joint1 = JointTranslational(None, _InnerBody())
+        self.joint2 = JointSpherical(None, _InnerBody())
+        body.joint = self
+
+    def reparam_(self):
+        """JointFree3D.m:27-31"""
+        did = self.joint2.reparam_()
+        self.q[3:6] = self.joint2.q
+        self.qdot[3:6] = self.joint2.qdot
+        return did
+
+    def resetChart_(self):
+        self.joint2.resetChart_()
+
+    def update_(self, deriv):
+        """JointFree3D.m:34-122"""
+        j1, j2 = self.joint1, self.joint2
+        j1.q = self.q[0:3].copy()
+        j2.q = self.q[3:6].copy()
+        j1.qdot = self.qdot[0:3].copy()
+        j2.qdot = self.qdot[3:6].copy()
+        p = j1.q
+        pdot = j1.qdot
+        rdot = j2.qdot
+        R, dRdr, Rdot, dRdotdr, T, _, dTdr, Tdot, dTdotdr = euler_chart(j2.chart, j2.q, j2.qdot)
+        self.Q[0:3, 0:3] = R
+        self.Q[0:3, 3] = p
+        self.A[0:3, 0:3] = R
+        self.A[3:6, 3:6] = R
+        pbrac = se3_brac(p)
+        self.A[3:6, 0:3] = pbrac @ R
+        pdotbrac = se3_brac(pdot)
+        self.Adot[0:3, 0:3] = Rdot
+        self.Adot[3:6, 3:6] = Rdot
+        self.Adot[3:6, 0:3] = pdotbrac @ R + pbrac @ Rdot
+        self.S[3:6, 0:3] = R.T
+        self.S[0:3, 3:6] = T
+        self.Sdot[3:6, 0:3] = Rdot.T
+        self.Sdot[0:3, 3:6] = Tdot
+        if deriv:
+            tmp = se3_brac(T @ rdot)
+            for k in range(3):
+                ek = np.zeros(3)
+                ek[k] = 1.0
+                ekbrac = se3_brac(ek)
+                dRk = dRdr[:, :, k]
+                dRdk = dRdotdr[:, :, k]
+                self.dAdq[0:3, 0:3, 3 + k] = dRk
+                self.dAdq[3:6, 3:6, 3 + k] = dRk
+                self.dAdq[3:6, 0:3, k] = ekbrac @ R
+                self.dAdq[3:6, 0:3, 3 + k] = pbrac @ dRk
+                self.dAdotdq[3:6, 0:3, k] = ekbrac @ Rdot
+                self.dAdotdq[0:3, 0:3, 3 + k] = dRdk
+                self.dAdotdq[3:6, 3:6, 3 + k] = dRdk
+                self.dAdotdq[3:6, 0:3, 3 + k] = pdotbrac @ dRk + pbrac @ dRdk
+                self.dSdq[3:6, 0:3, 3 + k] = dRk.T
+                self.dSdq[0:3, 3:6, 3 + k] = dTdr[:, :, k]
+                self.dSdotdq[3:6, 0:3, 3 + k] = -se3_brac(dTdr[:, :, k] @ rdot) @ R.T - tmp @ dRk.T
+                self.dSdotdq[0:3, 3:6, 3 + k] = dTdotdr[:, :, k]
 
 
 # ----------------------------------------------------------------------------------------------
@@ -1251,6 +1500,7 @@ class Scene:
         for j in self.joints:
             j.q0[: j.ndof] = q[j.idxR]
             j.qdot0[: j.ndof] = qdot[j.idxR]
+            j.setAux0_()  # Joint.m:283
 
     def getQ1(self):
         q = np.zeros(self.nr)
@@ -1267,6 +1517,14 @@ class Scene:
         for j in self.joints:
             j.q1[: j.ndof] = q[j.idxR]
             j.qdot1[: j.ndof] = qdot[j.idxR]
+            j.setAux1_()  # Joint.m:350
+
+    def reparam(self):
+        """jroot.reparam(): Joint.m:372-379.  chart_switch_steps (test aid): 0-based index of every step whose result was
+        re-parameterised."""
+        for j in self.joints:
+            if j.reparam_():
+                self.chart_switch_steps.append(self.k)
 
     def update(self, deriv=True):
         """jroot.update(deriv): Joint.m:382-434; only the root sees `deriv` (Joint.m:432)."""
@@ -1305,7 +1563,11 @@ class Scene:
         return T, V
 
     def reset(self):
-        """Scene.m:122"""
+        """Scene.m:122 (plus, so that one scene object can be rolled out repeatedly by the tests: Euler-chart joints go back
+        to the chart they were built in -- the reference builds a fresh scene per run)"""
+        for j in self.joints:
+            j.resetChart_()
+        self.chart_switch_steps = []
         self.setQ(self.qInit, self.qdotInit)
         self.t = 0.0
         self.k = 0
@@ -1536,6 +1798,7 @@ def sim_loop_bdf1(scene, nsteps=None, stats=None):
         q1 = newton(lambda x, d: eval_bdf1(x, scene, d), q1, scene, stats)
         qdot1 = (q1 - q0) / h
         scene.setQ(q1, qdot1)
+        scene.reparam()  # :78
         scene.update()
         scene.t = scene.t + h
         scene.k = k + 1
@@ -1569,6 +1832,7 @@ def sim_loop_bdf2(scene, nsteps=None, stats=None):
             q2 = newton(lambda x, d: eval_bdf2(x, scene, d), q2, scene, stats)
             qdot2 = (3 / (2 * h)) * (q2 - (4 / 3) * q1 + (1 / 3) * q0)
             scene.setQ(q2, qdot2)
+        scene.reparam()  # :112
         scene.update()
         scene.t = scene.t + h
         scene.k = k + 1

@@ -23,7 +23,9 @@ RMX_JOINT_PLANAR = 3
 RMX_JOINT_TRANSLATIONAL = 4
 RMX_JOINT_FREE2D = 5
 RMX_JOINT_UNIVERSAL = 6
-RMX_MAX_JOINT_DOF = 3
+RMX_JOINT_SPHERICAL = 7
+RMX_JOINT_FREE3D = 8
+RMX_MAX_JOINT_DOF = 6
 RMX_FORCE_POINTPOINT = 0
 RMX_FORCE_SPRINGDAMPER = 1
 RMX_MAX_CABLE_POINTS = 4
@@ -38,6 +40,7 @@ RMX_ST_DIVERGED = 1
 RMX_ST_MAXITER = 2
 RMX_ST_LSFAIL = 4
 RMX_ST_NAN = 8
+RMX_ST_CHART = 32
 
 _pd = C.POINTER(C.c_double)
 _pi = C.POINTER(C.c_int32)

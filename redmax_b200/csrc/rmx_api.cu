@@ -62,7 +62,7 @@ struct DevCopy {
 
 struct rmx_scene {
     int n = 0, nr = 0, nm = 0;
-    int is_chain = 0, has_ground = 0;
+    int is_chain = 0, has_ground = 0, has_chart = 0;
     double grav[3] = {0, 0, 0};
     std::vector<JointConst> jc;   // internal (preorder) order
     std::vector<int> ends_list;
@@ -127,6 +127,7 @@ struct ExpandedScene {
     std::vector<int> parent, type, idx, user;  // type: RMX_JOINT_FIXED / REVOLUTE / PRISMATIC; idx: reduced index or -1
     std::vector<double> E0_pj, E0_ji, axis, I_i, sides, stiffness, damping, qRest, qLimL, qLimU, qLimK, qLimD;
     std::vector<int> body_of_user;             // user joint/body -> index (in this list) of the virtual joint carrying the body
+    std::vector<int> chart_mid;                // middle Euler angle of a spherical / Free3D joint
 };
 
 static int joint_ndof(int jtype) {
@@ -134,7 +135,8 @@ static int joint_ndof(int jtype) {
         case RMX_JOINT_FIXED: return 0;
         case RMX_JOINT_REVOLUTE: case RMX_JOINT_PRISMATIC: return 1;
         case RMX_JOINT_PLANAR: case RMX_JOINT_UNIVERSAL: return 2;
-        case RMX_JOINT_TRANSLATIONAL: case RMX_JOINT_FREE2D: return 3;
+        case RMX_JOINT_TRANSLATIONAL: case RMX_JOINT_FREE2D: case RMX_JOINT_SPHERICAL: return 3;
+        case RMX_JOINT_FREE3D: return 6;
         default: return -1;
     }
 }
@@ -148,9 +150,9 @@ static void expand_scene(const rmx_scene_desc* d, const std::vector<int>& base, 
         const int jt = d->jtype[j];
         const double* ax1 = d->axis + 3 * j;
         const double* ax2 = d->axis2 ? d->axis2 + 3 * j : EY;
-        int vt[3] = {RMX_JOINT_FIXED, 0, 0};
-        const double* va[3] = {Z3, Z3, Z3};
-        int nv = 1;
+        int vt[6] = {RMX_JOINT_FIXED, 0, 0, 0, 0, 0};
+        const double* va[6] = {Z3, Z3, Z3, Z3, Z3, Z3};
+        int nv = 1, mid = -1;
         switch (jt) {
             case RMX_JOINT_REVOLUTE: vt[0] = RMX_JOINT_REVOLUTE; va[0] = ax1; break;
             case RMX_JOINT_PRISMATIC: vt[0] = RMX_JOINT_PRISMATIC; va[0] = ax1; break;
@@ -158,6 +160,17 @@ static void expand_scene(const rmx_scene_desc* d, const std::vector<int>& base, 
             case RMX_JOINT_TRANSLATIONAL: nv = 3; vt[0] = vt[1] = vt[2] = RMX_JOINT_PRISMATIC; va[0] = EX; va[1] = EY; va[2] = EZ; break;
             case RMX_JOINT_FREE2D: nv = 3; vt[0] = vt[1] = RMX_JOINT_PRISMATIC; vt[2] = RMX_JOINT_REVOLUTE; va[0] = EX; va[1] = EY; va[2] = EZ; break;
             case RMX_JOINT_UNIVERSAL: nv = 2; vt[0] = vt[1] = RMX_JOINT_REVOLUTE; va[0] = EX; va[1] = EY; break;
+            // Euler chart XYZ, R = X(q1) Y(q2) Z(q3) (JointSpherical.m:33,1086): g and dg/dq depend on the motion only, so the
+            // reference's T(q), Tdot and their derivatives are reproduced by three revolute virtual joints
+            case RMX_JOINT_SPHERICAL: nv = 3; vt[0] = vt[1] = vt[2] = RMX_JOINT_REVOLUTE; va[0] = EX; va[1] = EY; va[2] = EZ; mid = 1; break;
+            // Q = [R p; 0 1] (JointFree3D.m:56-58): translate in the parent frame, then rotate
+            case RMX_JOINT_FREE3D:
+                nv = 6;
+                vt[0] = vt[1] = vt[2] = RMX_JOINT_PRISMATIC;
+                vt[3] = vt[4] = vt[5] = RMX_JOINT_REVOLUTE;
+                va[0] = va[3] = EX; va[1] = va[4] = EY; va[2] = va[5] = EZ;
+                mid = 4;
+                break;
             default: break;
         }
         for (int v = 0; v < nv; ++v) {
@@ -165,6 +178,7 @@ static void expand_scene(const rmx_scene_desc* d, const std::vector<int>& base, 
             x.parent.push_back(first ? (d->parent[j] < 0 ? -1 : x.body_of_user[d->parent[j]]) : x.n - 1);
             x.type.push_back(vt[v]);
             x.user.push_back(j);
+            x.chart_mid.push_back(v == mid ? 1 : 0);
             x.idx.push_back(vt[v] == RMX_JOINT_FIXED ? -1 : base[j] + v);
             const double* Epj = first ? d->E0_pj + 16 * j : ID4;
             const double* Eji = last ? d->E0_ji + 16 * j : ID4;
@@ -333,6 +347,8 @@ extern "C" int rmx_scene_create(const rmx_scene_desc* d, rmx_scene** out) {
         J.parent = x.parent[j] < 0 ? -1 : s->user2int[x.parent[j]];
         if (J.parent != k - 1) s->is_chain = 0;
         J.prismatic = x.type[j] == RMX_JOINT_PRISMATIC;
+        J.chart_mid = x.chart_mid[j];
+        if (J.chart_mid) s->has_chart = 1;
         J.idx = idxR[j];
         // se3.aaToMat classification (se3.m:118-176)
         J.axtype = 0;
@@ -632,6 +648,7 @@ static DevScene make_devscene(const rmx_scene* s, const DevCopy* dc) {
     ds.pf = dc->pf;
     ds.pf_ep = dc->pf_ep;
     ds.npf = (int)s->pf.size();
+    ds.has_chart = s->has_chart;
     return ds;
 }
 

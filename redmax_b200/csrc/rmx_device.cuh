@@ -51,6 +51,7 @@ struct JointConst {
     int pf_cnt;
     int ends_ptr;   // CSR into DevScene.ends_list: joints k whose subtree ends exactly at this index
     int ends_cnt;
+    int chart_mid;  // 1: this one-DOF virtual joint is the middle Euler angle of a spherical / Free3D joint (chart XYZ: det T = cos q)
 };
 
 // Forces between body points (matlab-diff/+redmax): ForcePointPoint.m (linear, zero rest length), ForceSpringDamper.m
@@ -83,6 +84,7 @@ struct DevScene {
     const PointForce* pf;  // [npf]
     const int* pf_ep;      // endpoint lists (see JointConst::pf_ptr)
     int npf;
+    int has_chart;         // some joint has chart_mid set
 };
 
 struct StepOpts {

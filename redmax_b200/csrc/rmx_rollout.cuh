@@ -515,6 +515,12 @@ __global__ void RMX_FWD_BOUNDS rollout_fwd_kernel(RolloutArgs a) {
                 }
             }
             tcur = tnext;
+            if (a.sc.has_chart && t < a.sc.n) {
+                // jroot.reparam() (driverRedMaxBDF1.m:78, driverRedMaxBDF2.m:112): the chart is fixed here, the place where
+                // JointSpherical.reparam_ would leave it (|det T| = |cos q2| <= 0.5, JointSpherical.m:63-67) is reported
+                const JointConst& Jc = a.sc.jc[t];
+                if (Jc.chart_mid && !(fabs(cos(c.q[Jc.idx])) > 0.5)) status |= 32;
+            }
             if (t < nr) {
                 const size_t o = ((size_t)b * op.nsteps + k) * nr + t;
                 if (a.q_out) a.q_out[o] = qc;
@@ -552,8 +558,14 @@ __global__ void RMX_FWD_BOUNDS rollout_fwd_kernel(RolloutArgs a) {
             }
             bsync<NW>();
         }
+        // block-wide OR of the two per-thread conditions in one reduction: non-finite state (units) and a chart flag (4096s)
         double bad = (t < nr && !(isfinite(qc) && isfinite(qdc))) ? 1.0 : 0.0;
+        if (status & 32) bad += 4096.0;
         bad = block_sum<NW>(bad, c.red);
+        if (bad >= 4096.0) {
+            status |= 32;
+            bad -= 4096.0 * floor(bad / 4096.0);
+        }
         if (bad > 0.0) status |= 8;
         if (CAN_SCHED && (seg_flags & 2)) {  // first part of a cut rollout: publish the trajectory written so far
             __threadfence();

@@ -182,6 +182,28 @@ class JointUniversal(Joint):
         self.axis = np.zeros(3)
 
 
+class JointSpherical(Joint):
+    """+redmax/JointSpherical.m -- Euler angles in the reference's initial chart XYZ (JointSpherical.m:33).  The CUDA path keeps
+    that chart for the whole rollout; where the reference would re-parameterise (JointSpherical.m:63-67, BDF2 only -- under
+    driverRedMaxBDF1 the reference itself stops there) the rollout's status gets RMX_ST_CHART."""
+    jtype = _ffi.RMX_JOINT_SPHERICAL
+    CHART_XYZ = 7
+
+    def __init__(self, parent, body):
+        super().__init__(parent, body, 3)
+        self.axis = np.zeros(3)
+        self.chart = self.CHART_XYZ
+
+
+class JointFree3D(Joint):
+    """+redmax/JointFree3D.m -- q = [x y z, Euler XYZ]"""
+    jtype = _ffi.RMX_JOINT_FREE3D
+
+    def __init__(self, parent, body):
+        super().__init__(parent, body, 6)
+        self.axis = np.zeros(3)
+
+
 class ForceGroundCuboid:
     """+redmax/ForceGroundCuboid.m:18-48"""
 

@@ -187,6 +187,38 @@ def scenesRedMax(sceneID, api=None):
             f.setDamping(3e1)
             f.setFriction(0.5)
             scene.forces = [f]
+    elif sceneID == 7:  # :204
+        scene.name = 'Spherical joint'
+        scene.Hexpected[:] = [-8.7859815791305155e+03, 8.6544602745403390e+03]
+        scene.tEnd = 1.0
+        scene.h = 2e-3
+        b1 = api.BodyCuboid(density, [1, 1, 10])
+        b1.setBodyTransform(_trans([0, 0, -5]))
+        j1 = api.JointSpherical(None, b1)
+        j1.setJointTransform(np.eye(4))
+        # getEulerInv(chart XYZ, aaToMat([1 0 0], pi/8)) = [pi/8 0 0] (JointSpherical.m:1887)
+        j1.q[:] = [math.atan2(math.sin(math.pi / 8), math.cos(math.pi / 8)), 0.0, 0.0]
+        j1.qdot[:] = [2, 2, 2]
+        b2 = api.BodyCuboid(density, [1, 1, 10])
+        b2.setBodyTransform(_trans([0, 0, -5]))
+        j2 = api.JointSpherical(j1, b2)
+        j2.setJointTransform(_trans([0, 0, -10]))
+        j2.q[0] = math.pi / 2
+        scene.bodies += [b1, b2]
+        scene.joints += [j1, j2]
+    elif sceneID == 9:  # :248
+        scene.name = 'Free3D joint'
+        scene.Hexpected[:] = [4.3970920953724946e+00, 4.5466508559364156e+00]
+        scene.h = 5e-2
+        scene.tEnd = 6.0
+        scene.grav = np.array([0.0, 0.0, -1.0])
+        b = api.BodyCuboid(density, [1, 1, 1])
+        j = api.JointFree3D(None, b)
+        j.qdot[:] = [0, 0, 3, 0.2, 0.4, 0.6]
+        j.setJointTransform(np.eye(4))
+        b.setBodyTransform(np.eye(4))
+        scene.bodies.append(b)
+        scene.joints.append(j)
     elif sceneID == 8:  # :233
         scene.name = 'Universal joint'
         scene.Hexpected[:] = [-2.5276246935781084e+04, -1.3781281283808785e+03]

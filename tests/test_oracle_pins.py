@@ -2,6 +2,8 @@
 
 Golden end-of-run energies Hexpected(BDF1/BDF2) from matlab-diff/scenesRedMax.m:54-55, 82-83, 108-109, 292-293,
 373-374 and 132-133, 146-147, 166-167, 190-191, 238-239; pass criterion |H(end) - Hexpected| <= 1e-2 as Scene.plotEnergies (Scene.m:171-177)."""
+import math
+
 import numpy as np
 import pytest
 
@@ -18,6 +20,9 @@ PINS = {
     5: (3.3661704151378050e+04, 3.3377464890219308e+04),
     6: (2.0322933333333378e+04, 2.1283333333333332e+04),
     8: (-2.5276246935781084e+04, -1.3781281283808785e+03),
+    # rank 3, Euler-chart joints: JointSpherical (scene 7, scenesRedMax.m:206-207) and JointFree3D (scene 9, :250-251)
+    7: (-8.7859815791305155e+03, 8.6544602745403390e+03),
+    9: (4.3970920953724946e+00, 4.5466508559364156e+00),
     # rank 2, first force with off-diagonal blocks: ForcePointPoint (scene 10 'Loop', scenesRedMax.m:264-265)
     10: (1.2376477982839792e+03, 4.1146190850293169e+03),
     # ForceSpringDamper (scene 12 'Spring-damper', scenesRedMax.m:314-315)
@@ -53,6 +58,55 @@ def test_hexpected_more_joint_types(oracle, sid, itype):
     ok, H = s.checkEnergy(itype)
     assert ok, (sid, itype, H)
     assert abs(H - PINS[sid][itype - 1]) < 1e-6
+
+
+@pytest.mark.parametrize('sid', [7, 9])
+@pytest.mark.parametrize('itype', [1, 2])
+def test_hexpected_euler_chart_joints(oracle, sid, itype):
+    """JointSpherical / JointFree3D against the reference's recorded energies.  Scene 7 under BDF2 is the one run of the
+    reference's scene list that re-parameterises (JointSpherical.reparam_, JointSpherical.m:63-103): joint 2 goes
+    XYZ -> XYX -> YXZ; under BDF1 and for JointFree3D no switch happens (the reference could not perform one there:
+    chart1 is never set)."""
+    import redmax_b200.scenes as scenes
+    s = scenes.scenesRedMax(sid, api=oracle)
+    s.init()
+    assert s.Hexpected[itype - 1] == PINS[sid][itype - 1]
+    (oracle.sim_loop_bdf1 if itype == 1 else oracle.sim_loop_bdf2)(s)
+    ok, H = s.checkEnergy(itype)
+    assert ok, (sid, itype, H)
+    assert abs(H - PINS[sid][itype - 1]) < 1e-6
+    sw = [j.switches for j in s.joints if hasattr(j, 'switches')]
+    if (sid, itype) == (7, 2):
+        assert sw == [[], [(7, 1), (1, 10)]] and len(s.chart_switch_steps) == 2
+    else:
+        assert not any(sw) and not s.chart_switch_steps
+
+
+@pytest.mark.parametrize('chart', range(1, 13))
+def test_euler_charts_fd_and_inverse(oracle, chart):
+    """euler_chart is restated from the definition (R = R_a R_b R_c, omega_body = T qdot), not from the generated closed
+    forms: check every output against central differences, T against R' dR/dq, and the inverse map's round trip."""
+    rng = np.random.default_rng(700 + chart)
+    q = rng.uniform(-1.2, 1.2, 3)
+    if chart <= 6:
+        q[1] = abs(q[1]) + 0.2  # proper Euler charts: q2 in (0, pi)
+    qd = rng.uniform(-1, 1, 3)
+    R, dR, Rdot, dRdot, T, detT, dT, Tdot, dTdot = oracle.euler_chart(chart, q, qd)
+    assert np.allclose(R.T @ R, np.eye(3), atol=1e-14) and abs(np.linalg.det(R) - 1) < 1e-14
+    np.testing.assert_allclose(oracle.euler_chart_inv(chart, R), q, atol=1e-12)
+    e = 1e-6
+    for k in range(3):
+        dq = np.zeros(3)
+        dq[k] = e
+        p, m = oracle.euler_chart(chart, q + dq, qd), oracle.euler_chart(chart, q - dq, qd)
+        for name, ana, i in (('dR', dR, 0), ('dRdot', dRdot, 2), ('dT', dT, 4), ('dTdot', dTdot, 7)):
+            fd = (p[i] - m[i]) / (2 * e)
+            assert np.max(np.abs(fd - ana[:, :, k])) < 1e-8, (chart, name, k)
+        w = R.T @ dR[:, :, k]  # = [T(:,k)]
+        np.testing.assert_allclose([w[2, 1], w[0, 2], w[1, 0]], T[:, k], atol=1e-14)
+    np.testing.assert_allclose(Rdot, sum(dR[:, :, k] * qd[k] for k in range(3)), atol=1e-14)
+    np.testing.assert_allclose(Tdot, sum(dT[:, :, k] * qd[k] for k in range(3)), atol=1e-14)
+    assert abs(abs(detT) - (abs(math.sin(q[1])) if chart <= 6 else abs(math.cos(q[1])))) < 1e-14
 
 
 @pytest.mark.parametrize('itype', [2, 1])
