@@ -30,6 +30,11 @@ def _report_status(status, out=sys.stdout):
         bad = np.nonzero(status & bit)[0]
         if len(bad):
             print('%s (rollouts %s%s)' % (msg, bad[:8].tolist(), ' ...' if len(bad) > 8 else ''), file=out)
+    bad = np.nonzero(status & _ffi.RMX_ST_CHART)[0]
+    if len(bad):
+        # where the reference prints e.g. 'XYZ->XYX' (JointSpherical.m:84) and carries on in the new chart
+        print('Euler chart XYZ left its well-conditioned range, no re-parameterisation on the GPU path (rollouts %s%s)'
+              % (bad[:8].tolist(), ' ...' if len(bad) > 8 else ''), file=out)
 
 
 def simLoop(scene, itype, q0=None, qdot0=None, tau=None, ngpus=1, out=sys.stdout):

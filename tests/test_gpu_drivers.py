@@ -7,11 +7,15 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-IN_SCOPE = [0, 1, 2, 3, 4, 5, 6, 8, 10, 12, 13, 14]
+# every scene of the reference's loop except 11 (the reference's own BDF1 driver skips it: "doesn't work",
+# driverRedMaxBDF1.m:16; its BDF2 pin is covered in test_gpu_joints.py) ...
+IN_SCOPE = [(sid, itype) for sid in (0, 1, 2, 3, 4, 5, 6, 8, 9, 10, 12, 13, 14) for itype in (1, 2)]
+# ... and scene 7 (two spherical joints) under BDF1; under BDF2 the reference switches Euler charts in that scene, which the
+# CUDA path reports instead of performing (test_scene7_bdf2_is_flagged below)
+IN_SCOPE.append((7, 1))
 
 
-@pytest.mark.parametrize('sid', IN_SCOPE)
-@pytest.mark.parametrize('itype', [1, 2])
+@pytest.mark.parametrize('sid,itype', IN_SCOPE)
 def test_batch_mode_drivers_pass_the_energy_pins(rb, sid, itype):
     out = io.StringIO()
     drv = rb.driverRedMaxBDF1 if itype == 1 else rb.driverRedMaxBDF2
@@ -20,6 +24,16 @@ def test_batch_mode_drivers_pass_the_energy_pins(rb, sid, itype):
     assert text.startswith("(%d) '%s': tEnd=" % (sid, res['scene'].name))
     assert res['pass'] is True and '### PASS ###' in text, text
     assert res['status'].tolist() == [0]
+
+
+def test_scene7_bdf2_is_flagged(rb):
+    """driverRedMaxBDF2(7): the reference re-parameterises joint 2 twice (XYZ -> XYX -> YXZ); the CUDA path stays in chart
+    XYZ, says so on the console and in the status word, and therefore does not claim the recorded energy."""
+    out = io.StringIO()
+    res = rb.driverRedMaxBDF2(7, True, out=out)
+    assert res['status'].tolist() == [rb.RMX_ST_CHART]
+    assert 'Euler chart' in out.getvalue()
+    assert np.isfinite(res['q']).all()
 
 
 def test_driver_with_a_batch_keeps_rollout_zero_on_the_pin(rb):
