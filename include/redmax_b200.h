@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RMX_VERSION 107
+#define RMX_VERSION 108
 
 /* error codes */
 #define RMX_OK 0
@@ -142,6 +142,8 @@ typedef struct rmx_scene_desc {
     const double* cable_ks;  /* [ncable] ForceCable.m:20 */
     const double* cable_kd;  /* [ncable] ForceCable.m:25 */
     const double* cable_L;   /* [ncable] rest length (ForceCable.m:30); <= 0 or NULL = routed length in the initial configuration */
+    const int32_t* chart;    /* [n] Euler chart of a spherical / Free3D joint in the reference's numbering 1..12 (XYX XZX YZY YXY
+                                ZXZ ZYZ XYZ XZY YZX YXZ ZXY ZYX, JointSpherical.m:5-16); 0 or NULL = XYZ, the constructor's default */
 } rmx_scene_desc;
 
 /* Solver constants hard-coded in the reference's newton() (driverRedMaxBDF1.m:95-98;
@@ -192,6 +194,15 @@ int rmx_scene_nm(const rmx_scene* s); /* redmax.Scene.countM(), Scene.m:398 */
  * (line-search) evaluations; may be NULL.  qdot_out may be NULL. */
 int rmx_rollout(rmx_scene* s, const rmx_opts* o, int64_t B, const double* q0, const double* qdot0,
                 const double* tau, double* q_out, double* qdot_out, int32_t* status, int32_t* iters);
+/* Continue rollouts mid-way (host pointers, current device): rollout b resumes at step k_begin[b] (0 .. nsteps) from the
+ * states the caller provides in q_out / qdot_out -- step k_begin-1 is the current state, step k_begin-2 (q0 / qdot0 when
+ * k_begin == 1) the BDF2 history joint.q1 / qdot1; k_begin == 0 starts from q0 / qdot0 as rmx_rollout does.  Steps below
+ * k_begin are left as given, status / iters count the resumed part only.  This is the hook for what the reference does
+ * between steps on the host side of simLoop -- jroot.reparam() (driverRedMaxBDF2.m:112, JointSpherical.m:63-103): the caller
+ * re-parameterises the flagged step (RMX_ST_CHART), rebuilds the scene with the new rmx_scene_desc.chart and resumes. */
+int rmx_rollout_resume(rmx_scene* s, const rmx_opts* o, int64_t B, const int32_t* k_begin, const double* q0,
+                       const double* qdot0, const double* tau, double* q_out, double* qdot_out, int32_t* status,
+                       int32_t* iters);
 int rmx_rollout_dev(rmx_scene* s, const rmx_opts* o, int64_t B, const double* q0, const double* qdot0,
                     const double* tau, double* q_out, double* qdot_out, int32_t* status, int32_t* iters,
                     void* cuda_stream);

@@ -62,6 +62,7 @@ class rmx_scene_desc(C.Structure):
         ('pf_kind', _pi), ('pf_L', _pd),
         ('ncable', C.c_int32),
         ('cable_npts', _pi), ('cable_body', _pi), ('cable_x', _pd), ('cable_ks', _pd), ('cable_kd', _pd), ('cable_L', _pd),
+        ('chart', _pi),
     ]
 
 
@@ -86,7 +87,7 @@ class rmx_task_pointpos(C.Structure):
 SYMBOLS = [
     'rmx_version', 'rmx_last_error', 'rmx_device_count', 'rmx_opts_default',
     'rmx_scene_create', 'rmx_scene_destroy', 'rmx_scene_nr', 'rmx_scene_nm',
-    'rmx_rollout', 'rmx_rollout_dev', 'rmx_rollout_adjoint', 'rmx_rollout_adjoint_dev',
+    'rmx_rollout', 'rmx_rollout_resume', 'rmx_rollout_dev', 'rmx_rollout_adjoint', 'rmx_rollout_adjoint_dev',
     'rmx_adjoint_tape_bytes', 'rmx_eval', 'rmx_eval_newton', 'rmx_energies', 'rmx_linsolve_stats', 'rmx_debug_schedule', 'rmx_body_frames',
 ]
 
@@ -118,6 +119,7 @@ def lib():
     L.rmx_scene_nr.argtypes = [vp]
     L.rmx_scene_nm.argtypes = [vp]
     L.rmx_rollout.argtypes = [vp, C.POINTER(rmx_opts), C.c_int64, vp, vp, vp, vp, vp, vp, vp]
+    L.rmx_rollout_resume.argtypes = [vp, C.POINTER(rmx_opts), C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp]
     L.rmx_rollout_dev.argtypes = [vp, C.POINTER(rmx_opts), C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp]
     L.rmx_rollout_adjoint.argtypes = [vp, C.POINTER(rmx_opts), C.POINTER(rmx_task_pointpos), C.c_int64,
                                       vp, vp, vp, vp, vp, vp, vp, vp]

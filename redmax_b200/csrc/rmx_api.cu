@@ -153,6 +153,14 @@ static void expand_scene(const rmx_scene_desc* d, const std::vector<int>& base, 
         int vt[6] = {RMX_JOINT_FIXED, 0, 0, 0, 0, 0};
         const double* va[6] = {Z3, Z3, Z3, Z3, Z3, Z3};
         int nv = 1, mid = -1;
+        // Euler charts in the reference's numbering (JointSpherical.m:5-16): axes of R = R_a(q1) R_b(q2) R_c(q3); det T is
+        // sin q2 for the proper Euler charts 1..6 and cos q2 for the Tait-Bryan charts 7..12
+        static const int CH[13][3] = {{0, 1, 2}, {0, 1, 0}, {0, 2, 0}, {1, 2, 1}, {1, 0, 1}, {2, 0, 2}, {2, 1, 2},
+                                      {0, 1, 2}, {0, 2, 1}, {1, 2, 0}, {1, 0, 2}, {2, 0, 1}, {2, 1, 0}};
+        const double* EA[3] = {EX, EY, EZ};
+        int ch = d->chart ? d->chart[j] : 0;
+        if (ch < 1 || ch > 12) ch = 7;
+        const int midkind = ch <= 6 ? 2 : 1;
         switch (jt) {
             case RMX_JOINT_REVOLUTE: vt[0] = RMX_JOINT_REVOLUTE; va[0] = ax1; break;
             case RMX_JOINT_PRISMATIC: vt[0] = RMX_JOINT_PRISMATIC; va[0] = ax1; break;
@@ -162,13 +170,19 @@ static void expand_scene(const rmx_scene_desc* d, const std::vector<int>& base, 
             case RMX_JOINT_UNIVERSAL: nv = 2; vt[0] = vt[1] = RMX_JOINT_REVOLUTE; va[0] = EX; va[1] = EY; break;
             // Euler chart XYZ, R = X(q1) Y(q2) Z(q3) (JointSpherical.m:33,1086): g and dg/dq depend on the motion only, so the
             // reference's T(q), Tdot and their derivatives are reproduced by three revolute virtual joints
-            case RMX_JOINT_SPHERICAL: nv = 3; vt[0] = vt[1] = vt[2] = RMX_JOINT_REVOLUTE; va[0] = EX; va[1] = EY; va[2] = EZ; mid = 1; break;
+            case RMX_JOINT_SPHERICAL:
+                nv = 3;
+                vt[0] = vt[1] = vt[2] = RMX_JOINT_REVOLUTE;
+                for (int v = 0; v < 3; ++v) va[v] = EA[CH[ch][v]];
+                mid = 1;
+                break;
             // Q = [R p; 0 1] (JointFree3D.m:56-58): translate in the parent frame, then rotate
             case RMX_JOINT_FREE3D:
                 nv = 6;
                 vt[0] = vt[1] = vt[2] = RMX_JOINT_PRISMATIC;
                 vt[3] = vt[4] = vt[5] = RMX_JOINT_REVOLUTE;
-                va[0] = va[3] = EX; va[1] = va[4] = EY; va[2] = va[5] = EZ;
+                va[0] = EX; va[1] = EY; va[2] = EZ;
+                for (int v = 0; v < 3; ++v) va[3 + v] = EA[CH[ch][v]];
                 mid = 4;
                 break;
             default: break;
@@ -178,7 +192,7 @@ static void expand_scene(const rmx_scene_desc* d, const std::vector<int>& base, 
             x.parent.push_back(first ? (d->parent[j] < 0 ? -1 : x.body_of_user[d->parent[j]]) : x.n - 1);
             x.type.push_back(vt[v]);
             x.user.push_back(j);
-            x.chart_mid.push_back(v == mid ? 1 : 0);
+            x.chart_mid.push_back(v == mid ? midkind : 0);
             x.idx.push_back(vt[v] == RMX_JOINT_FIXED ? -1 : base[j] + v);
             const double* Epj = first ? d->E0_pj + 16 * j : ID4;
             const double* Eji = last ? d->E0_ji + 16 * j : ID4;
@@ -276,6 +290,7 @@ extern "C" int rmx_scene_create(const rmx_scene_desc* d, rmx_scene** out) {
     for (int j = 0; j < n_user; ++j) {
         if (d->parent[j] >= j || d->parent[j] < -1)
             return fail(RMX_EINVAL, "rmx_scene_create: joints must be listed parents-before-children (Joint.m:134)");
+        if (d->chart && (d->chart[j] < 0 || d->chart[j] > 12)) return fail(RMX_EINVAL, "rmx_scene_create: chart must be 0 (default) or 1..12");
         if (joint_ndof(d->jtype[j]) < 0)
             return fail(RMX_EINVAL, "rmx_scene_create: joint type is not on the hot path (fixed, revolute, prismatic, planar, "
                                     "translational, free2d, universal are)");
@@ -917,6 +932,81 @@ extern "C" int rmx_rollout(rmx_scene* s, const rmx_opts* o, int64_t B, const dou
     }
     cudaSetDevice(cur);
     return ret;
+}
+
+// Host-pointer resume (see the header): one launch on the current device, one block per rollout, each running the single
+// segment {b, k_begin[b], nsteps} of the schedule mechanism the load-balanced launches use.
+extern "C" int rmx_rollout_resume(rmx_scene* s, const rmx_opts* o, int64_t B, const int32_t* k_begin, const double* q0,
+                                  const double* qdot0, const double* tau, double* q_out, double* qdot_out, int32_t* status,
+                                  int32_t* iters) {
+    StepOpts so;
+    int rc = check_opts(s, o, &so, 0);
+    if (rc) return rc;
+    if (B < 1 || B >= (1ll << 30) || !k_begin || !q0 || !qdot0 || !q_out || !qdot_out || !status)
+        return fail(RMX_EINVAL, "rmx_rollout_resume: bad arguments");
+    if (o->linsolve != RMX_LINSOLVE_LU) return fail(RMX_EINVAL, "rmx_rollout_resume: LU linear solve only");
+    if (so.tau_mode != RMX_TAU_NONE && !tau) return fail(RMX_EINVAL, "rmx_rollout_resume: tau_mode set but tau == NULL");
+    for (int64_t b = 0; b < B; ++b)
+        if (k_begin[b] < 0 || k_begin[b] > so.nsteps) return fail(RMX_EINVAL, "rmx_rollout_resume: k_begin out of range");
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (ndev < 1) return fail(RMX_ENOGPU, "rmx_rollout_resume: no CUDA device (there is no CPU fallback)");
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    DevCopy* dc;
+    rc = scene_on_device(s, dev, &dc);
+    if (rc) return rc;
+    const int nr = s->nr;
+    const size_t per = (size_t)nr * so.nsteps;
+    const size_t tau_per = so.tau_mode == RMX_TAU_PER_STEP ? per : (size_t)nr;
+    std::vector<int4> seg((size_t)B);
+    std::vector<int> off((size_t)B + 1);
+    for (int64_t b = 0; b < B; ++b) {
+        seg[b] = make_int4((int)b, k_begin[b], so.nsteps, 0);
+        off[b] = (int)b;
+    }
+    off[B] = (int)B;
+    size_t sz[7] = {B * nr * sizeof(double), B * nr * sizeof(double), tau ? B * tau_per * sizeof(double) : 0,
+                    B * per * sizeof(double), B * per * sizeof(double), B * sizeof(int), 2 * B * sizeof(int)};
+    for (int i = 0; i < 7; ++i)
+        if (sz[i] && (rc = dev_reserve(dc->buf[i], sz[i]))) return rc;
+    const size_t sb = seg.size() * sizeof(int4), ob = off.size() * sizeof(int);
+    if ((rc = dev_reserve(dc->buf[13], sb)) || (rc = dev_reserve(dc->buf[14], ob))) return rc;
+    dc->plan = SchedPlan();  // the cached load-balancing plan no longer matches what is in buf[13], buf[14]
+    dc->plan_dev = nullptr;
+    cudaStream_t st = dc->stream;
+    CUDA_TRY(cudaMemcpyAsync(dc->buf[0].p, q0, sz[0], cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(dc->buf[1].p, qdot0, sz[1], cudaMemcpyHostToDevice, st));
+    if (tau) CUDA_TRY(cudaMemcpyAsync(dc->buf[2].p, tau, sz[2], cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(dc->buf[3].p, q_out, sz[3], cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(dc->buf[4].p, qdot_out, sz[4], cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(dc->buf[13].p, seg.data(), sb, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(dc->buf[14].p, off.data(), ob, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(dc->buf[5].p, 0, sz[5], st));
+    CUDA_TRY(cudaMemsetAsync(dc->buf[6].p, 0, sz[6], st));
+    RolloutArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.sc = make_devscene(s, dc);
+    a.op = so;
+    a.B = B;
+    a.q0 = (const double*)dc->buf[0].p;
+    a.qd0 = (const double*)dc->buf[1].p;
+    a.tau = tau ? (const double*)dc->buf[2].p : nullptr;
+    a.q_out = (double*)dc->buf[3].p;
+    a.qd_out = (double*)dc->buf[4].p;
+    a.status = (int*)dc->buf[5].p;
+    a.iters = (int*)dc->buf[6].p;
+    a.seg = (const int4*)dc->buf[13].p;
+    a.seg_off = (const int*)dc->buf[14].p;
+    rc = launch_fwd<false>(s, a, st, nullptr);  // no DevCopy: the launch keeps our segments, grid = B
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(q_out, dc->buf[3].p, sz[3], cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(qdot_out, dc->buf[4].p, sz[4], cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(status, dc->buf[5].p, sz[5], cudaMemcpyDeviceToHost, st));
+    if (iters) CUDA_TRY(cudaMemcpyAsync(iters, dc->buf[6].p, sz[6], cudaMemcpyDeviceToHost, st));
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail(RMX_ECUDA, std::string("rollout_resume: ") + cudaGetErrorString(e));
+    return RMX_OK;
 }
 
 extern "C" int rmx_linsolve_stats(rmx_scene* s, int64_t* krylov_iterations) {

@@ -51,7 +51,7 @@ struct JointConst {
     int pf_cnt;
     int ends_ptr;   // CSR into DevScene.ends_list: joints k whose subtree ends exactly at this index
     int ends_cnt;
-    int chart_mid;  // 1: this one-DOF virtual joint is the middle Euler angle of a spherical / Free3D joint (chart XYZ: det T = cos q)
+    int chart_mid;  // this one-DOF virtual joint is the middle Euler angle of a spherical / Free3D joint: 1 det T = cos q, 2 sin q
 };
 
 // Forces between body points (matlab-diff/+redmax): ForcePointPoint.m (linear, zero rest length), ForceSpringDamper.m

@@ -517,9 +517,13 @@ __global__ void RMX_FWD_BOUNDS rollout_fwd_kernel(RolloutArgs a) {
             tcur = tnext;
             if (a.sc.has_chart && t < a.sc.n) {
                 // jroot.reparam() (driverRedMaxBDF1.m:78, driverRedMaxBDF2.m:112): the chart is fixed here, the place where
-                // JointSpherical.reparam_ would leave it (|det T| = |cos q2| <= 0.5, JointSpherical.m:63-67) is reported
+                // JointSpherical.reparam_ would leave it (|det T| <= 0.5, JointSpherical.m:63-67) is reported
                 const JointConst& Jc = a.sc.jc[t];
-                if (Jc.chart_mid && !(fabs(cos(c.q[Jc.idx])) > 0.5)) status |= 32;
+                if (Jc.chart_mid) {
+                    const double qm = c.q[Jc.idx];
+                    const double detT = Jc.chart_mid == 2 ? sin(qm) : cos(qm);  // proper Euler / Tait-Bryan chart
+                    if (!(fabs(detT) > 0.5)) status |= 32;
+                }
             }
             if (t < nr) {
                 const size_t o = ((size_t)b * op.nsteps + k) * nr + t;

@@ -18,7 +18,7 @@ import sys
 
 import numpy as np
 
-from . import _ffi
+from . import _ffi, euler
 from .scenes import scenesRedMax
 
 BDF1, BDF2 = 1, 2
@@ -32,8 +32,8 @@ def _report_status(status, out=sys.stdout):
             print('%s (rollouts %s%s)' % (msg, bad[:8].tolist(), ' ...' if len(bad) > 8 else ''), file=out)
     bad = np.nonzero(status & _ffi.RMX_ST_CHART)[0]
     if len(bad):
-        # where the reference prints e.g. 'XYZ->XYX' (JointSpherical.m:84) and carries on in the new chart
-        print('Euler chart XYZ left its well-conditioned range, no re-parameterisation on the GPU path (rollouts %s%s)'
+        # the states at which the reference itself stops: reparam_ without chart1 (driverRedMaxBDF1, JointFree3D)
+        print('Euler chart left its well-conditioned range and cannot be re-parameterised here (rollouts %s%s)'
               % (bad[:8].tolist(), ' ...' if len(bad) > 8 else ''), file=out)
 
 
@@ -42,11 +42,14 @@ def simLoop(scene, itype, q0=None, qdot0=None, tau=None, ngpus=1, out=sys.stdout
     states (default: the scene's own, batch of one).  Returns dict(q, qdot, status, iters, T, V, H): q[b, k] = history(k).q,
     H[b] = T_end + V_end - V_0 as Scene.plotEnergies forms it."""
     res = scene.rollout(q0, qdot0, tau=tau, scheme=itype, ngpus=ngpus)
+    for b, sw in enumerate(res.get('chart_switches', ())):
+        for _, _, old, new in sw:  # JointSpherical.m:84
+            print('%s->%s' % (euler.CHART_NAMES[old], euler.CHART_NAMES[new]), file=out)
     _report_status(res['status'], out)
     q_start = np.atleast_2d(scene.qInit if q0 is None else q0)
     qd_start = np.atleast_2d(scene.qdotInit if qdot0 is None else qdot0)
     _, V0 = scene.energies(q_start, qd_start)
-    T1, V1 = scene.energies(res['q'][:, -1], res['qdot'][:, -1])
+    T1, V1 = scene.energies(res['q'][:, -1], res['qdot'][:, -1], chart=res.get('chart'))
     res['T'], res['V'], res['H'] = T1, V1 - V0, T1 + (V1 - V0)
     return res
 

@@ -22,7 +22,7 @@ import math
 
 import numpy as np
 
-from . import _ffi
+from . import _ffi, euler
 from ._ffi import RmxError, f64, i32, ptr
 
 
@@ -388,6 +388,34 @@ class Scene:
         return self
 
     def _create_handle(self, index):
+        h = self._build_handle(index)
+        self.close()
+        self._handle = h
+        self._index = index
+        self._variants = {}
+
+    def _spherical(self):
+        return [j for j in self.joints if isinstance(j, JointSpherical)]
+
+    def _variant(self, charts):
+        """Library handle of this scene with its JointSpherical joints in the given Euler charts (the scene's own charts: the
+        main handle).  Built on first use, destroyed with the scene."""
+        sph = self._spherical()
+        charts = tuple(int(c) for c in charts)
+        if charts == tuple(j.chart for j in sph):
+            return self._handle
+        if charts not in self._variants:
+            own = [j.chart for j in sph]
+            try:
+                for j, c in zip(sph, charts):
+                    j.chart = c
+                self._variants[charts] = self._build_handle(self._index)
+            finally:
+                for j, c in zip(sph, own):
+                    j.chart = c
+        return self._variants[charts]
+
+    def _build_handle(self, index):
         n = len(self.joints)
         L = _ffi.lib()
         d = _ffi.rmx_scene_desc()
@@ -463,13 +491,16 @@ class Scene:
             d.ground_kt = arr([f.kt for f in grounds], f64)
             d.ground_kd = arr([f.kd for f in grounds], f64)
             d.ground_mu = arr([f.mu for f in grounds], f64)
+        d.chart = arr([int(getattr(j, 'chart', 0)) for j in self.joints], i32)
         h = C.c_void_p()
         _ffi.check(L.rmx_scene_create(C.byref(d), C.byref(h)), 'rmx_scene_create')
-        self.close()
-        self._handle = h
         assert L.rmx_scene_nr(h) == self.nr and L.rmx_scene_nm(h) == self.nm
+        return h
 
     def close(self):
+        for h in getattr(self, '_variants', {}).values():
+            _ffi.lib().rmx_scene_destroy(h)
+        self._variants = {}
         if self._handle is not None:
             _ffi.lib().rmx_scene_destroy(self._handle)
             self._handle = None
@@ -504,7 +535,7 @@ class Scene:
         return _ffi.lib()
 
     # -- forward rollouts: simLoop of driverRedMaxBDF1.m:57 / driverRedMaxBDF2.m:57, batched ----------------
-    def rollout(self, q0=None, qdot0=None, tau=None, scheme=1, nsteps=None, ngpus=1, want_qdot=True, **kw):
+    def rollout(self, q0=None, qdot0=None, tau=None, scheme=1, nsteps=None, ngpus=1, want_qdot=True, reparam=True, **kw):
         """Host-buffer call.  q0, qdot0: [B, nr] (row b = rollout b; memory layout nr x B column-major as the
         C ABI wants).  tau: None, [B, nr] (constant) or [B, nsteps, nr].  Returns dict(q=[B,nsteps,nr],
         qdot=..., status=[B], iters=[B,2])."""
@@ -531,7 +562,103 @@ class Scene:
         iters = np.empty((B, 2), dtype=np.int32)
         _ffi.check(L.rmx_rollout(self._handle, C.byref(o), B, ptr(q0), ptr(qdot0), ptr(tau), ptr(q), ptr(qd),
                                  ptr(status), ptr(iters)), 'rmx_rollout')
-        return dict(q=q, qdot=qd, status=status, iters=iters)
+        out = dict(q=q, qdot=qd, status=status, iters=iters)
+        if reparam and scheme == 2 and want_qdot and self._spherical() and (status & _ffi.RMX_ST_CHART).any():
+            self._reparam_rollouts(out, q0, qdot0, tau, tau_mode, o)
+        return out
+
+    def _reparam_rollouts(self, out, q0, qdot0, tau, tau_mode, o):
+        """jroot.reparam() of driverRedMaxBDF2.m:112 for the rollouts the library flagged with RMX_ST_CHART: every such
+        rollout is taken up to the first step whose result leaves the well-conditioned range of a JointSpherical chart
+        (|det T| <= 0.5), that step and the BDF2 history are re-expressed in the chart JointSpherical.reparam_ picks
+        (euler.reparam), and the rollout resumes (rmx_rollout_resume) under the scene variant with the new charts -- until
+        it reaches the end.  Adds out['chart'] [B, nspherical] (the charts q(t_end) is expressed in) and
+        out['chart_switches'] (per rollout: (step, spherical joint, old chart, new chart)); q, qdot of a switch step are
+        the re-parameterised ones, as in the reference's history.  status / iters of these rollouts are rebuilt from the
+        pieces that were kept.  JointFree3D cannot switch in the reference (its inner joint never gets chart1:
+        JointFree3D.m:27-31, JointSpherical.m:73 stops with an error) and stays flagged."""
+        L = _ffi.lib()
+        sph = self._spherical()
+        nsteps, nr, B = o.nsteps, self.nr, out['q'].shape[0]
+        own = tuple(j.chart for j in sph)
+        out['chart'] = np.tile(np.array(own, dtype=np.int32), (B, 1))
+        out['chart_switches'] = [[] for _ in range(B)]
+        free3d_mid = [j.idxR[4] for j in self.joints if isinstance(j, JointFree3D)]
+
+        def resume(handle, kb, ns, qb, qdb, q0b, qd0b, taub):
+            o2 = self.opts(scheme=2, nsteps=ns, tau_mode=tau_mode)
+            for f in ('h', 'tol', 'dxMax', 'iterMaxFactor', 'iterLsMax', 'linsolve'):
+                setattr(o2, f, getattr(o, f))
+            st = np.zeros(1, dtype=np.int32)
+            it = np.zeros((1, 2), dtype=np.int32)
+            _ffi.check(L.rmx_rollout_resume(handle, C.byref(o2), 1, ptr(np.array([kb], dtype=np.int32)), ptr(q0b), ptr(qd0b),
+                                            ptr(taub), ptr(qb), ptr(qdb), ptr(st), ptr(it)), 'rmx_rollout_resume')
+            return int(st[0]), it[0]
+
+        for b in np.nonzero(out['status'] & _ffi.RMX_ST_CHART)[0]:
+            charts = list(own)
+            qb, qdb = out['q'][b:b + 1].copy(), out['qdot'][b:b + 1].copy()
+            q0b, qd0b = q0[b:b + 1].copy(), qdot0[b:b + 1].copy()
+            taub = None if tau is None else np.ascontiguousarray(tau[b:b + 1])
+            status, iters, kb = 0, np.zeros(2, dtype=np.int64), 0
+            hist = None  # (step index or -1 for the initial state, q, qdot): joint.q1 / qdot1 in the charts now in force
+
+            def run(kb, ns, qbuf, qdbuf):
+                """resume [kb, ns) with the re-expressed BDF2 history in place; the stored (old-chart) step is put back"""
+                q0r, qd0r, saved = q0b, qd0b, None
+                if hist is not None and hist[0] < 0:
+                    q0r, qd0r = hist[1][None, :].copy(), hist[2][None, :].copy()
+                elif hist is not None:
+                    saved = (qbuf[0, hist[0]].copy(), qdbuf[0, hist[0]].copy())
+                    qbuf[0, hist[0]], qdbuf[0, hist[0]] = hist[1], hist[2]
+                ts = taub if (taub is None or taub.ndim == 2) else np.ascontiguousarray(taub[:, :ns])
+                r = resume(self._variant(charts), kb, ns, qbuf, qdbuf, q0r, qd0r, ts)
+                if saved is not None:
+                    qbuf[0, hist[0]], qdbuf[0, hist[0]] = saved
+                return r
+
+            while kb < nsteps:
+                # first step at or after kb whose result needs a new chart
+                need = np.zeros(nsteps - kb, dtype=bool)
+                for j, c in zip(sph, charts):
+                    need |= euler.chart_det(c, qb[0, kb:, j.idxR[1]]) <= 0.5
+                k1 = kb + int(np.argmax(need)) if need.any() else nsteps - 1
+                # the piece [kb, k1] again on its own: its status and iteration counts, without the discarded tail
+                ns = k1 + 1
+                qs, qds = np.ascontiguousarray(qb[:, :ns]), np.ascontiguousarray(qdb[:, :ns])
+                st, it = run(kb, ns, qs, qds)
+                if np.isfinite(qs).all() and not np.array_equal(qs[0, kb:], qb[0, kb:ns]):
+                    raise RmxError('re-parameterised rollout: the piece does not reproduce the pass it was cut from')
+                status |= st & ~_ffi.RMX_ST_CHART
+                iters += it
+                if not need.any():
+                    break
+                # JointSpherical.reparam_ for every spherical joint that asks for it at step k1
+                hq = (q0b[0] if k1 == 0 else qb[0, k1 - 1]).copy()
+                hqd = (qd0b[0] if k1 == 0 else qdb[0, k1 - 1]).copy()
+                if hist is not None and hist[0] == k1 - 1:  # consecutive switch steps: the history is already re-expressed
+                    hq, hqd = hist[1].copy(), hist[2].copy()
+                for i, (j, c) in enumerate(zip(sph, charts)):
+                    r = j.idxR
+                    if euler.chart_det(c, qb[0, k1, r[1]]) > 0.5:
+                        continue
+                    new, qn, qdn, q1n, qd1n = euler.reparam(c, qb[0, k1, r], qdb[0, k1, r], c, hq[r], hqd[r])
+                    out['chart_switches'][b].append((int(k1), i, int(c), int(new)))
+                    charts[i] = new
+                    qb[0, k1, r], qdb[0, k1, r] = qn, qdn
+                    hq[r], hqd[r] = q1n, qd1n
+                hist = (k1 - 1, hq, hqd)
+                kb = k1 + 1
+                if kb < nsteps:
+                    run(kb, nsteps, qb, qdb)  # the rest of the rollout in the new charts (cut again if it switches again)
+            # a JointFree3D that left its chart stays flagged
+            for m in free3d_mid:
+                if (np.abs(np.cos(qb[0, :, m])) <= 0.5).any():
+                    status |= _ffi.RMX_ST_CHART
+            out['q'][b], out['qdot'][b] = qb[0], qdb[0]
+            out['status'][b] = status
+            out['iters'][b] = iters
+            out['chart'][b] = charts
 
     def rollout_into(self, q0, qdot0, q_out, qdot_out=None, tau=None, scheme=1, nsteps=None, ngpus=1, **kw):
         """rmx_rollout with caller-owned host buffers (e.g. pinned memory): q0, qdot0 [B, nr] float64 C-contiguous,
@@ -650,8 +777,9 @@ class Scene:
         _ffi.check(L.rmx_body_frames(self._handle, B, ptr(q), ptr(E)), 'rmx_body_frames')
         return np.ascontiguousarray(np.swapaxes(E, 2, 3))  # column-major 4x4 blocks -> [row, col]
 
-    def energies(self, q, qdot):
-        """T, V of Scene.saveHistory (Scene.m:155-160) for B states."""
+    def energies(self, q, qdot, chart=None):
+        """T, V of Scene.saveHistory (Scene.m:155-160) for B states.  chart [B, nspherical]: the Euler charts the states are
+        expressed in (out['chart'] of a rollout that re-parameterised); default: the scene's own."""
         L = self._require()
         q, qdot = f64(q), f64(qdot)
         if q.ndim == 1:
@@ -659,5 +787,14 @@ class Scene:
         B = q.shape[0]
         T = np.empty(B)
         V = np.empty(B)
-        _ffi.check(L.rmx_energies(self._handle, B, ptr(q), ptr(qdot), ptr(T), ptr(V)), 'rmx_energies')
+        if chart is None or not self._spherical():
+            _ffi.check(L.rmx_energies(self._handle, B, ptr(q), ptr(qdot), ptr(T), ptr(V)), 'rmx_energies')
+            return T, V
+        chart = np.asarray(chart, dtype=np.int32).reshape(B, -1)
+        for ct in {tuple(r) for r in chart.tolist()}:
+            sel = np.nonzero((chart == np.array(ct, dtype=np.int32)).all(axis=1))[0]
+            qs, qds = np.ascontiguousarray(q[sel]), np.ascontiguousarray(qdot[sel])
+            Ts, Vs = np.empty(len(sel)), np.empty(len(sel))
+            _ffi.check(L.rmx_energies(self._variant(ct), len(sel), ptr(qs), ptr(qds), ptr(Ts), ptr(Vs)), 'rmx_energies')
+            T[sel], V[sel] = Ts, Vs
         return T, V

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol(rb):
     assert sorted(_ffi.SYMBOLS) == syms
     for s in syms:
         assert hasattr(L, s), s
-    assert L.rmx_version() == 107
+    assert L.rmx_version() == 108
 
 
 def test_opts_default_are_the_references(rb):
@@ -125,7 +125,7 @@ def test_scene_create_validates_forces(rb):
 
 def test_scene_create_accepts_every_hot_path_joint_type(rb):
     s = rb.Scene()
-    bs = [rb.BodyCuboid(1, [1, 1, 1]) for _ in range(7)]
+    bs = [rb.BodyCuboid(1, [1, 1, 1]) for _ in range(9)]
     js = [rb.JointFixed(None, bs[0])]
     js.append(rb.JointRevolute(js[0], bs[1], [0, 0, 1]))
     js.append(rb.JointPrismatic(js[1], bs[2], [1, 0, 0]))
@@ -133,8 +133,10 @@ def test_scene_create_accepts_every_hot_path_joint_type(rb):
     js.append(rb.JointTranslational(js[3], bs[4]))
     js.append(rb.JointFree2D(js[4], bs[5]))
     js.append(rb.JointUniversal(js[5], bs[6]))
+    js.append(rb.JointSpherical(js[6], bs[7]))
+    js.append(rb.JointFree3D(js[7], bs[8]))
     s.bodies, s.joints = bs, js
     s.init()
-    assert s.nr == 0 + 1 + 1 + 2 + 3 + 3 + 2 and s.nm == 42
+    assert s.nr == 0 + 1 + 1 + 2 + 3 + 3 + 2 + 3 + 6 and s.nm == 54
     # leaf-to-root numbering with consecutive DOFs per joint (Scene.m:69-71, Joint.m:152)
-    assert js[-1].idxR.tolist() == [0, 1] and js[1].idxR.tolist() == [11]
+    assert js[-1].idxR.tolist() == [0, 1, 2, 3, 4, 5] and js[-2].idxR.tolist() == [6, 7, 8] and js[1].idxR.tolist() == [20]

@@ -10,9 +10,9 @@ pytestmark = pytest.mark.gpu
 # every scene of the reference's loop except 11 (the reference's own BDF1 driver skips it: "doesn't work",
 # driverRedMaxBDF1.m:16; its BDF2 pin is covered in test_gpu_joints.py) ...
 IN_SCOPE = [(sid, itype) for sid in (0, 1, 2, 3, 4, 5, 6, 8, 9, 10, 12, 13, 14) for itype in (1, 2)]
-# ... and scene 7 (two spherical joints) under BDF1; under BDF2 the reference switches Euler charts in that scene, which the
-# CUDA path reports instead of performing (test_scene7_bdf2_is_flagged below)
-IN_SCOPE.append((7, 1))
+# ... and scene 7 (two spherical joints): under BDF2 the reference switches Euler charts twice in that scene, and so does
+# the host side of the rollout (Scene._reparam_rollouts)
+IN_SCOPE += [(7, 1), (7, 2)]
 
 
 @pytest.mark.parametrize('sid,itype', IN_SCOPE)
@@ -26,14 +26,13 @@ def test_batch_mode_drivers_pass_the_energy_pins(rb, sid, itype):
     assert res['status'].tolist() == [0]
 
 
-def test_scene7_bdf2_is_flagged(rb):
-    """driverRedMaxBDF2(7): the reference re-parameterises joint 2 twice (XYZ -> XYX -> YXZ); the CUDA path stays in chart
-    XYZ, says so on the console and in the status word, and therefore does not claim the recorded energy."""
+def test_scene7_bdf2_prints_the_chart_switches(rb):
+    """driverRedMaxBDF2(7): the reference prints 'XYZ->XYX' and 'XYX->YXZ' (JointSpherical.m:84) on its way to PASS."""
     out = io.StringIO()
     res = rb.driverRedMaxBDF2(7, True, out=out)
-    assert res['status'].tolist() == [rb.RMX_ST_CHART]
-    assert 'Euler chart' in out.getvalue()
-    assert np.isfinite(res['q']).all()
+    text = out.getvalue()
+    assert 'XYZ->XYX' in text and 'XYX->YXZ' in text and '### PASS ###' in text, text
+    assert res['status'].tolist() == [0] and res['chart'].tolist() == [[7, 10]]
 
 
 def test_driver_with_a_batch_keeps_rollout_zero_on_the_pin(rb):

@@ -62,22 +62,71 @@ def test_rollout_and_golden_energy(rb, oracle, sid, scheme):
 
 
 @pytest.mark.timeout(600)
-def test_scene7_bdf2_reports_the_chart_switch(rb, oracle):
-    """Scene 7 under BDF2 is the one reference run that re-parameterises (joint 2: XYZ -> XYX -> YXZ).  The CUDA path keeps
-    chart XYZ: it must agree with the oracle up to the step whose result the reference re-parameterises, and flag the
-    rollout with RMX_ST_CHART (the trajectory after that step is the same motion integrated in other coordinates)."""
+def test_scene7_bdf2_switches_charts_like_the_reference(rb, oracle):
+    """Scene 7 under BDF2 is the one reference run that re-parameterises (joint 2: XYZ -> XYX -> YXZ,
+    JointSpherical.reparam_).  The library flags the step (RMX_ST_CHART), the host re-expresses it and the BDF2 history in
+    the chart the reference picks, and the rollout resumes under that chart (rmx_rollout_resume): same switch steps and
+    charts as the oracle, q(t) within 1e-10 over the whole run, same Newton counts, and the recorded Hexpected(BDF2)."""
     sg, so = both(rb, oracle, rb.scenesRedMax, 7)
-    out = sg.rollout(scheme=2)
-    qs, _ = oracle.run_forward(so, 2, sg.qInit, sg.qdotInit)
-    assert len(so.chart_switch_steps) == 2
-    k1 = so.chart_switch_steps[0]
-    assert k1 > 50
-    assert rel_err(out['q'][0, :k1], qs[:k1]) < TOL_Q, rel_err(out['q'][0, :k1], qs[:k1])
-    assert out['status'][0] == rmx.RMX_ST_CHART
-    # a rollout cut before the switch carries no flag
-    short = sg.rollout(scheme=2, nsteps=k1)
+    B = 3
+    rng = np.random.default_rng(20260107)
+    q0 = sg.qInit[None, :] + 0.05 * rng.uniform(-1, 1, (B, sg.nr))
+    qd0 = sg.qdotInit[None, :] + 0.05 * rng.uniform(-1, 1, (B, sg.nr))
+    q0[0], qd0[0] = sg.qInit, sg.qdotInit
+    out = sg.rollout(q0, qd0, scheme=2)
+    assert out['status'].tolist() == [0] * B
+    nsw = 0
+    for b in range(B):
+        stats = []
+        qs, qds = oracle.run_forward(so, 2, q0[b], qd0[b], stats=stats)
+        sw_o = [s for j in so.joints for s in j.switches]
+        assert [k for k, _, _, _ in out['chart_switches'][b]] == so.chart_switch_steps
+        assert sorted((o_, n_) for _, _, o_, n_ in out['chart_switches'][b]) == sorted(sw_o)
+        assert out['chart'][b].tolist() == [j.chart for j in so.joints]
+        assert rel_err(out['q'][b], qs) < TOL_Q, (b, rel_err(out['q'][b], qs))
+        assert rel_err(out['qdot'][b], qds) < 1e-8, (b, rel_err(out['qdot'][b], qds))
+        it = np.array(stats)
+        assert out['iters'][b, 0] == it[:, 0].sum() and out['iters'][b, 1] == it[:, 1].sum()
+        nsw += len(so.chart_switch_steps)
+    assert out['chart_switches'][0] == [(out['chart_switches'][0][0][0], 1, 7, 1), (out['chart_switches'][0][1][0], 1, 1, 10)]
+    assert nsw >= 2
+    T1, V1 = sg.energies(out['q'][:, -1], out['qdot'][:, -1], chart=out['chart'])
+    _, V0 = sg.energies(q0, qd0)
+    assert abs(T1[0] + V1[0] - V0[0] - sg.Hexpected[1]) <= 1e-2, (T1[0] + V1[0] - V0[0], sg.Hexpected[1])
+    # without the host step the library only reports: flag set, trajectory identical up to the first switch step
+    raw = sg.rollout(q0, qd0, scheme=2, reparam=False)
+    k1 = out['chart_switches'][0][0][0]
+    assert raw['status'][0] == rmx.RMX_ST_CHART
+    np.testing.assert_array_equal(raw['q'][0, :k1], out['q'][0, :k1])
+    short = sg.rollout(scheme=2, nsteps=k1)  # cut before the switch: no flag
     assert short['status'][0] == 0
     np.testing.assert_array_equal(short['q'][0], out['q'][0, :k1])
+
+
+def test_resume_reproduces_the_uncut_rollout(rb):
+    """rmx_rollout_resume from the states of an earlier call is bitwise the uncut rollout, for BDF1 and BDF2, from step 0, 1,
+    2 and mid-way, per rollout."""
+    import ctypes as C
+    from redmax_b200 import _ffi
+    sg = rb.chain_scene(6, nsteps=12, h=1e-3)
+    sg.init()
+    B = 5
+    q0, qd0 = rb.synthetic_inputs(sg, B, seed=3)
+    for scheme in (1, 2):
+        ref = sg.rollout(q0, qd0, scheme=scheme)
+        q, qd = ref['q'].copy(), ref['qdot'].copy()
+        kb = np.array([0, 1, 2, 7, 12], dtype=np.int32)
+        for b in range(B):
+            q[b, kb[b]:] = np.nan
+            qd[b, kb[b]:] = np.nan
+        st = np.zeros(B, dtype=np.int32)
+        it = np.zeros((B, 2), dtype=np.int32)
+        o = sg.opts(scheme=scheme)
+        _ffi.check(_ffi.lib().rmx_rollout_resume(sg._handle, C.byref(o), B, _ffi.ptr(kb), _ffi.ptr(q0), _ffi.ptr(qd0), None,
+                                                 _ffi.ptr(q), _ffi.ptr(qd), _ffi.ptr(st), _ffi.ptr(it)), 'rmx_rollout_resume')
+        np.testing.assert_array_equal(q, ref['q'])
+        np.testing.assert_array_equal(qd, ref['qdot'])
+        assert st.tolist() == [0] * B and it[0].tolist() == ref['iters'][0].tolist() and it[4].tolist() == [0, 0]
 
 
 def test_free3d_under_a_revolute_parent_with_ground(rb, oracle):
