@@ -49,10 +49,11 @@ extern "C" {
 #define RMX_JOINT_TRANSLATIONAL 4 /* JointTranslational.m  [3] translation x, y, z */
 #define RMX_JOINT_FREE2D 5        /* JointFree2D.m         [3] translation x, y then rotation about z */
 #define RMX_JOINT_UNIVERSAL 6     /* JointUniversal.m      [2] rotation about x then y */
-#define RMX_JOINT_SPHERICAL 7     /* JointSpherical.m      [3] Euler angles in the reference's initial chart XYZ: R = X(q1) Y(q2) Z(q3)
-                                     (JointSpherical.m:33,1086).  The chart is fixed: where the reference would re-parameterise
-                                     (|det T| = |cos q2| <= 0.5 after a step, JointSpherical.m:63-67) the rollout sets RMX_ST_CHART
-                                     and carries on in chart XYZ */
+#define RMX_JOINT_SPHERICAL 7     /* JointSpherical.m      [3] Euler angles R = R_a(q1) R_b(q2) R_c(q3) in the chart given by
+                                     rmx_scene_desc.chart (default XYZ, the constructor's: JointSpherical.m:33).  A rollout never
+                                     changes chart by itself: where the reference re-parameterises (|det T| <= 0.5 after a step,
+                                     JointSpherical.m:63-67) it sets RMX_ST_CHART and carries on; the caller re-expresses that step
+                                     and resumes under the new chart (rmx_rollout_resume) */
 #define RMX_JOINT_FREE3D 8        /* JointFree3D.m         [6] translation x, y, z (q1..q3) then a spherical joint (q4..q6) */
 #define RMX_MAX_JOINT_DOF 6
 #define RMX_MAX_POINTFORCE 8
@@ -81,8 +82,10 @@ extern "C" {
 #define RMX_ST_NAN 8       /* non-finite state produced */
 #define RMX_ST_SCHED 16    /* internal: a load-balanced rollout never received its first part (should not happen) */
 #define RMX_ST_CHART 32    /* a spherical / Free3D joint left the well-conditioned part of its Euler chart after some step
-                              (|cos q2| <= 0.5): driverRedMaxBDF2 would switch charts there (JointSpherical.m:63-103);
-                              driverRedMaxBDF1 and JointFree3D stop with an error at that point (chart1 is never set) */
+                              (|det T| <= 0.5: |cos q2| in the charts 7..12, |sin q2| in 1..6); steps after the first such step
+                              are the same motion in coordinates the reference would have left.  driverRedMaxBDF2 switches
+                              charts there (JointSpherical.m:63-103 -> rmx_rollout_resume); driverRedMaxBDF1 and JointFree3D
+                              stop with an error at that point (chart1 is never set) */
 
 /* tau layout for rmx_rollout */
 #define RMX_TAU_NONE 0     /* tau == NULL: joint.tau = 0 */

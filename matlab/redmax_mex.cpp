@@ -96,6 +96,12 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         sd.qLimK = mxGetDoubles(field(d, "qLimK"));
         sd.qLimD = mxGetDoubles(field(d, "qLimD"));
         std::memcpy(sd.grav, mxGetDoubles(field(d, "grav")), 3 * sizeof(double));
+        std::vector<int32_t> chart;
+        const mxArray* ch = field(d, "chart", false);  // Euler chart per joint (JointSpherical.chart), optional
+        if (ch && mxGetNumberOfElements(ch) == (size_t)sd.n) {
+            chart = to_i32(ch);
+            sd.chart = chart.data();
+        }
         std::vector<int32_t> pfb1, pfb2, pfkind;
         const mxArray* pf1 = field(d, "pf_body1", false);
         if (pf1 && mxGetNumberOfElements(pf1) > 0) {
@@ -161,6 +167,28 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         check(rmx_rollout(s, &o, (int64_t)B, mxGetDoubles(prhs[3]), mxGetDoubles(prhs[4]), tau ? mxGetDoubles(tau) : nullptr,
                           mxGetDoubles(plhs[0]), mxGetDoubles(qd), (int32_t*)mxGetData(st), (int32_t*)mxGetData(it)),
               "rmx_rollout");
+        if (nlhs > 1) plhs[1] = qd; else mxDestroyArray(qd);
+        if (nlhs > 2) plhs[2] = st; else mxDestroyArray(st);
+        if (nlhs > 3) plhs[3] = it; else mxDestroyArray(it);
+    } else if (!std::strcmp(cmd, "resume")) {
+        // [q, qdot, status, iters] = redmax_mex('resume', h, opts, kbegin, q0, qdot0, tau, q, qdot): continue the rollouts from
+        // step kbegin(b) (0-based) with the states in q / qdot (nr x nsteps x B) -- after jroot.reparam() re-expressed a step
+        rmx_scene* s = handle(prhs[1]);
+        rmx_opts o = opts_from(prhs[2], 0);
+        const int nr = rmx_scene_nr(s);
+        const mwSize B = mxGetN(prhs[4]);
+        std::vector<int32_t> kb = to_i32(prhs[3]);
+        if (kb.size() != (size_t)B) mexErrMsgIdAndTxt("redmax:resume", "kbegin needs one entry per rollout");
+        const mxArray* tau = !mxIsEmpty(prhs[6]) ? prhs[6] : nullptr;
+        o.tau_mode = !tau ? RMX_TAU_NONE : (mxGetNumberOfElements(tau) == (size_t)nr * B ? RMX_TAU_CONST : RMX_TAU_PER_STEP);
+        plhs[0] = mxDuplicateArray(prhs[7]);
+        mxArray* qd = mxDuplicateArray(prhs[8]);
+        mxArray* st = mxCreateNumericMatrix(B, 1, mxINT32_CLASS, mxREAL);
+        mxArray* it = mxCreateNumericMatrix(2, B, mxINT32_CLASS, mxREAL);
+        check(rmx_rollout_resume(s, &o, (int64_t)B, kb.data(), mxGetDoubles(prhs[4]), mxGetDoubles(prhs[5]),
+                                 tau ? mxGetDoubles(tau) : nullptr, mxGetDoubles(plhs[0]), mxGetDoubles(qd),
+                                 (int32_t*)mxGetData(st), (int32_t*)mxGetData(it)),
+              "rmx_rollout_resume");
         if (nlhs > 1) plhs[1] = qd; else mxDestroyArray(qd);
         if (nlhs > 2) plhs[2] = st; else mxDestroyArray(st);
         if (nlhs > 3) plhs[3] = it; else mxDestroyArray(it);

@@ -19,6 +19,7 @@ d.parent = zeros(1,n); d.jtype = zeros(1,n);
 d.E0_pj = zeros(4,4,n); d.E0_ji = zeros(4,4,n); d.axis = zeros(3,n); d.I_i = zeros(6,n); d.sides = zeros(3,n);
 d.axis2 = repmat([0;1;0],1,n);
 d.stiffness = zeros(1,n); d.damping = zeros(1,n); d.qRest = zeros(6,n); % RMX_MAX_JOINT_DOF x n
+d.chart = zeros(1,n,'int32');
 d.qLimL = zeros(1,n); d.qLimU = zeros(1,n); d.qLimK = zeros(1,n); d.qLimD = zeros(1,n);
 for i = 1 : n
 	j = scene.joints{i};
@@ -43,12 +44,10 @@ for i = 1 : n
 	elseif isa(j,'redmax.JointUniversal')
 		d.jtype(i) = 6;
 	elseif isa(j,'redmax.JointSpherical')
-		% fixed chart XYZ (the constructor's default, JointSpherical.m:33); status bit 32 marks rollouts that would re-parameterise
-		assert(j.chart == redmax.JointSpherical.CHART_XYZ);
-		d.jtype(i) = 7;
+		% status bit 32 marks rollouts that need jroot.reparam(): re-express that step, rebuild d with the new charts, 'resume'
+		d.jtype(i) = 7; d.chart(i) = j.chart;
 	elseif isa(j,'redmax.JointFree3D')
-		assert(j.joint2.chart == redmax.JointSpherical.CHART_XYZ);
-		d.jtype(i) = 8;
+		d.jtype(i) = 8; d.chart(i) = j.joint2.chart;
 	else
 		error('joint type %s is not on the GPU hot path',class(j));
 	end

@@ -183,9 +183,10 @@ class JointUniversal(Joint):
 
 
 class JointSpherical(Joint):
-    """+redmax/JointSpherical.m -- Euler angles in the reference's initial chart XYZ (JointSpherical.m:33).  The CUDA path keeps
-    that chart for the whole rollout; where the reference would re-parameterise (JointSpherical.m:63-67, BDF2 only -- under
-    driverRedMaxBDF1 the reference itself stops there) the rollout's status gets RMX_ST_CHART."""
+    """+redmax/JointSpherical.m -- Euler angles in one of the reference's twelve charts (`chart`, default XYZ as
+    JointSpherical.m:33).  Under BDF2 a rollout that leaves the chart's well-conditioned range is re-parameterised as the
+    reference does (Scene._reparam_rollouts); under BDF1 the reference itself stops there and the rollout stays flagged
+    RMX_ST_CHART."""
     jtype = _ffi.RMX_JOINT_SPHERICAL
     CHART_XYZ = 7
 
