@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RMX_VERSION 108
+#define RMX_VERSION 109
 
 /* error codes */
 #define RMX_OK 0
@@ -197,15 +197,16 @@ int rmx_scene_nm(const rmx_scene* s); /* redmax.Scene.countM(), Scene.m:398 */
  * (line-search) evaluations; may be NULL.  qdot_out may be NULL. */
 int rmx_rollout(rmx_scene* s, const rmx_opts* o, int64_t B, const double* q0, const double* qdot0,
                 const double* tau, double* q_out, double* qdot_out, int32_t* status, int32_t* iters);
-/* Continue rollouts mid-way (host pointers, current device): rollout b resumes at step k_begin[b] (0 .. nsteps) from the
- * states the caller provides in q_out / qdot_out -- step k_begin-1 is the current state, step k_begin-2 (q0 / qdot0 when
- * k_begin == 1) the BDF2 history joint.q1 / qdot1; k_begin == 0 starts from q0 / qdot0 as rmx_rollout does.  Steps below
- * k_begin are left as given, status / iters count the resumed part only.  This is the hook for what the reference does
+/* Continue rollouts mid-way (host pointers, current device): rollout b runs the steps k_begin[b] .. k_end[b]-1
+ * (0 <= k_begin <= k_end <= nsteps; k_end == NULL: to nsteps) from the states the caller provides in q_out / qdot_out --
+ * step k_begin-1 is the current state, step k_begin-2 (q0 / qdot0 when k_begin == 1) the BDF2 history joint.q1 / qdot1;
+ * k_begin == 0 starts from q0 / qdot0 as rmx_rollout does.  Steps outside [k_begin, k_end) are left as given, status / iters
+ * count the steps run by this call only.  This is the hook for what the reference does
  * between steps on the host side of simLoop -- jroot.reparam() (driverRedMaxBDF2.m:112, JointSpherical.m:63-103): the caller
  * re-parameterises the flagged step (RMX_ST_CHART), rebuilds the scene with the new rmx_scene_desc.chart and resumes. */
-int rmx_rollout_resume(rmx_scene* s, const rmx_opts* o, int64_t B, const int32_t* k_begin, const double* q0,
-                       const double* qdot0, const double* tau, double* q_out, double* qdot_out, int32_t* status,
-                       int32_t* iters);
+int rmx_rollout_resume(rmx_scene* s, const rmx_opts* o, int64_t B, const int32_t* k_begin, const int32_t* k_end,
+                       const double* q0, const double* qdot0, const double* tau, double* q_out, double* qdot_out,
+                       int32_t* status, int32_t* iters);
 int rmx_rollout_dev(rmx_scene* s, const rmx_opts* o, int64_t B, const double* q0, const double* qdot0,
                     const double* tau, double* q_out, double* qdot_out, int32_t* status, int32_t* iters,
                     void* cuda_stream);

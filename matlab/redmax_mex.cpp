@@ -185,7 +185,7 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         mxArray* qd = mxDuplicateArray(prhs[8]);
         mxArray* st = mxCreateNumericMatrix(B, 1, mxINT32_CLASS, mxREAL);
         mxArray* it = mxCreateNumericMatrix(2, B, mxINT32_CLASS, mxREAL);
-        check(rmx_rollout_resume(s, &o, (int64_t)B, kb.data(), mxGetDoubles(prhs[4]), mxGetDoubles(prhs[5]),
+        check(rmx_rollout_resume(s, &o, (int64_t)B, kb.data(), nullptr, mxGetDoubles(prhs[4]), mxGetDoubles(prhs[5]),
                                  tau ? mxGetDoubles(tau) : nullptr, mxGetDoubles(plhs[0]), mxGetDoubles(qd),
                                  (int32_t*)mxGetData(st), (int32_t*)mxGetData(it)),
               "rmx_rollout_resume");

@@ -119,7 +119,7 @@ def lib():
     L.rmx_scene_nr.argtypes = [vp]
     L.rmx_scene_nm.argtypes = [vp]
     L.rmx_rollout.argtypes = [vp, C.POINTER(rmx_opts), C.c_int64, vp, vp, vp, vp, vp, vp, vp]
-    L.rmx_rollout_resume.argtypes = [vp, C.POINTER(rmx_opts), C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.rmx_rollout_resume.argtypes = [vp, C.POINTER(rmx_opts), C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.rmx_rollout_dev.argtypes = [vp, C.POINTER(rmx_opts), C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp]
     L.rmx_rollout_adjoint.argtypes = [vp, C.POINTER(rmx_opts), C.POINTER(rmx_task_pointpos), C.c_int64,
                                       vp, vp, vp, vp, vp, vp, vp, vp]

@@ -936,9 +936,9 @@ extern "C" int rmx_rollout(rmx_scene* s, const rmx_opts* o, int64_t B, const dou
 
 // Host-pointer resume (see the header): one launch on the current device, one block per rollout, each running the single
 // segment {b, k_begin[b], nsteps} of the schedule mechanism the load-balanced launches use.
-extern "C" int rmx_rollout_resume(rmx_scene* s, const rmx_opts* o, int64_t B, const int32_t* k_begin, const double* q0,
-                                  const double* qdot0, const double* tau, double* q_out, double* qdot_out, int32_t* status,
-                                  int32_t* iters) {
+extern "C" int rmx_rollout_resume(rmx_scene* s, const rmx_opts* o, int64_t B, const int32_t* k_begin, const int32_t* k_end,
+                                  const double* q0, const double* qdot0, const double* tau, double* q_out, double* qdot_out,
+                                  int32_t* status, int32_t* iters) {
     StepOpts so;
     int rc = check_opts(s, o, &so, 0);
     if (rc) return rc;
@@ -946,8 +946,11 @@ extern "C" int rmx_rollout_resume(rmx_scene* s, const rmx_opts* o, int64_t B, co
         return fail(RMX_EINVAL, "rmx_rollout_resume: bad arguments");
     if (o->linsolve != RMX_LINSOLVE_LU) return fail(RMX_EINVAL, "rmx_rollout_resume: LU linear solve only");
     if (so.tau_mode != RMX_TAU_NONE && !tau) return fail(RMX_EINVAL, "rmx_rollout_resume: tau_mode set but tau == NULL");
-    for (int64_t b = 0; b < B; ++b)
-        if (k_begin[b] < 0 || k_begin[b] > so.nsteps) return fail(RMX_EINVAL, "rmx_rollout_resume: k_begin out of range");
+    for (int64_t b = 0; b < B; ++b) {
+        const int ke = k_end ? k_end[b] : so.nsteps;
+        if (k_begin[b] < 0 || k_begin[b] > ke || ke > so.nsteps)
+            return fail(RMX_EINVAL, "rmx_rollout_resume: need 0 <= k_begin <= k_end <= nsteps");
+    }
     int ndev = 0;
     CUDA_TRY(cudaGetDeviceCount(&ndev));
     if (ndev < 1) return fail(RMX_ENOGPU, "rmx_rollout_resume: no CUDA device (there is no CPU fallback)");
@@ -962,7 +965,7 @@ extern "C" int rmx_rollout_resume(rmx_scene* s, const rmx_opts* o, int64_t B, co
     std::vector<int4> seg((size_t)B);
     std::vector<int> off((size_t)B + 1);
     for (int64_t b = 0; b < B; ++b) {
-        seg[b] = make_int4((int)b, k_begin[b], so.nsteps, 0);
+        seg[b] = make_int4((int)b, k_begin[b], k_end ? k_end[b] : so.nsteps, 0);
         off[b] = (int)b;
     }
     off[B] = (int)B;

@@ -569,97 +569,115 @@ class Scene:
         return out
 
     def _reparam_rollouts(self, out, q0, qdot0, tau, tau_mode, o):
-        """jroot.reparam() of driverRedMaxBDF2.m:112 for the rollouts the library flagged with RMX_ST_CHART: every such
-        rollout is taken up to the first step whose result leaves the well-conditioned range of a JointSpherical chart
-        (|det T| <= 0.5), that step and the BDF2 history are re-expressed in the chart JointSpherical.reparam_ picks
-        (euler.reparam), and the rollout resumes (rmx_rollout_resume) under the scene variant with the new charts -- until
-        it reaches the end.  Adds out['chart'] [B, nspherical] (the charts q(t_end) is expressed in) and
-        out['chart_switches'] (per rollout: (step, spherical joint, old chart, new chart)); q, qdot of a switch step are
-        the re-parameterised ones, as in the reference's history.  status / iters of these rollouts are rebuilt from the
-        pieces that were kept.  JointFree3D cannot switch in the reference (its inner joint never gets chart1:
+        """jroot.reparam() of driverRedMaxBDF2.m:112 for the rollouts the library flagged with RMX_ST_CHART, all of them
+        together, in rounds: (1) every active rollout is cut at the first step whose result leaves the well-conditioned range
+        of a JointSpherical chart (|det T| <= 0.5); the piece up to that step is run once more on its own (one
+        rmx_rollout_resume per group of rollouts with equal charts, per-rollout [k_begin, k_end)), which gives its status and
+        iteration counts without the discarded tail; (2) that step and the BDF2 history joint.q1 / qdot1 are re-expressed in
+        the chart JointSpherical.reparam_ picks (euler.reparam); (3) the rollouts resume from the next step to the end under
+        the scene variant of their new charts, and the next round cuts them again if they switch again.
+        Adds out['chart'] [B, nspherical] (the charts q(t_end) is expressed in) and out['chart_switches'] (per rollout:
+        (step, spherical joint, old chart, new chart)); q, qdot of a switch step are the re-parameterised ones, as in the
+        reference's history.  JointFree3D cannot switch in the reference (its inner joint never gets chart1:
         JointFree3D.m:27-31, JointSpherical.m:73 stops with an error) and stays flagged."""
         L = _ffi.lib()
         sph = self._spherical()
-        nsteps, nr, B = o.nsteps, self.nr, out['q'].shape[0]
+        nsteps, B = o.nsteps, out['q'].shape[0]
+        Q, QD = out['q'], out['qdot']
         own = tuple(j.chart for j in sph)
         out['chart'] = np.tile(np.array(own, dtype=np.int32), (B, 1))
         out['chart_switches'] = [[] for _ in range(B)]
-        free3d_mid = [j.idxR[4] for j in self.joints if isinstance(j, JointFree3D)]
+        active = [int(b) for b in np.nonzero(out['status'] & _ffi.RMX_ST_CHART)[0]]
+        charts = {b: list(own) for b in active}
+        kb = {b: 0 for b in active}
+        hist = {b: None for b in active}  # (step or -1 = initial state, q, qdot): joint.q1 / qdot1 in the charts in force
+        status = {b: 0 for b in active}
+        iters = {b: np.zeros(2, dtype=np.int64) for b in active}
 
-        def resume(handle, kb, ns, qb, qdb, q0b, qd0b, taub):
-            o2 = self.opts(scheme=2, nsteps=ns, tau_mode=tau_mode)
-            for f in ('h', 'tol', 'dxMax', 'iterMaxFactor', 'iterLsMax', 'linsolve'):
-                setattr(o2, f, getattr(o, f))
-            st = np.zeros(1, dtype=np.int32)
-            it = np.zeros((1, 2), dtype=np.int32)
-            _ffi.check(L.rmx_rollout_resume(handle, C.byref(o2), 1, ptr(np.array([kb], dtype=np.int32)), ptr(q0b), ptr(qd0b),
-                                            ptr(taub), ptr(qb), ptr(qdb), ptr(st), ptr(it)), 'rmx_rollout_resume')
-            return int(st[0]), it[0]
-
-        for b in np.nonzero(out['status'] & _ffi.RMX_ST_CHART)[0]:
-            charts = list(own)
-            qb, qdb = out['q'][b:b + 1].copy(), out['qdot'][b:b + 1].copy()
-            q0b, qd0b = q0[b:b + 1].copy(), qdot0[b:b + 1].copy()
-            taub = None if tau is None else np.ascontiguousarray(tau[b:b + 1])
-            status, iters, kb = 0, np.zeros(2, dtype=np.int64), 0
-            hist = None  # (step index or -1 for the initial state, q, qdot): joint.q1 / qdot1 in the charts now in force
-
-            def run(kb, ns, qbuf, qdbuf):
-                """resume [kb, ns) with the re-expressed BDF2 history in place; the stored (old-chart) step is put back"""
-                q0r, qd0r, saved = q0b, qd0b, None
-                if hist is not None and hist[0] < 0:
-                    q0r, qd0r = hist[1][None, :].copy(), hist[2][None, :].copy()
-                elif hist is not None:
-                    saved = (qbuf[0, hist[0]].copy(), qdbuf[0, hist[0]].copy())
-                    qbuf[0, hist[0]], qdbuf[0, hist[0]] = hist[1], hist[2]
-                ts = taub if (taub is None or taub.ndim == 2) else np.ascontiguousarray(taub[:, :ns])
-                r = resume(self._variant(charts), kb, ns, qbuf, qdbuf, q0r, qd0r, ts)
-                if saved is not None:
-                    qbuf[0, hist[0]], qdbuf[0, hist[0]] = saved
-                return r
-
-            while kb < nsteps:
-                # first step at or after kb whose result needs a new chart
-                need = np.zeros(nsteps - kb, dtype=bool)
-                for j, c in zip(sph, charts):
-                    need |= euler.chart_det(c, qb[0, kb:, j.idxR[1]]) <= 0.5
-                k1 = kb + int(np.argmax(need)) if need.any() else nsteps - 1
-                # the piece [kb, k1] again on its own: its status and iteration counts, without the discarded tail
-                ns = k1 + 1
-                qs, qds = np.ascontiguousarray(qb[:, :ns]), np.ascontiguousarray(qdb[:, :ns])
-                st, it = run(kb, ns, qs, qds)
-                if np.isfinite(qs).all() and not np.array_equal(qs[0, kb:], qb[0, kb:ns]):
-                    raise RmxError('re-parameterised rollout: the piece does not reproduce the pass it was cut from')
-                status |= st & ~_ffi.RMX_ST_CHART
-                iters += it
-                if not need.any():
-                    break
-                # JointSpherical.reparam_ for every spherical joint that asks for it at step k1
-                hq = (q0b[0] if k1 == 0 else qb[0, k1 - 1]).copy()
-                hqd = (qd0b[0] if k1 == 0 else qdb[0, k1 - 1]).copy()
-                if hist is not None and hist[0] == k1 - 1:  # consecutive switch steps: the history is already re-expressed
-                    hq, hqd = hist[1].copy(), hist[2].copy()
-                for i, (j, c) in enumerate(zip(sph, charts)):
-                    r = j.idxR
-                    if euler.chart_det(c, qb[0, k1, r[1]]) > 0.5:
+        def run(rows, k0, k1, verify):
+            """rmx_rollout_resume of the steps [k0[b], k1[b]) for the rollouts `rows`, grouped by chart tuple, each with its
+            re-expressed BDF2 history in place of the stored (old-chart) step; results go back into Q, QD."""
+            groups = {}
+            for b in rows:
+                groups.setdefault(tuple(charts[b]), []).append(b)
+            for ct, rs in groups.items():
+                idx = np.array(rs)
+                qs, qds = np.ascontiguousarray(Q[idx]), np.ascontiguousarray(QD[idx])
+                q0s, qd0s = np.ascontiguousarray(q0[idx]), np.ascontiguousarray(qdot0[idx])
+                ts = None if tau is None else np.ascontiguousarray(tau[idx])
+                saved = {}
+                for i, b in enumerate(rs):
+                    if hist[b] is None:
                         continue
-                    new, qn, qdn, q1n, qd1n = euler.reparam(c, qb[0, k1, r], qdb[0, k1, r], c, hq[r], hqd[r])
-                    out['chart_switches'][b].append((int(k1), i, int(c), int(new)))
-                    charts[i] = new
-                    qb[0, k1, r], qdb[0, k1, r] = qn, qdn
+                    k, hq, hqd = hist[b]
+                    if k < 0:
+                        q0s[i], qd0s[i] = hq, hqd
+                    else:
+                        saved[i] = (k, qs[i, k].copy(), qds[i, k].copy())
+                        qs[i, k], qds[i, k] = hq, hqd
+                st = np.zeros(len(rs), dtype=np.int32)
+                it = np.zeros((len(rs), 2), dtype=np.int32)
+                ka = np.array([k0[b] for b in rs], dtype=np.int32)
+                ke = np.array([k1[b] for b in rs], dtype=np.int32)
+                _ffi.check(L.rmx_rollout_resume(self._variant(ct), C.byref(o), len(rs), ptr(ka), ptr(ke), ptr(q0s), ptr(qd0s),
+                                                ptr(ts), ptr(qs), ptr(qds), ptr(st), ptr(it)), 'rmx_rollout_resume')
+                for i, (k, sq, sqd) in saved.items():
+                    qs[i, k], qds[i, k] = sq, sqd
+                for i, b in enumerate(rs):
+                    if verify:
+                        a, e = k0[b], k1[b]
+                        if np.isfinite(qs[i]).all() and not np.array_equal(qs[i, a:e], Q[b, a:e]):
+                            raise RmxError('re-parameterised rollout %d: piece [%d, %d) does not reproduce the pass it was '
+                                           'cut from' % (b, a, e))
+                        status[b] |= int(st[i]) & ~_ffi.RMX_ST_CHART
+                        iters[b] += it[i]
+                    Q[b], QD[b] = qs[i], qds[i]
+
+        while active:
+            # (1) cut: first step at or after kb whose result needs a new chart; the piece [kb, k1] on its own
+            k1, sw = {}, {}
+            for b in active:
+                need = np.zeros(nsteps - kb[b], dtype=bool)
+                for j, c in zip(sph, charts[b]):
+                    need |= euler.chart_det(c, Q[b, kb[b]:, j.idxR[1]]) <= 0.5
+                sw[b] = bool(need.any())
+                k1[b] = kb[b] + int(np.argmax(need)) if sw[b] else nsteps - 1
+            run(active, kb, {b: k1[b] + 1 for b in active}, verify=True)
+            # (2) JointSpherical.reparam_ at step k1 for every spherical joint that asks for it
+            nxt = []
+            for b in active:
+                if not sw[b]:
+                    continue
+                k = k1[b]
+                hq = (q0[b] if k == 0 else Q[b, k - 1]).copy()
+                hqd = (qdot0[b] if k == 0 else QD[b, k - 1]).copy()
+                if hist[b] is not None and hist[b][0] == k - 1:  # consecutive switch steps: history already re-expressed
+                    hq, hqd = hist[b][1].copy(), hist[b][2].copy()
+                for i, (j, c) in enumerate(zip(sph, charts[b])):
+                    r = j.idxR
+                    if euler.chart_det(c, Q[b, k, r[1]]) > 0.5:
+                        continue
+                    new, qn, qdn, q1n, qd1n = euler.reparam(c, Q[b, k, r], QD[b, k, r], c, hq[r], hqd[r])
+                    out['chart_switches'][b].append((int(k), i, int(c), int(new)))
+                    charts[b][i] = new
+                    Q[b, k, r], QD[b, k, r] = qn, qdn
                     hq[r], hqd[r] = q1n, qd1n
-                hist = (k1 - 1, hq, hqd)
-                kb = k1 + 1
-                if kb < nsteps:
-                    run(kb, nsteps, qb, qdb)  # the rest of the rollout in the new charts (cut again if it switches again)
-            # a JointFree3D that left its chart stays flagged
-            for m in free3d_mid:
-                if (np.abs(np.cos(qb[0, :, m])) <= 0.5).any():
-                    status |= _ffi.RMX_ST_CHART
-            out['q'][b], out['qdot'][b] = qb[0], qdb[0]
-            out['status'][b] = status
-            out['iters'][b] = iters
-            out['chart'][b] = charts
+                hist[b] = (k - 1, hq, hqd)
+                kb[b] = k + 1
+                if kb[b] < nsteps:
+                    nxt.append(b)
+            # (3) the rest of those rollouts in their new charts
+            if nxt:
+                run(nxt, kb, {b: nsteps for b in nxt}, verify=False)
+            active = nxt
+        free3d_mid = [j.idxR[4] for j in self.joints if isinstance(j, JointFree3D)]
+        for b in charts:
+            for m in free3d_mid:  # a JointFree3D that left its chart stays flagged
+                if (np.abs(np.cos(Q[b, :, m])) <= 0.5).any():
+                    status[b] |= _ffi.RMX_ST_CHART
+            out['status'][b] = status[b]
+            out['iters'][b] = iters[b]
+            out['chart'][b] = charts[b]
 
     def rollout_into(self, q0, qdot0, q_out, qdot_out=None, tau=None, scheme=1, nsteps=None, ngpus=1, **kw):
         """rmx_rollout with caller-owned host buffers (e.g. pinned memory): q0, qdot0 [B, nr] float64 C-contiguous,

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol(rb):
     assert sorted(_ffi.SYMBOLS) == syms
     for s in syms:
         assert hasattr(L, s), s
-    assert L.rmx_version() == 108
+    assert L.rmx_version() == 109
 
 
 def test_opts_default_are_the_references(rb):

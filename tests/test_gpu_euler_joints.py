@@ -122,11 +122,25 @@ def test_resume_reproduces_the_uncut_rollout(rb):
         st = np.zeros(B, dtype=np.int32)
         it = np.zeros((B, 2), dtype=np.int32)
         o = sg.opts(scheme=scheme)
-        _ffi.check(_ffi.lib().rmx_rollout_resume(sg._handle, C.byref(o), B, _ffi.ptr(kb), _ffi.ptr(q0), _ffi.ptr(qd0), None,
+        _ffi.check(_ffi.lib().rmx_rollout_resume(sg._handle, C.byref(o), B, _ffi.ptr(kb), None, _ffi.ptr(q0), _ffi.ptr(qd0), None,
                                                  _ffi.ptr(q), _ffi.ptr(qd), _ffi.ptr(st), _ffi.ptr(it)), 'rmx_rollout_resume')
         np.testing.assert_array_equal(q, ref['q'])
         np.testing.assert_array_equal(qd, ref['qdot'])
         assert st.tolist() == [0] * B and it[0].tolist() == ref['iters'][0].tolist() and it[4].tolist() == [0, 0]
+        # with an end step: only [k_begin, k_end) is touched, and the pieces' iteration counts add up
+        ke = np.array([5, 1, 9, 12, 12], dtype=np.int32)
+        q2, qd2 = ref['q'].copy(), ref['qdot'].copy()
+        for b in range(B):
+            q2[b, kb[b]:ke[b]] = np.nan
+        it2 = np.zeros((B, 2), dtype=np.int32)
+        _ffi.check(_ffi.lib().rmx_rollout_resume(sg._handle, C.byref(o), B, _ffi.ptr(kb), _ffi.ptr(ke), _ffi.ptr(q0), _ffi.ptr(qd0),
+                                                 None, _ffi.ptr(q2), _ffi.ptr(qd2), _ffi.ptr(st), _ffi.ptr(it2)),
+                   'rmx_rollout_resume')
+        np.testing.assert_array_equal(q2, ref['q'])
+        it3 = np.zeros((B, 2), dtype=np.int32)
+        _ffi.check(_ffi.lib().rmx_rollout_resume(sg._handle, C.byref(o), B, _ffi.ptr(ke), None, _ffi.ptr(q0), _ffi.ptr(qd0), None,
+                                                 _ffi.ptr(q2), _ffi.ptr(qd2), _ffi.ptr(st), _ffi.ptr(it3)), 'rmx_rollout_resume')
+        np.testing.assert_array_equal(it2 + it3, it)
 
 
 def test_free3d_under_a_revolute_parent_with_ground(rb, oracle):
