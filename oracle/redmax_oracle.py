@@ -747,7 +747,13 @@ def euler_chart(chart, q, qdot):
     d2T[:, 1, 2, 2] = br[2] @ br[2] @ RcT @ E[1]
     Tdot = dTdq @ qdot
     dTdotdq = d2T @ qdot
-    detT = float(np.linalg.det(T))
+    # det T in the reference's closed forms (detS = -sin q2 for the proper Euler charts, JointSpherical.m:452...1072;
+    # +cos q2 for XYZ, YZX, ZXY and -cos q2 for XZY, YXZ, ZYX, :1190...1795): charts that share their middle angle (XYX / XZX,
+    # YZY / YXY, ZXZ / ZYZ) tie exactly in reparam_'s max(min(abs(detTs))), and MATLAB's max takes the first
+    if chart <= 6:
+        detT = -math.sin(q[1])
+    else:
+        detT = math.cos(q[1]) if chart in (7, 9, 11) else -math.cos(q[1])
     return R, dRdq, Rdot, dRdotdq, T, detT, dTdq, Tdot, dTdotdq
 
 

@@ -69,7 +69,9 @@ def reparam(chart, q, qdot, chart1, q1, qdot1):
     for k in range(1, 13):
         for row, Rk in ((0, R), (1, R1)):
             qk = chart_inv(k, Rk)
-            dets[row, k - 1] = abs(np.linalg.det(chart_R_T(k, qk)[1])) if np.isfinite(qk).all() else 0.0
+            # closed form, as the reference's detS: the pairs XYX / XZX, YZY / YXY, ZXZ / ZYZ share their middle angle and tie
+            # exactly; argmax takes the first, as MATLAB's max
+            dets[row, k - 1] = chart_det(k, qk[1]) if np.isfinite(qk).all() else 0.0
     new = int(np.argmax(np.min(dets, axis=0))) + 1
     qn = chart_inv(new, R)
     qdn = np.linalg.solve(chart_R_T(new, qn)[1], Told @ qdot)

@@ -103,6 +103,38 @@ def test_scene7_bdf2_switches_charts_like_the_reference(rb, oracle):
     np.testing.assert_array_equal(short['q'][0], out['q'][0, :k1])
 
 
+@pytest.mark.timeout(900)
+def test_chart_switching_in_a_batch(rb, oracle):
+    """96 differently started rollouts of the double spherical pendulum, BDF2: they switch at different steps into different
+    charts, some several times, some never; the rounds of Scene._reparam_rollouts handle them together.  Spot checks against
+    the oracle, every rollout ends unflagged, and the final energies (evaluated in each rollout's own charts) are those of a
+    plausible run (no energy blow-up from a mis-expressed history)."""
+    sg, so = both(rb, oracle, rb.scenesRedMax, 7)
+    B = 96
+    rng = np.random.default_rng(20260777)
+    q0 = sg.qInit[None, :] + 0.3 * rng.uniform(-1, 1, (B, sg.nr))
+    qd0 = sg.qdotInit[None, :] + 0.5 * rng.uniform(-1, 1, (B, sg.nr))
+    ns = 250
+    out = sg.rollout(q0, qd0, scheme=2, nsteps=ns)
+    nsw = np.array([len(s) for s in out['chart_switches']])
+    assert (out['status'] == 0).all(), out['status']
+    assert (nsw > 0).sum() >= 10 and (nsw == 0).sum() >= 1, nsw
+    assert len({tuple(c) for c in out['chart'].tolist()}) >= 3  # several different final chart combinations
+    multi = int(np.argmax(nsw))
+    for b in sorted({0, multi, int(np.nonzero(nsw > 0)[0][-1]), int(np.nonzero(nsw == 0)[0][0])}):
+        stats = []
+        qs, qds = oracle.run_forward(so, 2, q0[b], qd0[b], nsteps=ns, stats=stats)
+        assert [k for k, _, _, _ in out['chart_switches'][b]] == so.chart_switch_steps, b
+        assert out['chart'][b].tolist() == [j.chart for j in so.joints], b
+        assert rel_err(out['q'][b], qs) < TOL_Q, (b, rel_err(out['q'][b], qs))
+        it = np.array(stats)
+        assert out['iters'][b, 0] == it[:, 0].sum() and out['iters'][b, 1] == it[:, 1].sum()
+    T1, V1 = sg.energies(out['q'][:, -1], out['qdot'][:, -1], chart=out['chart'])
+    T0, V0 = sg.energies(q0, qd0)
+    dH = (T1 + V1) - (T0 + V0)
+    assert np.isfinite(dH).all() and np.abs(dH).max() < 0.5 * np.abs(V0).max(), (np.abs(dH).max(), np.abs(V0).max())
+
+
 def test_resume_reproduces_the_uncut_rollout(rb):
     """rmx_rollout_resume from the states of an earlier call is bitwise the uncut rollout, for BDF1 and BDF2, from step 0, 1,
     2 and mid-way, per rollout."""

@@ -106,7 +106,7 @@ def test_euler_charts_fd_and_inverse(oracle, chart):
         np.testing.assert_allclose([w[2, 1], w[0, 2], w[1, 0]], T[:, k], atol=1e-14)
     np.testing.assert_allclose(Rdot, sum(dR[:, :, k] * qd[k] for k in range(3)), atol=1e-14)
     np.testing.assert_allclose(Tdot, sum(dT[:, :, k] * qd[k] for k in range(3)), atol=1e-14)
-    assert abs(abs(detT) - (abs(math.sin(q[1])) if chart <= 6 else abs(math.cos(q[1])))) < 1e-14
+    assert abs(detT - np.linalg.det(T)) < 1e-14  # the reference's closed form (-sin q2 / +-cos q2) is det T, sign included
 
 
 @pytest.mark.parametrize('itype', [2, 1])
