@@ -23,13 +23,18 @@ FORWARD = [
     ('scene1', 'scenesRedMax', (1,), {}, None),
     ('scene2', 'scenesRedMax', (2,), {}, None),
     ('scene14', 'scenesRedMax', (14,), {}, None),
+    # Euler-chart joints; scene 7 under BDF2 re-parameterises twice (XYZ -> XYX -> YXZ)
+    ('scene7', 'scenesRedMax', (7,), {}, None),
+    ('scene9', 'scenesRedMax', (9,), {}, None),
     ('chain10', 'chain_scene', (10,), dict(h=1e-3), 30),
     ('chain6ground', 'chain_scene', (6,), dict(ground=True, h=5e-4, ground_z=-48.5), 80),
 ]
 
 
-def forward():
+def forward(only=None):
     for name, fac, a, kw, ns in FORWARD:
+        if only and name not in only:
+            continue
         for scheme in (1, 2):
             so = getattr(scenes, fac)(*a, api=oracle, **kw)
             so.init()
@@ -41,7 +46,9 @@ def forward():
             so.update()
             T, V = so.computeEnergies()
             np.savez_compressed(os.path.join(HERE, 'fwd_%s_bdf%d.npz' % (name, scheme)), q=qs, qdot=qds,
-                                iters=np.array(stats), H_end=T + V - V0, Hexpected=so.Hexpected[scheme - 1], nsteps=ns_)
+                                iters=np.array(stats), H_end=T + V - V0, Hexpected=so.Hexpected[scheme - 1], nsteps=ns_,
+                                switch_steps=np.array(so.chart_switch_steps, dtype=np.int32),
+                                charts=np.array([j.chart for j in so.joints if hasattr(j, 'switches')], dtype=np.int32))
             print(name, scheme, 'H_end', T + V - V0, 'Hexpected', so.Hexpected[scheme - 1])
 
 
@@ -80,5 +87,8 @@ def adjoint():
 
 
 if __name__ == '__main__':
-    forward()
-    adjoint()
+    if len(sys.argv) > 1:  # python make_golden.py scene7 scene9: only these forward fixtures
+        forward(set(sys.argv[1:]))
+    else:
+        forward()
+        adjoint()
