@@ -33,15 +33,16 @@ def rotation_to_quaternion(R):
     return out
 
 
-def brender_scene(scene, q_traj, names=None, obj_paths=('cube.obj',), group='bodies', every=1):
+def brender_scene(scene, q_traj, names=None, obj_paths=('cube.obj',), group='bodies', every=1, chart=None):
     """Dict in the reference exporter's layout for one rollout q_traj [nsteps, nr]: {'header': {'objs', 'states'},
     'body': [{'frame': k, name: {'scale', 'location', 'quat'}, ...}, ...]}.  `scale` is the cuboid's side lengths (the exporter
-    scales a unit cube), `location` / `quat` the body frame."""
+    scales a unit cube), `location` / `quat` the body frame.  chart [nsteps, nspherical]: scene.chart_history(out, b) for a
+    rollout that re-parameterised its spherical joints."""
     q_traj = np.asarray(q_traj, dtype=float)
     nb = len(scene.bodies)
     names = names or [(b.name or 'body%d' % i) for i, b in enumerate(scene.bodies)]
     frames = np.arange(0, q_traj.shape[0], every)
-    E = scene.body_frames(q_traj[frames])  # [nframes, nb, 4, 4]
+    E = scene.body_frames(q_traj[frames], chart=None if chart is None else np.asarray(chart)[frames])  # [nframes, nb, 4, 4]
     quat = rotation_to_quaternion(E[:, :, :3, :3])
     header = {'objs': list(obj_paths), 'states': [{'obj': 0, 'name': names[i], 'group': group} for i in range(nb)]}
     body = []

@@ -785,16 +785,36 @@ class Scene:
                                      ptr(H), ptr(dx)), 'rmx_eval_newton')
         return dict(H=H.T.copy(), dx=dx)
 
-    def body_frames(self, q):
-        """World frames E_wi of all bodies (Body.update, Body.m:70-80) for B configurations q [B, nr] -> [B, nbodies, 4, 4]."""
+    def body_frames(self, q, chart=None):
+        """World frames E_wi of all bodies (Body.update, Body.m:70-80) for B configurations q [B, nr] -> [B, nbodies, 4, 4].
+        chart [B, nspherical]: the Euler charts the configurations are expressed in (see chart_history); default: the
+        scene's own."""
         L = self._require()
         q = f64(q)
         if q.ndim == 1:
             q = q[None, :]
         B = q.shape[0]
         E = np.empty((B, len(self.bodies), 4, 4))
-        _ffi.check(L.rmx_body_frames(self._handle, B, ptr(q), ptr(E)), 'rmx_body_frames')
+        if chart is None or not self._spherical():
+            _ffi.check(L.rmx_body_frames(self._handle, B, ptr(q), ptr(E)), 'rmx_body_frames')
+        else:
+            chart = np.asarray(chart, dtype=np.int32).reshape(B, -1)
+            for ct in {tuple(r) for r in chart.tolist()}:
+                sel = np.nonzero((chart == np.array(ct, dtype=np.int32)).all(axis=1))[0]
+                qs = np.ascontiguousarray(q[sel])
+                Es = np.empty((len(sel), len(self.bodies), 4, 4))
+                _ffi.check(L.rmx_body_frames(self._variant(ct), len(sel), ptr(qs), ptr(Es)), 'rmx_body_frames')
+                E[sel] = Es
         return np.ascontiguousarray(np.swapaxes(E, 2, 3))  # column-major 4x4 blocks -> [row, col]
+
+    def chart_history(self, out, b=0):
+        """[nsteps, nspherical] Euler charts in which q(t_k) of rollout b of a rollout() result is expressed (the scene's own
+        up to the first re-parameterised step, JointSpherical.m:84-87)."""
+        sph = self._spherical()
+        ch = np.tile(np.array([j.chart for j in sph], dtype=np.int32), (out['q'].shape[1], 1))
+        for k, i, _, new in (out.get('chart_switches') or [[]] * (b + 1))[b]:
+            ch[k:, i] = new
+        return ch
 
     def energies(self, q, qdot, chart=None):
         """T, V of Scene.saveHistory (Scene.m:155-160) for B states.  chart [B, nspherical]: the Euler charts the states are

@@ -24,6 +24,28 @@ def test_body_frames_match_oracle(rb, oracle, sid):
             np.testing.assert_allclose(E[b, i], body.E_wi, rtol=0, atol=1e-12 * max(1.0, np.abs(body.E_wi).max()))
 
 
+def test_body_frames_across_a_chart_switch(rb, oracle, tmp_path):
+    """Scene 7 under BDF2: q(t) changes coordinates at the two re-parameterised steps, the bodies do not -- frames evaluated
+    in each step's own charts are continuous across the switches and equal the oracle's at the switch steps and at the end;
+    the exporter takes the same chart history."""
+    from redmax_b200 import export
+    sg, so = both(rb, oracle, rb.scenesRedMax, 7)
+    out = sg.rollout(scheme=2)
+    ch = sg.chart_history(out, 0)
+    ks = [k for k, _, _, _ in out['chart_switches'][0]]
+    assert len(ks) == 2 and ch[0].tolist() == [7, 7] and ch[-1].tolist() == out['chart'][0].tolist() == [7, 10]
+    E = sg.body_frames(out['q'][0], chart=ch)
+    step = np.abs(np.diff(E, axis=0)).max(axis=(1, 2, 3))
+    for k in ks:
+        assert np.abs(out['q'][0, k] - out['q'][0, k - 1]).max() > 0.5       # the coordinates jump ...
+        assert step[k - 1] < 2.0 * max(step[k - 2], step[k])                # ... the frames do not
+    qs, _ = oracle.run_forward(so, 2, sg.qInit, sg.qdotInit)                # leaves `so` at the end of the run
+    for i, body in enumerate(so.bodies):
+        np.testing.assert_allclose(E[-1, i], body.E_wi, rtol=0, atol=1e-8)
+    d = export.brender_scene(sg, out['q'][0], every=50, chart=ch)
+    np.testing.assert_allclose(d['body'][-1]['body1']['location'], E[450, 1, :3, 3], atol=1e-12)
+
+
 def test_export_layout_and_content(rb, oracle, tmp_path):
     from redmax_b200 import export
     sg, so = both(rb, oracle, rb.scenesRedMax, 1)
