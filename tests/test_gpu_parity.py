@@ -258,6 +258,40 @@ def test_page_locked_outputs_are_written_by_the_kernel_and_bitwise_identical(rb,
 
 
 @pytest.mark.timeout(300)
+def test_batch_sharded_over_gpus_is_bitwise_identical(rb):
+    """rmx_rollout with opts.ngpus = G shards the batch contiguously over G devices from one process, no communication
+    (SURVEY.md 8(e)): every trajectory, status and iteration count equals the one-GPU call bit for bit -- with pageable
+    buffers (staged copies per device) and with page-locked ones (each device's kernel writes its slice of the caller's
+    buffers).  Needs at least two GPUs; the one-process-per-GPU path is what bench.py --gpus N runs."""
+    import torch
+    G = _ffi_device_count(rb)
+    if G < 2:
+        pytest.skip('needs >= 2 GPUs (run under gpurun --gpus 2)')
+    G = min(G, 4)
+    sg = rb.chain_scene(8, nsteps=9, h=1e-3)
+    sg.init()
+    B = 2 * 1184 + 37  # uneven shards, each above the resident blocks of a device
+    q0, qd0 = rb.synthetic_inputs(sg, B, seed=11)
+    tau = 30.0 * np.random.default_rng(6).uniform(-1, 1, (B, sg.nsteps, sg.nr))
+    for scheme in (1, 2):
+        ref = sg.rollout(q0, qd0, tau=tau, scheme=scheme, ngpus=1)
+        out = sg.rollout(q0, qd0, tau=tau, scheme=scheme, ngpus=G)
+        for k in ('q', 'qdot', 'status', 'iters'):
+            np.testing.assert_array_equal(out[k], ref[k])
+        hq = torch.full((B, sg.nsteps, sg.nr), float('nan'), dtype=torch.float64).pin_memory()
+        hqd = torch.full((B, sg.nsteps, sg.nr), float('nan'), dtype=torch.float64).pin_memory()
+        res = sg.rollout_into(q0, qd0, hq.numpy(), hqd.numpy(), tau=tau, scheme=scheme, ngpus=G)
+        np.testing.assert_array_equal(hq.numpy(), ref['q'])
+        np.testing.assert_array_equal(hqd.numpy(), ref['qdot'])
+        np.testing.assert_array_equal(res['iters'], ref['iters'])
+
+
+def _ffi_device_count(rb):
+    from redmax_b200 import _ffi
+    return int(_ffi.lib().rmx_device_count())
+
+
+@pytest.mark.timeout(300)
 @pytest.mark.parametrize('scheme', [1, 2])
 def test_load_balanced_schedule_is_bitwise_identical(rb, scheme):
     """More rollouts than co-resident blocks, and not a multiple of them: the launch cuts rollouts across blocks (McNaughton
