@@ -10,6 +10,75 @@ h = redmax_mex('create',flattenScene(scene));
 opts = struct('scheme',scheme,'nsteps',scene.nsteps,'h',scene.h);
 [q,qdot,status,iters] = redmax_mex('rollout',h,opts,q0,qdot0,tau);
 redmax_mex('destroy',h);
+if scheme == 2
+	[q,qdot,status,iters] = reparamRollouts(scene,opts,q0,qdot0,tau,q,qdot,status,iters);
+end
+end
+
+function [q,qdot,status,iters] = reparamRollouts(scene,opts,q0,qdot0,tau,q,qdot,status,iters)
+% jroot.reparam() (driverRedMaxBDF2.m:112) for the rollouts the library flagged with RMX_ST_CHART (bit 32): cut the rollout at
+% the first step whose result leaves the well-conditioned range of a JointSpherical chart, let the joint objects themselves
+% re-express that step and the BDF2 history (JointSpherical.reparam_, JointSpherical.m:63-103), rebuild the scene description
+% with the new charts and resume from the next step.  Same loop as redmax_b200/scene.py _reparam_rollouts, one rollout at a
+% time for clarity.  After a switch q(:,k,b) is expressed in the new chart, as history(k).q is in the reference.
+sph = scene.joints(cellfun(@(j) isa(j,'redmax.JointSpherical'), scene.joints));
+if isempty(sph), return; end
+chart0 = cellfun(@(j) j.chart, sph);
+z = zeros(3,1);
+for b = find(bitand(status(:)',32))
+	for i = 1 : length(sph), sph{i}.chart = chart0(i); end
+	kb = 0; st = int32(0); it = zeros(2,1,'int32'); hist = []; % hist: {step (0-based, -1 = initial state), q1, qdot1}
+	qb = q(:,:,b); qdb = qdot(:,:,b); taub = []; if ~isempty(tau), taub = tau(:,:,b); end
+	while kb < opts.nsteps
+		% first step (0-based) at or after kb with |det T| <= 0.5 for some spherical joint
+		k1 = opts.nsteps - 1; sw = false;
+		for k = kb : opts.nsteps-1
+			for i = 1 : length(sph)
+				[~,~,~,~,~,detT] = redmax.JointSpherical.getEuler(sph{i}.chart,qb(sph{i}.idxR,k+1),z);
+				sw = sw || abs(detT) <= 0.5;
+			end
+			if sw, k1 = k; break; end
+		end
+		% the piece [kb, k1] on its own: its status and iteration counts, without the discarded tail
+		o = opts; o.nsteps = k1 + 1;
+		[~,~,s1,i1] = resumeWith(scene,o,kb,q0(:,b),qdot0(:,b),sliceTau(taub,o.nsteps),qb(:,1:k1+1),qdb(:,1:k1+1),hist);
+		st = bitor(st,bitand(s1,int32(bitcmp(uint32(32))))); it = it + i1;
+		if ~sw, break; end
+		% the joint objects re-express step k1 and the history (joint.q1 = step k1-1, or the initial state)
+		if ~isempty(hist) && hist{1} == k1-1, hq = hist{2}; hqd = hist{3};
+		elseif k1 == 0, hq = q0(:,b); hqd = qdot0(:,b);
+		else, hq = qb(:,k1); hqd = qdb(:,k1); end
+		for i = 1 : length(sph)
+			j = sph{i}; r = j.idxR;
+			j.q = qb(r,k1+1); j.qdot = qdb(r,k1+1); j.q1 = hq(r); j.qdot1 = hqd(r); j.chart1 = j.chart;
+			j.reparam_();
+			qb(r,k1+1) = j.q; qdb(r,k1+1) = j.qdot; hq(r) = j.q1; hqd(r) = j.qdot1;
+		end
+		hist = {k1-1,hq,hqd}; kb = k1 + 1;
+		if kb < opts.nsteps
+			[qb,qdb] = resumeWith(scene,opts,kb,q0(:,b),qdot0(:,b),taub,qb,qdb,hist);
+		end
+	end
+	q(:,:,b) = qb; qdot(:,:,b) = qdb; status(b) = st; iters(:,b) = it;
+end
+for i = 1 : length(sph), sph{i}.chart = chart0(i); end
+end
+
+function [qb,qdb,st,it] = resumeWith(scene,opts,kb,q0,qdot0,tau,qb,qdb,hist)
+% redmax_mex('resume') under the charts the joint objects hold now, with the re-expressed BDF2 history in place of the stored step
+keep = [];
+if ~isempty(hist)
+	if hist{1} < 0, q0 = hist{2}; qdot0 = hist{3};
+	else, keep = {qb(:,hist{1}+1),qdb(:,hist{1}+1)}; qb(:,hist{1}+1) = hist{2}; qdb(:,hist{1}+1) = hist{3}; end
+end
+h = redmax_mex('create',flattenScene(scene));
+[qb,qdb,st,it] = redmax_mex('resume',h,opts,int32(kb),q0,qdot0,tau,qb,qdb);
+redmax_mex('destroy',h);
+if ~isempty(keep), qb(:,hist{1}+1) = keep{1}; qdb(:,hist{1}+1) = keep{2}; end
+end
+
+function t = sliceTau(tau,ns)
+t = tau; if size(tau,2) > 1, t = tau(:,1:ns); end
 end
 
 function d = flattenScene(scene)
