@@ -18,7 +18,7 @@ end
 function [q,qdot,status,iters] = reparamRollouts(scene,opts,q0,qdot0,tau,q,qdot,status,iters)
 % jroot.reparam() (driverRedMaxBDF2.m:112) for the rollouts the library flagged with RMX_ST_CHART (bit 32): cut the rollout at
 % the first step whose result leaves the well-conditioned range of a JointSpherical chart, let the joint objects themselves
-% re-express that step and the BDF2 history (JointSpherical.reparam_, JointSpherical.m:63-103), rebuild the scene description
+% re-express that step and the BDF2 history (jroot.reparam() -> JointSpherical.reparam_, JointSpherical.m:63-103), rebuild the scene description
 % with the new charts and resume from the next step.  Same loop as redmax_b200/scene.py _reparam_rollouts, one rollout at a
 % time for clarity.  After a switch q(:,k,b) is expressed in the new chart, as history(k).q is in the reference.
 sph = scene.joints(cellfun(@(j) isa(j,'redmax.JointSpherical'), scene.joints));
@@ -51,7 +51,10 @@ for b = find(bitand(status(:)',32))
 		for i = 1 : length(sph)
 			j = sph{i}; r = j.idxR;
 			j.q = qb(r,k1+1); j.qdot = qdb(r,k1+1); j.q1 = hq(r); j.qdot1 = hqd(r); j.chart1 = j.chart;
-			j.reparam_();
+		end
+		scene.joints{1}.reparam(); % Joint.m:372: reparam_ is protected; the walk is a no-op for every other joint type
+		for i = 1 : length(sph)
+			j = sph{i}; r = j.idxR;
 			qb(r,k1+1) = j.q; qdb(r,k1+1) = j.qdot; hq(r) = j.q1; hqd(r) = j.qdot1;
 		end
 		hist = {k1-1,hq,hqd}; kb = k1 + 1;
