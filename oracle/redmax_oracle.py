@@ -1899,6 +1899,7 @@ def sim_loop_adjoint_bdf1(scene, stats=None):
         q1, tape = newton_adjoint(lambda x: eval_bdf1(x, scene, True, True), q1, stats)
         qdot1 = (q1 - q0) / h
         scene.setQ(q1, qdot1)
+        scene.reparam()  # driverRedMaxAdjointBDF1.m:89 / driverRedMaxAdjointBDF2.m:123
         scene.update()
         scene.t = scene.t + h
         scene.k = k + 1
@@ -1932,6 +1933,7 @@ def sim_loop_adjoint_bdf2(scene, stats=None):
             q2, tape = newton_adjoint(lambda x: eval_bdf2(x, scene, True, True), q2, stats)
             qdot2 = (3 / (2 * h)) * (q2 - (4 / 3) * q1 + (1 / 3) * q0)
             scene.setQ(q2, qdot2)
+        scene.reparam()  # driverRedMaxAdjointBDF1.m:89 / driverRedMaxAdjointBDF2.m:123
         scene.update()
         scene.t = scene.t + h
         scene.k = k + 1

@@ -76,6 +76,64 @@ def test_adjoint_hand_c4(rb, oracle, scheme):
         assert rel_err(res['dPdp'][b], dPdp) < TOL_G, (rel_err(res['dPdp'][b], dPdp))
 
 
+@pytest.mark.parametrize('scheme', [1, 2])
+def test_adjoint_with_a_spherical_joint(rb, oracle, scheme):
+    """Objective and gradient through an Euler-angle joint (JointSpherical in its chart XYZ, a revolute link below it): the
+    parameters are the joint torques in the Euler coordinates (TaskBDF1PointPos.applyStep, :58-64), dP/dq uses the joint's
+    S = T(q) (Joint.computeJacobian) -- reproduced by the three virtual revolute joints.  No chart switch in this run."""
+    def build(api):
+        s = api.Scene()
+        b1 = api.BodyCuboid(1.0, [1, 1, 8])
+        j1 = api.JointSpherical(None, b1)
+        j1.setJointTransform(np.eye(4))
+        E = np.eye(4)
+        E[0:3, 3] = [0, 0, -4]
+        b1.setBodyTransform(E)
+        j1.q[:] = [0.4, -0.3, 0.2]
+        j1.qdot[:] = [0.5, -0.2, 0.3]
+        j1.setStiffness(1e4)
+        j1.setDamping(1e4)
+        b2 = api.BodyCuboid(1.0, [6, 1, 1])
+        j2 = api.JointRevolute(j1, b2, [0, 1, 0])
+        E2 = np.eye(4)
+        E2[0:3, 3] = [0, 0, -8]
+        j2.setJointTransform(E2)
+        E3 = np.eye(4)
+        E3[0:3, 3] = [3, 0, 0]
+        b2.setBodyTransform(E3)
+        j2.q[0] = 0.5
+        j2.setStiffness(1e4)
+        j2.setDamping(1e4)
+        s.bodies = [b1, b2]
+        s.joints = [j1, j2]
+        s.h = 1e-2
+        s.tEnd = 0.3
+        s.task = (api.TaskBDF1PointPos if scheme == 1 else api.TaskBDF2PointPos)(s)
+        s.task.setTime(s.tEnd)
+        s.task.setBody(b2)
+        s.task.setPoint([3, 0, 0])
+        s.task.setTarget([4, 2, -9])
+        s.task.setScale(1e5)
+        s.task.setWeights(1e-2, 1e2)
+        return s
+    sg, so = build(rb), build(oracle)
+    sg.init()
+    so.init()
+    assert sg.nr == so.nr == 4
+    rng = np.random.default_rng(77 + scheme)
+    p = np.vstack([np.zeros(4), 0.02 * rng.uniform(-1, 1, (2, 4))])
+    res = sg.rollout_adjoint(p, want_q=True)
+    assert res['status'].tolist() == [0, 0, 0]
+    for b in range(3):
+        P, dPdp = oracle.task_objective(p[b], so, scheme)
+        assert not so.chart_switch_steps
+        qs = np.array([r['q'] for r in so.history])
+        assert rel_err(res['q'][b], qs) < 1e-10
+        assert abs(res['P'][b] - P) <= TOL_P * abs(P), (res['P'][b], P)
+        assert rel_err(res['dPdp'][b], dPdp) < TOL_G, (res['dPdp'][b], dPdp)
+        assert np.linalg.norm(dPdp - sg.task.wreg * p[b]) > 1e-3
+
+
 def test_adjoint_sharded_over_gpus_is_bitwise_identical(rb):
     """rmx_rollout_adjoint with opts.ngpus = G (C4: batch 8192 on 4 GPUs, 2048 each; here a small uneven batch): objective and
     gradient of every rollout equal the one-GPU call bit for bit.  Needs at least two GPUs."""
