@@ -62,3 +62,23 @@ def test_well_conditioned_state_is_left_alone(oracle):
     assert j.reparam_() is False and j.chart == oracle.CHART_XYZ
     assert euler.chart_det(euler.CHART_XYZ, 0.4) > 0.5
     assert euler.CHART_NAMES[7] == 'XYZ' and euler.CHART_NAMES[1] == 'XYX' and euler.CHART_NAMES[10] == 'YXZ'
+
+
+def test_chart_history_and_scene_variants(rb):
+    """Host bookkeeping of a re-parameterised rollout (no GPU needed: scene handles are host objects until a rollout runs)."""
+    sg = rb.scenesRedMax(7)
+    sg.init()
+    out = dict(q=np.zeros((2, 10, sg.nr)), chart_switches=[[(3, 1, 7, 1), (6, 1, 1, 10)], []])
+    ch = sg.chart_history(out, 0)
+    assert ch.shape == (10, 2) and ch[:, 0].tolist() == [7] * 10
+    assert ch[:, 1].tolist() == [7, 7, 7, 1, 1, 1, 10, 10, 10, 10]
+    assert (sg.chart_history(out, 1) == 7).all()
+    # one library handle per chart combination, the scene's own charts map to the main handle, joints keep their charts
+    h1 = sg._variant((7, 1))
+    assert h1 is not None and sg._variant((7, 1)) is h1 and sg._variant((7, 7)) is sg._handle
+    assert [j.chart for j in sg.joints] == [7, 7] and len(sg._variants) == 1
+    with pytest.raises(rb.RmxError):
+        sg._variant((7, 13))  # rmx_scene_create rejects charts outside 0..12
+    assert [j.chart for j in sg.joints] == [7, 7]
+    sg.close()
+    assert sg._variants == {} and sg._handle is None
