@@ -183,6 +183,13 @@ __device__ __forceinline__ void lu_solve_warp_tc(int nr, double* H, int* perm, i
             // |v| >= 0, so the IEEE bit pattern orders like the value: one warp reduction on the high words decides unless two
             // rows agree in their top 32 bits; only then the low words and the positions are consulted (warp-uniform branch).
             const double v = fabs(a[i]);
+#ifdef RMX_LU_RCP_EARLY
+            // Experiment (off by default, not yet measured on the GPU): every lane takes the reciprocal of its own candidate while
+            // the argmax reductions are in flight and the pivot lane publishes its one with the row, so the ~60-cycle
+            // MUFU.RCP64H + Newton chain of __drcp_rn leaves the dependency path broadcast -> multiplier -> rank-1 update.
+            // Same number (the pivot lane's correctly rounded 1 / a[i]), hence bitwise the same factors.
+            const double rp_own = __drcp_rn(a[i]);
+#endif
             const unsigned hi = done ? 0u : (unsigned)__double2hiint(v);
             const unsigned mh = __reduce_max_sync(FULL, hi);
             const bool c1 = !done && hi == mh;
@@ -210,15 +217,23 @@ __device__ __forceinline__ void lu_solve_warp_tc(int nr, double* H, int* perm, i
             if (lane == src) {
 #pragma unroll
                 for (int j = i / 2; j < 4; ++j) buf[j] = make_double2(a[2 * j], a[2 * j + 1]);
+#ifdef RMX_LU_RCP_EARLY
+                buf[4] = make_double2(b, rp_own);
+#else
                 buf[4] = make_double2(b, 0.0);
+#endif
             }
             __syncwarp();
             double2 u2[4];
 #pragma unroll
             for (int j = i / 2; j < 4; ++j) u2[j] = buf[j];
             const double ub = buf[4].x;
+#ifdef RMX_LU_RCP_EARLY
+            const double rp = buf[4].y;
+#else
             const double piv = (i & 1) ? u2[i / 2].y : u2[i / 2].x;
             const double rp = __drcp_rn(piv);  // == 1.0 / piv, correctly rounded
+#endif
             rdiag = (lane == src) ? rp : rdiag;
             const double l = done ? 0.0 : a[i] * rp;  // l == 0 for rows that are already pivots
             a[i] = done ? a[i] : l;
