@@ -3,62 +3,21 @@
 // Scene flattening follows Scene.init (matlab-diff/+redmax/Scene.m:59-119): joints listed parents-first,
 // reduced indices assigned leaf-to-root (Scene.m:69-71 + Joint.countDofs, Joint.m:149).  Internally joints are
 // renumbered in DFS preorder so that every subtree is a contiguous index range.
-#include <cuda_runtime.h>
-
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <map>
-#include <string>
-#include <vector>
 
-#include "../../include/redmax_b200.h"
-#include "rmx_adjoint.cuh"
-#include "rmx_rollout.cuh"
+#include "rmx_host.h"
 
 using namespace rmx;
 
 static thread_local std::string g_err;
-static int fail(int code, const std::string& msg) {
+int rmx_fail(int code, const std::string& msg) {
     g_err = msg;
     return code;
 }
-#define CUDA_TRY(x)                                                                                      \
-    do {                                                                                                 \
-        cudaError_t e_ = (x);                                                                            \
-        if (e_ != cudaSuccess) {                                                                         \
-            cudaGetLastError();                                                                          \
-            return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ? RMX_ENOGPU : RMX_ECUDA, \
-                        std::string(#x) + ": " + cudaGetErrorString(e_));                                \
-        }                                                                                                \
-    } while (0)
-
-struct DevBuf {
-    void* p = nullptr;
-    size_t cap = 0;
-};
-// Load-balancing plan of a forward launch (see RolloutArgs::seg): cached per device for the last (B, nsteps, slots)
-struct SchedPlan {
-    long long B = -1;
-    int nsteps = -1;
-    long long slots = -1;
-    std::vector<int4> seg;
-    std::vector<int> off;
-};
-
-struct DevCopy {
-    SchedPlan plan;
-    JointConst* jc = nullptr;
-    int* ends = nullptr;
-    int* anc = nullptr;
-    PointForce* pf = nullptr;
-    int* pf_ep = nullptr;
-    unsigned long long* kry = nullptr;  // Krylov iteration counter
-    cudaStream_t stream = nullptr;
-    DevBuf buf[16];
-    void* plan_dev = nullptr;  // device copy of `plan` currently in buf[13]/buf[14]
-};
+static int fail(int code, const std::string& msg) { return rmx_fail(code, msg); }
 
 struct rmx_scene {
     int n = 0, nr = 0, nm = 0;
@@ -639,7 +598,7 @@ static int scene_on_device(rmx_scene* s, int dev, DevCopy** out) {
     return RMX_OK;
 }
 
-static int dev_reserve(DevBuf& b, size_t bytes) {
+int rmx_dev_reserve(DevBuf& b, size_t bytes) {
     if (bytes <= b.cap) return RMX_OK;
     if (b.p) cudaFree(b.p);
     b.p = nullptr;
@@ -648,6 +607,8 @@ static int dev_reserve(DevBuf& b, size_t bytes) {
     b.cap = bytes;
     return RMX_OK;
 }
+
+static int dev_reserve(DevBuf& b, size_t bytes) { return rmx_dev_reserve(b, bytes); }
 
 static DevScene make_devscene(const rmx_scene* s, const DevCopy* dc) {
     DevScene ds;
@@ -701,16 +662,7 @@ static int check_opts(const rmx_scene* s, const rmx_opts* o, StepOpts* so, int a
     return RMX_OK;
 }
 
-template <typename K>
-static int set_smem(K kernel, size_t bytes) {
-    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    // as many rollouts per SM as shared memory allows: ask for the full shared-memory carve-out
-    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    return RMX_OK;
-}
-
-
-static bool sched_enabled() {
+bool rmx_sched_enabled() {
     const char* e = std::getenv("RMX_SCHED");  // developer switch: RMX_SCHED=0 launches one block per rollout
     return !(e && e[0] == '0');
 }
@@ -719,7 +671,7 @@ static bool sched_enabled() {
 // T = ceil(B nsteps / slots) steps; a rollout that does not fit the rest of a block's quota is cut there -- its LAST steps fill
 // the tail of that block (and wait), its FIRST steps open the next block's list (and signal).  nsteps <= T, so the two
 // parts never overlap in time.
-static void build_plan(SchedPlan& p, long long B, int nsteps, long long slots) {
+void rmx_build_plan(SchedPlan& p, long long B, int nsteps, long long slots) {
     p.B = B;
     p.nsteps = nsteps;
     p.slots = slots;
@@ -746,43 +698,13 @@ static void build_plan(SchedPlan& p, long long B, int nsteps, long long slots) {
     for (long long k = m + 1; k <= slots; ++k) p.off[k] = (int)p.seg.size();
 }
 
-template <int NW, bool GROUND, bool ADJ, int IMPL, int LIN = 0>
-static int launch_fwd_t(const RolloutArgs& a0, size_t smem, cudaStream_t st, DevCopy* dc = nullptr) {
-    auto kernel = rollout_fwd_kernel<NW, GROUND, ADJ, IMPL, LIN>;
-    int rc = set_smem(kernel, smem);
-    if (rc) return rc;
-    RolloutArgs a = a0;
-    long long grid = a.B;
-    if (!ADJ && LIN == 0 && dc && a.qd_out && a.op.nsteps >= 2 && a.B < (1ll << 30) && sched_enabled()) {
-        int nb = 0, dev = 0, sms = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, 32 * NW, smem));
-        CUDA_TRY(cudaGetDevice(&dev));
-        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        const long long slots = (long long)nb * sms;
-        if (slots > 0 && a.B > slots && a.B % slots != 0) {
-            SchedPlan& p = dc->plan;
-            const bool fresh = !(p.B == a.B && p.nsteps == a.op.nsteps && p.slots == slots);
-            if (fresh) build_plan(p, a.B, a.op.nsteps, slots);
-            const size_t sb = p.seg.size() * sizeof(int4), ob = p.off.size() * sizeof(int), fb = (size_t)a.B * sizeof(int);
-            if ((rc = dev_reserve(dc->buf[13], sb)) || (rc = dev_reserve(dc->buf[14], ob)) || (rc = dev_reserve(dc->buf[15], fb)))
-                return rc;
-            if (fresh || dc->plan_dev != dc->buf[13].p) {
-                CUDA_TRY(cudaMemcpyAsync(dc->buf[13].p, p.seg.data(), sb, cudaMemcpyHostToDevice, st));
-                CUDA_TRY(cudaMemcpyAsync(dc->buf[14].p, p.off.data(), ob, cudaMemcpyHostToDevice, st));
-                dc->plan_dev = dc->buf[13].p;
-            }
-            CUDA_TRY(cudaMemsetAsync(dc->buf[15].p, 0, fb, st));
-            CUDA_TRY(cudaMemsetAsync(a.status, 0, (size_t)a.B * sizeof(int), st));
-            if (a.iters) CUDA_TRY(cudaMemsetAsync(a.iters, 0, 2 * (size_t)a.B * sizeof(int), st));
-            a.seg = (const int4*)dc->buf[13].p;
-            a.seg_off = (const int*)dc->buf[14].p;
-            a.flags = (int*)dc->buf[15].p;
-            grid = slots;
-        }
-    }
-    kernel<<<(unsigned)grid, 32 * NW, smem, st>>>(a);
-    CUDA_TRY(cudaGetLastError());
-    return RMX_OK;
+// the launcher of one kernel instance (rmx_host.h), or null if that combination is not built
+static rmx_fwd_launcher fwd_launcher(int impl, int nw, bool ground, bool adj, int lin) {
+#define X(IMPL, NW, G, A, L) \
+    if (impl == IMPL && nw == NW && ground == (G != 0) && adj == (A != 0) && lin == L) return RMX_FWD_NAME(IMPL, NW, G, A, L);
+    RMX_FWD_ALL(X)
+#undef X
+    return nullptr;
 }
 
 // forward rollout with the Krylov linear solve (fast path only: it needs the world-frame fields of rmx_fast.cuh)
@@ -792,8 +714,9 @@ static int launch_fwd_pcg(const rmx_scene* s, const RolloutArgs& a, cudaStream_t
     const bool g = s->has_ground != 0;
     const size_t smem = (scene_smem_doubles(s, true) + pcg_doubles(s->n, s->nr)) * sizeof(double);
     if (smem > 227 * 1024) return fail(RMX_ELIMIT, "scene does not fit the 227 KB shared memory of one SM");
-    if (nw == 1) return g ? launch_fwd_t<1, true, false, 2, 1>(a, smem, st) : launch_fwd_t<1, false, false, 2, 1>(a, smem, st);
-    return g ? launch_fwd_t<2, true, false, 2, 1>(a, smem, st) : launch_fwd_t<2, false, false, 2, 1>(a, smem, st);
+    rmx_fwd_launcher f = fwd_launcher(2, nw, g, false, 1);
+    if (!f) return fail(RMX_ELIMIT, "linsolve=PCG: no kernel for this scene size");
+    return f(a, smem, st, nullptr);
 }
 
 template <bool ADJ>
@@ -802,13 +725,9 @@ static int launch_fwd(const rmx_scene* s, const RolloutArgs& a, cudaStream_t st,
     const bool g = s->has_ground != 0;
     const size_t smem = (scene_smem_doubles(s, ADJ) + (ADJ ? 6 * (size_t)s->nr : 0)) * sizeof(double);
     if (smem > 227 * 1024) return fail(RMX_ELIMIT, "scene does not fit the 227 KB shared memory of one SM");
-    if (s->impl == 2) {
-        if (nw == 1) return g ? launch_fwd_t<1, true, ADJ, 2>(a, smem, st, dc) : launch_fwd_t<1, false, ADJ, 2>(a, smem, st, dc);
-        return g ? launch_fwd_t<2, true, ADJ, 2>(a, smem, st, dc) : launch_fwd_t<2, false, ADJ, 2>(a, smem, st, dc);
-    }
-    if (nw == 1) return g ? launch_fwd_t<1, true, ADJ, 1>(a, smem, st, dc) : launch_fwd_t<1, false, ADJ, 1>(a, smem, st, dc);
-    if (nw == 2) return g ? launch_fwd_t<2, true, ADJ, 1>(a, smem, st, dc) : launch_fwd_t<2, false, ADJ, 1>(a, smem, st, dc);
-    return g ? launch_fwd_t<4, true, ADJ, 1>(a, smem, st, dc) : launch_fwd_t<4, false, ADJ, 1>(a, smem, st, dc);
+    rmx_fwd_launcher f = fwd_launcher(s->impl, nw, g, ADJ, 0);
+    if (!f) return fail(RMX_ELIMIT, "no forward kernel for this scene size");
+    return f(a, smem, st, dc);
 }
 
 static int rollout_dev_impl(rmx_scene* s, const rmx_opts* o, int64_t B, const double* q0, const double* qdot0,
@@ -1034,16 +953,6 @@ extern "C" int rmx_linsolve_stats(rmx_scene* s, int64_t* krylov_iterations) {
 // ---------------------------------------------------------------------------------------------------
 // rmx_eval test hook
 // ---------------------------------------------------------------------------------------------------
-template <int NW, bool GROUND, int IMPL>
-static int launch_eval_t(const EvalArgs& a, size_t smem) {
-    int rc = set_smem(eval_kernel<NW, GROUND, IMPL>, smem);
-    if (rc) return rc;
-    eval_kernel<NW, GROUND, IMPL><<<1, 32 * NW, smem>>>(a);
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaDeviceSynchronize());
-    return RMX_OK;
-}
-
 extern "C" int rmx_eval(rmx_scene* s, const double* q, const double* qdot, const double* dqtmp, const double* tau,
                         double cK, double beta, double* g, double* H, double* M, double* D, double* f) {
     if (!s || !q || !qdot || !dqtmp) return fail(RMX_EINVAL, "rmx_eval: null argument");
@@ -1089,17 +998,7 @@ extern "C" int rmx_eval(rmx_scene* s, const double* q, const double* qdot, const
     const int nw = warps_for(s);
     const bool gr = s->has_ground != 0;
     const size_t smem = scene_smem_doubles(s) * sizeof(double);
-    if (s->impl == 2) {
-        if (nw == 1)
-            rc = gr ? launch_eval_t<1, true, 2>(a, smem) : launch_eval_t<1, false, 2>(a, smem);
-        else
-            rc = gr ? launch_eval_t<2, true, 2>(a, smem) : launch_eval_t<2, false, 2>(a, smem);
-    } else if (nw == 1)
-        rc = gr ? launch_eval_t<1, true, 1>(a, smem) : launch_eval_t<1, false, 1>(a, smem);
-    else if (nw == 2)
-        rc = gr ? launch_eval_t<2, true, 1>(a, smem) : launch_eval_t<2, false, 1>(a, smem);
-    else
-        rc = gr ? launch_eval_t<4, true, 1>(a, smem) : launch_eval_t<4, false, 1>(a, smem);
+    rc = rmx_launch_eval(s->impl, nw, gr, a, smem);
     if (rc == RMX_OK) {
         std::vector<double> hg(nr), hM((size_t)nr * nr);
         cudaMemcpy(hg.data(), dg, v, cudaMemcpyDeviceToHost);
@@ -1121,17 +1020,6 @@ extern "C" int rmx_eval(rmx_scene* s, const double* q, const double* qdot, const
     }
     cudaFree(d);
     return rc;
-}
-
-// rmx_eval_newton test hook: H and dx = -H\g through the forward kernel's own assembly + factorisation path
-template <int NW, bool GROUND>
-static int launch_eval_newton_t(const EvalArgs& a, double* dx, size_t smem) {
-    int rc = set_smem(eval_newton_kernel<NW, GROUND>, smem);
-    if (rc) return rc;
-    eval_newton_kernel<NW, GROUND><<<1, 32 * NW, smem>>>(a, dx);
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaDeviceSynchronize());
-    return RMX_OK;
 }
 
 extern "C" int rmx_eval_newton(rmx_scene* s, const double* q, const double* qdot, const double* dqtmp, const double* tau,
@@ -1174,10 +1062,7 @@ extern "C" int rmx_eval_newton(rmx_scene* s, const double* q, const double* qdot
     const int nw = warps_for(s);
     const bool gr = s->has_ground != 0;
     const size_t smem = scene_smem_doubles(s, false) * sizeof(double);
-    if (nw == 1)
-        rc = gr ? launch_eval_newton_t<1, true>(a, ddx, smem) : launch_eval_newton_t<1, false>(a, ddx, smem);
-    else
-        rc = gr ? launch_eval_newton_t<2, true>(a, ddx, smem) : launch_eval_newton_t<2, false>(a, ddx, smem);
+    rc = rmx_launch_eval_newton(nw, gr, a, ddx, smem);
     if (rc == RMX_OK) {
         if (H) cudaMemcpy(H, dH, m, cudaMemcpyDeviceToHost);
         if (dx) cudaMemcpy(dx, ddx, v, cudaMemcpyDeviceToHost);
@@ -1195,7 +1080,7 @@ extern "C" int rmx_debug_schedule(int64_t B, int32_t nsteps, int64_t slots, int3
     if (B < 1 || nsteps < 1 || slots < 1 || !seg || !off) return fail(RMX_EINVAL, "rmx_debug_schedule: bad arguments");
     if (B <= slots) return fail(RMX_EINVAL, "rmx_debug_schedule: B <= slots launches one block per rollout (no plan)");
     SchedPlan p;
-    build_plan(p, B, nsteps, slots);
+    rmx_build_plan(p, B, nsteps, slots);
     if ((int64_t)p.seg.size() > seg_capacity) return fail(RMX_EINVAL, "rmx_debug_schedule: seg_capacity too small");
     for (size_t i = 0; i < p.seg.size(); ++i) {
         seg[4 * i] = p.seg[i].x;

@@ -320,7 +320,7 @@ __device__ __forceinline__ void pf_gammaT(const double* xl, const double* M36, d
 struct PfEnd {
     double R[9], p[3], phi[6], x[3];
 };
-__device__ __noinline__ void pf_spring(const PfEnd* E, int sd, double ks, double kd, double L, double* f6, double* Kown, double* Down,
+static __device__ __noinline__ void pf_spring(const PfEnd* E, int sd, double ks, double kd, double L, double* f6, double* Kown, double* Down,
                                        double* Kab, double* Dab, bool deriv) {
     double xw[2][3], vl[2][3], vw[2][3];
 #pragma unroll
@@ -497,7 +497,7 @@ struct Wrench6 {
 // rate, the normalised generalised force fxn = [G1'R1'dx ; -G2'R2'dx] / |dx|, the gradients dldq, dldotdq (1 x 12), the
 // damping row dqd = [-dxnor'R1G1, dxnor'R2G2], and -- for the end `side` (0: a, 1: b, < 0: none) -- the six rows of the
 // normalised-vector stiffness K1 + K2/|dx| (6 x 12 row-major in Knr).
-__device__ __noinline__ void pf_segment(const PfEnd& Ea, const PfEnd& Eb, int side, bool deriv, double* dxlen_out, double* ldot_out,
+static __device__ __noinline__ void pf_segment(const PfEnd& Ea, const PfEnd& Eb, int side, bool deriv, double* dxlen_out, double* ldot_out,
                                         double* fxn, double* dldq, double* dldotdq, double* dqd, double* Knr) {
     const PfEnd* E[2] = {&Ea, &Eb};
     double xw[2][3], vl[2][3], vw[2][3];
@@ -630,7 +630,7 @@ __device__ __noinline__ void pf_segment(const PfEnd& Ea, const PfEnd& Eb, int si
 // ForceCable through attachment `me` of force P (ForceSpringMultiPointGeneric.m:29-190, ForceCable.m:66-81): adds this body's
 // wrench to fb and, if K != null, its diagonal blocks to K, D and writes its cross blocks K(me,k2), D(me,k2) (world frame) to
 // shared memory.  K = fn dfsdq - fs Kn, D = fn dfsdqdot.
-__device__ __noinline__ void pf_cable(PfCtx c, const PointForce& P, int me, const double* Rb, const double* pb, double* fb, double* K,
+static __device__ __noinline__ void pf_cable(PfCtx c, const PointForce& P, int me, const double* Rb, const double* pb, double* fb, double* K,
                                       double* D) {
     const int np = P.npts;
     const double* recs = c.pf_s + P.rec_off;
@@ -707,7 +707,7 @@ __device__ __noinline__ void pf_cable(PfCtx c, const PointForce& P, int me, cons
 // -c X'DX, -c X'KX to the external-force fields aext / cext of joint t in the SoA block (after the caller has stored or zeroed
 // them) and writes the cross blocks of its ordered pairs to shared memory.  Kept out of line and off the caller's registers:
 // scenes without point forces must not pay for it.
-__device__ __noinline__ Wrench6 pf_body(PfCtx c, int pf_ptr, int pf_cnt, BodyFrame B, bool deriv, double* sa, int NS, int aext,
+static __device__ __noinline__ Wrench6 pf_body(PfCtx c, int pf_ptr, int pf_cnt, BodyFrame B, bool deriv, double* sa, int NS, int aext,
                                         int cext, int t) {
     const double* Rb = B.R;
     const double* pb = B.p;

@@ -1,0 +1,97 @@
+// rmx_host.h -- host-side declarations shared by the translation units of libredmax_b200.so.
+//
+// The library is built from several .cu files compiled in parallel (one per kernel family, see __graft_entry__.py):
+// rmx_api.cu holds the C ABI and all host logic, the rmx_k_*.cu files hold nothing but explicit kernel instantiations
+// behind plain launcher functions (RMX_DEFINE_* below).  Nothing here is part of the public interface.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/redmax_b200.h"
+#include "rmx_adjoint.cuh"
+#include "rmx_rollout.cuh"
+
+int rmx_fail(int code, const std::string& msg);  // records the message for rmx_last_error(), returns code
+
+#define CUDA_TRY(x)                                                                                          \
+    do {                                                                                                     \
+        cudaError_t e_ = (x);                                                                                \
+        if (e_ != cudaSuccess) {                                                                             \
+            cudaGetLastError();                                                                              \
+            return rmx_fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ? RMX_ENOGPU : RMX_ECUDA, \
+                            std::string(#x) + ": " + cudaGetErrorString(e_));                                \
+        }                                                                                                    \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+// Load-balancing plan of a forward launch (see RolloutArgs::seg): cached per device for the last (B, nsteps, slots)
+struct SchedPlan {
+    long long B = -1;
+    int nsteps = -1;
+    long long slots = -1;
+    std::vector<int4> seg;
+    std::vector<int> off;
+};
+
+struct DevCopy {
+    SchedPlan plan;
+    rmx::JointConst* jc = nullptr;
+    int* ends = nullptr;
+    int* anc = nullptr;
+    rmx::PointForce* pf = nullptr;
+    int* pf_ep = nullptr;
+    unsigned long long* kry = nullptr;  // Krylov iteration counter
+    cudaStream_t stream = nullptr;
+    DevBuf buf[16];
+    void* plan_dev = nullptr;  // device copy of `plan` currently in buf[13]/buf[14]
+};
+
+int rmx_dev_reserve(DevBuf& b, size_t bytes);
+void rmx_build_plan(SchedPlan& p, long long B, int nsteps, long long slots);
+bool rmx_sched_enabled();
+
+template <typename K>
+static inline int rmx_set_smem(K kernel, size_t bytes) {
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    // as many rollouts per SM as shared memory allows: ask for the full shared-memory carve-out
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    return RMX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// launchers (defined once each in a rmx_k_*.cu file)
+// ---------------------------------------------------------------------------------------------------
+typedef int (*rmx_fwd_launcher)(const rmx::RolloutArgs& a, size_t smem, cudaStream_t st, DevCopy* dc);
+typedef int (*rmx_eval_launcher)(const rmx::EvalArgs& a, size_t smem);
+typedef int (*rmx_evaln_launcher)(const rmx::EvalArgs& a, double* dx, size_t smem);
+typedef int (*rmx_energy_launcher)(const rmx::EnergyArgs& a, size_t smem);
+
+// forward rollout kernels: IMPL (1 sweep / 2 composite), NW warps per rollout, GROUND, ADJ (tape-writing), LIN (0 LU, 1 Krylov)
+#define RMX_FWD_NAME(IMPL, NW, G, A, L) rmx_fwd_i##IMPL##_w##NW##_g##G##_a##A##_l##L
+#define RMX_DECLARE_FWD(IMPL, NW, G, A, L) \
+    int RMX_FWD_NAME(IMPL, NW, G, A, L)(const rmx::RolloutArgs& a, size_t smem, cudaStream_t st, DevCopy* dc);
+#define RMX_DEFINE_FWD(IMPL, NW, G, A, L)                                                                    \
+    int RMX_FWD_NAME(IMPL, NW, G, A, L)(const rmx::RolloutArgs& a, size_t smem, cudaStream_t st, DevCopy* dc) { \
+        return rmx_launch_fwd_t<NW, G != 0, A != 0, IMPL, L>(a, smem, st, dc);                                  \
+    }
+
+#define RMX_FWD_ALL(X)                                                                                      \
+    X(2, 1, 0, 0, 0) X(2, 1, 1, 0, 0) X(2, 1, 0, 1, 0) X(2, 1, 1, 1, 0)                                      \
+    X(2, 2, 0, 0, 0) X(2, 2, 1, 0, 0) X(2, 2, 0, 1, 0) X(2, 2, 1, 1, 0)                                      \
+    X(2, 1, 0, 0, 1) X(2, 1, 1, 0, 1) X(2, 2, 0, 0, 1) X(2, 2, 1, 0, 1)                                      \
+    X(1, 1, 0, 0, 0) X(1, 1, 1, 0, 0) X(1, 1, 0, 1, 0) X(1, 1, 1, 1, 0)                                      \
+    X(1, 2, 0, 0, 0) X(1, 2, 1, 0, 0) X(1, 2, 0, 1, 0) X(1, 2, 1, 1, 0)                                      \
+    X(1, 4, 0, 0, 0) X(1, 4, 1, 0, 0) X(1, 4, 0, 1, 0) X(1, 4, 1, 1, 0)
+RMX_FWD_ALL(RMX_DECLARE_FWD)
+
+// test hooks and diagnostics (rmx_k_misc.cu)
+int rmx_launch_eval(int impl, int nw, bool ground, const rmx::EvalArgs& a, size_t smem);
+int rmx_launch_eval_newton(int nw, bool ground, const rmx::EvalArgs& a, double* dx, size_t smem);
+int rmx_launch_energy(int impl, int nw, bool ground, const rmx::EnergyArgs& a, size_t smem);
+int rmx_launch_bwd(int nw, const rmx::BwdArgs& a, cudaStream_t st);

@@ -1,0 +1,46 @@
+// rmx_launch.cuh -- launch of one forward-kernel instance (included by the rmx_k_fwd_*.cu files only).
+#pragma once
+#include "rmx_host.h"
+
+// One persistent launch of rollout_fwd_kernel<NW, GROUND, ADJ, IMPL, LIN>.  Forward launches whose batch is not a multiple of
+// the co-resident blocks run the load-balanced segment schedule (rmx_build_plan); everything else one block per rollout.
+template <int NW, bool GROUND, bool ADJ, int IMPL, int LIN>
+static int rmx_launch_fwd_t(const rmx::RolloutArgs& a0, size_t smem, cudaStream_t st, DevCopy* dc) {
+    using namespace rmx;
+    auto kernel = rollout_fwd_kernel<NW, GROUND, ADJ, IMPL, LIN>;
+    int rc = rmx_set_smem(kernel, smem);
+    if (rc) return rc;
+    RolloutArgs a = a0;
+    long long grid = a.B;
+    if (!ADJ && LIN == 0 && dc && a.qd_out && a.op.nsteps >= 2 && a.B < (1ll << 30) && rmx_sched_enabled()) {
+        int nb = 0, dev = 0, sms = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, 32 * NW, smem));
+        CUDA_TRY(cudaGetDevice(&dev));
+        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const long long slots = (long long)nb * sms;
+        if (slots > 0 && a.B > slots && a.B % slots != 0) {
+            SchedPlan& p = dc->plan;
+            const bool fresh = !(p.B == a.B && p.nsteps == a.op.nsteps && p.slots == slots);
+            if (fresh) rmx_build_plan(p, a.B, a.op.nsteps, slots);
+            const size_t sb = p.seg.size() * sizeof(int4), ob = p.off.size() * sizeof(int), fb = (size_t)a.B * sizeof(int);
+            if ((rc = rmx_dev_reserve(dc->buf[13], sb)) || (rc = rmx_dev_reserve(dc->buf[14], ob)) ||
+                (rc = rmx_dev_reserve(dc->buf[15], fb)))
+                return rc;
+            if (fresh || dc->plan_dev != dc->buf[13].p) {
+                CUDA_TRY(cudaMemcpyAsync(dc->buf[13].p, p.seg.data(), sb, cudaMemcpyHostToDevice, st));
+                CUDA_TRY(cudaMemcpyAsync(dc->buf[14].p, p.off.data(), ob, cudaMemcpyHostToDevice, st));
+                dc->plan_dev = dc->buf[13].p;
+            }
+            CUDA_TRY(cudaMemsetAsync(dc->buf[15].p, 0, fb, st));
+            CUDA_TRY(cudaMemsetAsync(a.status, 0, (size_t)a.B * sizeof(int), st));
+            if (a.iters) CUDA_TRY(cudaMemsetAsync(a.iters, 0, 2 * (size_t)a.B * sizeof(int), st));
+            a.seg = (const int4*)dc->buf[13].p;
+            a.seg_off = (const int*)dc->buf[14].p;
+            a.flags = (int*)dc->buf[15].p;
+            grid = slots;
+        }
+    }
+    kernel<<<(unsigned)grid, 32 * NW, smem, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    return RMX_OK;
+}
