@@ -25,6 +25,7 @@
 #ifndef REDMAX_B200_H
 #define REDMAX_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -80,7 +81,9 @@ extern "C" {
 #define RMX_ST_MAXITER 2   /* 'Newton did not converge'    (iter >= iterMax) in some step */
 #define RMX_ST_LSFAIL 4    /* line search exhausted iterLsMax halvings in some step (silent in reference) */
 #define RMX_ST_NAN 8       /* non-finite state produced */
-#define RMX_ST_SCHED 16    /* internal: a load-balanced rollout never received its first part (should not happen) */
+#define RMX_ST_SCHED 16    /* a load-balanced launch gave up waiting for the earlier steps of this rollout (blocks not co-resident,
+                              e.g. a shared GPU): the trajectory is NOT valid.  rmx_rollout re-runs such rollouts itself and never
+                              returns this bit; callers of rmx_rollout_dev check for it after synchronising their stream */
 #define RMX_ST_CHART 32    /* a spherical / Free3D joint left the well-conditioned part of its Euler chart after some step
                               (|det T| <= 0.5: |cos q2| in the charts 7..12, |sin q2| in 1..6); steps after the first such step
                               are the same motion in coordinates the reference would have left.  driverRedMaxBDF2 switches
@@ -246,6 +249,19 @@ int rmx_eval_newton(rmx_scene* s, const double* q, const double* qdot, const dou
  * part closes the previous block's list and waits).  seg: 4 ints per segment {rollout, first step, end step, flags: 1 wait,
  * 2 signal}; off: slots + 1 offsets.  Returns the number of segments or a negative RMX_E* code. */
 int rmx_debug_schedule(int64_t B, int32_t nsteps, int64_t slots, int32_t seg_capacity, int32_t* seg, int32_t* off);
+
+/* Measurement aid: sustained FP64 rate of the current device in TFLOP/s, from two micro-kernels run on every SM at full
+ * occupancy -- independent DFMA chains (2 flop per lane and instruction) and independent DMMA.8x8x4 chains (mma.sync m8n8k4 f64,
+ * 512 flop per warp instruction), the two instruction kinds the rollout kernels spend their FP64 time in.  bench.py reports
+ * them as the measured FP64 roofline (MEASURED_PEAKS.json holds no FP64 figure).  Either pointer may be NULL. */
+int rmx_fp64_probe(double* dfma_tflops, double* dmma_tflops);
+
+/* Page-lock / release a caller-owned host buffer (cudaHostRegister, portable + mapped).  rmx_rollout stores q(t), qdot(t)
+ * straight into page-locked output buffers while the kernel runs (no device-to-host copy afterwards); pageable buffers take
+ * the staged copy.  Registration costs about as much as one copy of the buffer, so it pays for buffers that are reused
+ * (MPC loops), not for arrays allocated per call. */
+int rmx_host_register(void* p, size_t bytes);
+int rmx_host_unregister(void* p);
 
 /* Scene.saveHistory energies (Scene.m:155-160; Joint.m:616, Body.m:167, ForceGroundCuboid.m:156) for B states:
  * T, V: B each. */

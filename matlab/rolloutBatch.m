@@ -28,7 +28,10 @@ z = zeros(3,1);
 for b = find(bitand(status(:)',32))
 	for i = 1 : length(sph), sph{i}.chart = chart0(i); end
 	kb = 0; st = int32(0); it = zeros(2,1,'int32'); hist = []; % hist: {step (0-based, -1 = initial state), q1, qdot1}
-	qb = q(:,:,b); qdb = qdot(:,:,b); taub = []; if ~isempty(tau), taub = tau(:,:,b); end
+	qb = q(:,:,b); qdb = qdot(:,:,b); taub = [];
+	if ~isempty(tau) % constant torque: nr x B ; per step: nr x nsteps x B
+		if numel(tau) == size(q,1)*size(q,3), taub = tau(:,b); else, taub = tau(:,:,b); end % same rule as the gateway
+	end
 	while kb < opts.nsteps
 		% first step (0-based) at or after kb with |det T| <= 0.5 for some spherical joint
 		k1 = opts.nsteps - 1; sw = false;
@@ -75,7 +78,7 @@ if ~isempty(hist)
 	else, keep = {qb(:,hist{1}+1),qdb(:,hist{1}+1)}; qb(:,hist{1}+1) = hist{2}; qdb(:,hist{1}+1) = hist{3}; end
 end
 h = redmax_mex('create',flattenScene(scene));
-[qb,qdb,st,it] = redmax_mex('resume',h,opts,int32(kb),q0,qdot0,tau,qb,qdb);
+[qb,qdb,st,it] = redmax_mex('resume',h,opts,double(kb),q0,qdot0,tau,qb,qdb);
 redmax_mex('destroy',h);
 if ~isempty(keep), qb(:,hist{1}+1) = keep{1}; qdb(:,hist{1}+1) = keep{2}; end
 end
@@ -91,7 +94,7 @@ d.parent = zeros(1,n); d.jtype = zeros(1,n);
 d.E0_pj = zeros(4,4,n); d.E0_ji = zeros(4,4,n); d.axis = zeros(3,n); d.I_i = zeros(6,n); d.sides = zeros(3,n);
 d.axis2 = repmat([0;1;0],1,n);
 d.stiffness = zeros(1,n); d.damping = zeros(1,n); d.qRest = zeros(6,n); % RMX_MAX_JOINT_DOF x n
-d.chart = zeros(1,n,'int32');
+d.chart = zeros(1,n); % double like every other index array (the gateway also accepts int32)
 d.qLimL = zeros(1,n); d.qLimU = zeros(1,n); d.qLimK = zeros(1,n); d.qLimD = zeros(1,n);
 for i = 1 : n
 	j = scene.joints{i};

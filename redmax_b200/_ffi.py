@@ -40,6 +40,7 @@ RMX_ST_DIVERGED = 1
 RMX_ST_MAXITER = 2
 RMX_ST_LSFAIL = 4
 RMX_ST_NAN = 8
+RMX_ST_SCHED = 16  # internal scheduling failure: the rollout's trajectory is not valid (Scene.rollout* raise on it)
 RMX_ST_CHART = 32
 
 _pd = C.POINTER(C.c_double)
@@ -89,6 +90,7 @@ SYMBOLS = [
     'rmx_scene_create', 'rmx_scene_destroy', 'rmx_scene_nr', 'rmx_scene_nm',
     'rmx_rollout', 'rmx_rollout_resume', 'rmx_rollout_dev', 'rmx_rollout_adjoint', 'rmx_rollout_adjoint_dev',
     'rmx_adjoint_tape_bytes', 'rmx_eval', 'rmx_eval_newton', 'rmx_energies', 'rmx_linsolve_stats', 'rmx_debug_schedule', 'rmx_body_frames',
+    'rmx_fp64_probe', 'rmx_host_register', 'rmx_host_unregister',
 ]
 
 _lib = None
@@ -133,6 +135,9 @@ def lib():
     L.rmx_body_frames.argtypes = [vp, C.c_int64, vp, vp]
     L.rmx_debug_schedule.argtypes = [C.c_int64, C.c_int32, C.c_int64, C.c_int32, vp, vp]
     L.rmx_linsolve_stats.argtypes = [vp, C.POINTER(C.c_int64)]
+    L.rmx_fp64_probe.argtypes = [_pd, _pd]
+    L.rmx_host_register.argtypes = [vp, C.c_size_t]
+    L.rmx_host_unregister.argtypes = [vp]
     _lib = L
     return L
 

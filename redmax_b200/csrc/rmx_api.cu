@@ -251,9 +251,12 @@ extern "C" int rmx_scene_create(const rmx_scene_desc* d, rmx_scene** out) {
             return fail(RMX_EINVAL, "rmx_scene_create: joints must be listed parents-before-children (Joint.m:134)");
         if (d->chart && (d->chart[j] < 0 || d->chart[j] > 12)) return fail(RMX_EINVAL, "rmx_scene_create: chart must be 0 (default) or 1..12");
         if (joint_ndof(d->jtype[j]) < 0)
-            return fail(RMX_EINVAL, "rmx_scene_create: joint type is not on the hot path (fixed, revolute, prismatic, planar, "
-                                    "translational, free2d, universal are)");
+            return fail(RMX_EINVAL, "rmx_scene_create: unknown joint type (fixed, revolute, prismatic, planar, translational, "
+                                    "free2d, universal, spherical and free3d are on the hot path)");
     }
+    if (d->nground < 0) return fail(RMX_EINVAL, "rmx_scene_create: nground < 0");
+    if (d->nground > 0 && (!d->ground_body || !d->ground_E || !d->ground_kn || !d->ground_kt || !d->ground_kd || !d->ground_mu))
+        return fail(RMX_EINVAL, "rmx_scene_create: missing ground_* array");
     // reference numbering: countDofs is called for i = n..1 (Scene.m:69-71); a joint's DOFs are consecutive (Joint.m:152)
     std::vector<int> base(n_user, 0);
     int nr = 0;
@@ -662,9 +665,10 @@ static int check_opts(const rmx_scene* s, const rmx_opts* o, StepOpts* so, int a
     return RMX_OK;
 }
 
+static thread_local bool g_no_sched = false;  // set while rmx_rollout re-runs rollouts a load-balanced launch gave up on
 bool rmx_sched_enabled() {
     const char* e = std::getenv("RMX_SCHED");  // developer switch: RMX_SCHED=0 launches one block per rollout
-    return !(e && e[0] == '0');
+    return !g_no_sched && !(e && e[0] == '0');
 }
 
 // McNaughton wrap-around schedule of B rollouts x nsteps steps over `slots` co-resident blocks: every block gets
@@ -788,6 +792,19 @@ static double* mapped_host_ptr(double* p) {
     return at.type == cudaMemoryTypeHost ? (double*)at.devicePointer : nullptr;
 }
 
+// Inside the per-device loops of the host-pointer entries an error must not return: the streams of the devices already
+// launched are synchronised and the caller's current device restored in the epilogue (their copies and mirrored stores are
+// still writing into the caller's buffers).
+#define CUDA_LOOP(x)                                                                   \
+    {                                                                                  \
+        cudaError_t e_ = (x);                                                          \
+        if (e_ != cudaSuccess) {                                                       \
+            cudaGetLastError();                                                        \
+            ret = fail(RMX_ECUDA, std::string(#x) + ": " + cudaGetErrorString(e_));    \
+            break;                                                                     \
+        }                                                                              \
+    }
+
 // Host-pointer entry: shards the batch contiguously over o->ngpus devices (no communication during the rollout),
 // each device copying its slice of the trajectories straight back into the caller's buffers.
 extern "C" int rmx_rollout(rmx_scene* s, const rmx_opts* o, int64_t B, const double* q0, const double* qdot0,
@@ -814,7 +831,7 @@ extern "C" int rmx_rollout(rmx_scene* s, const rmx_opts* o, int64_t B, const dou
     int ret = RMX_OK;
     for (int gi = 0; gi < G && ret == RMX_OK; ++gi) {
         const int64_t b0 = B * gi / G, b1 = B * (gi + 1) / G, nb = b1 - b0;
-        CUDA_TRY(cudaSetDevice(devs[gi]));
+        CUDA_LOOP(cudaSetDevice(devs[gi]));
         DevCopy* dc;
         ret = scene_on_device(s, devs[gi], &dc);
         if (ret) break;
@@ -825,9 +842,9 @@ extern "C" int rmx_rollout(rmx_scene* s, const rmx_opts* o, int64_t B, const dou
             if (sz[i]) ret = dev_reserve(dc->buf[i], sz[i]);
         if (ret) break;
         cudaStream_t st = dc->stream;
-        CUDA_TRY(cudaMemcpyAsync(dc->buf[0].p, q0 + b0 * nr, sz[0], cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(dc->buf[1].p, qdot0 + b0 * nr, sz[1], cudaMemcpyHostToDevice, st));
-        if (tau) CUDA_TRY(cudaMemcpyAsync(dc->buf[2].p, tau + b0 * tau_per, sz[2], cudaMemcpyHostToDevice, st));
+        CUDA_LOOP(cudaMemcpyAsync(dc->buf[0].p, q0 + b0 * nr, sz[0], cudaMemcpyHostToDevice, st));
+        CUDA_LOOP(cudaMemcpyAsync(dc->buf[1].p, qdot0 + b0 * nr, sz[1], cudaMemcpyHostToDevice, st));
+        if (tau) CUDA_LOOP(cudaMemcpyAsync(dc->buf[2].p, tau + b0 * tau_per, sz[2], cudaMemcpyHostToDevice, st));
         // Page-locked output buffers are written by the kernel itself while it runs (mirrored stores over PCIe, hidden
         // behind the rollout); pageable ones get the staged copy after it.
         double* qh = mapped_host_ptr(q_out + b0 * per);
@@ -836,10 +853,10 @@ extern "C" int rmx_rollout(rmx_scene* s, const rmx_opts* o, int64_t B, const dou
                                (double*)dc->buf[3].p, qdot_out ? (double*)dc->buf[4].p : nullptr, (int*)dc->buf[5].p,
                                iters ? (int*)dc->buf[6].p : nullptr, st, qh, qdh);
         if (ret) break;
-        if (!qh) CUDA_TRY(cudaMemcpyAsync(q_out + b0 * per, dc->buf[3].p, sz[3], cudaMemcpyDeviceToHost, st));
-        if (qdot_out && !qdh) CUDA_TRY(cudaMemcpyAsync(qdot_out + b0 * per, dc->buf[4].p, sz[4], cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(status + b0, dc->buf[5].p, sz[5], cudaMemcpyDeviceToHost, st));
-        if (iters) CUDA_TRY(cudaMemcpyAsync(iters + 2 * b0, dc->buf[6].p, sz[6], cudaMemcpyDeviceToHost, st));
+        if (!qh) CUDA_LOOP(cudaMemcpyAsync(q_out + b0 * per, dc->buf[3].p, sz[3], cudaMemcpyDeviceToHost, st));
+        if (qdot_out && !qdh) CUDA_LOOP(cudaMemcpyAsync(qdot_out + b0 * per, dc->buf[4].p, sz[4], cudaMemcpyDeviceToHost, st));
+        CUDA_LOOP(cudaMemcpyAsync(status + b0, dc->buf[5].p, sz[5], cudaMemcpyDeviceToHost, st));
+        if (iters) CUDA_LOOP(cudaMemcpyAsync(iters + 2 * b0, dc->buf[6].p, sz[6], cudaMemcpyDeviceToHost, st));
     }
     for (int gi = 0; gi < G; ++gi) {
         cudaSetDevice(devs[gi]);
@@ -850,7 +867,38 @@ extern "C" int rmx_rollout(rmx_scene* s, const rmx_opts* o, int64_t B, const dou
         }
     }
     cudaSetDevice(cur);
-    return ret;
+    if (ret != RMX_OK || g_no_sched) return ret;
+    // A load-balanced launch hands the later steps of some rollouts to another block, which waits (bounded) for the earlier
+    // steps to be published.  If that wait ever ran out (RMX_ST_SCHED: the blocks were not co-resident, e.g. a shared GPU), the
+    // trajectory after the hand-over is not valid: run those rollouts again, one block per rollout.
+    std::vector<int64_t> redo;
+    for (int64_t b = 0; b < B; ++b)
+        if (status[b] & RMX_ST_SCHED) redo.push_back(b);
+    if (redo.empty()) return RMX_OK;
+    const int64_t R = (int64_t)redo.size();
+    std::vector<double> rq0((size_t)R * nr), rqd0((size_t)R * nr), rtau(tau ? (size_t)R * tau_per : 0), rq((size_t)R * per),
+        rqd(qdot_out ? (size_t)R * per : 0);
+    std::vector<int32_t> rst(R), rit(2 * R);
+    for (int64_t i = 0; i < R; ++i) {
+        std::memcpy(&rq0[i * nr], q0 + redo[i] * nr, nr * sizeof(double));
+        std::memcpy(&rqd0[i * nr], qdot0 + redo[i] * nr, nr * sizeof(double));
+        if (tau) std::memcpy(&rtau[i * tau_per], tau + redo[i] * tau_per, tau_per * sizeof(double));
+    }
+    g_no_sched = true;
+    ret = rmx_rollout(s, o, R, rq0.data(), rqd0.data(), tau ? rtau.data() : nullptr, rq.data(), qdot_out ? rqd.data() : nullptr,
+                      rst.data(), rit.data());
+    g_no_sched = false;
+    if (ret != RMX_OK) return ret;
+    for (int64_t i = 0; i < R; ++i) {
+        std::memcpy(q_out + redo[i] * per, &rq[i * per], per * sizeof(double));
+        if (qdot_out) std::memcpy(qdot_out + redo[i] * per, &rqd[i * per], per * sizeof(double));
+        status[redo[i]] = rst[i];
+        if (iters) {
+            iters[2 * redo[i]] = rit[2 * i];
+            iters[2 * redo[i] + 1] = rit[2 * i + 1];
+        }
+    }
+    return RMX_OK;
 }
 
 // Host-pointer resume (see the header): one launch on the current device, one block per rollout, each running the single

@@ -715,6 +715,17 @@ class Scene:
         _ffi.check(L.rmx_rollout_dev(self._handle, C.byref(o), B, ptr(q0), ptr(qdot0), ptr(tau), ptr(q_out),
                                      ptr(qdot_out), ptr(status), ptr(iters), st), 'rmx_rollout_dev')
 
+    @staticmethod
+    def check_status(status):
+        """Raise if a device-buffer launch flagged an internal scheduling failure (RMX_ST_SCHED): those trajectories are not
+        valid.  The host-pointer calls (rollout, rollout_into) re-run such rollouts inside the library; rollout_dev is
+        asynchronous, so its caller checks the status array once the stream has been synchronised."""
+        st = status.cpu().numpy() if hasattr(status, 'cpu') else np.asarray(status)
+        bad = np.nonzero(st & _ffi.RMX_ST_SCHED)[0]
+        if len(bad):
+            raise _ffi.RmxError('rmx_rollout_dev: %d rollout(s) hit RMX_ST_SCHED (first: %d); re-run them with RMX_SCHED=0 or '
+                                'through the host-pointer call' % (len(bad), int(bad[0])))
+
     def linsolve_stats(self):
         """Total Krylov iterations of the last rollout with linsolve=RMX_LINSOLVE_PCG (rmx_linsolve_stats)."""
         L = self._require()
@@ -755,6 +766,33 @@ class Scene:
         _ffi.check(L.rmx_rollout_adjoint(self._handle, C.byref(o), C.byref(t), B, ptr(q0), ptr(qdot0), ptr(p), ptr(xt),
                                          ptr(P), ptr(dPdp), ptr(q), ptr(status)), 'rmx_rollout_adjoint')
         return dict(P=P, dPdp=dPdp, q=q, status=status)
+
+    def rollout_adjoint_dev(self, q0, qdot0, p, xtarget, P, dPdp, status, q_out=None, nsteps=None, stream=None, **kw):
+        """Device-buffer form of rollout_adjoint (rmx_rollout_adjoint_dev): tape-writing forward rollout + backward sweep
+        enqueued on `stream`; every argument is a torch CUDA tensor (or a raw device address), q_out optional."""
+        L = self._require()
+        B = int(p.shape[0])
+        o = self.opts(scheme=self.task.scheme, adjoint=True, nsteps=nsteps, **kw)
+        t = self._task_struct()
+        st = None
+        if stream is not None:
+            st = C.c_void_p(int(getattr(stream, 'cuda_stream', stream)))
+        _ffi.check(L.rmx_rollout_adjoint_dev(self._handle, C.byref(o), C.byref(t), B, ptr(q0), ptr(qdot0), ptr(p), ptr(xtarget),
+                                             ptr(P), ptr(dPdp), ptr(q_out), ptr(status), st), 'rmx_rollout_adjoint_dev')
+
+    def rollout_adjoint_into(self, q0, qdot0, p, xtarget, P, dPdp, status, nsteps=None, ngpus=1, **kw):
+        """rmx_rollout_adjoint with caller-owned host buffers (float64 / int32, C-contiguous), nothing allocated here."""
+        L = self._require()
+        B = int(p.shape[0])
+        o = self.opts(scheme=self.task.scheme, adjoint=True, nsteps=nsteps, ngpus=ngpus, **kw)
+        t = self._task_struct()
+        _ffi.check(L.rmx_rollout_adjoint(self._handle, C.byref(o), C.byref(t), B, ptr(q0), ptr(qdot0), ptr(p), ptr(xtarget),
+                                         ptr(P), ptr(dPdp), None, ptr(status)), 'rmx_rollout_adjoint')
+
+    def adjoint_tape_bytes(self, B, nsteps=None):
+        """Bytes of the adjoint tape (LU(H) + perm + dP/dq, M, D per rollout-step) a batch of B rollouts writes and reads."""
+        o = self.opts(scheme=self.task.scheme if self.task is not None else 1, adjoint=True, nsteps=nsteps)
+        return int(self._require().rmx_adjoint_tape_bytes(self._handle, C.byref(o), B))
 
     # -- test hooks ---------------------------------------------------------------------------------------
     def eval(self, q, qdot, dqtmp, cK, beta, tau=None):

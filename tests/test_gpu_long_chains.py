@@ -1,0 +1,96 @@
+"""GPU parity at the sizes of BASELINE config C5 (64-link chain: two warps per rollout) and beyond 64 joints (the sweep kernels,
+four warps per rollout), against the reference's dense algorithm (C twin of the oracle; the NumPy oracle needs minutes per
+rollout at these sizes).  Bars as everywhere: q(t) within 1e-10 relative, single evaluations within 1e-11, identical Newton and
+line-search counts."""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def oc():
+    import oracle_c
+    if not oracle_c.available():
+        import __graft_entry__ as ge
+        ge.build_oracle()
+    return oracle_c
+
+
+def both(rb, oracle, n, **kw):
+    sg = rb.chain_scene(n, **kw)
+    sg.init()
+    so = rb.chain_scene(n, api=oracle, **kw)
+    so.init()
+    return sg, so
+
+
+@pytest.mark.parametrize('n', [48, 64, 72, 100])
+def test_eval_long_chain_vs_c_oracle(rb, oracle, oc, n):
+    sg, so = both(rb, oracle, n, h=2e-4)
+    rng = np.random.default_rng(7 + n)
+    h = sg.h
+    for trial in range(2):
+        q = sg.qInit + 0.3 * rng.uniform(-1, 1, n)
+        q0 = q - 0.002 * rng.uniform(-1, 1, n)
+        qdot0 = rng.uniform(-1, 1, n)
+        tau = 100 * rng.uniform(-1, 1, n)
+        qd, dq = (q - q0) / h, q - q0 - h * qdot0
+        ref = oc.eval_direct(so, q, qd, dq, h, h * h, tau=tau)
+        out = sg.eval(q, qd, dq, h * h, 1.0 / h, tau=tau)
+        for key, tol in (('g', 1e-11), ('H', 1e-11), ('M', 1e-11), ('D', 1e-10)):
+            assert rel_err(out[key], ref[key]) < tol, (key, rel_err(out[key], ref[key]))
+
+
+@pytest.mark.parametrize('n', [48, 64])
+def test_newton_system_two_warps(rb, oracle, oc, n):
+    """The Newton matrix and step dx = -H\\g exactly as the two-warp forward kernel forms and solves them."""
+    sg, so = both(rb, oracle, n, h=2e-4)
+    rng = np.random.default_rng(11 + n)
+    h = sg.h
+    q = sg.qInit + 0.3 * rng.uniform(-1, 1, n)
+    q0 = q - 0.002 * rng.uniform(-1, 1, n)
+    qdot0 = rng.uniform(-1, 1, n)
+    qd, dq = (q - q0) / h, q - q0 - h * qdot0
+    ref = oc.eval_direct(so, q, qd, dq, h, h * h)
+    out = sg.eval_newton(q, qd, dq, h * h, 1.0 / h)
+    assert rel_err(out['H'], ref['H']) < 1e-11
+    dx = -np.linalg.solve(ref['H'], ref['g'])
+    assert rel_err(out['dx'], dx) < 1e-9, rel_err(out['dx'], dx)
+    # backward error of the in-kernel factorisation on its own matrix
+    r = out['H'] @ out['dx'] + ref['g']
+    assert np.linalg.norm(r) <= 1e-13 * (np.linalg.norm(out['H']) * np.linalg.norm(out['dx']) + np.linalg.norm(ref['g']))
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize('scheme', [1, 2])
+def test_c5_chain64_full_length_vs_c_oracle(rb, oracle, oc, scheme):
+    """BASELINE config C5 shape at full length: 64-link chain, 100 steps (h = 2e-4, bench.py's chain64 workload)."""
+    sg, so = both(rb, oracle, 64, h=2e-4)
+    B = 8
+    q0, qd0 = rb.synthetic_inputs(sg, B, seed=20260005)
+    out = sg.rollout(q0, qd0, scheme=scheme)
+    q, qd, st = oc.run_forward_batch(so, scheme, q0, qd0, threads=min(B, oc.max_threads()))
+    assert (st[:, 2] == 0).all()
+    assert (out['status'] == 0).all(), out['status']
+    assert rel_err(out['q'], q) < 1e-10, rel_err(out['q'], q)
+    assert rel_err(out['qdot'], qd) < 1e-8
+    np.testing.assert_array_equal(out['iters'], st[:, :2])
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize('n,scheme', [(72, 1), (72, 2), (100, 1)])
+def test_beyond_64_joints_sweep_kernels_vs_c_oracle(rb, oracle, oc, n, scheme):
+    """n > 64: the sweep kernels (rmx_device.cuh), four warps per rollout."""
+    sg, so = both(rb, oracle, n, h=2e-4)
+    B, ns = 4, 20
+    q0, qd0 = rb.synthetic_inputs(sg, B, seed=20260006)
+    out = sg.rollout(q0, qd0, scheme=scheme, nsteps=ns)
+    q, qd, st = oc.run_forward_batch(so, scheme, q0, qd0, nsteps=ns, threads=min(B, oc.max_threads()))
+    ok = st[:, 2] == 0
+    assert ok.any()
+    assert rel_err(out['q'][ok], q[ok]) < 1e-10, rel_err(out['q'][ok], q[ok])
+    np.testing.assert_array_equal(out['iters'][ok], st[ok, :2])
+    np.testing.assert_array_equal(out['status'][ok], st[ok, 2])
