@@ -185,6 +185,7 @@ __global__ void __launch_bounds__(32 * NW) energies_kernel(EnergyArgs a) {
     const int n = a.sc.n, nr = a.sc.nr;
     typename E::C c;
     StepOpts op0;
+    op0.shortcuts = 0;
     op0.lin_tol = 0.0;
     op0.lin_maxit = 0;
     E::setup(c, sm, a.sc, op0);

@@ -657,6 +657,10 @@ static int check_opts(const rmx_scene* s, const rmx_opts* o, StepOpts* so, int a
     so->iterLsMax = o->iterLsMax > 0 ? o->iterLsMax : 20;
     so->tau_mode = o->tau_mode;
     so->adjoint_newton = adjoint;
+    {
+        const char* e = std::getenv("RMX_NO_SHORTCUTS");  // developer switch: run stalled Newton solves the long way (A/B of bitwise equality)
+        so->shortcuts = !(e && e[0] == '1');
+    }
     so->h = o->h;
     so->tol = o->tol > 0 ? o->tol : 1e-9;
     so->dxMax = o->dxMax > 0 ? o->dxMax : 1e3;

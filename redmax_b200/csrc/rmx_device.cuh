@@ -89,6 +89,7 @@ struct DevScene {
 
 struct StepOpts {
     int scheme, nsteps, iterMax, iterLsMax, tau_mode, adjoint_newton;
+    int shortcuts;   // forward Newton: skip work of stalled solves whose outcome is known bit for bit (newton_forward)
     double h, tol, dxMax;
     double lin_tol;  // Krylov linear solve: relative residual tolerance (c++/PCG Solver.h:43: 1e-6)
     int lin_maxit;

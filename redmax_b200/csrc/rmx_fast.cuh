@@ -48,66 +48,59 @@ struct Fld {
     static constexpr int HROOM = 12 + NCOMP;
 };
 
-// Joint stride of the SoA block.  One-warp kernels (n, nr <= 32) always use 33, so that every field offset is a compile-time
-// immediate there (const int NS = NW == 1 ? 33 : c.NS): no address arithmetic per shared-memory access.
-__host__ __device__ inline int soa_stride(int n, int nr) { return (n <= 32 && nr <= 32) ? 33 : (n | 1); }
-// leading dimension of H: the tensor-core forward path fixes it at 33 for the same reason
-__host__ __device__ inline int h_ld2(int n, int nr, bool keep) { return (!keep && n <= 32 && nr <= 32) ? 33 : h_ld(nr); }
+// Joint stride of the SoA block: 33 for one-warp kernels (n, nr <= 32), 65 for two-warp kernels (n, nr <= 64), so that every
+// field offset is a compile-time immediate (const int NS = NW == 1 ? 33 : 65): no address arithmetic per shared-memory access.
+__host__ __device__ inline int soa_stride(int n, int nr) { return (n <= 32 && nr <= 32) ? 33 : 65; }
+// leading dimension of H: the tensor-core forward path (!keep) fixes it at 33 / 65 for the same reason
+__host__ __device__ inline int h_ld2(int n, int nr, bool keep) { return keep ? h_ld(nr) : soa_stride(n, nr); }
 
 __host__ __device__ inline int fld_total(bool ground, bool keep) {
     return ground ? (keep ? Fld<true, true>::TOTAL : Fld<true, false>::TOTAL)
                   : (keep ? Fld<false, true>::TOTAL : Fld<false, false>::TOTAL);
 }
-// Tensor-core forward path (rmx_tc.cuh; one warp, n <= 32, nr <= 32, !KEEP): during the assembly the SoA block is overlaid by
-//   W  [n][NW_] at 0 (rows [L_k ; s_k]),  RZ [n][NW_] at n*NW_ (rows [Rt_i ; Z_i]),  H [nr][ld] at tc_h_offset (column-major)
-__host__ __device__ inline bool tc_layout(int n, int nr, bool keep) { return !keep && n <= 32 && nr <= 32; }
-__host__ __device__ inline size_t tc_h_offset(int n, bool ground) {
-    const size_t o = 2 * (size_t)n * (ground ? Fld<true, false>::NW_ : Fld<false, false>::NW_);
-    return (o + 1) & ~(size_t)1;
-}
-__host__ __device__ inline bool h_aliased(int n, int nr, bool ground, bool keep) {
-    if (tc_layout(n, nr, keep)) return true;
-    const int room = ground ? Fld<true, false>::HROOM : Fld<false, false>::HROOM;
-    return !keep && (size_t)nr * h_ld(nr) <= (size_t)room * soa_stride(n, nr);
-}
+// Tensor-core forward path (rmx_tc.cuh; one or two warps, n, nr <= 64, !KEEP): during the assembly the SoA block is overlaid by
+//   W  [CAP][NW_] at 0 (rows [L_k ; s_k]),  RZ [CAP][NW_] behind it (rows [Rt_i ; Z_i]),  H [CAP][LD] behind both (column-major)
+__host__ __device__ inline bool tc_layout(int n, int nr, bool keep) { return !keep && n <= 64 && nr <= 64; }
 __host__ __device__ inline size_t soa_doubles(int n, int nr, bool ground, bool keep) {
-    size_t d = (size_t)soa_stride(n, nr) * fld_total(ground, keep);
-    if (tc_layout(n, nr, keep)) {
-        const size_t need = tc_h_offset(n, ground) + (size_t)((nr + 7) & ~7) * h_ld2(n, nr, keep);  // H padded to whole 8x8 tiles
-        if (need > d) d = need;
-    }
+    const size_t d = (size_t)soa_stride(n, nr) * fld_total(ground, keep);
     return (d + 1) & ~(size_t)1;
 }
 
-// Static shared-memory layout of the tensor-core forward kernels (capacity n = nr = 32 whatever the scene): every vector and
-// table sits at a compile-time offset from the block's base, so no pointer lives in a register and no address is computed.
-template <bool GROUND>
+// Static shared-memory layout of the tensor-core forward kernels (capacity n = nr = 32 NW whatever the scene): every vector
+// and table sits at a compile-time offset from the block's base, so no pointer lives in a register and no address is computed.
+template <bool GROUND, int NW>
 struct TcLayout {
     typedef Fld<GROUND, false> F;
-    static constexpr int CAP = 32, NS = 33, LD = 33;
-    static constexpr int W_OFF = 0;                   // W  [32][NW_]  rows [L_k ; s_k]
-    static constexpr int RZ_OFF = CAP * F::NW_;       // RZ [32][NW_]  rows [Rt_i ; Z_i]
-    static constexpr int H_OFF = 2 * CAP * F::NW_;    // H  [32][33]   column-major, identity padded to whole tiles
+    static constexpr int CAP = 32 * NW, NS = CAP + 1, LD = CAP + 1;
+    static constexpr int W_OFF = 0;                   // W  [CAP][NW_]  rows [L_k ; s_k]
+    static constexpr int RZ_OFF = CAP * F::NW_;       // RZ [CAP][NW_]  rows [Rt_i ; Z_i]
+    static constexpr int H_OFF = 2 * CAP * F::NW_;    // H  [CAP][LD]   column-major, identity padded to whole tiles
     static constexpr int SOA_FIELDS = NS * F::TOTAL;  // the SoA block of eval_base2 (overlaid by W, RZ, H during assembly + LU)
     static constexpr int SOA = ((SOA_FIELDS > H_OFF + CAP * LD ? SOA_FIELDS : H_OFF + CAP * LD) + 1) & ~1;
     static constexpr int NV = 12;                     // q qd dq g dx tau hq0 hqd0 hq1 hqd1 sp1 sp2 (x0, sp0 are unused)
-    static constexpr int VEC = SOA;                   // NV vectors of 32
+    static constexpr int VEC = SOA;                   // NV vectors of CAP
     static constexpr int RED = VEC + NV * CAP;        // 16 + 8 reduction scratch
     static constexpr int ROWBUF = RED + 24;           // 2 x 5 double2 pivot-row buffers (16B aligned: all terms even)
-    static constexpr int IE = ROWBUF + 20;            // int2 ie_s[32]
-    static constexpr int PAR = IE + CAP;              // int par_s[32]
-    static constexpr int REM = PAR + CAP / 2;         // int rem_s[32]
-    static constexpr int TIDX = REM + CAP / 2;        // int tcidx_s[32]
-    static constexpr int TSUB = TIDX + CAP / 2;       // unsigned tcsub_s[32]
-    static constexpr int TANC = TSUB + CAP / 2;       // unsigned tcanc_s[32]
-    static constexpr int TOTAL = (TANC + CAP / 2 + 1) & ~1;
+    static constexpr int IE = ROWBUF + 20;            // int2 ie_s[CAP]
+    static constexpr int PAR = IE + CAP;              // int par_s[CAP]
+    static constexpr int REM = PAR + CAP / 2;         // int rem_s[CAP]
+    static constexpr int TIDX = REM + CAP / 2;        // int tcidx_s[CAP]
+    static constexpr int MASKD = (NW == 1) ? CAP / 2 : CAP;  // tree-relation masks: one bit per joint (32 / 64 bits)
+    static constexpr int TSUB = TIDX + CAP / 2;       // mask tcsub_s[CAP]
+    static constexpr int TANC = TSUB + MASKD;         // mask tcanc_s[CAP]
+    static constexpr int TOTAL = (TANC + MASKD + 1) & ~1;
 };
+template <int NW> struct TcMask { typedef unsigned type; };
+template <> struct TcMask<2> { typedef unsigned long long type; };
 constexpr int LUBUF = 2 * (32 / 2 + 1) * 2;  // doubles: two pivot-row buffers of the warp LU (lu_solve_warp_sm), 16B aligned
 
 __host__ __device__ inline size_t smem_doubles2(int n, int nr, bool ground, bool keep) {
-    if (tc_layout(n, nr, keep)) return ground ? TcLayout<true>::TOTAL : TcLayout<false>::TOTAL;
+    if (tc_layout(n, nr, keep)) {
+        if (n <= 32 && nr <= 32) return ground ? TcLayout<true, 1>::TOTAL : TcLayout<false, 1>::TOTAL;
+        return ground ? TcLayout<true, 2>::TOTAL : TcLayout<false, 2>::TOTAL;
+    }
     size_t d = soa_doubles(n, nr, ground, keep) + LUBUF + (size_t)NVEC * nr + 16 + 8;
-    if (!h_aliased(n, nr, ground, keep)) d += (size_t)nr * h_ld2(n, nr, keep);
+    d += (size_t)nr * h_ld2(n, nr, keep);   // H has its own storage
     d += (size_t)(3 * n + 1) / 2 + 1 + 16;  // int tables {idx,end}/parent, rem[32]
     return (d + 1) & ~(size_t)1;
 }
@@ -118,10 +111,10 @@ struct Ctx2 : Ctx {
     int NS;      // stride (= n|1: odd, so that component-major accesses are conflict free too)
     int2* ie_s;  // [n] {reduced index or -1, subtree end}
     int* par_s;  // [n] parent
-    int* rem_s;  // [32] rows still to be eliminated (blocked LU, rmx_tc.cuh)
-    int* tcidx_s;         // [32] reduced index of joint i or -1            (tensor-core path only)
-    unsigned* tcsub_s;    // [32] bit i set: joint k is in sub(i)
-    unsigned* tcanc_s;    // [32] bit i set: joint k is a proper ancestor of i
+    int* rem_s;  // [CAP] rows still to be eliminated (blocked LU, rmx_tc.cuh)
+    int* tcidx_s;         // [CAP] reduced index of joint i or -1            (tensor-core path only)
+    void* tcsub_s;        // [CAP] TcMask<NW>: bit i set: joint k is in sub(i)
+    void* tcanc_s;        // [CAP] bit i set: joint k is a proper ancestor of i
     double2* tcrow_s;     // [2][5] pivot-row buffers of the blocked LU
     const int* __restrict__ anc;  // [nrounds][n] ancestor tables (global)
     int nrounds;
@@ -168,18 +161,14 @@ __device__ __forceinline__ void ctx2_carve(Ctx2& c, double* sm, int n, int nr, b
     c.tcsub_s = nullptr;
     c.tcanc_s = nullptr;
     c.tcrow_s = nullptr;
-    if (h_aliased(n, nr, ground, keep)) {
-        c.H = c.sa + (size_t)(ground ? Fld<true, false>::HALIAS : Fld<false, false>::HALIAS) * c.NS;
-    } else {
-        p = (double*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
-        c.H = p;
-    }
+    p = (double*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
+    c.H = p;
 }
 
 // Tensor-core forward kernels: the static layout above (nothing depends on n or nr).
-template <bool GROUND>
+template <bool GROUND, int NW>
 __device__ __forceinline__ void ctx2_carve_tc(Ctx2& c, double* sm, int n, int nr) {
-    typedef TcLayout<GROUND> T;
+    typedef TcLayout<GROUND, NW> T;
     c.n = n;
     c.nr = nr;
     c.ld = T::LD;
@@ -210,8 +199,8 @@ __device__ __forceinline__ void ctx2_carve_tc(Ctx2& c, double* sm, int n, int nr
     c.par_s = reinterpret_cast<int*>(sm + T::PAR);
     c.rem_s = reinterpret_cast<int*>(sm + T::REM);
     c.tcidx_s = reinterpret_cast<int*>(sm + T::TIDX);
-    c.tcsub_s = reinterpret_cast<unsigned*>(sm + T::TSUB);
-    c.tcanc_s = reinterpret_cast<unsigned*>(sm + T::TANC);
+    c.tcsub_s = sm + T::TSUB;
+    c.tcanc_s = sm + T::TANC;
     c.H = sm + T::H_OFF;
 }
 
@@ -901,7 +890,7 @@ template <int NW, bool GROUND, bool KEEP>
 __device__ void eval_base2(Ctx2& c, bool deriv) {
     typedef Fld<GROUND, KEEP> F;
     const int t = threadIdx.x;
-    const int n = c.n, NS = (NW == 1) ? 33 : c.NS;
+    const int n = c.n, NS = (NW == 1) ? 33 : 65;
     const int NT = 32 * NW;
     // ---- stage kinematics + joint-local transforms --------------------------------------------------------
     if (t < c.nr) {
@@ -1238,7 +1227,7 @@ template <int NW, bool GROUND, bool KEEP>
 __device__ __forceinline__ void columns_joint(Ctx2& c, int t, int myidx, double sq, double sqd, double sd, double* L, double* s,
                                               double* Rt, double* Z) {
     typedef Fld<GROUND, KEEP> F;
-    const int NS = (NW == 1) ? 33 : c.NS;
+    const int NS = (NW == 1) ? 33 : 65;
     const double cc = c.c;
     if (myidx >= 0) {
         double Vp[6] = {0, 0, 0, 0, 0, 0}, Up[6] = {0, 0, 0, 0, 0, 0};
@@ -1379,7 +1368,7 @@ template <int NW, bool GROUND, bool KEEP>
 __device__ void eval_columns2(Ctx2& c, double sq, double sqd, double sd, double scale, double* out) {
     typedef Fld<GROUND, KEEP> F;
     const int t = threadIdx.x;
-    const int n = c.n, NS = (NW == 1) ? 33 : c.NS, ld = c.ld;
+    const int n = c.n, NS = (NW == 1) ? 33 : 65, ld = c.ld;
     const double cc = c.c;
     const int myidx = (t < n) ? c.ie_s[t].x : -1;
     double Rt[F::NL];  // [c2 (6) ; c1 (3 or 6) ; sq s (3 or 6)]

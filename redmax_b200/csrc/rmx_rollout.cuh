@@ -134,11 +134,11 @@ template <int NW, bool GROUND, bool KEEP, int LIN>
 struct Eval<2, NW, GROUND, KEEP, LIN> {
     typedef Ctx2L C;
     typedef Fld<GROUND, KEEP> F;
-    // one-warp forward kernels assemble and factor the Newton matrix on the FP64 tensor cores (rmx_tc.cuh)
-    static constexpr bool TC = (NW == 1 && !KEEP && LIN == 0);
+    // one- and two-warp forward kernels assemble and factor the Newton matrix on the FP64 tensor cores (rmx_tc.cuh)
+    static constexpr bool TC = (NW <= 2 && !KEEP && LIN == 0);
     static __device__ __forceinline__ void setup(C& c, double* sm, const DevScene& sc, const StepOpts& op) {
         if (TC)
-            ctx2_carve_tc<GROUND>(c, sm, sc.n, sc.nr);
+            ctx2_carve_tc<GROUND, NW>(c, sm, sc.n, sc.nr);
         else
             ctx2_carve(c, sm, sc.n, sc.nr, GROUND, KEEP);
         c.lin_tol = op.lin_tol;
@@ -164,34 +164,35 @@ struct Eval<2, NW, GROUND, KEEP, LIN> {
             c.par_s[j] = sc.jc[j].parent;
         }
         bsync<NW>();
-        if (TC) {  // tree relation as bit masks (lane = joint k): the tile epilogue tests one bit per matrix entry
+        if (TC) {  // tree relation as bit masks (thread = joint k): the tile epilogue tests one bit per matrix entry
+            typedef typename TcMask<NW>::type mask_t;
             const int k = threadIdx.x;
-            unsigned sub = 0u, anc = 0u;
+            mask_t sub = 0, anc = 0;
             int idx = -1;
             if (k < sc.n) {
                 idx = c.ie_s[k].x;
                 const int endk = c.ie_s[k].y;
                 for (int i = 0; i < sc.n; ++i) {
-                    if (i <= k && k < c.ie_s[i].y) sub |= 1u << i;
-                    if (k < i && i < endk) anc |= 1u << i;
+                    if (i <= k && k < c.ie_s[i].y) sub |= (mask_t)1 << i;
+                    if (k < i && i < endk) anc |= (mask_t)1 << i;
                 }
             }
             c.tcidx_s[k] = idx;
-            c.tcsub_s[k] = sub;
-            c.tcanc_s[k] = anc;
+            reinterpret_cast<mask_t*>(c.tcsub_s)[k] = sub;
+            reinterpret_cast<mask_t*>(c.tcanc_s)[k] = anc;
             bsync<NW>();
         }
     }
     static __device__ __forceinline__ void base(C& c, bool deriv) { eval_base2<NW, GROUND, KEEP>(c, deriv); }
     static __device__ __forceinline__ void columns(C& c, double sq, double sqd, double sd, double scale, double* out) {
         if (TC)
-            eval_columns_tc<GROUND>(c, sq, sqd, sd, scale, out);
+            eval_columns_tc<NW, GROUND>(c, sq, sqd, sd, scale, out);
         else
             eval_columns2<NW, GROUND, KEEP>(c, sq, sqd, sd, scale, out);
     }
     static __device__ __forceinline__ void factor_solve(C& c, int* perm, double scale, bool write_back) {
         if (TC) {
-            lu_solve_warp_tc(c.nr, c.H, perm, c.rem_s, c.tcrow_s, c.g, scale, c.dx);
+            lu_solve_tc<NW>(c.nr, c.H, perm, c.rem_s, c.tcrow_s, c.g, scale, c.dx);
         } else if (LIN == 1) {
             c.kry_iters += krylov_solve<NW, GROUND>(c, c.pm, c.H, c.g, scale, c.lin_tol, c.lin_maxit);
         } else if (NW == 1) {
@@ -228,6 +229,13 @@ __device__ __forceinline__ void krylov_reset(Ctx2L& c) { c.kry_iters = 0; }
 // Written as a two-state machine (FULL evaluation with H / residual-only line-search trial) so that the
 // evaluation code has a single call site.
 // ---------------------------------------------------------------------------------------------
+// block-wide AND of a per-thread predicate (all decisions of the Newton loop are block-uniform)
+template <int NW>
+__device__ __forceinline__ bool block_all(bool p) {
+    if (NW == 1) return __all_sync(0xffffffffu, p);
+    return __syncthreads_and(p) != 0;
+}
+
 template <class E, int NW>
 __device__ __forceinline__ int newton_forward(typename E::C& c, const StepOpts& op, int* perm, int& n_iter, int& n_ls) {
     // The reference evaluates g at every line-search trial (nargout == 1) and then [g,H] again at the accepted point when
@@ -235,6 +243,14 @@ __device__ __forceinline__ int newton_forward(typename E::C& c, const StepOpts& 
     // Newton matrix needs; an accepted, not yet converged trial is reused as the next iteration's evaluation (bitwise the
     // same numbers, one forward-kinematics pass less per iteration).  n_iter / n_ls count what the reference would do.
     // Written as a state machine so that the evaluation, assembly and LU code each have a single call site.
+    //
+    // Stalled solves (||g|| cannot get below tol: the reference then runs 10 nr iterations x 20 halvings, silently) are the
+    // stragglers that set the makespan of a batch.  Two shortcuts remove the part of that work whose outcome is already known,
+    // bit for bit (the evaluation is a pure function of the iterate and the step's history):
+    //   * a trial point x0 + alpha dx that rounds to x0 in every component evaluates to f == f0, which the strict `<` rejects,
+    //     and so does every later trial (alpha only shrinks): one evaluation at x0 stands for all of them;
+    //   * if the line search ends there (x == x0), the next iteration starts from the very state this one started from and
+    //     repeats it exactly, until iterMax: counted, not executed.
     const int t = threadIdx.x;
     const int nr = c.nr;
     int status = 0;
@@ -242,6 +258,7 @@ __device__ __forceinline__ int newton_forward(typename E::C& c, const StepOpts& 
     bool trial = false;  // false: first evaluation of the solve; true: line-search trial at x0 + alpha dx
     double f0 = 0.0, x0t = 0.0, dxt = 0.0, alpha = 1.0;
     int iterLs = 1;
+    bool at_x0 = false;  // the trial being evaluated is x0 itself (and it is the last of this line search)
     while (true) {
         E::base(c, true);
         const double gt = (t < nr) ? c.g[t] : 0.0;
@@ -256,12 +273,29 @@ __device__ __forceinline__ int newton_forward(typename E::C& c, const StepOpts& 
             if (!accept) {
                 alpha = 0.5 * alpha;
                 ++iterLs;
-                if (t < nr) c.q[t] = __dadd_rn(x0t, __dmul_rn(alpha, dxt));
+                double xt = x0t;
+                if (t < nr) {
+                    xt = __dadd_rn(x0t, __dmul_rn(alpha, dxt));
+                    c.q[t] = xt;
+                }
+                if (op.shortcuts && iterLs < op.iterLsMax && block_all<NW>(xt == x0t)) {
+                    // this and every remaining trial are x0: evaluate it once, as the last one
+                    n_ls += op.iterLsMax - iterLs;
+                    iterLs = op.iterLsMax;
+                    at_x0 = true;
+                }
                 bsync<NW>();
                 continue;
             }
             if (sqrt(gsum) < op.tol) break;
             if (iter >= op.iterMax) {
+                status |= 2;
+                break;
+            }
+            if (op.shortcuts && (status & 4) && (at_x0 || block_all<NW>(t >= nr || c.q[t] == x0t))) {
+                // exhausted line search that ended on x0: iterations iter+1 .. iterMax repeat this one exactly
+                n_iter += op.iterMax - iter;
+                n_ls += (op.iterMax - iter) * op.iterLsMax;
                 status |= 2;
                 break;
             }
@@ -284,6 +318,7 @@ __device__ __forceinline__ int newton_forward(typename E::C& c, const StepOpts& 
         }
         alpha = 1.0;
         iterLs = 1;
+        at_x0 = false;
         trial = true;
         bsync<NW>();
     }
@@ -625,6 +660,7 @@ __global__ void __launch_bounds__(32 * NW) eval_kernel(EvalArgs a) {
     const int nr = a.sc.nr;
     typename E::C c;
     StepOpts op0;
+    op0.shortcuts = 0;
     op0.lin_tol = 0.0;
     op0.lin_maxit = 0;
     E::setup(c, sm, a.sc, op0);
@@ -672,6 +708,7 @@ __global__ void __launch_bounds__(32 * NW) eval_newton_kernel(EvalArgs a, double
     const int nr = a.sc.nr;
     typename E::C c;
     StepOpts op0;
+    op0.shortcuts = 0;
     op0.lin_tol = 0.0;
     op0.lin_maxit = 0;
     E::setup(c, sm, a.sc, op0);

@@ -20,8 +20,6 @@
 
 namespace rmx {
 
-constexpr int TC_LD = 33;  // leading dimension of H on this path (h_ld2)
-
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
     // volatile: a .sync.aligned instruction must stay where the warp is converged (never sunk into a divergent consumer)
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -30,30 +28,34 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 }
 
 // ---------------------------------------------------------------------------------------------
-// eval_columns_tc: same result as eval_columns2 (out = scale * (sq dg/dq + sqd dg/dqdot + sd dg/d(dqtmp))), one warp,
-// plus the identity padding of rows / columns nr .. 8*ceil(nr/8)-1.
+// eval_columns_tc: same result as eval_columns2 (out = scale * (sq dg/dq + sqd dg/dqdot + sd dg/d(dqtmp))), NW = 1 or 2
+// warps (thread = joint in the per-joint part, the tile rows are dealt round-robin to the warps), plus the identity padding
+// of rows / columns nr .. 8*ceil(nr/8)-1.
 // ---------------------------------------------------------------------------------------------
-template <bool GROUND>
+template <int NW, bool GROUND>
 __device__ __forceinline__ void eval_columns_tc(Ctx2& c, double sq, double sqd, double sd, double scale, double* out) {
     typedef Fld<GROUND, false> F;
-    constexpr int NL = F::NL, NWD = F::NW_, LD = TC_LD;
+    typedef TcLayout<GROUND, NW> T;
+    typedef typename TcMask<NW>::type mask_t;
+    constexpr int NL = F::NL, NWD = F::NW_, LD = T::LD;
     constexpr int KS1 = (NL + 3) / 4;  // k-steps of the subtree part (k = NL, zero padded)
-    const int lane = threadIdx.x & 31;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t4 = lane & 3;
     const int n = c.n, nr = c.nr;
     const double cc = c.c;
     __builtin_assume(__isShared(c.sa));
     __builtin_assume(__isShared(out));
-    const int myidx = (lane < n) ? c.ie_s[lane].x : -1;
+    const int myidx = (tid < n) ? c.ie_s[tid].x : -1;
     double* __restrict__ Wb = c.sa;
-    double* __restrict__ RZb = c.sa + TcLayout<GROUND>::RZ_OFF;
+    double* __restrict__ RZb = c.sa + T::RZ_OFF;
     {
         double Rt[NL], Z[6], L[NL], s[6];
-        columns_joint<1, GROUND, false>(c, lane, myidx, sq, sqd, sd, L, s, Rt, Z);
-        __syncwarp();  // every lane has read S, V, U and its composite blocks: the SoA block may be overwritten
-        if (lane < n) {
-            double* W = Wb + lane * NWD;
-            double* RZ = RZb + lane * NWD;
+        columns_joint<NW, GROUND, false>(c, tid, myidx, sq, sqd, sd, L, s, Rt, Z);
+        bsync<NW>();  // every thread has read S, V, U and its composite blocks: the SoA block may be overwritten
+        if (tid < n) {
+            double* W = Wb + tid * NWD;
+            double* RZ = RZb + tid * NWD;
             if (myidx >= 0) {
 #pragma unroll
                 for (int i = 0; i < NL; ++i) {
@@ -74,12 +76,16 @@ __device__ __forceinline__ void eval_columns_tc(Ctx2& c, double sq, double sqd, 
             }
         }
     }
-    __syncwarp();
+    bsync<NW>();
     const int nT = (n + 7) >> 3;
     const int* __restrict__ idxs = c.tcidx_s;
+    const mask_t* __restrict__ subs = reinterpret_cast<const mask_t*>(c.tcsub_s);
+    const mask_t* __restrict__ ancs = reinterpret_cast<const mask_t*>(c.tcanc_s);
     __builtin_assume(__isShared(idxs));
+    __builtin_assume(__isShared(subs));
+    __builtin_assume(__isShared(ancs));
     // rows >= n of W / RZ are never written: whatever is there only reaches C rows / columns >= n, which are not stored
-    for (int I = 0; I < nT; ++I) {
+    for (int I = (NW == 1 ? 0 : warp); I < nT; I += NW) {
         const int k = 8 * I + g;  // row joint of this lane's A fragments and C elements
         const double* wk = Wb + k * NWD + t4;
         double a1[KS1], a2[2];
@@ -89,14 +95,14 @@ __device__ __forceinline__ void eval_columns_tc(Ctx2& c, double sq, double sqd, 
         a2[1] = (t4 < 2) ? wk[NL + 4] : 0.0;
         // tree relation of row joint k with every column joint, and its reduced index (no row if fixed or k >= n)
         const int idxk = (k < n) ? idxs[k] : -1;
-        const unsigned subk = (idxk >= 0) ? c.tcsub_s[k] : 0u;
-        const unsigned anck = (idxk >= 0) ? c.tcanc_s[k] : 0u;
+        const mask_t subk = (idxk >= 0) ? subs[k] : (mask_t)0;
+        const mask_t anck = (idxk >= 0) ? ancs[k] : (mask_t)0;
         double* orow = out + idxk;
         // epilogue of one tile: pick subtree / ancestor / zero per entry (one bit test each) and store
         auto store_tile = [&](int J, double s0, double s1, double z0, double z1) {
-            const int i0 = 8 * J + 2 * t4;  // column joints i0, i0+1 of this lane's C elements (tcidx_s has 32 entries)
+            const int i0 = 8 * J + 2 * t4;  // column joints i0, i0+1 of this lane's C elements (tcidx_s has CAP entries)
             const int2 ix = *reinterpret_cast<const int2*>(idxs + i0);
-            const unsigned sb = subk >> i0, ab = anck >> i0;
+            const unsigned sb = (unsigned)(subk >> i0), ab = (unsigned)(anck >> i0);
             const double v0 = (sb & 1u) ? s0 : ((ab & 1u) ? z0 : 0.0);  // k in sub(i): L_k . Rt_i ; k proper ancestor of i: s_k . Z_i
             const double v1 = (sb & 2u) ? s1 : ((ab & 2u) ? z1 : 0.0);
             if (idxk >= 0) {
@@ -129,33 +135,40 @@ __device__ __forceinline__ void eval_columns_tc(Ctx2& c, double sq, double sqd, 
             if (two) store_tile(J + 1, sB0, sB1, zB0, zB1);
         }
     }
-    __syncwarp();
+    bsync<NW>();
     // diagonal: joint stiffness / damping / limit terms Kr, Dr (Joint.m:470-481)
     if (myidx >= 0) out[myidx * (LD + 1)] += scale * (-cc * (sq * c.sp2[myidx] + sqd * c.sp1[myidx]));
     if (GROUND && c.npf > 0) {  // off-diagonal blocks of the point forces; RZ row = [c2 ; c1 ; sq s ; Z]
-        const double* rzl = RZb + lane * NWD;
-        pf_cross_pass(c, lane, myidx, rzl + 6, rzl + 12, scale, out, LD, Wb, NWD, NL);
+        const double* rzl = RZb + tid * NWD;
+        pf_cross_pass(c, tid, myidx, rzl + 6, rzl + 12, scale, out, LD, Wb, NWD, NL);
     }
     // identity padding up to a multiple of 8 (the blocked LU runs whole panels and whole tiles)
     const int np8 = (nr + 7) & ~7;
-    for (int col = nr; col < np8; ++col) out[col * LD + lane] = (lane == col) ? 1.0 : 0.0;
-    if (lane < nr)
-        for (int row = nr; row < np8; ++row) out[lane * LD + row] = 0.0;
-    __syncwarp();
+    for (int col = nr; col < np8; ++col) out[col * LD + tid] = (tid == col) ? 1.0 : 0.0;
+    if (tid < nr)
+        for (int row = nr; row < np8; ++row) out[tid * LD + row] = 0.0;
+    bsync<NW>();
 }
 
 // ---------------------------------------------------------------------------------------------
-// lu_solve_warp_tc: dx = scale * H \ rhs for one warp, nr <= 32.  H: column-major, leading dimension 33, padded with an
-// identity block to np8 = 8*ceil(nr/8) rows and columns, in shared memory; overwritten by its factors (rows stay where they
-// are: row perm[k] is the k-th pivot row, unit-lower multipliers left of the diagonal position).  perm, rem: int[32] shared;
-// rowbuf: 2 x 5 double2 shared (pivot-row broadcast inside a panel).
+// lu_solve_tc: dx = scale * H \ rhs for a block of NW = 1 or 2 warps, nr <= 32 NW.  H: column-major, leading dimension
+// 32 NW + 1, padded with an identity block to np8 = 8*ceil(nr/8) rows and columns, in shared memory; overwritten by its factors
+// (rows stay where they are: row perm[k] is the k-th pivot row, unit-lower multipliers left of the diagonal position).
+// perm, rem: int[32 NW] shared; rowbuf: 2 x 5 double2 shared (pivot-row broadcast inside a panel).
+// The panel factorisation (the pivot search is one dependent chain per column) runs in warp 0, lane l holding rows l and, with
+// two warps, l + 32; U12 and the trailing update are spread over all warps.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void lu_solve_warp_tc(int nr, double* H, int* perm, int* rem, double2* rowbuf, const double* rhs,
-                                                 double scale, double* dx) {
-    constexpr int LD = TC_LD;
+template <int NW>
+__device__ __forceinline__ void lu_solve_tc(int nr, double* H, int* perm, int* rem, double2* rowbuf, const double* rhs,
+                                            double scale, double* dx) {
+    constexpr int LD = 32 * NW + 1;
+    constexpr int R = NW;             // rows per lane of warp 0
+    constexpr int MAXI = 4 * NW - 1;  // trailing tile rows / columns at most
     const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t4 = lane & 3;
+    const unsigned ltmask = (1u << lane) - 1u;
     __builtin_assume(__isShared(H));
     __builtin_assume(__isShared(perm));
     __builtin_assume(__isShared(rem));
@@ -164,101 +177,141 @@ __device__ __forceinline__ void lu_solve_warp_tc(int nr, double* H, int* perm, i
     __builtin_assume(__isShared(dx));
     const int NP = (nr + 7) >> 3;
     const int np8 = 8 * NP;
-    bool done = lane >= np8;  // lanes beyond the padded matrix never take part
-    int pos = lane, mypos = -1;
-    double b = (lane < nr) ? scale * rhs[lane] : 0.0;
-    double rdiag = 1.0;
-    double* Hrow = H + lane;  // this lane's row: entry c at Hrow[c * LD]
+    const bool w0 = (NW == 1) || warp == 0;
+    bool done[R];  // rows beyond the padded matrix never take part
+    int pos[R], mypos[R];
+    double b[R], rdiag[R];
+#pragma unroll
+    for (int h = 0; h < R; ++h) {
+        const int row = lane + 32 * h;
+        done[h] = row >= np8;
+        pos[h] = row;
+        mypos[h] = -1;
+        b[h] = (row < nr) ? scale * rhs[row] : 0.0;
+        rdiag[h] = 1.0;
+    }
+    double* Hrow = H + lane;  // this lane's rows: entry c of row lane + 32 h at Hrow[c * LD + 32 h]
     for (int p = 0; p < NP; ++p) {
         const int c0 = 8 * p;
-        // ---- panel: columns c0 .. c0+7 of every row, 8 entries per lane ---------------------------------------------
-        double* Hp = Hrow + c0 * LD;
-        double a[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) a[i] = Hp[i * LD];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int k = c0 + i;
-            // argmax |a[i]| over the rows that are not pivots yet; ties -> smallest LAPACK position (dgetf2's idamax).
-            // |v| >= 0, so the IEEE bit pattern orders like the value: one warp reduction on the high words decides unless two
-            // rows agree in their top 32 bits; only then the low words and the positions are consulted (warp-uniform branch).
-            const double v = fabs(a[i]);
-#ifdef RMX_LU_RCP_EARLY
-            // Experiment (off by default, not yet measured on the GPU): every lane takes the reciprocal of its own candidate while
-            // the argmax reductions are in flight and the pivot lane publishes its one with the row, so the ~60-cycle
-            // MUFU.RCP64H + Newton chain of __drcp_rn leaves the dependency path broadcast -> multiplier -> rank-1 update.
-            // Same number (the pivot lane's correctly rounded 1 / a[i]), hence bitwise the same factors.
-            const double rp_own = __drcp_rn(a[i]);
-#endif
-            const unsigned hi = done ? 0u : (unsigned)__double2hiint(v);
-            const unsigned mh = __reduce_max_sync(FULL, hi);
-            const bool c1 = !done && hi == mh;
-            unsigned cand = __ballot_sync(FULL, c1);
-            if (cand & (cand - 1)) {
-                const unsigned lo = c1 ? (unsigned)__double2loint(v) : 0u;
-                const unsigned ml = __reduce_max_sync(FULL, lo);
-                const bool c2 = c1 && lo == ml;
-                const unsigned pm = __reduce_min_sync(FULL, c2 ? (unsigned)pos : 0xffffu);
-                cand = __ballot_sync(FULL, c2 && (unsigned)pos == pm);
-            }
-            const int src = __ffs(cand) - 1;
-            const int kl = __ffs(__ballot_sync(FULL, !done && pos == k)) - 1;
-            const int pos_src = __shfl_sync(FULL, pos, src);
-            if (lane == kl) pos = pos_src;
-            if (lane == src) {
-                pos = k;
-                done = true;
-                mypos = k;
-            }
-            if (lane == k) perm[k] = src;
-            // the pivot lane publishes its panel row (entries i.. as 128-bit pairs) and right-hand side; two alternating buffers,
-            // so one __syncwarp per pivot step orders both the read-after-write and the next write-after-read
-            double2* buf = rowbuf + 5 * (i & 1);
-            if (lane == src) {
-#pragma unroll
-                for (int j = i / 2; j < 4; ++j) buf[j] = make_double2(a[2 * j], a[2 * j + 1]);
-#ifdef RMX_LU_RCP_EARLY
-                buf[4] = make_double2(b, rp_own);
-#else
-                buf[4] = make_double2(b, 0.0);
-#endif
-            }
-            __syncwarp();
-            double2 u2[4];
-#pragma unroll
-            for (int j = i / 2; j < 4; ++j) u2[j] = buf[j];
-            const double ub = buf[4].x;
-#ifdef RMX_LU_RCP_EARLY
-            const double rp = buf[4].y;
-#else
-            const double piv = (i & 1) ? u2[i / 2].y : u2[i / 2].x;
-            const double rp = __drcp_rn(piv);  // == 1.0 / piv, correctly rounded
-#endif
-            rdiag = (lane == src) ? rp : rdiag;
-            const double l = done ? 0.0 : a[i] * rp;  // l == 0 for rows that are already pivots
-            a[i] = done ? a[i] : l;
-            if (!(i & 1)) a[i + 1] = fma(-l, u2[i / 2].y, a[i + 1]);
-#pragma unroll
-            for (int j = i / 2 + 1; j < 4; ++j) {
-                a[2 * j] = fma(-l, u2[j].x, a[2 * j]);
-                a[2 * j + 1] = fma(-l, u2[j].y, a[2 * j + 1]);
-            }
-            b = fma(-l, ub, b);
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) Hp[i * LD] = a[i];
         const int nt = NP - p - 1;  // trailing tile rows == trailing tile columns
-        if (nt == 0) break;         // warp-uniform
-        // ---- compact list of the rows still to be eliminated: exactly 8*nt of them ----------------------------------
-        const unsigned live = __ballot_sync(FULL, !done);
-        if (!done) rem[__popc(live & ((1u << lane) - 1u))] = lane;
-        __syncwarp();
-        // ---- U12 = L11^-1 A12(pivot rows): lane = trailing column ------------------------------------------------
+        if (w0) {
+            // ---- panel: columns c0 .. c0+7 of every row, 8 entries per row ---------------------------------------------
+            double* Hp = Hrow + c0 * LD;
+            double a[R][8];
+#pragma unroll
+            for (int h = 0; h < R; ++h)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) a[h][i] = Hp[i * LD + 32 * h];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int k = c0 + i;
+                // argmax |a[i]| over the rows that are not pivots yet; ties -> smallest LAPACK position (dgetf2's idamax).
+                // |v| >= 0, so the IEEE bit pattern orders like the value: one warp reduction on the high words decides unless two
+                // rows agree in their top 32 bits; only then the low words and the positions are consulted (warp-uniform branch).
+                double v[R];
+                unsigned hi[R];
+#pragma unroll
+                for (int h = 0; h < R; ++h) {
+                    v[h] = fabs(a[h][i]);
+                    hi[h] = done[h] ? 0u : (unsigned)__double2hiint(v[h]);
+                }
+                const unsigned mh = __reduce_max_sync(FULL, R == 1 ? hi[0] : max(hi[0], hi[R - 1]));
+                bool c1[R];
+                unsigned cand[R];
+#pragma unroll
+                for (int h = 0; h < R; ++h) {
+                    c1[h] = !done[h] && hi[h] == mh;
+                    cand[h] = __ballot_sync(FULL, c1[h]);
+                }
+                const bool multi = (R == 1) ? ((cand[0] & (cand[0] - 1)) != 0u)
+                                            : (__popc(cand[0]) + __popc(cand[R - 1]) > 1);
+                if (multi) {
+                    unsigned lo[R];
+#pragma unroll
+                    for (int h = 0; h < R; ++h) lo[h] = c1[h] ? (unsigned)__double2loint(v[h]) : 0u;
+                    const unsigned ml = __reduce_max_sync(FULL, R == 1 ? lo[0] : max(lo[0], lo[R - 1]));
+                    bool c2[R];
+                    unsigned pl = 0xffffu;
+#pragma unroll
+                    for (int h = 0; h < R; ++h) {
+                        c2[h] = c1[h] && lo[h] == ml;
+                        pl = c2[h] ? min(pl, (unsigned)pos[h]) : pl;
+                    }
+                    const unsigned pm = __reduce_min_sync(FULL, pl);
+#pragma unroll
+                    for (int h = 0; h < R; ++h) cand[h] = __ballot_sync(FULL, c2[h] && (unsigned)pos[h] == pm);
+                }
+                const int sh = (R == 2 && cand[0] == 0u) ? 1 : 0;  // pivot row = src + 32 sh (warp-uniform)
+                const int src = __ffs(sh ? cand[R - 1] : cand[0]) - 1;
+                // LAPACK swaps the pivot row with the row in position k: that row takes over the pivot row's position
+                const int pos_src = __shfl_sync(FULL, sh ? pos[R - 1] : pos[0], src);
+#pragma unroll
+                for (int h = 0; h < R; ++h) {
+                    if (!done[h] && pos[h] == k) pos[h] = pos_src;
+                    if (lane == src && h == sh) {
+                        pos[h] = k;
+                        done[h] = true;
+                        mypos[h] = k;
+                    }
+                }
+                if (lane == (k & 31)) perm[k] = src + 32 * sh;
+                // the pivot lane publishes its panel row (entries i.. as 128-bit pairs) and right-hand side; two alternating buffers,
+                // so one __syncwarp per pivot step orders both the read-after-write and the next write-after-read
+                double2* buf = rowbuf + 5 * (i & 1);
+                if (lane == src) {
+                    if (R == 1 || sh == 0) {
+#pragma unroll
+                        for (int j = i / 2; j < 4; ++j) buf[j] = make_double2(a[0][2 * j], a[0][2 * j + 1]);
+                        buf[4] = make_double2(b[0], 0.0);
+                    } else {
+#pragma unroll
+                        for (int j = i / 2; j < 4; ++j) buf[j] = make_double2(a[R - 1][2 * j], a[R - 1][2 * j + 1]);
+                        buf[4] = make_double2(b[R - 1], 0.0);
+                    }
+                }
+                __syncwarp();
+                double2 u2[4];
+#pragma unroll
+                for (int j = i / 2; j < 4; ++j) u2[j] = buf[j];
+                const double ub = buf[4].x;
+                const double piv = (i & 1) ? u2[i / 2].y : u2[i / 2].x;
+                const double rp = __drcp_rn(piv);  // == 1.0 / piv, correctly rounded
+#pragma unroll
+                for (int h = 0; h < R; ++h) {
+                    rdiag[h] = (lane == src && h == sh) ? rp : rdiag[h];
+                    const double l = done[h] ? 0.0 : a[h][i] * rp;  // l == 0 for rows that are already pivots
+                    a[h][i] = done[h] ? a[h][i] : l;
+                    if (!(i & 1)) a[h][i + 1] = fma(-l, u2[i / 2].y, a[h][i + 1]);
+#pragma unroll
+                    for (int j = i / 2 + 1; j < 4; ++j) {
+                        a[h][2 * j] = fma(-l, u2[j].x, a[h][2 * j]);
+                        a[h][2 * j + 1] = fma(-l, u2[j].y, a[h][2 * j + 1]);
+                    }
+                    b[h] = fma(-l, ub, b[h]);
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < R; ++h)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) Hp[i * LD + 32 * h] = a[h][i];
+            if (nt > 0) {
+                // ---- compact list of the rows still to be eliminated: exactly 8*nt of them ----------------------------------
+                const unsigned live0 = __ballot_sync(FULL, !done[0]);
+                if (!done[0]) rem[__popc(live0 & ltmask)] = lane;
+                if (R == 2) {
+                    const unsigned live1 = __ballot_sync(FULL, !done[R - 1]);
+                    if (!done[R - 1]) rem[__popc(live0) + __popc(live1 & ltmask)] = lane + 32;
+                }
+            }
+        }
+        if (nt == 0) break;  // block-uniform
+        bsync<NW>();
+        // ---- U12 = L11^-1 A12(pivot rows): thread = trailing column ------------------------------------------------
         int pr[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) pr[i] = perm[c0 + i];
-        if (lane < 8 * nt) {
-            double* colp = H + (c0 + 8 + lane) * LD;
+        if (tid < 8 * nt) {
+            double* colp = H + (c0 + 8 + tid) * LD;
             const double* Lp = H + c0 * LD;
             double x[8];
 #pragma unroll
@@ -271,16 +324,16 @@ __device__ __forceinline__ void lu_solve_warp_tc(int nr, double* H, int* perm, i
 #pragma unroll
             for (int i = 1; i < 8; ++i) colp[pr[i]] = x[i];
         }
-        __syncwarp();
-        // ---- A22 -= L21 U12 : 8x8 tiles, 2 DMMAs each ----------------------------------------------------------------
+        bsync<NW>();
+        // ---- A22 -= L21 U12 : 8x8 tiles, 2 DMMAs each; the tile columns are dealt round-robin to the warps ---------------
         // pivot rows of this lane's k-indices t4 and 4 + t4 (B fragments)
         const int prt0 = (t4 == 0) ? pr[0] : (t4 == 1) ? pr[1] : (t4 == 2) ? pr[2] : pr[3];
         const int prt1 = (t4 == 0) ? pr[4] : (t4 == 1) ? pr[5] : (t4 == 2) ? pr[6] : pr[7];
         const double* La = H + (c0 + t4) * LD;  // multipliers of k-index t4 (column c0 + t4): row r at La[r]; 4 + t4 at La[4 LD + r]
-        double af0[3], af1[3];
-        int rI[3];
+        double af0[MAXI], af1[MAXI];
+        int rI[MAXI];
 #pragma unroll
-        for (int I = 0; I < 3; ++I) {
+        for (int I = 0; I < MAXI; ++I) {
             if (I < nt) {
                 const int r = rem[8 * I + g];
                 rI[I] = r;
@@ -288,44 +341,50 @@ __device__ __forceinline__ void lu_solve_warp_tc(int nr, double* H, int* perm, i
                 af1[I] = -La[4 * LD + r];
             }
         }
-        for (int J = 0; J < nt; ++J) {
+        for (int J = (NW == 1 ? 0 : warp); J < nt; J += NW) {
             const int cJ = c0 + 8 + 8 * J;
             const double* Ub = H + (cJ + g) * LD;  // B fragments: U12[k-index][column cJ + g]
             const double bf0 = Ub[prt0], bf1 = Ub[prt1];
             double* Cc = H + (cJ + 2 * t4) * LD;   // C elements: columns cJ + 2 t4, + 1
-            double v0[3], v1[3];
+            double v0[MAXI], v1[MAXI];
 #pragma unroll
-            for (int I = 0; I < 3; ++I)
+            for (int I = 0; I < MAXI; ++I)
                 if (I < nt) {
                     v0[I] = Cc[rI[I]];
                     v1[I] = Cc[LD + rI[I]];
                 }
 #pragma unroll
-            for (int I = 0; I < 3; ++I)  // first k-step of every tile of this column, then the second: independent chains
+            for (int I = 0; I < MAXI; ++I)  // first k-step of every tile of this column, then the second: independent chains
                 if (I < nt) dmma884(v0[I], v1[I], af0[I], bf0);
 #pragma unroll
-            for (int I = 0; I < 3; ++I)
+            for (int I = 0; I < MAXI; ++I)
                 if (I < nt) dmma884(v0[I], v1[I], af1[I], bf1);
 #pragma unroll
-            for (int I = 0; I < 3; ++I)
+            for (int I = 0; I < MAXI; ++I)
                 if (I < nt) {
                     Cc[rI[I]] = v0[I];
                     Cc[LD + rI[I]] = v1[I];
                 }
         }
-        __syncwarp();
+        bsync<NW>();
     }
-    __syncwarp();
-    // ---- back substitution U x = y: the row with pivot position k lives in lane perm[k], y there is b (padding rows: x = 0) --
+    bsync<NW>();
+    // ---- back substitution U x = y: the row with pivot position k is row perm[k], y there is b (padding rows: x = 0) --------
+    if (w0) {
 #pragma unroll 4
-    for (int k = nr - 1; k >= 0; --k) {
-        const int src = perm[k];
-        const double xk = __shfl_sync(FULL, b * rdiag, src);
-        const double u = Hrow[k * LD];
-        b = (mypos >= 0 && mypos < k) ? fma(-u, xk, b) : b;
-        if (lane == k) dx[k] = xk;
+        for (int k = nr - 1; k >= 0; --k) {
+            const int srow = perm[k];
+            const double mine = (R == 2 && (srow & 32)) ? b[R - 1] * rdiag[R - 1] : b[0] * rdiag[0];
+            const double xk = __shfl_sync(FULL, mine, srow & 31);
+#pragma unroll
+            for (int h = 0; h < R; ++h) {
+                const double u = Hrow[k * LD + 32 * h];
+                b[h] = (mypos[h] >= 0 && mypos[h] < k) ? fma(-u, xk, b[h]) : b[h];
+            }
+            if (lane == (k & 31)) dx[k] = xk;
+        }
     }
-    __syncwarp();
+    bsync<NW>();
 }
 
 }  // namespace rmx
