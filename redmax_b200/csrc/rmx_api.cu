@@ -731,7 +731,9 @@ template <bool ADJ>
 static int launch_fwd(const rmx_scene* s, const RolloutArgs& a, cudaStream_t st, DevCopy* dc = nullptr) {
     const int nw = warps_for(s);
     const bool g = s->has_ground != 0;
-    const size_t smem = (scene_smem_doubles(s, ADJ) + (ADJ ? 6 * (size_t)s->nr : 0)) * sizeof(double);
+    size_t smem = (scene_smem_doubles(s, ADJ) + (ADJ ? 6 * (size_t)s->nr : 0)) * sizeof(double);
+    // the one-warp adjoint forward kernel of a scene without external forces runs on the tensor-core path (TcLayoutA)
+    if (ADJ && s->impl == 2 && nw == 1 && tc_adjoint(s->n, s->nr, g)) smem = (size_t)TcLayoutA::TOTAL * sizeof(double);
     if (smem > 227 * 1024) return fail(RMX_ELIMIT, "scene does not fit the 227 KB shared memory of one SM");
     rmx_fwd_launcher f = fwd_launcher(s->impl, nw, g, ADJ, 0);
     if (!f) return fail(RMX_ELIMIT, "no forward kernel for this scene size");

@@ -19,9 +19,10 @@
 
 namespace rmx {
 
-// Field offsets in the SoA block (units: NS doubles, NS = n|1).  KEEP = body frames stay in shared memory and H has its
-// own storage (adjoint / test kernels); otherwise H aliases the fields that are dead once the Newton matrix is assembled.
-template <bool GROUND, bool KEEP>
+// Field offsets in the SoA block (units: NS doubles).  KEEP = 1: body frames and twists stay in shared memory and H has its
+// own storage (test hooks, Krylov and external-force adjoint kernels); KEEP = 2: body frames only (tensor-core adjoint kernel);
+// KEEP = 0: nothing kept, H aliases the fields that are dead once the Newton matrix is assembled.
+template <bool GROUND, int KEEP>
 struct Fld {
     static constexpr int NL = GROUND ? 18 : 12;  // length of L_k
     static constexpr int NW_ = NL + 6;           // W_k = [L_k ; s_k], stored joint-major (AoS) in region XA
@@ -42,8 +43,8 @@ struct Fld {
     static constexpr int NCOMP = GROUND ? 100 : 28;  // composite components starting at CF
     static constexpr int RB = CF + NCOMP;        // 9  body frame            (KEEP only)
     static constexpr int PB = RB + 9;            // 3
-    static constexpr int PHI = PB + 3;           // 6
-    static constexpr int TOTAL = CF + NCOMP + (KEEP ? 18 : 0);
+    static constexpr int PHI = PB + 3;           // 6  body twist            (KEEP == 1 only)
+    static constexpr int TOTAL = CF + NCOMP + (KEEP == 1 ? 18 : (KEEP == 2 ? 12 : 0));
     static constexpr int HALIAS = V;             // H may live in [V, CF + NCOMP) when !KEEP
     static constexpr int HROOM = 12 + NCOMP;
 };
@@ -55,8 +56,8 @@ __host__ __device__ inline int soa_stride(int n, int nr) { return (n <= 32 && nr
 __host__ __device__ inline int h_ld2(int n, int nr, bool keep) { return keep ? h_ld(nr) : soa_stride(n, nr); }
 
 __host__ __device__ inline int fld_total(bool ground, bool keep) {
-    return ground ? (keep ? Fld<true, true>::TOTAL : Fld<true, false>::TOTAL)
-                  : (keep ? Fld<false, true>::TOTAL : Fld<false, false>::TOTAL);
+    return ground ? (keep ? Fld<true, 1>::TOTAL : Fld<true, 0>::TOTAL)
+                  : (keep ? Fld<false, 1>::TOTAL : Fld<false, 0>::TOTAL);
 }
 // Tensor-core forward path (rmx_tc.cuh; one or two warps, n, nr <= 64, !KEEP): during the assembly the SoA block is overlaid by
 //   W  [CAP][NW_] at 0 (rows [L_k ; s_k]),  RZ [CAP][NW_] behind it (rows [Rt_i ; Z_i]),  H [CAP][LD] behind both (column-major)
@@ -70,7 +71,8 @@ __host__ __device__ inline size_t soa_doubles(int n, int nr, bool ground, bool k
 // and table sits at a compile-time offset from the block's base, so no pointer lives in a register and no address is computed.
 template <bool GROUND, int NW>
 struct TcLayout {
-    typedef Fld<GROUND, false> F;
+    typedef Fld<GROUND, 0> F;
+    static constexpr int KEEP = 0;
     static constexpr int CAP = 32 * NW, NS = CAP + 1, LD = CAP + 1;
     static constexpr int W_OFF = 0;                   // W  [CAP][NW_]  rows [L_k ; s_k]
     static constexpr int RZ_OFF = CAP * F::NW_;       // RZ [CAP][NW_]  rows [Rt_i ; Z_i]
@@ -90,6 +92,35 @@ struct TcLayout {
     static constexpr int TANC = TSUB + MASKD;         // mask tcanc_s[CAP]
     static constexpr int TOTAL = (TANC + MASKD + 1) & ~1;
 };
+// Tensor-core adjoint forward kernel (one warp, no external forces): the composite blocks must survive the assembly, because
+// the tape needs M and D (two more passes with other seeds) besides the Newton matrix.  W overlays region XA (the joint frames
+// of the scans, dead after eval_base2), RZ has its own storage, the M and D tiles go straight to the tape in global memory and
+// the H pass comes last, so H may overlay the fields from S on; the body frames (task Jacobian rows) sit behind it.
+struct TcLayoutA {
+    typedef Fld<false, 2> F;
+    static constexpr int KEEP = 2;
+    static constexpr int CAP = 32, NS = 33, LD = 33;
+    static constexpr int W_OFF = 0;
+    static constexpr int H_OFF = F::XA * NS;          // 594: behind W, over S, V, U, composite blocks (ends before RB)
+    static constexpr int SOA = (NS * F::TOTAL + 1) & ~1;
+    static constexpr int RZ_OFF = SOA;
+    static constexpr int JROWS = RZ_OFF + CAP * F::NW_;  // 6 x CAP rows of J of the task body
+    static constexpr int NV = 12;
+    static constexpr int VEC = JROWS + 6 * CAP;
+    static constexpr int RED = VEC + NV * CAP;
+    static constexpr int ROWBUF = RED + 24;
+    static constexpr int IE = ROWBUF + 20;
+    static constexpr int PAR = IE + CAP;
+    static constexpr int REM = PAR + CAP / 2;
+    static constexpr int TIDX = REM + CAP / 2;
+    static constexpr int TSUB = TIDX + CAP / 2;
+    static constexpr int TANC = TSUB + CAP / 2;
+    static constexpr int TOTAL = (TANC + CAP / 2 + 1) & ~1;
+    static_assert(CAP * F::NW_ <= F::XA * NS, "W must fit region XA");
+    static_assert(H_OFF + CAP * LD <= NS * F::RB, "H must end before the kept body frames");
+};
+// the adjoint forward kernel of a scene runs on the tensor-core path if ...
+__host__ __device__ inline bool tc_adjoint(int n, int nr, bool ground) { return !ground && n <= 32 && nr <= 32; }
 template <int NW> struct TcMask { typedef unsigned type; };
 template <> struct TcMask<2> { typedef unsigned long long type; };
 constexpr int LUBUF = 2 * (32 / 2 + 1) * 2;  // doubles: two pivot-row buffers of the warp LU (lu_solve_warp_sm), 16B aligned
@@ -115,6 +146,7 @@ struct Ctx2 : Ctx {
     int* tcidx_s;         // [CAP] reduced index of joint i or -1            (tensor-core path only)
     void* tcsub_s;        // [CAP] TcMask<NW>: bit i set: joint k is in sub(i)
     void* tcanc_s;        // [CAP] bit i set: joint k is a proper ancestor of i
+    double* jrows;        // [6][CAP] rows of J of the task body (adjoint kernels)
     double2* tcrow_s;     // [2][5] pivot-row buffers of the blocked LU
     const int* __restrict__ anc;  // [nrounds][n] ancestor tables (global)
     int nrounds;
@@ -161,6 +193,7 @@ __device__ __forceinline__ void ctx2_carve(Ctx2& c, double* sm, int n, int nr, b
     c.tcsub_s = nullptr;
     c.tcanc_s = nullptr;
     c.tcrow_s = nullptr;
+    c.jrows = nullptr;
     p = (double*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
     c.H = p;
 }
@@ -202,6 +235,46 @@ __device__ __forceinline__ void ctx2_carve_tc(Ctx2& c, double* sm, int n, int nr
     c.tcsub_s = sm + T::TSUB;
     c.tcanc_s = sm + T::TANC;
     c.H = sm + T::H_OFF;
+    c.jrows = nullptr;
+}
+
+// Tensor-core adjoint forward kernel: TcLayoutA
+__device__ __forceinline__ void ctx2_carve_tca(Ctx2& c, double* sm, int n, int nr) {
+    typedef TcLayoutA T;
+    c.n = n;
+    c.nr = nr;
+    c.ld = T::LD;
+    c.NS = T::NS;
+    c.sa = sm;
+    c.lubuf = nullptr;
+    c.rec1 = nullptr;
+    c.rec2 = nullptr;
+    c.KD = nullptr;
+    double* v = sm + T::VEC;
+    c.q = v;
+    c.qd = v + 1 * T::CAP;
+    c.dq = v + 2 * T::CAP;
+    c.g = v + 3 * T::CAP;
+    c.dx = v + 4 * T::CAP;
+    c.x0 = nullptr;
+    c.sp0 = nullptr;
+    c.tau = v + 5 * T::CAP;
+    c.hq0 = v + 6 * T::CAP;
+    c.hqd0 = v + 7 * T::CAP;
+    c.hq1 = v + 8 * T::CAP;
+    c.hqd1 = v + 9 * T::CAP;
+    c.sp1 = v + 10 * T::CAP;
+    c.sp2 = v + 11 * T::CAP;
+    c.red = sm + T::RED;
+    c.tcrow_s = reinterpret_cast<double2*>(sm + T::ROWBUF);
+    c.ie_s = reinterpret_cast<int2*>(sm + T::IE);
+    c.par_s = reinterpret_cast<int*>(sm + T::PAR);
+    c.rem_s = reinterpret_cast<int*>(sm + T::REM);
+    c.tcidx_s = reinterpret_cast<int*>(sm + T::TIDX);
+    c.tcsub_s = sm + T::TSUB;
+    c.tcanc_s = sm + T::TANC;
+    c.H = sm + T::H_OFF;
+    c.jrows = sm + T::JROWS;
 }
 
 #define SA(f, k, j) c.sa[(size_t)((f) + (k)) * NS + (j)]
@@ -886,7 +959,7 @@ __device__ __forceinline__ void pf_cross_pass(Ctx2& c, int t, int myidx, const d
 // ---------------------------------------------------------------------------------------------
 // eval_base2: residual g at iterate c.q (and, if deriv, the composite blocks eval_columns2 needs).
 // ---------------------------------------------------------------------------------------------
-template <int NW, bool GROUND, bool KEEP>
+template <int NW, bool GROUND, int KEEP>
 __device__ void eval_base2(Ctx2& c, bool deriv) {
     typedef Fld<GROUND, KEEP> F;
     const int t = threadIdx.x;
@@ -1119,8 +1192,10 @@ __device__ void eval_base2(Ctx2& c, bool deriv) {
             for (int i = 0; i < 9; ++i) SA(F::RB, i, t) = Rb[i];
 #pragma unroll
             for (int i = 0; i < 3; ++i) SA(F::PB, i, t) = pb[i];
+            if (KEEP == 1) {
 #pragma unroll
-            for (int i = 0; i < 6; ++i) SA(F::PHI, i, t) = phi[i];
+                for (int i = 0; i < 6; ++i) SA(F::PHI, i, t) = phi[i];
+            }
         }
 #pragma unroll
         for (int i = 0; i < 6; ++i) SA(F::CF, i, t) = Fw[i];
@@ -1223,7 +1298,7 @@ __device__ void eval_base2(Ctx2& c, bool deriv) {
 // Per-joint part of the Newton-matrix assembly: from joint t's screw, its parent's V and U and its composite blocks, the
 // row vector L_t (so that H[t][i] = L_t . Rt_i for t in sub(i)), and the column vectors Rt_t = [c2 ; c1 ; sq s] and Z_t
 // (H[k][t] = s_k . Z_t for proper ancestors k).  Reads shared memory only; results stay in registers.
-template <int NW, bool GROUND, bool KEEP>
+template <int NW, bool GROUND, int KEEP>
 __device__ __forceinline__ void columns_joint(Ctx2& c, int t, int myidx, double sq, double sqd, double sd, double* L, double* s,
                                               double* Rt, double* Z) {
     typedef Fld<GROUND, KEEP> F;
@@ -1364,7 +1439,7 @@ __device__ __forceinline__ void columns_joint(Ctx2& c, int t, int myidx, double 
 // ---------------------------------------------------------------------------------------------
 // eval_columns2: out (nr x ld column-major) = scale * ( sq dg/dq + sqd dg/dqdot + sd dg/d(dqtmp) ), from the composite blocks.
 // ---------------------------------------------------------------------------------------------
-template <int NW, bool GROUND, bool KEEP>
+template <int NW, bool GROUND, int KEEP>
 __device__ void eval_columns2(Ctx2& c, double sq, double sqd, double sd, double scale, double* out) {
     typedef Fld<GROUND, KEEP> F;
     const int t = threadIdx.x;

@@ -77,7 +77,7 @@ __device__ __forceinline__ void krylov_reset(Ctx&) {}
 //   IMPL 1 : rmx_device.cuh  -- serial tree sweeps + per-(column, body) tangent sweep (kept for n > 64 and as cross-check)
 //   IMPL 2 : rmx_fast.cuh    -- scans + composite blocks + (one warp) register LU
 // ---------------------------------------------------------------------------------------------
-template <int IMPL, int NW, bool GROUND, bool KEEP, int LIN>
+template <int IMPL, int NW, bool GROUND, bool KEEP, int LIN, bool ATC = false>
 struct Eval;
 
 struct Ctx2L : Ctx2 {  // fast-path context + state of the Krylov linear solve (LIN == 1)
@@ -87,9 +87,11 @@ struct Ctx2L : Ctx2 {  // fast-path context + state of the Krylov linear solve (
     int kry_iters;
 };
 
-template <int NW, bool GROUND, bool KEEP, int LIN>
-struct Eval<1, NW, GROUND, KEEP, LIN> {
+template <int NW, bool GROUND, bool KEEP, int LIN, bool ATC>
+struct Eval<1, NW, GROUND, KEEP, LIN, ATC> {
     typedef Ctx C;
+    static constexpr bool TCA = false;
+    static __device__ __forceinline__ double* jrows(const C& c) { return c.H + (size_t)c.nr * c.ld; }
     static __device__ __forceinline__ size_t extra_off(const C& c) { return (size_t)c.nr * c.ld; }
     static __device__ __forceinline__ void setup(C& c, double* sm, const DevScene& sc, const StepOpts&) {
         ctx_carve(c, sm, sc.n, sc.nr, GROUND);
@@ -130,15 +132,21 @@ struct Eval<1, NW, GROUND, KEEP, LIN> {
     }
 };
 
-template <int NW, bool GROUND, bool KEEP, int LIN>
-struct Eval<2, NW, GROUND, KEEP, LIN> {
+template <int NW, bool GROUND, bool KEEP, int LIN, bool ATC>
+struct Eval<2, NW, GROUND, KEEP, LIN, ATC> {
     typedef Ctx2L C;
-    typedef Fld<GROUND, KEEP> F;
-    // one- and two-warp forward kernels assemble and factor the Newton matrix on the FP64 tensor cores (rmx_tc.cuh)
+    // one- and two-warp forward kernels assemble and factor the Newton matrix on the FP64 tensor cores (rmx_tc.cuh); so does
+    // the one-warp adjoint forward kernel of scenes without external forces (TCA, layout TcLayoutA)
     static constexpr bool TC = (NW <= 2 && !KEEP && LIN == 0);
+    static constexpr bool TCA = (ATC && NW == 1 && !GROUND && KEEP && LIN == 0);
+    static constexpr int KF = TCA ? 2 : (KEEP ? 1 : 0);  // which fields eval_base2 keeps (Fld<GROUND, KF>)
+    typedef Fld<GROUND, KF> F;
+    static __device__ __forceinline__ double* jrows(const C& c) { return TCA ? c.jrows : c.H + (size_t)c.nr * c.ld; }
     static __device__ __forceinline__ void setup(C& c, double* sm, const DevScene& sc, const StepOpts& op) {
         if (TC)
             ctx2_carve_tc<GROUND, NW>(c, sm, sc.n, sc.nr);
+        else if (TCA)
+            ctx2_carve_tca(c, sm, sc.n, sc.nr);
         else
             ctx2_carve(c, sm, sc.n, sc.nr, GROUND, KEEP);
         c.lin_tol = op.lin_tol;
@@ -164,7 +172,7 @@ struct Eval<2, NW, GROUND, KEEP, LIN> {
             c.par_s[j] = sc.jc[j].parent;
         }
         bsync<NW>();
-        if (TC) {  // tree relation as bit masks (thread = joint k): the tile epilogue tests one bit per matrix entry
+        if (TC || TCA) {  // tree relation as bit masks (thread = joint k): the tile epilogue tests one bit per matrix entry
             typedef typename TcMask<NW>::type mask_t;
             const int k = threadIdx.x;
             mask_t sub = 0, anc = 0;
@@ -183,15 +191,21 @@ struct Eval<2, NW, GROUND, KEEP, LIN> {
             bsync<NW>();
         }
     }
-    static __device__ __forceinline__ void base(C& c, bool deriv) { eval_base2<NW, GROUND, KEEP>(c, deriv); }
+    static __device__ __forceinline__ void base(C& c, bool deriv) { eval_base2<NW, GROUND, KF>(c, deriv); }
     static __device__ __forceinline__ void columns(C& c, double sq, double sqd, double sd, double scale, double* out) {
         if (TC)
-            eval_columns_tc<NW, GROUND>(c, sq, sqd, sd, scale, out);
+            eval_columns_tc<NW, GROUND, TcLayout<GROUND, NW>, false>(c, sq, sqd, sd, scale, out);
+        else if (TCA)
+            eval_columns_tc<1, false, TcLayoutA, false>(c, sq, sqd, sd, scale, out);
         else
-            eval_columns2<NW, GROUND, KEEP>(c, sq, sqd, sd, scale, out);
+            eval_columns2<NW, GROUND, KF>(c, sq, sqd, sd, scale, out);
+    }
+    // adjoint tape: scale * (...) as nr x nr row-major straight to global memory (TCA only)
+    static __device__ __forceinline__ void columns_global(C& c, double sq, double sqd, double sd, double scale, double* out) {
+        eval_columns_tc<1, false, TcLayoutA, true>(c, sq, sqd, sd, scale, out);
     }
     static __device__ __forceinline__ void factor_solve(C& c, int* perm, double scale, bool write_back) {
-        if (TC) {
+        if (TC || TCA) {
             lu_solve_tc<NW>(c.nr, c.H, perm, c.rem_s, c.tcrow_s, c.g, scale, c.dx);
         } else if (LIN == 1) {
             c.kry_iters += krylov_solve<NW, GROUND>(c, c.pm, c.H, c.g, scale, c.lin_tol, c.lin_maxit);
@@ -372,7 +386,7 @@ __device__ __forceinline__ int newton_adjoint(typename E::C& c, const StepOpts& 
             store_rowmajor<NW>(c, c.H, tD);
             if (want_J) {
                 // J(idxM(body), :) : column of joint k is Ad(E_body^-1) s_k for ancestors-or-self k of the body, else 0
-                double* Jb = c.H + (size_t)nr * ld;
+                double* Jb = E::jrows(c);
                 if (t < c.n && c.jc[t].idx >= 0) {
                     double col[6] = {0, 0, 0, 0, 0, 0};
                     if (t <= jb && jb < c.jc[t].end) {
@@ -403,6 +417,91 @@ __device__ __forceinline__ int newton_adjoint(typename E::C& c, const StepOpts& 
     return status;
 }
 
+// The same Newton iteration for the tensor-core adjoint kernel (Eval::TCA).  The assembly overwrites the composite blocks, and
+// the tape needs three matrices of the last evaluation point (H, M, D): whether an evaluation is the last one is known from its
+// residual before anything is assembled (converged, or iterMax reached), so M and D are formed first, their tiles going
+// straight to the tape, and the Newton matrix last.  Only a diverging step (||dx|| > dxMax, known after the solve) has to
+// evaluate the point once more for M and D.
+template <class E>
+__device__ __forceinline__ void adjoint_tape_md(typename E::C& c, double* __restrict__ tM, double* __restrict__ tD, bool want_J, int jb) {
+    const int t = threadIdx.x;
+    E::columns_global(c, 0.0, 0.0, 1.0, 1.0, tM);           // M = dg/d(dqtmp)
+    E::columns_global(c, 0.0, 1.0, 0.0, -1.0 / c.c, tD);    // D = df/dqdot = -(1/cK) dg/dqdot
+    if (want_J) {
+        // J(idxM(body), :) : column of joint k is Ad(E_body^-1) s_k for ancestors-or-self k of the body, else 0
+        double* Jb = E::jrows(c);
+        if (t < c.n && c.jc[t].idx >= 0) {
+            double col[6] = {0, 0, 0, 0, 0, 0};
+            if (t <= jb && jb < c.jc[t].end) {
+                double Rb[9], pb[3], st[6];
+                E::body_frame(c, jb, Rb, pb);
+                E::screw(c, t, st);
+                xm_w2b(Rb, pb, st, col);
+            }
+#pragma unroll
+            for (int i = 0; i < 6; ++i) Jb[6 * c.jc[t].idx + i] = col[i];
+        }
+        __syncwarp();
+    }
+}
+
+template <class E>
+__device__ __forceinline__ int newton_adjoint_tc(typename E::C& c, const StepOpts& op, int* perm, int& n_iter, bool save,
+                                                 double* __restrict__ tA, double* __restrict__ tM, double* __restrict__ tD,
+                                                 bool want_J, int jb) {
+    const int t = threadIdx.x;
+    const int nr = c.nr, ldt = h_ld(nr);
+    constexpr int LD = TcLayoutA::LD;
+    int status = 0;
+    int iter = 1;
+    bool redo = false;  // second evaluation of a diverged point, for M and D only (single call site for every phase)
+    while (true) {
+        E::base(c, true);
+        const double gt = (t < nr) ? c.g[t] : 0.0;
+        const double gsum = block_sum<1>(gt * gt, c.red);
+        const bool conv = sqrt(gsum) < op.tol;
+        const bool lastk = conv || iter >= op.iterMax;
+        if ((lastk || redo) && save) adjoint_tape_md<E>(c, tM, tD, want_J, jb);
+        if (redo) {
+            status |= 1;
+            break;
+        }
+        E::columns(c, 1.0, c.beta, 1.0, 1.0, c.H);
+        E::factor_solve(c, perm, -1.0, false);
+        const double dxt = (t < nr) ? c.dx[t] : 0.0;
+        const double dxn = sqrt(block_sum<1>(dxt * dxt, c.red));
+        ++n_iter;
+        const bool diverged = dxn > op.dxMax;
+        if ((lastk || diverged) && save) {
+            // lu(H,'vector'): the blocked LU leaves every row where it was (row perm[k] is the k-th pivot row); the tape wants
+            // the factors in pivot order, column-major with leading dimension nr|1
+            for (int e = t; e < nr * ldt; e += 32) {
+                const int cI = e / ldt, k = e - cI * ldt;
+                tA[e] = (k < nr) ? c.H[cI * LD + perm[k]] : 0.0;
+            }
+            if (t < nr) reinterpret_cast<int*>(tA + (size_t)nr * ldt + nr)[t] = perm[t];
+            __syncwarp();
+        }
+        if (diverged) {
+            if (save && !lastk) {  // x stays at this evaluation point: evaluate it once more for M, D (and J)
+                redo = true;
+                continue;
+            }
+            status |= 1;
+            break;
+        }
+        if (t < nr) c.q[t] = __dadd_rn(c.q[t], dxt);
+        __syncwarp();
+        if (conv) break;
+        if (iter >= op.iterMax) {
+            status |= 2;
+            break;
+        }
+        ++iter;
+    }
+    return status;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Forward rollout kernel: simLoop of driverRedMaxBDF1.m:57-91 / driverRedMaxBDF2.m:57-125 (ADJ = false) and of
 // driverRedMaxAdjointBDF1.m:65-102 / driverRedMaxAdjointBDF2.m:65-136 (ADJ = true), one block per rollout.
@@ -418,7 +517,7 @@ __device__ __forceinline__ int newton_adjoint(typename E::C& c, const StepOpts& 
 #define RMX_FWD_BOUNDS __maxnreg__((NW == 1 && !ADJ && LIN == 0 && IMPL == 2) ? RMX_MAXNREG_FWD : 255)
 template <int NW, bool GROUND, bool ADJ, int IMPL, int LIN>
 __global__ void RMX_FWD_BOUNDS rollout_fwd_kernel(RolloutArgs a) {
-    typedef Eval<IMPL, NW, GROUND, ADJ || LIN == 1, LIN> E;
+    typedef Eval<IMPL, NW, GROUND, ADJ || LIN == 1, LIN, ADJ> E;
     extern __shared__ double2 smem_raw[];
     double* sm = reinterpret_cast<double*>(smem_raw);
     __shared__ int perm_s[32 * NW];
@@ -525,9 +624,14 @@ __global__ void RMX_FWD_BOUNDS rollout_fwd_kernel(RolloutArgs a) {
                     // the BDF2 adjoint driver keeps only the second SDIRK sub-solve's tape (driverRedMaxAdjointBDF2.m:88,96)
                     const bool save = stage != ST_SDIRK_A;
                     const size_t rec = (size_t)b * op.nsteps + k;
-                    status |= newton_adjoint<E, NW>(c, op, perm_s, n_iter, save, a.tape.A + rec * a.tape.sza,
-                                                         a.tape.M + rec * nr * nr, a.tape.D + rec * nr * nr,
-                                                         save && is_obj, a.task.body);
+                    if constexpr (E::TCA)
+                        status |= newton_adjoint_tc<E>(c, op, perm_s, n_iter, save, a.tape.A + rec * a.tape.sza,
+                                                       a.tape.M + rec * nr * nr, a.tape.D + rec * nr * nr, save && is_obj,
+                                                       a.task.body);
+                    else
+                        status |= newton_adjoint<E, NW>(c, op, perm_s, n_iter, save, a.tape.A + rec * a.tape.sza,
+                                                        a.tape.M + rec * nr * nr, a.tape.D + rec * nr * nr, save && is_obj,
+                                                        a.task.body);
                 } else {
                     status |= newton_forward<E, NW>(c, op, perm_s, n_iter, n_ls);
                 }
@@ -588,11 +692,11 @@ __global__ void RMX_FWD_BOUNDS rollout_fwd_kernel(RolloutArgs a) {
                         v6[i] *= a.task.wpos;
                         v6[3 + i] = y[i] * a.task.wpos;
                     }
-                    if (t < nr) dPdq = dot6(c.H + (size_t)nr * c.ld + 6 * t, v6);
+                    if (t < nr) dPdq = dot6(E::jrows(c) + 6 * t, v6);
                 }
                 if (t < nr) {
                     double* recA = a.tape.A + ((size_t)b * op.nsteps + k) * a.tape.sza;
-                    recA[(size_t)nr * c.ld + t] = dPdq;
+                    recA[(size_t)nr * h_ld(nr) + t] = dPdq;
                 }
             }
             bsync<NW>();

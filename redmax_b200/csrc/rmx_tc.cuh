@@ -32,10 +32,12 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // warps (thread = joint in the per-joint part, the tile rows are dealt round-robin to the warps), plus the identity padding
 // of rows / columns nr .. 8*ceil(nr/8)-1.
 // ---------------------------------------------------------------------------------------------
-template <int NW, bool GROUND>
+// T: the shared-memory layout (TcLayout<GROUND, NW> of the forward kernels, TcLayoutA of the adjoint forward kernel).
+// TOGLOBAL: the tiles go straight to `out` in GLOBAL memory, nr x nr ROW-major (the adjoint tape's M and D), with the
+// joint-level diagonal term folded into the epilogue; otherwise `out` is the shared-memory image of H (column-major, T::LD).
+template <int NW, bool GROUND, class T, bool TOGLOBAL>
 __device__ __forceinline__ void eval_columns_tc(Ctx2& c, double sq, double sqd, double sd, double scale, double* out) {
-    typedef Fld<GROUND, false> F;
-    typedef TcLayout<GROUND, NW> T;
+    typedef typename T::F F;
     typedef typename TcMask<NW>::type mask_t;
     constexpr int NL = F::NL, NWD = F::NW_, LD = T::LD;
     constexpr int KS1 = (NL + 3) / 4;  // k-steps of the subtree part (k = NL, zero padded)
@@ -45,13 +47,13 @@ __device__ __forceinline__ void eval_columns_tc(Ctx2& c, double sq, double sqd, 
     const int n = c.n, nr = c.nr;
     const double cc = c.c;
     __builtin_assume(__isShared(c.sa));
-    __builtin_assume(__isShared(out));
+    if (!TOGLOBAL) __builtin_assume(__isShared(out));
     const int myidx = (tid < n) ? c.ie_s[tid].x : -1;
-    double* __restrict__ Wb = c.sa;
+    double* __restrict__ Wb = c.sa + T::W_OFF;
     double* __restrict__ RZb = c.sa + T::RZ_OFF;
     {
         double Rt[NL], Z[6], L[NL], s[6];
-        columns_joint<NW, GROUND, false>(c, tid, myidx, sq, sqd, sd, L, s, Rt, Z);
+        columns_joint<NW, GROUND, T::KEEP>(c, tid, myidx, sq, sqd, sd, L, s, Rt, Z);
         bsync<NW>();  // every thread has read S, V, U and its composite blocks: the SoA block may be overwritten
         if (tid < n) {
             double* W = Wb + tid * NWD;
@@ -97,7 +99,9 @@ __device__ __forceinline__ void eval_columns_tc(Ctx2& c, double sq, double sqd, 
         const int idxk = (k < n) ? idxs[k] : -1;
         const mask_t subk = (idxk >= 0) ? subs[k] : (mask_t)0;
         const mask_t anck = (idxk >= 0) ? ancs[k] : (mask_t)0;
-        double* orow = out + idxk;
+        double* orow = TOGLOBAL ? out + (idxk >= 0 ? idxk : 0) * nr : out + idxk;
+        // joint stiffness / damping / limit terms Kr, Dr (Joint.m:470-481) of this row's diagonal entry
+        const double dgk = (TOGLOBAL && idxk >= 0) ? -cc * (sq * c.sp2[idxk] + sqd * c.sp1[idxk]) : 0.0;
         // epilogue of one tile: pick subtree / ancestor / zero per entry (one bit test each) and store
         auto store_tile = [&](int J, double s0, double s1, double z0, double z1) {
             const int i0 = 8 * J + 2 * t4;  // column joints i0, i0+1 of this lane's C elements (tcidx_s has CAP entries)
@@ -106,8 +110,13 @@ __device__ __forceinline__ void eval_columns_tc(Ctx2& c, double sq, double sqd, 
             const double v0 = (sb & 1u) ? s0 : ((ab & 1u) ? z0 : 0.0);  // k in sub(i): L_k . Rt_i ; k proper ancestor of i: s_k . Z_i
             const double v1 = (sb & 2u) ? s1 : ((ab & 2u) ? z1 : 0.0);
             if (idxk >= 0) {
-                if (i0 < n && ix.x >= 0) orow[ix.x * LD] = scale * v0;
-                if (i0 + 1 < n && ix.y >= 0) orow[ix.y * LD] = scale * v1;
+                if (TOGLOBAL) {
+                    if (i0 < n && ix.x >= 0) orow[ix.x] = scale * (ix.x == idxk ? v0 + dgk : v0);
+                    if (i0 + 1 < n && ix.y >= 0) orow[ix.y] = scale * (ix.y == idxk ? v1 + dgk : v1);
+                } else {
+                    if (i0 < n && ix.x >= 0) orow[ix.x * LD] = scale * v0;
+                    if (i0 + 1 < n && ix.y >= 0) orow[ix.y * LD] = scale * v1;
+                }
             }
         };
         // two tiles of the row at a time: their DMMA chains (3 or 5 + 2 dependent instructions each, 26 cycles apart) interleave
@@ -136,6 +145,7 @@ __device__ __forceinline__ void eval_columns_tc(Ctx2& c, double sq, double sqd, 
         }
     }
     bsync<NW>();
+    if (TOGLOBAL) return;
     // diagonal: joint stiffness / damping / limit terms Kr, Dr (Joint.m:470-481)
     if (myidx >= 0) out[myidx * (LD + 1)] += scale * (-cc * (sq * c.sp2[myidx] + sqd * c.sp1[myidx]));
     if (GROUND && c.npf > 0) {  // off-diagonal blocks of the point forces; RZ row = [c2 ; c1 ; sq s ; Z]
