@@ -189,13 +189,14 @@ __device__ __forceinline__ void lu_solve_tc(int nr, double* H, int* perm, int* r
     const int np8 = 8 * NP;
     const bool w0 = (NW == 1) || warp == 0;
     bool done[R];  // rows beyond the padded matrix never take part
-    int pos[R], mypos[R];
+    int pos[R], mypos[R];  // pos: LAPACK position of each row (RMX_PIVOT_EXACT only)
     double b[R], rdiag[R];
 #pragma unroll
     for (int h = 0; h < R; ++h) {
         const int row = lane + 32 * h;
         done[h] = row >= np8;
         pos[h] = row;
+        (void)pos[h];
         mypos[h] = -1;
         b[h] = (row < nr) ? scale * rhs[row] : 0.0;
         rdiag[h] = 1.0;
@@ -215,6 +216,31 @@ __device__ __forceinline__ void lu_solve_tc(int nr, double* H, int* perm, int* r
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int k = c0 + i;
+#ifndef RMX_PIVOT_EXACT
+                // Pivot row: ONE warp reduction per column.  Key = [not a pivot yet | top 25 bits of |a[i]| (sign, exponent, 14
+                // mantissa bits dropped of the IEEE high word's 20) | 63 - row]: its maximum names a row whose entry is within
+                // 2^-14 of the largest in the column (the lowest such row), which is all partial pivoting needs -- the growth
+                // bound changes by that factor.  The exact dgetf2 rule (idamax, first maximum in LAPACK's current row order: a second
+                // reduction, two votes and a position exchange per column, all on the factorisation's critical path) is kept
+                // behind -DRMX_PIVOT_EXACT; both give factors of the same quality, neither is bitwise MATLAB's.
+                unsigned key = 0u;
+#pragma unroll
+                for (int h = 0; h < R; ++h) {
+                    const unsigned hi = (unsigned)__double2hiint(a[h][i]) & 0x7fffffc0u;
+                    const unsigned kh = done[h] ? 0u : (0x80000000u | hi | (unsigned)(63 - lane - 32 * h));
+                    key = (h == 0) ? kh : max(key, kh);
+                }
+                const int srow = 63 - (int)(__reduce_max_sync(FULL, key) & 63u);
+                const int src = srow & 31, sh = srow >> 5;  // pivot row = src + 32 sh (warp-uniform)
+#pragma unroll
+                for (int h = 0; h < R; ++h) {
+                    if (lane == src && h == sh) {
+                        done[h] = true;
+                        mypos[h] = k;
+                    }
+                }
+                if (lane == (k & 31)) perm[k] = srow;
+#else
                 // argmax |a[i]| over the rows that are not pivots yet; ties -> smallest LAPACK position (dgetf2's idamax).
                 // |v| >= 0, so the IEEE bit pattern orders like the value: one warp reduction on the high words decides unless two
                 // rows agree in their top 32 bits; only then the low words and the positions are consulted (warp-uniform branch).
@@ -265,6 +291,7 @@ __device__ __forceinline__ void lu_solve_tc(int nr, double* H, int* perm, int* r
                     }
                 }
                 if (lane == (k & 31)) perm[k] = src + 32 * sh;
+#endif
                 // the pivot lane publishes its panel row (entries i.. as 128-bit pairs) and right-hand side; two alternating buffers,
                 // so one __syncwarp per pivot step orders both the read-after-write and the next write-after-read
                 double2* buf = rowbuf + 5 * (i & 1);

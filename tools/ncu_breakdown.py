@@ -24,12 +24,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 # named regions: (file suffix, first line, last line, name); first match wins, anything else goes by file name
 REGIONS = [
-    ('rmx_tc.cuh', 1, 31, 'tc:dmma wrapper'),
-    ('rmx_tc.cuh', 32, 147, 'tc:columns (per-joint vectors, tiles)'),
-    ('rmx_tc.cuh', 148, 235, 'tc:LU panel (pivot search, broadcast, rank-1 updates)'),
-    ('rmx_tc.cuh', 236, 262, 'tc:LU remaining rows + U12'),
-    ('rmx_tc.cuh', 263, 290, 'tc:LU trailing update'),
-    ('rmx_tc.cuh', 291, 400, 'tc:LU back substitution'),
+    ('rmx_tc.cuh', 1, 30, 'tc:dmma wrapper'),
+    ('rmx_tc.cuh', 31, 163, 'tc:columns (per-joint vectors, tiles)'),
+    ('rmx_tc.cuh', 164, 306, 'tc:LU panel (pivot search, broadcast, rank-1 updates)'),
+    ('rmx_tc.cuh', 307, 337, 'tc:LU remaining rows + U12'),
+    ('rmx_tc.cuh', 338, 381, 'tc:LU trailing update'),
+    ('rmx_tc.cuh', 382, 500, 'tc:LU back substitution'),
     ('rmx_rollout.cuh', 1, 10000, 'rollout (newton, line search, time loop, schedule)'),
     ('rmx_fast.cuh', 1, 10000, 'fast: composite base evaluation'),
     ('rmx_device.cuh', 1, 10000, 'device helpers (se3, reductions)'),
