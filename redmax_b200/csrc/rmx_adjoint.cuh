@@ -176,7 +176,7 @@ struct EnergyArgs {
     int nbody;
 };
 
-template <int NW, bool GROUND, int IMPL>
+template <int NW, int GROUND, int IMPL>
 __global__ void __launch_bounds__(32 * NW) energies_kernel(EnergyArgs a) {
     typedef Eval<IMPL, NW, GROUND, true, 0> E;
     extern __shared__ double2 smem_raw[];
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(32 * NW) energies_kernel(EnergyArgs a) {
                 }
             }
         }
-        if (GROUND && t < c.npf) {  // Force*.computeEnergy_ (ForcePointPoint.m:116, ForceSpringGeneric.m:146, ForceSpringMultiPointGeneric.m:193)
+        if (GROUND == 2 && t < c.npf) {  // Force*.computeEnergy_ (ForcePointPoint.m:116, ForceSpringGeneric.m:146, ForceSpringMultiPointGeneric.m:193)
             const PointForce& P = c.pf[t];
             double xprev[3] = {0, 0, 0}, len = 0.0, l2 = 0.0;
             for (int k = 0; k < P.npts; ++k) {

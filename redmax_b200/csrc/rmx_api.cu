@@ -631,6 +631,9 @@ static DevScene make_devscene(const rmx_scene* s, const DevCopy* dc) {
     return ds;
 }
 
+// external-force level of the kernels a scene needs: 0 none, 1 ground contact, 2 ground contact + forces between body points
+static int ext_level(const rmx_scene* s) { return !s->pf.empty() ? 2 : (s->has_ground ? 1 : 0); }
+
 static int warps_for(const rmx_scene* s) {
     const int m = s->n > s->nr ? s->n : s->nr;
     if (m <= 32) return 1;
@@ -707,9 +710,9 @@ void rmx_build_plan(SchedPlan& p, long long B, int nsteps, long long slots) {
 }
 
 // the launcher of one kernel instance (rmx_host.h), or null if that combination is not built
-static rmx_fwd_launcher fwd_launcher(int impl, int nw, bool ground, bool adj, int lin) {
+static rmx_fwd_launcher fwd_launcher(int impl, int nw, int ground, bool adj, int lin) {
 #define X(IMPL, NW, G, A, L) \
-    if (impl == IMPL && nw == NW && ground == (G != 0) && adj == (A != 0) && lin == L) return RMX_FWD_NAME(IMPL, NW, G, A, L);
+    if (impl == IMPL && nw == NW && ground == G && adj == (A != 0) && lin == L) return RMX_FWD_NAME(IMPL, NW, G, A, L);
     RMX_FWD_ALL(X)
 #undef X
     return nullptr;
@@ -719,7 +722,7 @@ static rmx_fwd_launcher fwd_launcher(int impl, int nw, bool ground, bool adj, in
 static int launch_fwd_pcg(const rmx_scene* s, const RolloutArgs& a, cudaStream_t st) {
     if (s->impl != 2) return fail(RMX_ELIMIT, "linsolve=PCG needs the composite kernels (n <= 64 joints)");
     const int nw = warps_for(s);
-    const bool g = s->has_ground != 0;
+    const int g = ext_level(s);
     const size_t smem = (scene_smem_doubles(s, true) + pcg_doubles(s->n, s->nr)) * sizeof(double);
     if (smem > 227 * 1024) return fail(RMX_ELIMIT, "scene does not fit the 227 KB shared memory of one SM");
     rmx_fwd_launcher f = fwd_launcher(2, nw, g, false, 1);
@@ -730,10 +733,10 @@ static int launch_fwd_pcg(const rmx_scene* s, const RolloutArgs& a, cudaStream_t
 template <bool ADJ>
 static int launch_fwd(const rmx_scene* s, const RolloutArgs& a, cudaStream_t st, DevCopy* dc = nullptr) {
     const int nw = warps_for(s);
-    const bool g = s->has_ground != 0;
+    const int g = ext_level(s);
     size_t smem = (scene_smem_doubles(s, ADJ) + (ADJ ? 6 * (size_t)s->nr : 0)) * sizeof(double);
     // the one-warp adjoint forward kernel of a scene without external forces runs on the tensor-core path (TcLayoutA)
-    if (ADJ && s->impl == 2 && nw == 1 && tc_adjoint(s->n, s->nr, g)) smem = (size_t)TcLayoutA::TOTAL * sizeof(double);
+    if (ADJ && s->impl == 2 && nw == 1 && tc_adjoint(s->n, s->nr, g != 0)) smem = (size_t)TcLayoutA::TOTAL * sizeof(double);
     if (smem > 227 * 1024) return fail(RMX_ELIMIT, "scene does not fit the 227 KB shared memory of one SM");
     rmx_fwd_launcher f = fwd_launcher(s->impl, nw, g, ADJ, 0);
     if (!f) return fail(RMX_ELIMIT, "no forward kernel for this scene size");
@@ -1050,7 +1053,7 @@ extern "C" int rmx_eval(rmx_scene* s, const double* q, const double* qdot, const
     a.M = dM;
     a.D = dD;
     const int nw = warps_for(s);
-    const bool gr = s->has_ground != 0;
+    const int gr = ext_level(s);
     const size_t smem = scene_smem_doubles(s) * sizeof(double);
     rc = rmx_launch_eval(s->impl, nw, gr, a, smem);
     if (rc == RMX_OK) {
@@ -1114,7 +1117,7 @@ extern "C" int rmx_eval_newton(rmx_scene* s, const double* q, const double* qdot
     a.beta = beta;
     a.H = dH;
     const int nw = warps_for(s);
-    const bool gr = s->has_ground != 0;
+    const int gr = ext_level(s);
     const size_t smem = scene_smem_doubles(s, false) * sizeof(double);
     rc = rmx_launch_eval_newton(nw, gr, a, ddx, smem);
     if (rc == RMX_OK) {

@@ -564,7 +564,7 @@ __device__ void ground_body(const JointConst& J, const double* R, const double* 
 //   == evalBDF1/evalSDIRK2a/evalSDIRK2b/evalBDF2 + jroot.update + computeValues of the reference.
 // seeds (sq, sqd, sd) select what the column sweep differentiates: (1, beta, 1) -> H;  (0,0,1) -> M;  (0,1,0) -> -c*D.
 // ---------------------------------------------------------------------------------------------
-template <int NW, bool GROUND>
+template <int NW, int GROUND>
 __device__ void eval_base(Ctx& c, bool deriv) {
     const int t = threadIdx.x;
     const int n = c.n;
@@ -770,7 +770,7 @@ __device__ void eval_base(Ctx& c, bool deriv) {
 
 // Column sweep: thread t (joint i = t with a dof) computes column idx[i] of
 //    sq * dg/dq + sqd * dg/dqdot + sd * dg/d(dqtmp)   into out (nr x ld, column-major), scaled by `scale`.
-template <int NW, bool GROUND>
+template <int NW, int GROUND>
 __device__ void eval_columns(Ctx& c, double sq, double sqd, double sd, double scale, double* out) {
     const int t = threadIdx.x;
     const int n = c.n;

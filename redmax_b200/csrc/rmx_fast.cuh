@@ -22,7 +22,10 @@ namespace rmx {
 // Field offsets in the SoA block (units: NS doubles).  KEEP = 1: body frames and twists stay in shared memory and H has its
 // own storage (test hooks, Krylov and external-force adjoint kernels); KEEP = 2: body frames only (tensor-core adjoint kernel);
 // KEEP = 0: nothing kept, H aliases the fields that are dead once the Newton matrix is assembled.
-template <bool GROUND, int KEEP>
+// GROUND (everywhere in these files) is the level of external forces compiled in: 0 none, 1 ForceGroundCuboid, 2 ground contact
+// and the forces between body points (springs, cables) -- scenes without those must not carry their code, stack frame and
+// registers.
+template <int GROUND, int KEEP>
 struct Fld {
     static constexpr int NL = GROUND ? 18 : 12;  // length of L_k
     static constexpr int NW_ = NL + 6;           // W_k = [L_k ; s_k], stored joint-major (AoS) in region XA
@@ -69,7 +72,7 @@ __host__ __device__ inline size_t soa_doubles(int n, int nr, bool ground, bool k
 
 // Static shared-memory layout of the tensor-core forward kernels (capacity n = nr = 32 NW whatever the scene): every vector
 // and table sits at a compile-time offset from the block's base, so no pointer lives in a register and no address is computed.
-template <bool GROUND, int NW>
+template <int GROUND, int NW>
 struct TcLayout {
     typedef Fld<GROUND, 0> F;
     static constexpr int KEEP = 0;
@@ -199,7 +202,7 @@ __device__ __forceinline__ void ctx2_carve(Ctx2& c, double* sm, int n, int nr, b
 }
 
 // Tensor-core forward kernels: the static layout above (nothing depends on n or nr).
-template <bool GROUND, int NW>
+template <int GROUND, int NW>
 __device__ __forceinline__ void ctx2_carve_tc(Ctx2& c, double* sm, int n, int nr) {
     typedef TcLayout<GROUND, NW> T;
     c.n = n;
@@ -959,7 +962,7 @@ __device__ __forceinline__ void pf_cross_pass(Ctx2& c, int t, int myidx, const d
 // ---------------------------------------------------------------------------------------------
 // eval_base2: residual g at iterate c.q (and, if deriv, the composite blocks eval_columns2 needs).
 // ---------------------------------------------------------------------------------------------
-template <int NW, bool GROUND, int KEEP>
+template <int NW, int GROUND, int KEEP>
 __device__ void eval_base2(Ctx2& c, bool deriv) {
     typedef Fld<GROUND, KEEP> F;
     const int t = threadIdx.x;
@@ -1098,7 +1101,7 @@ __device__ void eval_base2(Ctx2& c, bool deriv) {
         bsync<NW>();
     }
     // ---- point forces: every attached body publishes its frame and twist for the other end -------------------------
-    if (GROUND && c.npf > 0) {  // uniform
+    if (GROUND == 2 && c.npf > 0) {  // uniform
         if (t < n && c.jc[t].pf_cnt > 0) {
             const JointConst& J = c.jc[t];
             double Rb[9], pb[3], phi[6];
@@ -1150,7 +1153,7 @@ __device__ void eval_base2(Ctx2& c, bool deriv) {
                 const double reach = fabs(nb[0]) * J.hs[0] + fabs(nb[1]) * J.hs[1] + fabs(nb[2]) * J.hs[2];
                 contact = dp - reach <= 1e-12 * (fabs(dp) + reach);
             }
-            myext = contact || (c.npf > 0 && J.pf_cnt > 0);
+            myext = contact || (GROUND == 2 && c.npf > 0 && J.pf_cnt > 0);
             if (contact) {
                 if (deriv) {
                     double K[36], D[36];
@@ -1165,7 +1168,7 @@ __device__ void eval_base2(Ctx2& c, bool deriv) {
             } else if (deriv) {
                 for (int i = 0; i < 72; ++i) SA(F::AEXT, i, t) = 0.0;
             }
-            if (c.npf > 0 && J.pf_cnt > 0) {
+            if (GROUND == 2 && c.npf > 0 && J.pf_cnt > 0) {
                 PfCtx pc;
                 pc.pf = c.pf;
                 pc.pf_ep = c.pf_ep;
@@ -1298,7 +1301,7 @@ __device__ void eval_base2(Ctx2& c, bool deriv) {
 // Per-joint part of the Newton-matrix assembly: from joint t's screw, its parent's V and U and its composite blocks, the
 // row vector L_t (so that H[t][i] = L_t . Rt_i for t in sub(i)), and the column vectors Rt_t = [c2 ; c1 ; sq s] and Z_t
 // (H[k][t] = s_k . Z_t for proper ancestors k).  Reads shared memory only; results stay in registers.
-template <int NW, bool GROUND, int KEEP>
+template <int NW, int GROUND, int KEEP>
 __device__ __forceinline__ void columns_joint(Ctx2& c, int t, int myidx, double sq, double sqd, double sd, double* L, double* s,
                                               double* Rt, double* Z) {
     typedef Fld<GROUND, KEEP> F;
@@ -1439,7 +1442,7 @@ __device__ __forceinline__ void columns_joint(Ctx2& c, int t, int myidx, double 
 // ---------------------------------------------------------------------------------------------
 // eval_columns2: out (nr x ld column-major) = scale * ( sq dg/dq + sqd dg/dqdot + sd dg/d(dqtmp) ), from the composite blocks.
 // ---------------------------------------------------------------------------------------------
-template <int NW, bool GROUND, int KEEP>
+template <int NW, int GROUND, int KEEP>
 __device__ void eval_columns2(Ctx2& c, double sq, double sqd, double sd, double scale, double* out) {
     typedef Fld<GROUND, KEEP> F;
     const int t = threadIdx.x;
@@ -1489,7 +1492,7 @@ __device__ void eval_columns2(Ctx2& c, double sq, double sqd, double sd, double 
             col[ie.x] = scale * (v + v2);
         }
     }
-    if (GROUND && c.npf > 0)  // off-diagonal blocks of the point forces (same thread owns the column: no barrier needed before)
+    if (GROUND == 2 && c.npf > 0)  // off-diagonal blocks of the point forces (same thread owns the column: no barrier needed before)
         pf_cross_pass(c, t, myidx, Rt + 6, Rt + 12, scale, out, ld, c.sa, F::NW_, F::NL);
     bsync<NW>();
 }

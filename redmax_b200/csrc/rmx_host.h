@@ -72,26 +72,27 @@ typedef int (*rmx_eval_launcher)(const rmx::EvalArgs& a, size_t smem);
 typedef int (*rmx_evaln_launcher)(const rmx::EvalArgs& a, double* dx, size_t smem);
 typedef int (*rmx_energy_launcher)(const rmx::EnergyArgs& a, size_t smem);
 
-// forward rollout kernels: IMPL (1 sweep / 2 composite), NW warps per rollout, GROUND, ADJ (tape-writing), LIN (0 LU, 1 Krylov)
+// forward rollout kernels: IMPL (1 sweep / 2 composite), NW warps per rollout, GROUND (external forces: 0 none, 1 ground
+// contact, 2 ground contact + point forces), ADJ (tape-writing), LIN (0 LU, 1 Krylov)
 #define RMX_FWD_NAME(IMPL, NW, G, A, L) rmx_fwd_i##IMPL##_w##NW##_g##G##_a##A##_l##L
 #define RMX_DECLARE_FWD(IMPL, NW, G, A, L) \
     int RMX_FWD_NAME(IMPL, NW, G, A, L)(const rmx::RolloutArgs& a, size_t smem, cudaStream_t st, DevCopy* dc);
 #define RMX_DEFINE_FWD(IMPL, NW, G, A, L)                                                                    \
     int RMX_FWD_NAME(IMPL, NW, G, A, L)(const rmx::RolloutArgs& a, size_t smem, cudaStream_t st, DevCopy* dc) { \
-        return rmx_launch_fwd_t<NW, G != 0, A != 0, IMPL, L>(a, smem, st, dc);                                  \
+        return rmx_launch_fwd_t<NW, G, A != 0, IMPL, L>(a, smem, st, dc);                                  \
     }
 
 #define RMX_FWD_ALL(X)                                                                                      \
-    X(2, 1, 0, 0, 0) X(2, 1, 1, 0, 0) X(2, 1, 0, 1, 0) X(2, 1, 1, 1, 0)                                      \
-    X(2, 2, 0, 0, 0) X(2, 2, 1, 0, 0) X(2, 2, 0, 1, 0) X(2, 2, 1, 1, 0)                                      \
-    X(2, 1, 0, 0, 1) X(2, 1, 1, 0, 1) X(2, 2, 0, 0, 1) X(2, 2, 1, 0, 1)                                      \
+    X(2, 1, 0, 0, 0) X(2, 1, 1, 0, 0) X(2, 1, 0, 1, 0) X(2, 1, 1, 1, 0) X(2, 1, 2, 0, 0) X(2, 1, 2, 1, 0)    \
+    X(2, 2, 0, 0, 0) X(2, 2, 1, 0, 0) X(2, 2, 0, 1, 0) X(2, 2, 1, 1, 0) X(2, 2, 2, 0, 0) X(2, 2, 2, 1, 0)    \
+    X(2, 1, 0, 0, 1) X(2, 1, 1, 0, 1) X(2, 2, 0, 0, 1) X(2, 2, 1, 0, 1) X(2, 1, 2, 0, 1) X(2, 2, 2, 0, 1)    \
     X(1, 1, 0, 0, 0) X(1, 1, 1, 0, 0) X(1, 1, 0, 1, 0) X(1, 1, 1, 1, 0)                                      \
     X(1, 2, 0, 0, 0) X(1, 2, 1, 0, 0) X(1, 2, 0, 1, 0) X(1, 2, 1, 1, 0)                                      \
     X(1, 4, 0, 0, 0) X(1, 4, 1, 0, 0) X(1, 4, 0, 1, 0) X(1, 4, 1, 1, 0)
 RMX_FWD_ALL(RMX_DECLARE_FWD)
 
 // test hooks and diagnostics (rmx_k_misc.cu)
-int rmx_launch_eval(int impl, int nw, bool ground, const rmx::EvalArgs& a, size_t smem);
-int rmx_launch_eval_newton(int nw, bool ground, const rmx::EvalArgs& a, double* dx, size_t smem);
-int rmx_launch_energy(int impl, int nw, bool ground, const rmx::EnergyArgs& a, size_t smem);
+int rmx_launch_eval(int impl, int nw, int ground, const rmx::EvalArgs& a, size_t smem);
+int rmx_launch_eval_newton(int nw, int ground, const rmx::EvalArgs& a, double* dx, size_t smem);
+int rmx_launch_energy(int impl, int nw, int ground, const rmx::EnergyArgs& a, size_t smem);
 int rmx_launch_bwd(int nw, const rmx::BwdArgs& a, cudaStream_t st);

@@ -1,0 +1,4 @@
+// rmx_k_fwd_pcg_g2.cu -- explicit instances of rollout_fwd_kernel (see rmx_host.h): IMPL, NW, GROUND, ADJ, LIN
+#include "rmx_launch.cuh"
+#define X(IMPL, NW, G, A, L) RMX_DEFINE_FWD(IMPL, NW, G, A, L)
+X(2,1,2,0,1) X(2,2,2,0,1)

@@ -4,7 +4,7 @@
 
 using namespace rmx;
 
-template <int NW, bool GROUND, int IMPL>
+template <int NW, int GROUND, int IMPL>
 static int launch_eval_t(const EvalArgs& a, size_t smem) {
     int rc = rmx_set_smem(eval_kernel<NW, GROUND, IMPL>, smem);
     if (rc) return rc;
@@ -14,18 +14,19 @@ static int launch_eval_t(const EvalArgs& a, size_t smem) {
     return RMX_OK;
 }
 
-int rmx_launch_eval(int impl, int nw, bool gr, const EvalArgs& a, size_t smem) {
+// gr: external-force level of the scene (0 none, 1 ground contact, 2 ground contact + point forces; composite kernels only)
+int rmx_launch_eval(int impl, int nw, int gr, const EvalArgs& a, size_t smem) {
     if (impl == 2) {
-        if (nw == 1) return gr ? launch_eval_t<1, true, 2>(a, smem) : launch_eval_t<1, false, 2>(a, smem);
-        return gr ? launch_eval_t<2, true, 2>(a, smem) : launch_eval_t<2, false, 2>(a, smem);
+        if (nw == 1) return gr == 2 ? launch_eval_t<1, 2, 2>(a, smem) : (gr ? launch_eval_t<1, 1, 2>(a, smem) : launch_eval_t<1, 0, 2>(a, smem));
+        return gr == 2 ? launch_eval_t<2, 2, 2>(a, smem) : (gr ? launch_eval_t<2, 1, 2>(a, smem) : launch_eval_t<2, 0, 2>(a, smem));
     }
-    if (nw == 1) return gr ? launch_eval_t<1, true, 1>(a, smem) : launch_eval_t<1, false, 1>(a, smem);
-    if (nw == 2) return gr ? launch_eval_t<2, true, 1>(a, smem) : launch_eval_t<2, false, 1>(a, smem);
-    return gr ? launch_eval_t<4, true, 1>(a, smem) : launch_eval_t<4, false, 1>(a, smem);
+    if (nw == 1) return gr ? launch_eval_t<1, 1, 1>(a, smem) : launch_eval_t<1, 0, 1>(a, smem);
+    if (nw == 2) return gr ? launch_eval_t<2, 1, 1>(a, smem) : launch_eval_t<2, 0, 1>(a, smem);
+    return gr ? launch_eval_t<4, 1, 1>(a, smem) : launch_eval_t<4, 0, 1>(a, smem);
 }
 
 // rmx_eval_newton test hook: H and dx = -H\g through the forward kernel's own assembly + factorisation path
-template <int NW, bool GROUND>
+template <int NW, int GROUND>
 static int launch_eval_newton_t(const EvalArgs& a, double* dx, size_t smem) {
     int rc = rmx_set_smem(eval_newton_kernel<NW, GROUND>, smem);
     if (rc) return rc;
@@ -35,12 +36,15 @@ static int launch_eval_newton_t(const EvalArgs& a, double* dx, size_t smem) {
     return RMX_OK;
 }
 
-int rmx_launch_eval_newton(int nw, bool gr, const EvalArgs& a, double* dx, size_t smem) {
-    if (nw == 1) return gr ? launch_eval_newton_t<1, true>(a, dx, smem) : launch_eval_newton_t<1, false>(a, dx, smem);
-    return gr ? launch_eval_newton_t<2, true>(a, dx, smem) : launch_eval_newton_t<2, false>(a, dx, smem);
+int rmx_launch_eval_newton(int nw, int gr, const EvalArgs& a, double* dx, size_t smem) {
+    if (nw == 1)
+        return gr == 2 ? launch_eval_newton_t<1, 2>(a, dx, smem)
+                       : (gr ? launch_eval_newton_t<1, 1>(a, dx, smem) : launch_eval_newton_t<1, 0>(a, dx, smem));
+    return gr == 2 ? launch_eval_newton_t<2, 2>(a, dx, smem)
+                   : (gr ? launch_eval_newton_t<2, 1>(a, dx, smem) : launch_eval_newton_t<2, 0>(a, dx, smem));
 }
 
-template <int NW, bool GROUND, int IMPL>
+template <int NW, int GROUND, int IMPL>
 static int launch_energy_t(const EnergyArgs& a, size_t smem) {
     int rc = rmx_set_smem(energies_kernel<NW, GROUND, IMPL>, smem);
     if (rc) return rc;
@@ -50,14 +54,14 @@ static int launch_energy_t(const EnergyArgs& a, size_t smem) {
     return RMX_OK;
 }
 
-int rmx_launch_energy(int impl, int nw, bool g, const EnergyArgs& a, size_t smem) {
+int rmx_launch_energy(int impl, int nw, int g, const EnergyArgs& a, size_t smem) {
     if (impl == 2) {
-        if (nw == 1) return g ? launch_energy_t<1, true, 2>(a, smem) : launch_energy_t<1, false, 2>(a, smem);
-        return g ? launch_energy_t<2, true, 2>(a, smem) : launch_energy_t<2, false, 2>(a, smem);
+        if (nw == 1) return g == 2 ? launch_energy_t<1, 2, 2>(a, smem) : (g ? launch_energy_t<1, 1, 2>(a, smem) : launch_energy_t<1, 0, 2>(a, smem));
+        return g == 2 ? launch_energy_t<2, 2, 2>(a, smem) : (g ? launch_energy_t<2, 1, 2>(a, smem) : launch_energy_t<2, 0, 2>(a, smem));
     }
-    if (nw == 1) return g ? launch_energy_t<1, true, 1>(a, smem) : launch_energy_t<1, false, 1>(a, smem);
-    if (nw == 2) return g ? launch_energy_t<2, true, 1>(a, smem) : launch_energy_t<2, false, 1>(a, smem);
-    return g ? launch_energy_t<4, true, 1>(a, smem) : launch_energy_t<4, false, 1>(a, smem);
+    if (nw == 1) return g ? launch_energy_t<1, 1, 1>(a, smem) : launch_energy_t<1, 0, 1>(a, smem);
+    if (nw == 2) return g ? launch_energy_t<2, 1, 1>(a, smem) : launch_energy_t<2, 0, 1>(a, smem);
+    return g ? launch_energy_t<4, 1, 1>(a, smem) : launch_energy_t<4, 0, 1>(a, smem);
 }
 
 template <int NW>

@@ -4,7 +4,7 @@
 
 // One persistent launch of rollout_fwd_kernel<NW, GROUND, ADJ, IMPL, LIN>.  Forward launches whose batch is not a multiple of
 // the co-resident blocks run the load-balanced segment schedule (rmx_build_plan); everything else one block per rollout.
-template <int NW, bool GROUND, bool ADJ, int IMPL, int LIN>
+template <int NW, int GROUND, bool ADJ, int IMPL, int LIN>
 static int rmx_launch_fwd_t(const rmx::RolloutArgs& a0, size_t smem, cudaStream_t st, DevCopy* dc) {
     using namespace rmx;
     auto kernel = rollout_fwd_kernel<NW, GROUND, ADJ, IMPL, LIN>;

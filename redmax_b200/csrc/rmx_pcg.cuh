@@ -50,7 +50,7 @@ __device__ __forceinline__ int sym_idx(int a, int b) {  // a <= b
 }
 
 // Preconditioner set-up for the current evaluation point (needs eval_base2's S, RB, PB fields: KEEP layout).
-template <int NW, bool GROUND>
+template <int NW, int GROUND>
 __device__ void precond_setup(Ctx2& c, PcgMem& m) {
     typedef Fld<GROUND, true> F;
     const int t = threadIdx.x;
@@ -127,7 +127,7 @@ __device__ void precond_setup(Ctx2& c, PcgMem& m) {
 }
 
 // y = (J' blkdiag(M_j) J + Pr)^-1 x    (x, y indexed by reduced index)
-template <int NW, bool GROUND>
+template <int NW, int GROUND>
 __device__ void precond_apply(Ctx2& c, PcgMem& m, const double* x, double* y) {
     typedef Fld<GROUND, true> F;
     const int t = threadIdx.x;
@@ -173,7 +173,7 @@ __device__ void precond_apply(Ctx2& c, PcgMem& m, const double* x, double* y) {
 }
 
 // Solves H x = scale * rhs with preconditioned BiCGStab; x -> c.dx.  Returns the number of iterations.
-template <int NW, bool GROUND>
+template <int NW, int GROUND>
 __device__ int krylov_solve(Ctx2& c, PcgMem& m, const double* H, const double* rhs, double scale, double tol, int maxit) {
     const int t = threadIdx.x;
     const int nr = c.nr, ld = c.ld;

@@ -77,7 +77,7 @@ __device__ __forceinline__ void krylov_reset(Ctx&) {}
 //   IMPL 1 : rmx_device.cuh  -- serial tree sweeps + per-(column, body) tangent sweep (kept for n > 64 and as cross-check)
 //   IMPL 2 : rmx_fast.cuh    -- scans + composite blocks + (one warp) register LU
 // ---------------------------------------------------------------------------------------------
-template <int IMPL, int NW, bool GROUND, bool KEEP, int LIN, bool ATC = false>
+template <int IMPL, int NW, int GROUND, bool KEEP, int LIN, bool ATC = false>
 struct Eval;
 
 struct Ctx2L : Ctx2 {  // fast-path context + state of the Krylov linear solve (LIN == 1)
@@ -87,7 +87,7 @@ struct Ctx2L : Ctx2 {  // fast-path context + state of the Krylov linear solve (
     int kry_iters;
 };
 
-template <int NW, bool GROUND, bool KEEP, int LIN, bool ATC>
+template <int NW, int GROUND, bool KEEP, int LIN, bool ATC>
 struct Eval<1, NW, GROUND, KEEP, LIN, ATC> {
     typedef Ctx C;
     static constexpr bool TCA = false;
@@ -132,7 +132,7 @@ struct Eval<1, NW, GROUND, KEEP, LIN, ATC> {
     }
 };
 
-template <int NW, bool GROUND, bool KEEP, int LIN, bool ATC>
+template <int NW, int GROUND, bool KEEP, int LIN, bool ATC>
 struct Eval<2, NW, GROUND, KEEP, LIN, ATC> {
     typedef Ctx2L C;
     // one- and two-warp forward kernels assemble and factor the Newton matrix on the FP64 tensor cores (rmx_tc.cuh); so does
@@ -515,7 +515,7 @@ __device__ __forceinline__ int newton_adjoint_tc(typename E::C& c, const StepOpt
 #define RMX_MAXNREG_FWD 255
 #endif
 #define RMX_FWD_BOUNDS __maxnreg__((NW == 1 && !ADJ && LIN == 0 && IMPL == 2) ? RMX_MAXNREG_FWD : 255)
-template <int NW, bool GROUND, bool ADJ, int IMPL, int LIN>
+template <int NW, int GROUND, bool ADJ, int IMPL, int LIN>
 __global__ void RMX_FWD_BOUNDS rollout_fwd_kernel(RolloutArgs a) {
     typedef Eval<IMPL, NW, GROUND, ADJ || LIN == 1, LIN, ADJ> E;
     extern __shared__ double2 smem_raw[];
@@ -755,7 +755,7 @@ struct EvalArgs {
     double* D;
 };
 
-template <int NW, bool GROUND, int IMPL>
+template <int NW, int GROUND, int IMPL>
 __global__ void __launch_bounds__(32 * NW) eval_kernel(EvalArgs a) {
     typedef Eval<IMPL, NW, GROUND, true, 0> E;
     extern __shared__ double2 smem_raw[];
@@ -802,7 +802,7 @@ __global__ void __launch_bounds__(32 * NW) eval_kernel(EvalArgs a) {
 // Test hook: one Newton linear system exactly as the forward rollout kernel forms and solves it (same Eval instance:
 // tensor-core assembly + blocked LU for one warp) -> H (before factorisation, nr x nr column-major) and dx = -H \ g.
 // ---------------------------------------------------------------------------------------------
-template <int NW, bool GROUND>
+template <int NW, int GROUND>
 __global__ void __launch_bounds__(32 * NW) eval_newton_kernel(EvalArgs a, double* dx_out) {
     typedef Eval<2, NW, GROUND, false, 0> E;
     extern __shared__ double2 smem_raw[];

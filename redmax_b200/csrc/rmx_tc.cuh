@@ -20,6 +20,21 @@
 
 namespace rmx {
 
+// Reciprocal of a pivot on the factorisation's critical path: the hardware seed (MUFU.RCP64H, relative error < 2^-20) and two
+// Newton steps, accurate to an ulp or so -- __drcp_rn's correctly rounded result costs two more dependent FMAs and a
+// slow-path test per pivot, and the multipliers it would make bitwise equal to LAPACK's are not compared with anything.
+__device__ __forceinline__ double rcp_pivot(double x) {
+#ifdef RMX_PIVOT_EXACT
+    return __drcp_rn(x);
+#else
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(r, fma(-x, r, 1.0), r);
+    r = fma(r, fma(-x, r, 1.0), r);
+    return r;
+#endif
+}
+
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
     // volatile: a .sync.aligned instruction must stay where the warp is converged (never sunk into a divergent consumer)
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -35,7 +50,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // T: the shared-memory layout (TcLayout<GROUND, NW> of the forward kernels, TcLayoutA of the adjoint forward kernel).
 // TOGLOBAL: the tiles go straight to `out` in GLOBAL memory, nr x nr ROW-major (the adjoint tape's M and D), with the
 // joint-level diagonal term folded into the epilogue; otherwise `out` is the shared-memory image of H (column-major, T::LD).
-template <int NW, bool GROUND, class T, bool TOGLOBAL>
+template <int NW, int GROUND, class T, bool TOGLOBAL>
 __device__ __forceinline__ void eval_columns_tc(Ctx2& c, double sq, double sqd, double sd, double scale, double* out) {
     typedef typename T::F F;
     typedef typename TcMask<NW>::type mask_t;
@@ -148,7 +163,7 @@ __device__ __forceinline__ void eval_columns_tc(Ctx2& c, double sq, double sqd, 
     if (TOGLOBAL) return;
     // diagonal: joint stiffness / damping / limit terms Kr, Dr (Joint.m:470-481)
     if (myidx >= 0) out[myidx * (LD + 1)] += scale * (-cc * (sq * c.sp2[myidx] + sqd * c.sp1[myidx]));
-    if (GROUND && c.npf > 0) {  // off-diagonal blocks of the point forces; RZ row = [c2 ; c1 ; sq s ; Z]
+    if (GROUND == 2 && c.npf > 0) {  // off-diagonal blocks of the point forces; RZ row = [c2 ; c1 ; sq s ; Z]
         const double* rzl = RZb + tid * NWD;
         pf_cross_pass(c, tid, myidx, rzl + 6, rzl + 12, scale, out, LD, Wb, NWD, NL);
     }
@@ -312,7 +327,7 @@ __device__ __forceinline__ void lu_solve_tc(int nr, double* H, int* perm, int* r
                 for (int j = i / 2; j < 4; ++j) u2[j] = buf[j];
                 const double ub = buf[4].x;
                 const double piv = (i & 1) ? u2[i / 2].y : u2[i / 2].x;
-                const double rp = __drcp_rn(piv);  // == 1.0 / piv, correctly rounded
+                const double rp = rcp_pivot(piv);
 #pragma unroll
                 for (int h = 0; h < R; ++h) {
                     rdiag[h] = (lane == src && h == sh) ? rp : rdiag[h];
@@ -367,41 +382,77 @@ __device__ __forceinline__ void lu_solve_tc(int nr, double* H, int* perm, int* r
         const int prt0 = (t4 == 0) ? pr[0] : (t4 == 1) ? pr[1] : (t4 == 2) ? pr[2] : pr[3];
         const int prt1 = (t4 == 0) ? pr[4] : (t4 == 1) ? pr[5] : (t4 == 2) ? pr[6] : pr[7];
         const double* La = H + (c0 + t4) * LD;  // multipliers of k-index t4 (column c0 + t4): row r at La[r]; 4 + t4 at La[4 LD + r]
-        double af0[MAXI], af1[MAXI];
-        int rI[MAXI];
-#pragma unroll
-        for (int I = 0; I < MAXI; ++I) {
-            if (I < nt) {
-                const int r = rem[8 * I + g];
-                rI[I] = r;
-                af0[I] = -La[r];
-                af1[I] = -La[4 * LD + r];
+        if (NW == 1) {
+            // one warp, at most 3 trailing tile rows: the A fragments of all of them stay in registers across the tile columns
+            double af0[MAXI], af1[MAXI];
+            int rI[MAXI];
+    #pragma unroll
+            for (int I = 0; I < MAXI; ++I) {
+                if (I < nt) {
+                    const int r = rem[8 * I + g];
+                    rI[I] = r;
+                    af0[I] = -La[r];
+                    af1[I] = -La[4 * LD + r];
+                }
             }
-        }
-        for (int J = (NW == 1 ? 0 : warp); J < nt; J += NW) {
-            const int cJ = c0 + 8 + 8 * J;
-            const double* Ub = H + (cJ + g) * LD;  // B fragments: U12[k-index][column cJ + g]
-            const double bf0 = Ub[prt0], bf1 = Ub[prt1];
-            double* Cc = H + (cJ + 2 * t4) * LD;   // C elements: columns cJ + 2 t4, + 1
-            double v0[MAXI], v1[MAXI];
-#pragma unroll
-            for (int I = 0; I < MAXI; ++I)
-                if (I < nt) {
-                    v0[I] = Cc[rI[I]];
-                    v1[I] = Cc[LD + rI[I]];
+            for (int J = (NW == 1 ? 0 : warp); J < nt; J += NW) {
+                const int cJ = c0 + 8 + 8 * J;
+                const double* Ub = H + (cJ + g) * LD;  // B fragments: U12[k-index][column cJ + g]
+                const double bf0 = Ub[prt0], bf1 = Ub[prt1];
+                double* Cc = H + (cJ + 2 * t4) * LD;   // C elements: columns cJ + 2 t4, + 1
+                double v0[MAXI], v1[MAXI];
+    #pragma unroll
+                for (int I = 0; I < MAXI; ++I)
+                    if (I < nt) {
+                        v0[I] = Cc[rI[I]];
+                        v1[I] = Cc[LD + rI[I]];
+                    }
+    #pragma unroll
+                for (int I = 0; I < MAXI; ++I)  // first k-step of every tile of this column, then the second: independent chains
+                    if (I < nt) dmma884(v0[I], v1[I], af0[I], bf0);
+    #pragma unroll
+                for (int I = 0; I < MAXI; ++I)
+                    if (I < nt) dmma884(v0[I], v1[I], af1[I], bf1);
+    #pragma unroll
+                for (int I = 0; I < MAXI; ++I)
+                    if (I < nt) {
+                        Cc[rI[I]] = v0[I];
+                        Cc[LD + rI[I]] = v1[I];
+                    }
+            }
+        } else {
+            // two warps, up to 7 trailing tile rows: a predicated, fully unrolled form would issue all 7 row slots for every
+            // tile column whatever nt is; here the row tiles are a plain loop (A fragments loaded once per row tile), the tile
+            // columns are dealt round-robin to the warps and taken two at a time so that their DMMA chains overlap
+            for (int I = 0; I < nt; ++I) {
+                const int r = rem[8 * I + g];
+                const double a0 = -La[r], a1 = -La[4 * LD + r];
+                for (int J = warp; J < nt; J += 2 * NW) {
+                    const bool two = J + NW < nt;  // warp-uniform
+                    const int cJ = c0 + 8 + 8 * J;
+                    const double* Ub = H + (cJ + g) * LD;  // B fragments: U12[k-index][column cJ + g]
+                    double* Cc = H + (cJ + 2 * t4) * LD + r;  // C elements: row r, columns cJ + 2 t4, + 1
+                    const double b0 = Ub[prt0], b1 = Ub[prt1];
+                    double v0 = Cc[0], v1 = Cc[LD];
+                    double e0 = 0.0, e1 = 0.0, w0v = 0.0, w1v = 0.0;
+                    if (two) {
+                        e0 = Ub[8 * NW * LD + prt0];
+                        e1 = Ub[8 * NW * LD + prt1];
+                        w0v = Cc[8 * NW * LD];
+                        w1v = Cc[8 * NW * LD + LD];
+                    }
+                    dmma884(v0, v1, a0, b0);
+                    if (two) dmma884(w0v, w1v, a0, e0);
+                    dmma884(v0, v1, a1, b1);
+                    if (two) dmma884(w0v, w1v, a1, e1);
+                    Cc[0] = v0;
+                    Cc[LD] = v1;
+                    if (two) {
+                        Cc[8 * NW * LD] = w0v;
+                        Cc[8 * NW * LD + LD] = w1v;
+                    }
                 }
-#pragma unroll
-            for (int I = 0; I < MAXI; ++I)  // first k-step of every tile of this column, then the second: independent chains
-                if (I < nt) dmma884(v0[I], v1[I], af0[I], bf0);
-#pragma unroll
-            for (int I = 0; I < MAXI; ++I)
-                if (I < nt) dmma884(v0[I], v1[I], af1[I], bf1);
-#pragma unroll
-            for (int I = 0; I < MAXI; ++I)
-                if (I < nt) {
-                    Cc[rI[I]] = v0[I];
-                    Cc[LD + rI[I]] = v1[I];
-                }
+            }
         }
         bsync<NW>();
     }
