@@ -78,8 +78,9 @@ struct TcLayout {
     static constexpr int KEEP = 0;
     static constexpr int CAP = 32 * NW, NS = CAP + 1, LD = CAP + 1;
     static constexpr int W_OFF = 0;                   // W  [CAP][NW_]  rows [L_k ; s_k]
-    static constexpr int RZ_OFF = CAP * F::NW_;       // RZ [CAP][NW_]  rows [Rt_i ; Z_i]
-    static constexpr int H_OFF = 2 * CAP * F::NW_;    // H  [CAP][LD]   column-major, identity padded to whole tiles
+    static constexpr int RZ_OFF = CAP * F::NW_;       // RZ [32][NW_]   rows [Rt_i ; Z_i], 32 column joints at a time
+    static constexpr int RZ_ROWS = 32;
+    static constexpr int H_OFF = (CAP + RZ_ROWS) * F::NW_;  // H  [CAP][LD]   column-major, identity padded to whole tiles
     static constexpr int SOA_FIELDS = NS * F::TOTAL;  // the SoA block of eval_base2 (overlaid by W, RZ, H during assembly + LU)
     static constexpr int SOA = ((SOA_FIELDS > H_OFF + CAP * LD ? SOA_FIELDS : H_OFF + CAP * LD) + 1) & ~1;
     static constexpr int NV = 12;                     // q qd dq g dx tau hq0 hqd0 hq1 hqd1 sp1 sp2 (x0, sp0 are unused)
@@ -104,6 +105,7 @@ struct TcLayoutA {
     static constexpr int KEEP = 2;
     static constexpr int CAP = 32, NS = 33, LD = 33;
     static constexpr int W_OFF = 0;
+    static constexpr int RZ_ROWS = 32;
     static constexpr int H_OFF = F::XA * NS;          // 594: behind W, over S, V, U, composite blocks (ends before RB)
     static constexpr int SOA = (NS * F::TOTAL + 1) & ~1;
     static constexpr int RZ_OFF = SOA;

@@ -66,31 +66,34 @@ __device__ __forceinline__ void eval_columns_tc(Ctx2& c, double sq, double sqd, 
     const int myidx = (tid < n) ? c.ie_s[tid].x : -1;
     double* __restrict__ Wb = c.sa + T::W_OFF;
     double* __restrict__ RZb = c.sa + T::RZ_OFF;
+    // Two-warp forward kernels keep 32 rows of RZ at a time (T::RZ_ROWS): the column joints are taken in two halves, the upper
+    // threads holding their RZ rows in registers through the first one -- 4.6 KB less per block, which is what lets a fourth
+    // 64-link rollout reside on an SM.
+    constexpr bool HALF = T::RZ_ROWS < T::CAP;
+    double Rt[NL], Z[6];
+    auto put_rz = [&](int row, bool has_dof) {
+        double* RZ = RZb + row * NWD;
+#pragma unroll
+        for (int i = 0; i < NL; ++i) RZ[i] = has_dof ? Rt[i] : 0.0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) RZ[NL + i] = has_dof ? Z[i] : 0.0;
+    };
     {
-        double Rt[NL], Z[6], L[NL], s[6];
+        double L[NL], s[6];
         columns_joint<NW, GROUND, T::KEEP>(c, tid, myidx, sq, sqd, sd, L, s, Rt, Z);
         bsync<NW>();  // every thread has read S, V, U and its composite blocks: the SoA block may be overwritten
         if (tid < n) {
             double* W = Wb + tid * NWD;
-            double* RZ = RZb + tid * NWD;
             if (myidx >= 0) {
 #pragma unroll
-                for (int i = 0; i < NL; ++i) {
-                    W[i] = L[i];
-                    RZ[i] = Rt[i];
-                }
+                for (int i = 0; i < NL; ++i) W[i] = L[i];
 #pragma unroll
-                for (int i = 0; i < 6; ++i) {
-                    W[NL + i] = s[i];
-                    RZ[NL + i] = Z[i];
-                }
+                for (int i = 0; i < 6; ++i) W[NL + i] = s[i];
             } else {  // fixed joint: no row / column of H
 #pragma unroll
-                for (int i = 0; i < NWD; ++i) {
-                    W[i] = 0.0;
-                    RZ[i] = 0.0;
-                }
+                for (int i = 0; i < NWD; ++i) W[i] = 0.0;
             }
+            if (!HALF || tid < 32) put_rz(tid, myidx >= 0);
         }
     }
     bsync<NW>();
@@ -102,6 +105,15 @@ __device__ __forceinline__ void eval_columns_tc(Ctx2& c, double sq, double sqd, 
     __builtin_assume(__isShared(subs));
     __builtin_assume(__isShared(ancs));
     // rows >= n of W / RZ are never written: whatever is there only reaches C rows / columns >= n, which are not stored
+    for (int half = 0; half < (HALF ? 2 : 1); ++half) {
+        if (HALF && half == 1) {
+            if (nT <= 4) break;  // block-uniform
+            bsync<NW>();         // every tile of the first half has read its RZ rows
+            if (tid >= 32 && tid < n) put_rz(tid - 32, myidx >= 0);
+            bsync<NW>();
+        }
+        const int J0 = HALF ? 4 * half : 0;
+        const int J1 = HALF ? (nT < 4 * half + 4 ? nT : 4 * half + 4) : nT;
     for (int I = (NW == 1 ? 0 : warp); I < nT; I += NW) {
         const int k = 8 * I + g;  // row joint of this lane's A fragments and C elements
         const double* wk = Wb + k * NWD + t4;
@@ -135,9 +147,9 @@ __device__ __forceinline__ void eval_columns_tc(Ctx2& c, double sq, double sqd, 
             }
         };
         // two tiles of the row at a time: their DMMA chains (3 or 5 + 2 dependent instructions each, 26 cycles apart) interleave
-        for (int J = 0; J < nT; J += 2) {
-            const bool two = J + 1 < nT;  // warp-uniform
-            const double* rzA = RZb + (8 * J + g) * NWD + t4;  // column joint 8J+g of this lane's B fragments
+        for (int J = J0; J < J1; J += 2) {
+            const bool two = J + 1 < J1;  // warp-uniform
+            const double* rzA = RZb + (8 * (J - J0) + g) * NWD + t4;  // column joint 8J+g of this lane's B fragments
             const double* rzB = two ? rzA + 8 * NWD : rzA;
             double sA0 = 0.0, sA1 = 0.0, zA0 = 0.0, zA1 = 0.0, sB0 = 0.0, sB1 = 0.0, zB0 = 0.0, zB1 = 0.0;
 #pragma unroll
@@ -158,6 +170,7 @@ __device__ __forceinline__ void eval_columns_tc(Ctx2& c, double sq, double sqd, 
             store_tile(J, sA0, sA1, zA0, zA1);
             if (two) store_tile(J + 1, sB0, sB1, zB0, zB1);
         }
+    }
     }
     bsync<NW>();
     if (TOGLOBAL) return;
