@@ -24,12 +24,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 # named regions: (file suffix, first line, last line, name); first match wins, anything else goes by file name
 REGIONS = [
-    ('rmx_tc.cuh', 1, 30, 'tc:dmma wrapper'),
-    ('rmx_tc.cuh', 31, 163, 'tc:columns (per-joint vectors, tiles)'),
-    ('rmx_tc.cuh', 164, 306, 'tc:LU panel (pivot search, broadcast, rank-1 updates)'),
-    ('rmx_tc.cuh', 307, 337, 'tc:LU remaining rows + U12'),
-    ('rmx_tc.cuh', 338, 381, 'tc:LU trailing update'),
-    ('rmx_tc.cuh', 382, 500, 'tc:LU back substitution'),
+    ('rmx_tc.cuh', 1, 45, 'tc:dmma wrapper, pivot reciprocal'),
+    ('rmx_tc.cuh', 46, 178, 'tc:columns (per-joint vectors, tiles)'),
+    ('rmx_tc.cuh', 179, 348, 'tc:LU panel (pivot search, broadcast, rank-1 updates)'),
+    ('rmx_tc.cuh', 349, 379, 'tc:LU remaining rows + U12'),
+    ('rmx_tc.cuh', 380, 459, 'tc:LU trailing update'),
+    ('rmx_tc.cuh', 460, 560, 'tc:LU back substitution'),
     ('rmx_rollout.cuh', 1, 10000, 'rollout (newton, line search, time loop, schedule)'),
     ('rmx_fast.cuh', 1, 10000, 'fast: composite base evaluation'),
     ('rmx_device.cuh', 1, 10000, 'device helpers (se3, reductions)'),
