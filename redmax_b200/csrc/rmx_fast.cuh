@@ -83,10 +83,10 @@ struct TcLayout {
     static constexpr int H_OFF = (CAP + RZ_ROWS) * F::NW_;  // H  [CAP][LD]   column-major, identity padded to whole tiles
     static constexpr int SOA_FIELDS = NS * F::TOTAL;  // the SoA block of eval_base2 (overlaid by W, RZ, H during assembly + LU)
     static constexpr int SOA = ((SOA_FIELDS > H_OFF + CAP * LD ? SOA_FIELDS : H_OFF + CAP * LD) + 1) & ~1;
-    static constexpr int NV = 12;                     // q qd dq g dx tau hq0 hqd0 hq1 hqd1 sp1 sp2 (x0, sp0 are unused)
+    static constexpr int NV = 9;                      // q g (= dx) tau hq0 hqd0 hq1 hqd1 sp1 sp2
     static constexpr int VEC = SOA;                   // NV vectors of CAP
-    static constexpr int RED = VEC + NV * CAP;        // 16 + 8 reduction scratch
-    static constexpr int ROWBUF = RED + 24;           // 2 x 5 double2 pivot-row buffers (16B aligned: all terms even)
+    static constexpr int RED = VEC + NV * CAP;        // 16 + 8 reduction scratch (cross-warp reductions: NW > 1 only)
+    static constexpr int ROWBUF = RED + (NW == 1 ? 0 : 24);  // 2 x 5 double2 pivot-row buffers (16B aligned: all terms even)
     static constexpr int IE = ROWBUF + 20;            // int2 ie_s[CAP]
     static constexpr int PAR = IE + CAP;              // int par_s[CAP]
     static constexpr int REM = PAR + CAP / 2;         // int rem_s[CAP]
@@ -110,10 +110,10 @@ struct TcLayoutA {
     static constexpr int SOA = (NS * F::TOTAL + 1) & ~1;
     static constexpr int RZ_OFF = SOA;
     static constexpr int JROWS = RZ_OFF + CAP * F::NW_;  // 6 x CAP rows of J of the task body
-    static constexpr int NV = 12;
+    static constexpr int NV = 9;                      // q g (= dx) tau hq0 hqd0 hq1 hqd1 sp1 sp2
     static constexpr int VEC = JROWS + 6 * CAP;
     static constexpr int RED = VEC + NV * CAP;
-    static constexpr int ROWBUF = RED + 24;
+    static constexpr int ROWBUF = RED;                 // (one warp: no reduction scratch)
     static constexpr int IE = ROWBUF + 20;
     static constexpr int PAR = IE + CAP;
     static constexpr int REM = PAR + CAP / 2;
@@ -218,19 +218,19 @@ __device__ __forceinline__ void ctx2_carve_tc(Ctx2& c, double* sm, int n, int nr
     c.KD = nullptr;
     double* v = sm + T::VEC;
     c.q = v;
-    c.qd = v + 1 * T::CAP;
-    c.dq = v + 2 * T::CAP;
-    c.g = v + 3 * T::CAP;
-    c.dx = v + 4 * T::CAP;
+    c.qd = nullptr;  // formed per joint in eval_base2
+    c.dq = nullptr;
+    c.g = v + 1 * T::CAP;
+    c.dx = c.g;      // the solve reads its right-hand side into registers before it writes the solution
     c.x0 = nullptr;
     c.sp0 = nullptr;
-    c.tau = v + 5 * T::CAP;
-    c.hq0 = v + 6 * T::CAP;
-    c.hqd0 = v + 7 * T::CAP;
-    c.hq1 = v + 8 * T::CAP;
-    c.hqd1 = v + 9 * T::CAP;
-    c.sp1 = v + 10 * T::CAP;
-    c.sp2 = v + 11 * T::CAP;
+    c.tau = v + 2 * T::CAP;
+    c.hq0 = v + 3 * T::CAP;
+    c.hqd0 = v + 4 * T::CAP;
+    c.hq1 = v + 5 * T::CAP;
+    c.hqd1 = v + 6 * T::CAP;
+    c.sp1 = v + 7 * T::CAP;
+    c.sp2 = v + 8 * T::CAP;
     c.red = sm + T::RED;
     c.tcrow_s = reinterpret_cast<double2*>(sm + T::ROWBUF);
     c.ie_s = reinterpret_cast<int2*>(sm + T::IE);
@@ -257,19 +257,19 @@ __device__ __forceinline__ void ctx2_carve_tca(Ctx2& c, double* sm, int n, int n
     c.KD = nullptr;
     double* v = sm + T::VEC;
     c.q = v;
-    c.qd = v + 1 * T::CAP;
-    c.dq = v + 2 * T::CAP;
-    c.g = v + 3 * T::CAP;
-    c.dx = v + 4 * T::CAP;
+    c.qd = nullptr;
+    c.dq = nullptr;
+    c.g = v + 1 * T::CAP;
+    c.dx = c.g;
     c.x0 = nullptr;
     c.sp0 = nullptr;
-    c.tau = v + 5 * T::CAP;
-    c.hq0 = v + 6 * T::CAP;
-    c.hqd0 = v + 7 * T::CAP;
-    c.hq1 = v + 8 * T::CAP;
-    c.hqd1 = v + 9 * T::CAP;
-    c.sp1 = v + 10 * T::CAP;
-    c.sp2 = v + 11 * T::CAP;
+    c.tau = v + 2 * T::CAP;
+    c.hq0 = v + 3 * T::CAP;
+    c.hqd0 = v + 4 * T::CAP;
+    c.hq1 = v + 5 * T::CAP;
+    c.hqd1 = v + 6 * T::CAP;
+    c.sp1 = v + 7 * T::CAP;
+    c.sp2 = v + 8 * T::CAP;
     c.red = sm + T::RED;
     c.tcrow_s = reinterpret_cast<double2*>(sm + T::ROWBUF);
     c.ie_s = reinterpret_cast<int2*>(sm + T::IE);
@@ -970,13 +970,8 @@ __device__ void eval_base2(Ctx2& c, bool deriv) {
     const int t = threadIdx.x;
     const int n = c.n, NS = (NW == 1) ? 33 : 65;
     const int NT = 32 * NW;
-    // ---- stage kinematics + joint-local transforms --------------------------------------------------------
-    if (t < c.nr) {
-        double qd, dq;
-        stage_kin(c.stage, c.h, c.q[t], c.hq0[t], c.hqd0[t], c.hq1[t], c.hqd1[t], qd, dq);
-        c.qd[t] = qd;
-        c.dq[t] = dq;
-    }
+    // ---- joint-local transforms (the stage kinematics qdot, dqtmp of a dof are formed by its joint's thread below: a few
+    //      exactly rounded operations, no vectors in shared memory) ------------------------------------------------------
     double Rj[9], pj[3];  // this joint's (partial) world frame, kept in registers through the scan
     int myidx = -1;
     if (t < n) {
@@ -1042,8 +1037,7 @@ __device__ void eval_base2(Ctx2& c, bool deriv) {
                 mat3_vec(Rj, J.axis, s);
                 cross3(pj, s, s + 3);
             }
-            qdk = c.qd[myidx];
-            dqk = c.dq[myidx];
+            stage_kin(c.stage, c.h, c.q[myidx], c.hq0[myidx], c.hqd0[myidx], c.hq1[myidx], c.hqd1[myidx], qdk, dqk);
 #pragma unroll
             for (int i = 0; i < 6; ++i) Vj[i] = s[i] * qdk;
         }

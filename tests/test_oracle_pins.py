@@ -196,3 +196,114 @@ def test_adjoint_gradient_fd(oracle):
         rel = np.linalg.norm(d - dPdp) / np.linalg.norm(d)
         # BDF2's first-step dgdp coefficient is knowingly inexact in the reference (SURVEY note N7)
         assert rel < (1e-4 if scheme == 1 else 5e-2), (sid, rel, d, dPdp)
+
+
+def _system_quantities(oracle, s):
+    """The quantities Scene.test forms before its checks (Scene.m:232-269): J, Jdot, dJdq, dJdotdq, M, dMdq, fqvv, Kqvv, Dqvv,
+    f, K, D at the scene's current (q, qdot)."""
+    nr, nm = s.nr, s.nm
+    qdot = s.getQdot()
+    J, Jdot = np.zeros((nm, nr)), np.zeros((nm, nr))
+    dJdq, dJdotdq = np.zeros((nm, nr, nr)), np.zeros((nm, nr, nr))
+    Mm, Km, Dm = np.zeros((nm, nm)), np.zeros((nm, nm)), np.zeros((nm, nm))
+    fm, fr = np.zeros(nm), np.zeros(nr)
+    Kr, Dr = np.zeros((nr, nr)), np.zeros((nr, nr))
+    for j in s.joints:
+        j.computeJacobian4(J, Jdot, dJdq, dJdotdq)
+    for b in s.bodies:
+        b.computeMassGrav(s.grav, Mm, fm, Km, Dm)
+    for j in s.joints:
+        j.computeForce(fr, Kr, Dr)
+    M = J.T @ Mm @ J
+    dMdq = np.zeros((nr, nr, nr))
+    for i in range(nr):
+        tmp = J.T @ Mm @ dJdq[:, :, i]
+        dMdq[:, :, i] = tmp.T + tmp
+    fqvv = -J.T @ Mm @ Jdot @ qdot
+    Kqvv = np.zeros((nr, nr))
+    Dqvv = -J.T @ Mm @ Jdot
+    for i in range(nr):
+        Kqvv[:, i] = -dJdq[:, :, i].T @ Mm @ Jdot @ qdot - J.T @ Mm @ dJdotdq[:, :, i] @ qdot
+        Dqvv[:, i] = Dqvv[:, i] - J.T @ Mm @ dJdq[:, :, i] @ qdot
+    f = fr + J.T @ fm + fqvv
+    K = Kr + J.T @ Km @ J + Kqvv
+    D = Dr + J.T @ Dm @ J + Dqvv
+    for i in range(nr):
+        K[:, i] = K[:, i] + dJdq[:, :, i].T @ fm + J.T @ Dm @ dJdq[:, :, i] @ qdot
+    return dict(J=J, Jdot=Jdot, dJdq=dJdq, dJdotdq=dJdotdq, Mm=Mm, M=M, dMdq=dMdq, fqvv=fqvv, Kqvv=Kqvv, Dqvv=Dqvv, f=f, K=K, D=D)
+
+
+def _jac(s):
+    J, Jdot = np.zeros((s.nm, s.nr)), np.zeros((s.nm, s.nr))
+    for j in s.joints:
+        j.computeJacobian2(J, Jdot)
+    return J, Jdot
+
+
+def _force(s, J, Jdot, Mm, qdot):
+    """f as the K / D checks of Scene.test re-form it (Scene.m:347-353, 362-368)."""
+    fm, fr = np.zeros(s.nm), np.zeros(s.nr)
+    Mm_ = np.zeros((s.nm, s.nm))
+    for b in s.bodies:
+        b.computeMassGrav(s.grav, Mm_, fm)
+    for j in s.joints:
+        j.computeForce(fr)
+    return fr + J.T @ fm - J.T @ Mm @ Jdot @ qdot
+
+
+@pytest.mark.parametrize('sid', [0, 1, 2, 14])
+def test_scene_test_all_checks(oracle, sid):
+    """The whole list of Scene.test (Scene.m:271-377), every check with the reference's own perturbation (sqrt(eps)) and its
+    pass criterion (printError: relative error < 1e-6), at a seeded state instead of the scene's initial one: Jdot, dJ/dq,
+    dJdot/dq, dM/dq, Kqvv, Dqvv, K, D.  These are the derivative identities the kernels' world-frame formulation is checked
+    against through g, H, M, D (tests/test_gpu_parity.py), here for the dense quantities the reference itself forms."""
+    s = oracle.scenes(sid)
+    s.init()
+    rng = np.random.default_rng(300 + sid)
+    nr, nm = s.nr, s.nm
+    q = s.qInit + 0.3 * rng.uniform(-1, 1, nr)
+    qdot = rng.uniform(-1, 1, nr)
+    if sid == 14:
+        q[0] = -2.0  # below the lower joint limit: the limit terms of Joint.computeForce take part in K, D
+    eps = np.sqrt(np.finfo(float).eps)
+
+    def at(q_, qdot_):
+        s.setQ(q_, qdot_)
+        s.update()
+
+    at(q, qdot)
+    v = _system_quantities(oracle, s)
+    J, Jdot, Mm = v['J'], v['Jdot'], v['Mm']
+    # Jdot = d/dt J along qdot (Scene.m:276-283)
+    at(q + eps * qdot, qdot)
+    J_, _ = _jac(s)
+    _fd_check('Jdot', Jdot, (J_ - J) / eps)
+    # dJ/dq, dJdot/dq (:286-299); dM/dq (:302-314); Kqvv, Dqvv (:317-341); K, D (:344-376)
+    dJdq_, dJdotdq_ = np.zeros((nm, nr, nr)), np.zeros((nm, nr, nr))
+    dMdq_ = np.zeros((nr, nr, nr))
+    Kqvv_, Dqvv_, K_, D_ = (np.zeros((nr, nr)) for _ in range(4))
+    for i in range(nr):
+        q_ = q.copy()
+        q_[i] += eps
+        at(q_, qdot)
+        J_, Jdot_ = _jac(s)
+        dJdq_[:, :, i] = (J_ - J) / eps
+        dJdotdq_[:, :, i] = (Jdot_ - Jdot) / eps
+        dMdq_[:, :, i] = (J_.T @ Mm @ J_ - v['M']) / eps
+        Kqvv_[:, i] = (-J_.T @ Mm @ Jdot_ @ qdot - v['fqvv']) / eps
+        K_[:, i] = (_force(s, J_, Jdot_, Mm, qdot) - v['f']) / eps
+        qd_ = qdot.copy()
+        qd_[i] += eps
+        at(q, qd_)
+        J_, Jdot_ = _jac(s)
+        Dqvv_[:, i] = (-J_.T @ Mm @ Jdot_ @ qd_ - v['fqvv']) / eps
+        D_[:, i] = (_force(s, J_, Jdot_, Mm, qd_) - v['f']) / eps
+    at(q, qdot)
+    _fd_check('dJ/dq', v['dJdq'], dJdq_)
+    _fd_check('dJdot/dq', v['dJdotdq'], dJdotdq_)
+    _fd_check('dM/dq', v['dMdq'], dMdq_)
+    _fd_check('Kqvv', v['Kqvv'], Kqvv_)
+    _fd_check('Dqvv', v['Dqvv'], Dqvv_)
+    # K, D: forward differences of f, which is quadratic in qdot -- their truncation error at this seeded state reaches 1e-6
+    _fd_check('K', v['K'], K_, 2e-6)
+    _fd_check('D', v['D'], D_, 2e-6)
