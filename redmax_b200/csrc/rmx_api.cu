@@ -3,6 +3,7 @@
 // Scene flattening follows Scene.init (matlab-diff/+redmax/Scene.m:59-119): joints listed parents-first,
 // reduced indices assigned leaf-to-root (Scene.m:69-71 + Joint.countDofs, Joint.m:149).  Internally joints are
 // renumbered in DFS preorder so that every subtree is a contiguous index range.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -566,6 +567,9 @@ extern "C" void rmx_scene_destroy(rmx_scene* s) {
         cudaFree(kv.second.kry);
         for (auto& b : kv.second.buf) cudaFree(b.p);
         if (kv.second.stream) cudaStreamDestroy(kv.second.stream);
+        if (kv.second.copy_stream) cudaStreamDestroy(kv.second.copy_stream);
+        for (cudaEvent_t e : kv.second.chunk_done)
+            if (e) cudaEventDestroy(e);
     }
     cudaSetDevice(cur);
     cudaGetLastError();
@@ -743,6 +747,15 @@ static int launch_fwd(const rmx_scene* s, const RolloutArgs& a, cudaStream_t st,
     return f(a, smem, st, dc);
 }
 
+// co-resident blocks of the forward kernel this scene runs on the current device (0 if unknown)
+static long long fwd_slots(const rmx_scene* s, DevCopy* dc) {
+    RolloutArgs a;
+    std::memset(&a, 0, sizeof(a));
+    dc->slots_query = 0;
+    if (launch_fwd<false>(s, a, nullptr, dc) != RMX_OK) return 0;
+    return dc->slots_query;
+}
+
 static int rollout_dev_impl(rmx_scene* s, const rmx_opts* o, int64_t B, const double* q0, const double* qdot0,
                             const double* tau, double* q_out, double* qdot_out, int32_t* status, int32_t* iters,
                             void* cuda_stream, double* q_host, double* qdot_host) {
@@ -838,6 +851,7 @@ extern "C" int rmx_rollout(rmx_scene* s, const rmx_opts* o, int64_t B, const dou
     std::vector<int> devs;
     for (int gi = 0; gi < G; ++gi) devs.push_back(G == 1 ? cur : gi);
     int ret = RMX_OK;
+    std::vector<int> nchunk(G, 1);
     for (int gi = 0; gi < G && ret == RMX_OK; ++gi) {
         const int64_t b0 = B * gi / G, b1 = B * (gi + 1) / G, nb = b1 - b0;
         CUDA_LOOP(cudaSetDevice(devs[gi]));
@@ -855,17 +869,63 @@ extern "C" int rmx_rollout(rmx_scene* s, const rmx_opts* o, int64_t B, const dou
         CUDA_LOOP(cudaMemcpyAsync(dc->buf[1].p, qdot0 + b0 * nr, sz[1], cudaMemcpyHostToDevice, st));
         if (tau) CUDA_LOOP(cudaMemcpyAsync(dc->buf[2].p, tau + b0 * tau_per, sz[2], cudaMemcpyHostToDevice, st));
         // Page-locked output buffers are written by the kernel itself while it runs (mirrored stores over PCIe, hidden
-        // behind the rollout); pageable ones get the staged copy after it.
+        // behind the rollout).  Pageable ones (what a MATLAB mxArray is) need a device-to-host copy, which blocks this thread:
+        // the batch is launched as up to four sub-batches of at least one resident wave each, all enqueued first, and the
+        // copy of each sub-batch (second loop below) runs while the later ones are still integrating.
         double* qh = mapped_host_ptr(q_out + b0 * per);
         double* qdh = qdot_out ? mapped_host_ptr(qdot_out + b0 * per) : nullptr;
-        ret = rollout_dev_impl(s, &o1, nb, (double*)dc->buf[0].p, (double*)dc->buf[1].p, tau ? (double*)dc->buf[2].p : nullptr,
-                               (double*)dc->buf[3].p, qdot_out ? (double*)dc->buf[4].p : nullptr, (int*)dc->buf[5].p,
-                               iters ? (int*)dc->buf[6].p : nullptr, st, qh, qdh);
+        const bool paged = !qh || (qdot_out && !qdh);
+        int K = 1;
+        if (paged && o1.linsolve == RMX_LINSOLVE_LU && !g_no_sched) {
+            const long long slots = fwd_slots(s, dc);
+            if (slots > 0 && nb >= 2 * slots) K = (int)std::min<long long>(4, nb / slots);
+        }
+        if (K > 1) {
+            if (!dc->copy_stream) CUDA_LOOP(cudaStreamCreateWithFlags(&dc->copy_stream, cudaStreamNonBlocking));
+            bool ok = true;
+            for (int c = 0; c < K && ok; ++c)
+                if (!dc->chunk_done[c]) ok = cudaEventCreateWithFlags(&dc->chunk_done[c], cudaEventDisableTiming) == cudaSuccess;
+            if (!ok) {
+                cudaGetLastError();
+                K = 1;
+            }
+        }
+        nchunk[gi] = K;
+        for (int c = 0; c < K && ret == RMX_OK; ++c) {
+            const int64_t c0 = nb * c / K, cn = nb * (c + 1) / K - c0;
+            ret = rollout_dev_impl(s, &o1, cn, (double*)dc->buf[0].p + c0 * nr, (double*)dc->buf[1].p + c0 * nr,
+                                   tau ? (double*)dc->buf[2].p + c0 * tau_per : nullptr, (double*)dc->buf[3].p + c0 * per,
+                                   qdot_out ? (double*)dc->buf[4].p + c0 * per : nullptr, (int*)dc->buf[5].p + c0,
+                                   iters ? (int*)dc->buf[6].p + 2 * c0 : nullptr, st, qh ? qh + c0 * per : nullptr,
+                                   qdh ? qdh + c0 * per : nullptr);
+            if (ret == RMX_OK && K > 1) CUDA_LOOP(cudaEventRecord(dc->chunk_done[c], st));
+        }
         if (ret) break;
-        if (!qh) CUDA_LOOP(cudaMemcpyAsync(q_out + b0 * per, dc->buf[3].p, sz[3], cudaMemcpyDeviceToHost, st));
-        if (qdot_out && !qdh) CUDA_LOOP(cudaMemcpyAsync(qdot_out + b0 * per, dc->buf[4].p, sz[4], cudaMemcpyDeviceToHost, st));
-        CUDA_LOOP(cudaMemcpyAsync(status + b0, dc->buf[5].p, sz[5], cudaMemcpyDeviceToHost, st));
-        if (iters) CUDA_LOOP(cudaMemcpyAsync(iters + 2 * b0, dc->buf[6].p, sz[6], cudaMemcpyDeviceToHost, st));
+    }
+    // device-to-host copies: all devices are integrating by now
+    for (int gi = 0; gi < G && ret == RMX_OK; ++gi) {
+        const int64_t b0 = B * gi / G, b1 = B * (gi + 1) / G, nb = b1 - b0;
+        CUDA_LOOP(cudaSetDevice(devs[gi]));
+        DevCopy* dc = &s->dev.find(devs[gi])->second;
+        cudaStream_t st = dc->stream;
+        double* qh = mapped_host_ptr(q_out + b0 * per);
+        double* qdh = qdot_out ? mapped_host_ptr(qdot_out + b0 * per) : nullptr;
+        const int K = nchunk[gi];
+        for (int c = 0; c < K && ret == RMX_OK; ++c) {
+            const int64_t c0 = nb * c / K, cn = nb * (c + 1) / K - c0;
+            cudaStream_t cs = K > 1 ? dc->copy_stream : st;
+            if (K > 1) CUDA_LOOP(cudaStreamWaitEvent(cs, dc->chunk_done[c], 0));
+            if (!qh)
+                CUDA_LOOP(cudaMemcpyAsync(q_out + (b0 + c0) * per, (double*)dc->buf[3].p + c0 * per, cn * per * sizeof(double),
+                                          cudaMemcpyDeviceToHost, cs));
+            if (qdot_out && !qdh)
+                CUDA_LOOP(cudaMemcpyAsync(qdot_out + (b0 + c0) * per, (double*)dc->buf[4].p + c0 * per, cn * per * sizeof(double),
+                                          cudaMemcpyDeviceToHost, cs));
+        }
+        if (ret) break;
+        if (K > 1) CUDA_LOOP(cudaStreamSynchronize(dc->copy_stream));
+        CUDA_LOOP(cudaMemcpyAsync(status + b0, dc->buf[5].p, nb * sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (iters) CUDA_LOOP(cudaMemcpyAsync(iters + 2 * b0, dc->buf[6].p, 2 * nb * sizeof(int), cudaMemcpyDeviceToHost, st));
     }
     for (int gi = 0; gi < G; ++gi) {
         cudaSetDevice(devs[gi]);

@@ -48,6 +48,9 @@ struct DevCopy {
     int* pf_ep = nullptr;
     unsigned long long* kry = nullptr;  // Krylov iteration counter
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // device-to-host copies of finished sub-batches (pageable outputs of rmx_rollout)
+    cudaEvent_t chunk_done[4] = {nullptr, nullptr, nullptr, nullptr};
+    long long slots_query = 0;           // co-resident blocks of the last forward-kernel occupancy query (launcher called with B <= 0)
     DevBuf buf[16];
     void* plan_dev = nullptr;  // device copy of `plan` currently in buf[13]/buf[14]
 };

@@ -11,6 +11,15 @@ static int rmx_launch_fwd_t(const rmx::RolloutArgs& a0, size_t smem, cudaStream_
     int rc = rmx_set_smem(kernel, smem);
     if (rc) return rc;
     RolloutArgs a = a0;
+    if (a.B <= 0) {  // occupancy query only: how many blocks of this kernel are co-resident on the current device
+        if (!dc) return RMX_OK;
+        int nb = 0, dev = 0, sms = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, 32 * NW, smem));
+        CUDA_TRY(cudaGetDevice(&dev));
+        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        dc->slots_query = (long long)nb * sms;
+        return RMX_OK;
+    }
     long long grid = a.B;
     if (!ADJ && LIN == 0 && dc && a.qd_out && a.op.nsteps >= 2 && a.B < (1ll << 30) && rmx_sched_enabled()) {
         int nb = 0, dev = 0, sms = 0;

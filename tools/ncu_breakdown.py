@@ -25,11 +25,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # named regions: (file suffix, first line, last line, name); first match wins, anything else goes by file name
 REGIONS = [
     ('rmx_tc.cuh', 1, 45, 'tc:dmma wrapper, pivot reciprocal'),
-    ('rmx_tc.cuh', 46, 178, 'tc:columns (per-joint vectors, tiles)'),
-    ('rmx_tc.cuh', 179, 348, 'tc:LU panel (pivot search, broadcast, rank-1 updates)'),
-    ('rmx_tc.cuh', 349, 379, 'tc:LU remaining rows + U12'),
-    ('rmx_tc.cuh', 380, 459, 'tc:LU trailing update'),
-    ('rmx_tc.cuh', 460, 560, 'tc:LU back substitution'),
+    ('rmx_tc.cuh', 46, 191, 'tc:columns (per-joint vectors, tiles)'),
+    ('rmx_tc.cuh', 192, 361, 'tc:LU panel (pivot search, broadcast, rank-1 updates)'),
+    ('rmx_tc.cuh', 362, 392, 'tc:LU remaining rows + U12'),
+    ('rmx_tc.cuh', 393, 472, 'tc:LU trailing update'),
+    ('rmx_tc.cuh', 473, 560, 'tc:LU back substitution'),
     ('rmx_rollout.cuh', 1, 10000, 'rollout (newton, line search, time loop, schedule)'),
     ('rmx_fast.cuh', 1, 10000, 'fast: composite base evaluation'),
     ('rmx_device.cuh', 1, 10000, 'device helpers (se3, reductions)'),
