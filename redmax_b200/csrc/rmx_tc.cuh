@@ -245,6 +245,13 @@ __device__ __forceinline__ void lu_solve_tc(int nr, double* H, int* perm, int* r
             for (int i = 0; i < 8; ++i) {
                 const int k = c0 + i;
 #ifndef RMX_PIVOT_EXACT
+                // Every lane takes the reciprocal of its own candidate(s) now, while the reduction below is in flight: the one of
+                // the row that wins is published with the pivot row, so the MUFU + two Newton steps (~50 cycles) leave the chain
+                // reduction -> broadcast -> multiplier -> update.  Same number as the reciprocal of the broadcast pivot (the seed
+                // instruction has no slow path, so zero / padding entries cost nothing), same instruction count.
+                double rp_own[R];
+#pragma unroll
+                for (int h = 0; h < R; ++h) rp_own[h] = rcp_pivot(a[h][i]);
                 // Pivot row: ONE warp reduction per column.  Key = [not a pivot yet | top 25 bits of |a[i]| (sign, exponent, 14
                 // mantissa bits dropped of the IEEE high word's 20) | 63 - row]: its maximum names a row whose entry is within
                 // 2^-14 of the largest in the column (the lowest such row), which is all partial pivoting needs -- the growth
@@ -323,24 +330,35 @@ __device__ __forceinline__ void lu_solve_tc(int nr, double* H, int* perm, int* r
                 // the pivot lane publishes its panel row (entries i.. as 128-bit pairs) and right-hand side; two alternating buffers,
                 // so one __syncwarp per pivot step orders both the read-after-write and the next write-after-read
                 double2* buf = rowbuf + 5 * (i & 1);
+#ifndef RMX_PIVOT_EXACT
+#define RMX_RP_SLOT(h) rp_own[h]
+#else
+#define RMX_RP_SLOT(h) 0.0
+#endif
                 if (lane == src) {
                     if (R == 1 || sh == 0) {
 #pragma unroll
                         for (int j = i / 2; j < 4; ++j) buf[j] = make_double2(a[0][2 * j], a[0][2 * j + 1]);
-                        buf[4] = make_double2(b[0], 0.0);
+                        buf[4] = make_double2(b[0], RMX_RP_SLOT(0));
                     } else {
 #pragma unroll
                         for (int j = i / 2; j < 4; ++j) buf[j] = make_double2(a[R - 1][2 * j], a[R - 1][2 * j + 1]);
-                        buf[4] = make_double2(b[R - 1], 0.0);
+                        buf[4] = make_double2(b[R - 1], RMX_RP_SLOT(R - 1));
                     }
                 }
+#undef RMX_RP_SLOT
                 __syncwarp();
                 double2 u2[4];
 #pragma unroll
                 for (int j = i / 2; j < 4; ++j) u2[j] = buf[j];
-                const double ub = buf[4].x;
+                const double2 ubrp = buf[4];
+                const double ub = ubrp.x;
+#ifndef RMX_PIVOT_EXACT
+                const double rp = ubrp.y;
+#else
                 const double piv = (i & 1) ? u2[i / 2].y : u2[i / 2].x;
                 const double rp = rcp_pivot(piv);
+#endif
 #pragma unroll
                 for (int h = 0; h < R; ++h) {
                     rdiag[h] = (lane == src && h == sh) ? rp : rdiag[h];
