@@ -244,6 +244,14 @@ int rmx_eval(rmx_scene* s, const double* q, const double* qdot, const double* dq
 int rmx_eval_newton(rmx_scene* s, const double* q, const double* qdot, const double* dqtmp, const double* tau,
                     double cK, double beta, double* H, double* dx);
 
+/* Test hook: the two operators of the Krylov linear solve (opts.linsolve = RMX_LINSOLVE_PCG, after c++/PCG) at one evaluation
+ * point, arguments as rmx_eval.  Hx = H x applied matrix-free -- a root-to-leaves and a leaves-to-root sweep over the joint
+ * tree, as the reference applies J x, LHS and J' y (c++/PCG/src/ConstraintJoint.cpp:1090, 1137, 1188) -- and
+ * Pinv_x = (J' blkdiag(M_j) J + Pr)^-1 x, the projected block-Jacobi preconditioner (ConstraintJoint.cpp:1236, 1455;
+ * notes.pdf Alg. 10).  Either output may be NULL. */
+int rmx_eval_krylov(rmx_scene* s, const double* q, const double* qdot, const double* dqtmp, const double* tau, double cK, double beta,
+                    const double* x, double* Hx, double* Pinv_x);
+
 /* Test hook (host only): the load-balancing plan of a forward launch -- B rollouts x nsteps steps over `slots` co-resident
  * blocks (McNaughton wrap-around: a rollout is cut at most once; its first part opens one block's list and signals, its second
  * part closes the previous block's list and waits).  seg: 4 ints per segment {rollout, first step, end step, flags: 1 wait,

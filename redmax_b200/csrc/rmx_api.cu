@@ -1190,6 +1190,61 @@ extern "C" int rmx_eval_newton(rmx_scene* s, const double* q, const double* qdot
     return rc;
 }
 
+// rmx_eval_krylov test hook: the two operators of the Krylov linear solve at one evaluation point
+extern "C" int rmx_eval_krylov(rmx_scene* s, const double* q, const double* qdot, const double* dqtmp, const double* tau,
+                               double cK, double beta, const double* x, double* Hx, double* Pinv_x) {
+    if (!s || !q || !qdot || !dqtmp || !x) return fail(RMX_EINVAL, "rmx_eval_krylov: null argument");
+    int ndev = 0;
+    cudaError_t e0 = cudaGetDeviceCount(&ndev);
+    if (e0 != cudaSuccess || ndev < 1) {
+        cudaGetLastError();
+        return fail(RMX_ENOGPU, "rmx_eval_krylov: no CUDA device");
+    }
+    if (s->impl != 2) return fail(RMX_ELIMIT, "rmx_eval_krylov: composite kernels only (n <= 64 joints)");
+    if (!s->pf.empty()) return fail(RMX_ELIMIT, "rmx_eval_krylov: scenes with forces between body points use the dense operator");
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    DevCopy* dc;
+    int rc = scene_on_device(s, dev, &dc);
+    if (rc) return rc;
+    const int nr = s->nr;
+    const size_t v = nr * sizeof(double);
+    double* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, 7 * v));
+    double *dq_ = d, *dqd = d + nr, *ddq = d + 2 * nr, *dtau = d + 3 * nr, *dx = d + 4 * nr, *dhx = d + 5 * nr, *dpx = d + 6 * nr;
+    cudaMemcpy(dq_, q, v, cudaMemcpyHostToDevice);
+    cudaMemcpy(dqd, qdot, v, cudaMemcpyHostToDevice);
+    cudaMemcpy(ddq, dqtmp, v, cudaMemcpyHostToDevice);
+    cudaMemcpy(dx, x, v, cudaMemcpyHostToDevice);
+    if (tau)
+        cudaMemcpy(dtau, tau, v, cudaMemcpyHostToDevice);
+    else
+        cudaMemset(dtau, 0, v);
+    EvalArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.sc = make_devscene(s, dc);
+    a.q = dq_;
+    a.qd = dqd;
+    a.dq = ddq;
+    a.tau = dtau;
+    a.cK = cK;
+    a.beta = beta;
+    const size_t smem = (scene_smem_doubles(s, true) + pcg_doubles(s->n, s->nr)) * sizeof(double);
+    if (smem > 227 * 1024) {
+        cudaFree(d);
+        return fail(RMX_ELIMIT, "scene does not fit the 227 KB shared memory of one SM");
+    }
+    rc = rmx_launch_eval_krylov(warps_for(s), ext_level(s), a, dx, dhx, dpx, smem);
+    if (rc == RMX_OK) {
+        if (Hx) cudaMemcpy(Hx, dhx, v, cudaMemcpyDeviceToHost);
+        if (Pinv_x) cudaMemcpy(Pinv_x, dpx, v, cudaMemcpyDeviceToHost);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) rc = fail(RMX_ECUDA, cudaGetErrorString(e));
+    }
+    cudaFree(d);
+    return rc;
+}
+
 // Test hook (host only, no GPU needed): the load-balancing plan a forward launch of B rollouts x nsteps steps would use on
 // `slots` co-resident blocks.  seg: 4 ints per segment {rollout, first step, end step, flags (1 wait, 2 signal)}; off: slots+1.
 // Returns the number of segments (at most B + slots), or a negative error code if seg_capacity is too small.

@@ -97,5 +97,6 @@ RMX_FWD_ALL(RMX_DECLARE_FWD)
 // test hooks and diagnostics (rmx_k_misc.cu)
 int rmx_launch_eval(int impl, int nw, int ground, const rmx::EvalArgs& a, size_t smem);
 int rmx_launch_eval_newton(int nw, int ground, const rmx::EvalArgs& a, double* dx, size_t smem);
+int rmx_launch_eval_krylov(int nw, int ground, const rmx::EvalArgs& a, const double* x, double* hx, double* pinvx, size_t smem);
 int rmx_launch_energy(int impl, int nw, int ground, const rmx::EnergyArgs& a, size_t smem);
 int rmx_launch_bwd(int nw, const rmx::BwdArgs& a, cudaStream_t st);

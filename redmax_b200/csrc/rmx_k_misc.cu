@@ -44,6 +44,22 @@ int rmx_launch_eval_newton(int nw, int gr, const EvalArgs& a, double* dx, size_t
                    : (gr ? launch_eval_newton_t<2, 1>(a, dx, smem) : launch_eval_newton_t<2, 0>(a, dx, smem));
 }
 
+// rmx_eval_krylov test hook: y = H x (matrix-free) and z = preconditioner^-1 x at one evaluation point
+template <int NW, int GROUND>
+static int launch_eval_krylov_t(const EvalArgs& a, const double* x, double* hx, double* pinvx, size_t smem) {
+    int rc = rmx_set_smem(eval_krylov_kernel<NW, GROUND>, smem);
+    if (rc) return rc;
+    eval_krylov_kernel<NW, GROUND><<<1, 32 * NW, smem>>>(a, x, hx, pinvx);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaDeviceSynchronize());
+    return RMX_OK;
+}
+
+int rmx_launch_eval_krylov(int nw, int gr, const EvalArgs& a, const double* x, double* hx, double* pinvx, size_t smem) {
+    if (nw == 1) return gr ? launch_eval_krylov_t<1, 1>(a, x, hx, pinvx, smem) : launch_eval_krylov_t<1, 0>(a, x, hx, pinvx, smem);
+    return gr ? launch_eval_krylov_t<2, 1>(a, x, hx, pinvx, smem) : launch_eval_krylov_t<2, 0>(a, x, hx, pinvx, smem);
+}
+
 template <int NW, int GROUND, int IMPL>
 static int launch_energy_t(const EnergyArgs& a, size_t smem) {
     int rc = rmx_set_smem(energies_kernel<NW, GROUND, IMPL>, smem);

@@ -17,8 +17,13 @@
 //        root->leaves : y_j = (u_j - U_j'a_parent) / d_j ;   a_j = a_parent + s_j y_j                            (Vdot, y)
 //     Mhat_j is the body inertia, Pr the joint-space diagonal -c (dfr/dq + beta dfr/dqdot) (joint stiffness, damping, limits);
 //     tools/proto_precond.py checks the recursion against a dense solve.
-//   * H itself is available densely in shared memory (its assembly costs 12 multiply-adds per entry), so the operator
-//     product is a dense shared-memory matvec rather than the reference's three tree sweeps.
+//   * the operator is applied MATRIX-FREE, as the reference applies J x / LHS / J' y (ConstraintJoint.cpp:1090, 1137, 1188): the
+//     Newton matrix is tree-semiseparable, H[k][i] = L_k . Rt_i for k in sub(i) and s_k . Z_i for k a proper ancestor of i
+//     (rmx_fast.cuh), so with the per-joint vectors (O(n) to form, no n x n matrix is ever assembled)
+//        (H x)_k = L_k . P_k + s_k . Q_k + dg_k x_k ,   P_k = sum_{i in anc*(k)} Rt_i x_i   (root -> leaves sweep)
+//                                                      Q_k = sum_{i in sub(k), i != k} Z_i x_i  (leaves -> root sweep)
+//     the first sweep a pointer-jumping prefix sum, the second the subtree accumulation the evaluation uses for its wrenches.
+//     Scenes with forces between body points (off-tree couplings) keep the dense matrix and a dense product.
 // Measured: for nr <= 64 the in-block LU is faster than this solve; LU stays the default and the parity path.
 #pragma once
 #include "rmx_fast.cuh"
@@ -32,9 +37,16 @@ struct PcgMem {
     double* dinv;  // [n]
     double* u;     // [n]
     double* vec;   // 8 nr-vectors: r, r0, p, v, s, t, phat, shat
+    double* WR;    // [n][2 * 24]  per joint [L_k ; s_k | Rt_k ; Z_k]  (matrix-free operator)
+    double* PS;    // [n][18]      prefix sums of Rt_i x_i along the root paths
+    double* QS;    // [n][6]       subtree sums of Z_i x_i
+    double* dgv;   // [nr]         joint-level diagonal of H
 };
+constexpr int PCG_WR = 48, PCG_PS = 18;
 
-__host__ __device__ inline size_t pcg_doubles(int n, int nr) { return (size_t)n * (21 + 6 + 6 + 2) + 8 * (size_t)nr + 2; }
+__host__ __device__ inline size_t pcg_doubles(int n, int nr) {
+    return (size_t)n * (21 + 6 + 6 + 2 + PCG_WR + PCG_PS + 6) + 9 * (size_t)nr + 2;
+}
 
 __device__ __forceinline__ void pcg_carve(PcgMem& m, double* p, int n, int nr) {
     m.IA = p; p += (size_t)n * 21;
@@ -42,7 +54,11 @@ __device__ __forceinline__ void pcg_carve(PcgMem& m, double* p, int n, int nr) {
     m.P = p; p += (size_t)n * 6;
     m.dinv = p; p += n;
     m.u = p; p += n;
-    m.vec = p;
+    m.vec = p; p += 8 * (size_t)nr;
+    m.WR = p; p += (size_t)n * PCG_WR;
+    m.PS = p; p += (size_t)n * PCG_PS;
+    m.QS = p; p += (size_t)n * 6;
+    m.dgv = p;
 }
 
 __device__ __forceinline__ int sym_idx(int a, int b) {  // a <= b
@@ -172,8 +188,101 @@ __device__ void precond_apply(Ctx2& c, PcgMem& m, const double* x, double* y) {
     bsync<NW>();
 }
 
-// Solves H x = scale * rhs with preconditioned BiCGStab; x -> c.dx.  Returns the number of iterations.
+// Matrix-free form of sq dg/dq + sqd dg/dqdot + sd dg/d(dqtmp): the per-joint vectors only (columns_joint), kept in shared memory.
 template <int NW, int GROUND>
+__device__ void eval_columns_mf(Ctx2& c, PcgMem& m, double sq, double sqd, double sd) {
+    typedef Fld<GROUND, 1> F;
+    constexpr int NL = F::NL;
+    const int t = threadIdx.x;
+    const int n = c.n;
+    const int myidx = (t < n) ? c.ie_s[t].x : -1;
+    double Rt[NL], Z[6], L[NL], s[6];
+    columns_joint<NW, GROUND, 1>(c, t, myidx, sq, sqd, sd, L, s, Rt, Z);
+    if (t < n) {
+        double* w = m.WR + (size_t)t * PCG_WR;
+        const bool dof = myidx >= 0;
+#pragma unroll
+        for (int i = 0; i < NL; ++i) {
+            w[i] = dof ? L[i] : 0.0;
+            w[24 + i] = dof ? Rt[i] : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            w[NL + i] = dof ? s[i] : 0.0;
+            w[24 + NL + i] = dof ? Z[i] : 0.0;
+        }
+        if (dof) m.dgv[myidx] = -c.c * (sq * c.sp2[myidx] + sqd * c.sp1[myidx]);  // Kr, Dr of Joint.m:470-481
+    }
+    bsync<NW>();
+}
+
+// y = H x through the two tree sweeps (x, y indexed by reduced index).
+template <int NW, int GROUND>
+__device__ void hx_apply(Ctx2& c, PcgMem& m, const double* x, double* y) {
+    typedef Fld<GROUND, 1> F;
+    constexpr int NL = F::NL;
+    const int t = threadIdx.x;
+    const int n = c.n;
+    const int myidx = (t < n) ? c.ie_s[t].x : -1;
+    const double* w = m.WR + (size_t)(t < n ? t : 0) * PCG_WR;
+    const double xi = (myidx >= 0) ? x[myidx] : 0.0;
+    double P[NL];
+    if (t < n) {
+#pragma unroll
+        for (int i = 0; i < NL; ++i) {
+            P[i] = w[24 + i] * xi;
+            m.PS[(size_t)t * PCG_PS + i] = P[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) m.QS[(size_t)t * 6 + i] = w[24 + NL + i] * xi;
+    }
+    bsync<NW>();
+    // root -> leaves (computeJ_x's direction): P_k = sum over anc*(k), pointer jumping
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        if (r >= c.nrounds) break;  // uniform
+        const int a = (t < n) ? c.anc_r[r] : -1;
+        if (a >= 0) {
+#pragma unroll
+            for (int i = 0; i < NL; ++i) P[i] += m.PS[(size_t)a * PCG_PS + i];
+        }
+        bsync<NW>();
+        if (a >= 0) {
+#pragma unroll
+            for (int i = 0; i < NL; ++i) m.PS[(size_t)t * PCG_PS + i] = P[i];
+        }
+        bsync<NW>();
+    }
+    // leaves -> root (computeJT_x's direction): subtree sums, one thread per component
+    if (t < 6) {
+        if (c.is_chain) {
+            double acc = 0.0;
+            for (int j = n - 1; j >= 0; --j) {
+                acc += m.QS[(size_t)j * 6 + t];
+                m.QS[(size_t)j * 6 + t] = acc;
+            }
+        } else {
+            for (int j = n - 1; j > 0; --j) {
+                const int par = c.par_s[j];
+                if (par >= 0) m.QS[(size_t)par * 6 + t] += m.QS[(size_t)j * 6 + t];
+            }
+        }
+    }
+    bsync<NW>();
+    if (myidx >= 0) {
+        double acc = m.dgv[myidx] * xi;
+#pragma unroll
+        for (int i = 0; i < NL; ++i) acc = fma(w[i], P[i], acc);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) acc = fma(w[NL + i], m.QS[(size_t)t * 6 + i] - w[24 + NL + i] * xi, acc);
+        y[myidx] = acc;
+    }
+    bsync<NW>();
+}
+
+// Solves H x = scale * rhs with preconditioned BiCGStab; x -> c.dx.  Returns the number of iterations.
+// MF: the operator is hx_apply (per-joint vectors from eval_columns_mf); otherwise the dense matrix H in shared memory.
+template <int NW, int GROUND, bool MF>
 __device__ int krylov_solve(Ctx2& c, PcgMem& m, const double* H, const double* rhs, double scale, double tol, int maxit) {
     const int t = threadIdx.x;
     const int nr = c.nr, ld = c.ld;
@@ -206,7 +315,10 @@ __device__ int krylov_solve(Ctx2& c, PcgMem& m, const double* H, const double* r
             bsync<NW>();
             precond_apply<NW, GROUND>(c, m, p, ph);
             vt = 0.0;
-            if (t < nr) {
+            if (MF) {
+                hx_apply<NW, GROUND>(c, m, ph, v);
+                if (t < nr) vt = v[t];
+            } else if (t < nr) {
                 for (int k = 0; k < nr; ++k) vt = fma(H[(size_t)k * ld + t], ph[k], vt);
             }
             alpha = rho_new / block_sum<NW>(r0t * vt, c.red);
@@ -221,7 +333,10 @@ __device__ int krylov_solve(Ctx2& c, PcgMem& m, const double* H, const double* r
             bsync<NW>();
             precond_apply<NW, GROUND>(c, m, s, sh);
             double tv = 0.0;
-            if (t < nr) {
+            if (MF) {
+                hx_apply<NW, GROUND>(c, m, sh, tt);
+                if (t < nr) tv = tt[t];
+            } else if (t < nr) {
                 for (int k = 0; k < nr; ++k) tv = fma(H[(size_t)k * ld + t], sh[k], tv);
             }
             const double ts = block_sum<NW>(tv * st, c.red);
@@ -237,7 +352,7 @@ __device__ int krylov_solve(Ctx2& c, PcgMem& m, const double* H, const double* r
     }
     (void)r;
     (void)r0;
-    (void)tt;
+    (void)ld;
     if (t < nr) c.dx[t] = xt;
     bsync<NW>();
     return it;

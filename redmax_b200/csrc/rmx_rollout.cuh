@@ -140,6 +140,8 @@ struct Eval<2, NW, GROUND, KEEP, LIN, ATC> {
     static constexpr bool TC = (NW <= 2 && !KEEP && LIN == 0);
     static constexpr bool TCA = (ATC && NW == 1 && !GROUND && KEEP && LIN == 0);
     static constexpr int KF = TCA ? 2 : (KEEP ? 1 : 0);  // which fields eval_base2 keeps (Fld<GROUND, KF>)
+    // Krylov solve: matrix-free operator unless forces between body points couple bodies off the tree (rmx_pcg.cuh)
+    static constexpr bool MF = (LIN == 1 && GROUND < 2);
     typedef Fld<GROUND, KF> F;
     static __device__ __forceinline__ double* jrows(const C& c) { return TCA ? c.jrows : c.H + (size_t)c.nr * c.ld; }
     static __device__ __forceinline__ void setup(C& c, double* sm, const DevScene& sc, const StepOpts& op) {
@@ -197,6 +199,8 @@ struct Eval<2, NW, GROUND, KEEP, LIN, ATC> {
             eval_columns_tc<NW, GROUND, TcLayout<GROUND, NW>, false>(c, sq, sqd, sd, scale, out);
         else if (TCA)
             eval_columns_tc<1, false, TcLayoutA, false>(c, sq, sqd, sd, scale, out);
+        else if (MF)
+            eval_columns_mf<NW, GROUND>(c, c.pm, sq, sqd, sd);  // (scale is 1 for the Newton matrix)
         else
             eval_columns2<NW, GROUND, KF>(c, sq, sqd, sd, scale, out);
     }
@@ -208,7 +212,7 @@ struct Eval<2, NW, GROUND, KEEP, LIN, ATC> {
         if (TC || TCA) {
             lu_solve_tc<NW>(c.nr, c.H, perm, c.rem_s, c.tcrow_s, c.g, scale, c.dx);
         } else if (LIN == 1) {
-            c.kry_iters += krylov_solve<NW, GROUND>(c, c.pm, c.H, c.g, scale, c.lin_tol, c.lin_maxit);
+            c.kry_iters += krylov_solve<NW, GROUND, MF>(c, c.pm, c.H, c.g, scale, c.lin_tol, c.lin_maxit);
         } else if (NW == 1) {
             lu_solve_warp(c.nr, c.ld, c.H, perm, c.g, scale, c.dx, write_back, c.lubuf);
         } else {
@@ -842,6 +846,49 @@ __global__ void __launch_bounds__(32 * NW) eval_newton_kernel(EvalArgs a, double
     E::factor_solve(c, perm_s, -1.0, false);
     bsync<NW>();
     if (t < nr && dx_out) dx_out[t] = c.dx[t];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Test hook: the two operators of the Krylov solve at one evaluation point -- y = H x through the matrix-free tree sweeps
+// and z = (J' blkdiag(M_j) J + Pr)^-1 x through the projected block-Jacobi preconditioner (notes.pdf Alg. 10).
+// ---------------------------------------------------------------------------------------------
+template <int NW, int GROUND>
+__global__ void __launch_bounds__(32 * NW) eval_krylov_kernel(EvalArgs a, const double* x, double* hx, double* pinvx) {
+    typedef Eval<2, NW, GROUND, true, 1> E;
+    extern __shared__ double2 smem_raw[];
+    double* sm = reinterpret_cast<double*>(smem_raw);
+    const int t = threadIdx.x;
+    const int nr = a.sc.nr;
+    typename E::C c;
+    StepOpts op0;
+    op0.shortcuts = 0;
+    op0.lin_tol = 0.0;
+    op0.lin_maxit = 0;
+    E::setup(c, sm, a.sc, op0);
+    c.stage = ST_DIRECT;
+    c.h = 1.0;
+    c.c = a.cK;
+    c.beta = a.beta;
+    double* xs = c.pm.vec;           // r slot
+    double* ys = c.pm.vec + nr;      // r0 slot
+    if (t < nr) {
+        c.q[t] = a.q[t];
+        c.hqd0[t] = a.qd[t];
+        c.hq1[t] = a.dq[t];
+        c.hq0[t] = 0;
+        c.hqd1[t] = 0;
+        c.tau[t] = a.tau ? a.tau[t] : 0.0;
+        xs[t] = x[t];
+    }
+    bsync<NW>();
+    E::base(c, true);
+    E::columns(c, 1.0, c.beta, 1.0, 1.0, c.H);
+    hx_apply<NW, GROUND>(c, c.pm, xs, ys);
+    if (t < nr && hx) hx[t] = ys[t];
+    bsync<NW>();
+    precond_setup<NW, GROUND>(c, c.pm);
+    precond_apply<NW, GROUND>(c, c.pm, xs, ys);
+    if (t < nr && pinvx) pinvx[t] = ys[t];
 }
 
 }  // namespace rmx

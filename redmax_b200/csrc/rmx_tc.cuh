@@ -218,6 +218,7 @@ __device__ __forceinline__ void lu_solve_tc(int nr, double* H, int* perm, int* r
     const bool w0 = (NW == 1) || warp == 0;
     bool done[R];  // rows beyond the padded matrix never take part
     int pos[R], mypos[R];  // pos: LAPACK position of each row (RMX_PIVOT_EXACT only)
+    unsigned kmask[R], kcode[R];  // pivot-search key of a row: (high word of the entry & kmask) | kcode
     double b[R], rdiag[R];
 #pragma unroll
     for (int h = 0; h < R; ++h) {
@@ -228,6 +229,10 @@ __device__ __forceinline__ void lu_solve_tc(int nr, double* H, int* perm, int* r
         mypos[h] = -1;
         b[h] = (row < nr) ? scale * rhs[row] : 0.0;
         rdiag[h] = 1.0;
+        kmask[h] = done[h] ? 0u : 0x7fffffc0u;
+        kcode[h] = done[h] ? 0u : (0x80000000u | (unsigned)(63 - row));
+        (void)kmask[h];
+        (void)kcode[h];
     }
     double* Hrow = H + lane;  // this lane's rows: entry c of row lane + 32 h at Hrow[c * LD + 32 h]
     for (int p = 0; p < NP; ++p) {
@@ -258,23 +263,24 @@ __device__ __forceinline__ void lu_solve_tc(int nr, double* H, int* perm, int* r
                 // bound changes by that factor.  The exact dgetf2 rule (idamax, first maximum in LAPACK's current row order: a second
                 // reduction, two votes and a position exchange per column, all on the factorisation's critical path) is kept
                 // behind -DRMX_PIVOT_EXACT; both give factors of the same quality, neither is bitwise MATLAB's.
-                unsigned key = 0u;
+                // On the chain: one LOP3 per row ((hi & kmask) | kcode; both words are zeroed once a row is a pivot), the
+                // reduction, one compare -- the keys are distinct, so the winner recognises itself and nobody decodes the row.
+                unsigned key[R];
+#pragma unroll
+                for (int h = 0; h < R; ++h) key[h] = ((unsigned)__double2hiint(a[h][i]) & kmask[h]) | kcode[h];
+                const unsigned kmax = __reduce_max_sync(FULL, R == 1 ? key[0] : max(key[0], key[R - 1]));
+                bool win[R];
 #pragma unroll
                 for (int h = 0; h < R; ++h) {
-                    const unsigned hi = (unsigned)__double2hiint(a[h][i]) & 0x7fffffc0u;
-                    const unsigned kh = done[h] ? 0u : (0x80000000u | hi | (unsigned)(63 - lane - 32 * h));
-                    key = (h == 0) ? kh : max(key, kh);
-                }
-                const int srow = 63 - (int)(__reduce_max_sync(FULL, key) & 63u);
-                const int src = srow & 31, sh = srow >> 5;  // pivot row = src + 32 sh (warp-uniform)
-#pragma unroll
-                for (int h = 0; h < R; ++h) {
-                    if (lane == src && h == sh) {
+                    win[h] = key[h] == kmax;  // (kmax != 0: some row is not a pivot yet)
+                    if (win[h]) {
                         done[h] = true;
                         mypos[h] = k;
+                        kmask[h] = 0u;
+                        kcode[h] = 0u;
+                        perm[k] = lane + 32 * h;
                     }
                 }
-                if (lane == (k & 31)) perm[k] = srow;
 #else
                 // argmax |a[i]| over the rows that are not pivots yet; ties -> smallest LAPACK position (dgetf2's idamax).
                 // |v| >= 0, so the IEEE bit pattern orders like the value: one warp reduction on the high words decides unless two
@@ -326,6 +332,9 @@ __device__ __forceinline__ void lu_solve_tc(int nr, double* H, int* perm, int* r
                     }
                 }
                 if (lane == (k & 31)) perm[k] = src + 32 * sh;
+                bool win[R];
+#pragma unroll
+                for (int h = 0; h < R; ++h) win[h] = lane == src && h == sh;
 #endif
                 // the pivot lane publishes its panel row (entries i.. as 128-bit pairs) and right-hand side; two alternating buffers,
                 // so one __syncwarp per pivot step orders both the read-after-write and the next write-after-read
@@ -335,16 +344,14 @@ __device__ __forceinline__ void lu_solve_tc(int nr, double* H, int* perm, int* r
 #else
 #define RMX_RP_SLOT(h) 0.0
 #endif
-                if (lane == src) {
-                    if (R == 1 || sh == 0) {
+                if (win[0]) {
 #pragma unroll
-                        for (int j = i / 2; j < 4; ++j) buf[j] = make_double2(a[0][2 * j], a[0][2 * j + 1]);
-                        buf[4] = make_double2(b[0], RMX_RP_SLOT(0));
-                    } else {
+                    for (int j = i / 2; j < 4; ++j) buf[j] = make_double2(a[0][2 * j], a[0][2 * j + 1]);
+                    buf[4] = make_double2(b[0], RMX_RP_SLOT(0));
+                } else if (R == 2 && win[R - 1]) {
 #pragma unroll
-                        for (int j = i / 2; j < 4; ++j) buf[j] = make_double2(a[R - 1][2 * j], a[R - 1][2 * j + 1]);
-                        buf[4] = make_double2(b[R - 1], RMX_RP_SLOT(R - 1));
-                    }
+                    for (int j = i / 2; j < 4; ++j) buf[j] = make_double2(a[R - 1][2 * j], a[R - 1][2 * j + 1]);
+                    buf[4] = make_double2(b[R - 1], RMX_RP_SLOT(R - 1));
                 }
 #undef RMX_RP_SLOT
                 __syncwarp();
@@ -361,7 +368,7 @@ __device__ __forceinline__ void lu_solve_tc(int nr, double* H, int* perm, int* r
 #endif
 #pragma unroll
                 for (int h = 0; h < R; ++h) {
-                    rdiag[h] = (lane == src && h == sh) ? rp : rdiag[h];
+                    rdiag[h] = win[h] ? rp : rdiag[h];
                     const double l = done[h] ? 0.0 : a[h][i] * rp;  // l == 0 for rows that are already pivots
                     a[h][i] = done[h] ? a[h][i] : l;
                     if (!(i & 1)) a[h][i + 1] = fma(-l, u2[i / 2].y, a[h][i + 1]);

@@ -823,6 +823,18 @@ class Scene:
                                      ptr(H), ptr(dx)), 'rmx_eval_newton')
         return dict(H=H.T.copy(), dx=dx)
 
+    def eval_krylov(self, q, qdot, dqtmp, cK, beta, x, tau=None):
+        """The operators of the Krylov linear solve at one evaluation point (rmx_eval_krylov): Hx = H x through the
+        matrix-free tree sweeps, Pinv_x = (J' blkdiag(M_j) J + Pr)^-1 x through the projected block-Jacobi preconditioner."""
+        L = self._require()
+        nr = self.nr
+        q, qdot, dqtmp, x = f64(q), f64(qdot), f64(dqtmp), f64(x)
+        tau = None if tau is None else f64(tau)
+        hx, px = np.empty(nr), np.empty(nr)
+        _ffi.check(L.rmx_eval_krylov(self._handle, ptr(q), ptr(qdot), ptr(dqtmp), ptr(tau), float(cK), float(beta), ptr(x),
+                                     ptr(hx), ptr(px)), 'rmx_eval_krylov')
+        return dict(Hx=hx, Pinv_x=px)
+
     def body_frames(self, q, chart=None):
         """World frames E_wi of all bodies (Body.update, Body.m:70-80) for B configurations q [B, nr] -> [B, nbodies, 4, 4].
         chart [B, nspherical]: the Euler charts the configurations are expressed in (see chart_history); default: the
