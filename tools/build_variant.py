@@ -1,6 +1,6 @@
 """Developer tool: build a tagged variant of the CUDA library with extra nvcc flags for A/B measurements, e.g.
-    python tools/build_variant.py rcp -DRMX_LU_RCP_EARLY      ->  build/lib_rcp/libredmax_b200.so
-and run anything against it with RMX_LIB=build/lib_rcp/libredmax_b200.so.  The product library is the untagged build."""
+    python tools/build_variant.py exact -DRMX_PIVOT_EXACT     ->  build/lib_exact/libredmax_b200.so
+and run anything against it with RMX_LIB=build/lib_exact/libredmax_b200.so.  The product library is the untagged build."""
 import os
 import sys
 
