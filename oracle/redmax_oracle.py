@@ -2089,8 +2089,11 @@ class _PointPosMixin:
 
     def applyStep(self):
         """TaskBDF1PointPos.m:58"""
+        # first_step_free: NOT the reference -- diagnostic mode of tests/test_oracle_pins.py in which the first time step takes
+        # no control (its dgdp block is zero), so that the parameters act through the plain BDF steps only
+        off = getattr(self, 'first_step_free', False) and self.scene.k == 0
         for j in self.scene.joints:
-            j.tau = self.pscale * self.p[j.idxR]
+            j.tau = (0.0 if off else self.pscale) * self.p[j.idxR]
 
     def calcStep(self):
         """TaskBDF1PointPos.m:67-107"""
@@ -2117,7 +2120,10 @@ class _PointPosMixin:
             self.dPdq[k - 1] = np.zeros(nr)
         h = scene.h
         kk = (k - 1) * nr + np.arange(nr)
-        self.dgdp[kk, :] = self._dgdp_coeff * h ** 2 * self.pscale * np.eye(nr)
+        coeff = self._dgdp_coeff
+        if k == 1 and getattr(self, 'first_step_free', False):
+            coeff = 0.0
+        self.dgdp[kk, :] = coeff * h ** 2 * self.pscale * np.eye(nr)
 
 
 class TaskBDF1PointPos(_PointPosMixin, TaskBDF1):

@@ -177,25 +177,40 @@ def test_ground_contact_fd(oracle):
     _fd_check('H(ground)', H, Hn, 1e-5)
 
 
-def test_adjoint_gradient_fd(oracle):
-    """The reference's own check of the adjoint (driverRedMaxAdjointBDF1.m:47-61): dP/dp against forward
-    differences of P obtained by re-simulating.  Scenes 100/101 carry no golden number."""
-    for sid, scheme in ((100, 1), (101, 2)):
-        s = oracle.scenes(sid)
-        s.tEnd = 0.2
-        s.init()
-        s.task.setTime(s.tEnd)
-        p = np.array([0.02, -0.01])
-        P, dPdp = oracle.task_objective(p, s, scheme)
-        d = np.zeros_like(dPdp)
-        eps = 1e-6
-        for i in range(len(p)):
-            pp = p.copy()
-            pp[i] += eps
-            d[i] = (oracle.task_objective(pp, s, scheme)[0] - P) / eps
-        rel = np.linalg.norm(d - dPdp) / np.linalg.norm(d)
-        # BDF2's first-step dgdp coefficient is knowingly inexact in the reference (SURVEY note N7)
-        assert rel < (1e-4 if scheme == 1 else 5e-2), (sid, rel, d, dPdp)
+def _central_richardson(P, p, eps):
+    g1, g2 = np.zeros_like(p), np.zeros_like(p)
+    for i in range(len(p)):
+        for g, e in ((g1, eps), (g2, 0.5 * eps)):
+            a, b = p.copy(), p.copy()
+            a[i] += e
+            b[i] -= e
+            g[i] = (P(a) - P(b)) / (2 * e)
+    return (4.0 * g2 - g1) / 3.0
+
+
+@pytest.mark.parametrize('sid,scheme,first_step_free,tol', [(100, 1, False, 1e-8), (101, 2, True, 1e-8), (101, 2, False, 5e-2)])
+def test_adjoint_gradient_fd(oracle, sid, scheme, first_step_free, tol):
+    """The reference's own check of the adjoint (driverRedMaxAdjointBDF1.m:47-61: dP/dp against differences of P obtained by
+    re-simulating), sharpened: central differences with one Richardson step.  Scenes 100/101 carry no golden number, so this
+    is what pins the oracle's (P, dP/dp).
+      * BDF1: the adjoint gradient is the derivative of P to 1e-10 (observed).
+      * BDF2 as the reference has it: 4.7 % off.  The reference treats the SDIRK2 first step like a BDF2 step (dgdp coefficient
+        -(4/9) h^2 where neither stage has it, and the first stage is ignored altogether, TaskBDF2.m:52-54; SURVEY note N7).
+      * BDF2 with the first step taking no control (oracle-only diagnostic switch `first_step_free`, so that the parameters act
+        through the plain BDF2 steps only): 3e-10 (observed).  So the treatment of the first step is the ONLY source of the
+        BDF2 gap; the backward recursion itself, special first-step blocks of the stencil included, is exact."""
+    s = oracle.scenes(sid)
+    s.tEnd = 0.2
+    s.init()
+    s.task.setTime(s.tEnd)
+    s.task.first_step_free = first_step_free
+    p = np.array([0.02, -0.01])
+    P, dPdp = oracle.task_objective(p, s, scheme)
+    d = _central_richardson(lambda x: oracle.task_objective(x, s, scheme)[0], p, 1e-4)
+    rel = np.linalg.norm(d - dPdp) / np.linalg.norm(d)
+    assert rel < tol, (sid, first_step_free, rel, d, dPdp)
+    if tol > 1e-3:
+        assert rel > 1e-3  # the reference's gradient really is inexact there; if this ever passes tightly, the note above is stale
 
 
 def _system_quantities(oracle, s):
