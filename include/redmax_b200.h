@@ -200,6 +200,17 @@ int rmx_scene_nm(const rmx_scene* s); /* redmax.Scene.countM(), Scene.m:398 */
  * (line-search) evaluations; may be NULL.  qdot_out may be NULL. */
 int rmx_rollout(rmx_scene* s, const rmx_opts* o, int64_t B, const double* q0, const double* qdot0,
                 const double* tau, double* q_out, double* qdot_out, int32_t* status, int32_t* iters);
+/* Device-resident rollouts on G GPUs driven by ONE process: the batch is sharded contiguously, rollouts
+ * [B g/G, B (g+1)/G) on devices[g], with no communication while the rollouts run.  q0[g], qdot0[g], tau[g], status[g], iters[g]
+ * are device pointers on devices[g] holding that device's SHARD; q_out[g] (and qdot_out[g], optional) point to FULL-size arrays
+ * (nr x nsteps x B) on devices[g]: every device integrates its shard into its own slice, then -- gather != 0 -- ONE in-place
+ * ncclAllGather per array over NVLink gives every device all trajectories (needs B % G == 0; NCCL is loaded at run time from
+ * libnccl.so.2, the call fails with RMX_ENOGPU if it cannot be).  gather == 0: no collective, the other slices stay untouched.
+ * Blocking; status bits as rmx_rollout_dev. */
+int rmx_rollout_multi_dev(rmx_scene* s, const rmx_opts* o, int32_t G, const int32_t* devices, int64_t B, const double* const* q0,
+                          const double* const* qdot0, const double* const* tau, double* const* q_out, double* const* qdot_out,
+                          int32_t* const* status, int32_t* const* iters, int32_t gather);
+
 /* Continue rollouts mid-way (host pointers, current device): rollout b runs the steps k_begin[b] .. k_end[b]-1
  * (0 <= k_begin <= k_end <= nsteps; k_end == NULL: to nsteps) from the states the caller provides in q_out / qdot_out --
  * step k_begin-1 is the current state, step k_begin-2 (q0 / qdot0 when k_begin == 1) the BDF2 history joint.q1 / qdot1;

@@ -90,7 +90,7 @@ SYMBOLS = [
     'rmx_scene_create', 'rmx_scene_destroy', 'rmx_scene_nr', 'rmx_scene_nm',
     'rmx_rollout', 'rmx_rollout_resume', 'rmx_rollout_dev', 'rmx_rollout_adjoint', 'rmx_rollout_adjoint_dev',
     'rmx_adjoint_tape_bytes', 'rmx_eval', 'rmx_eval_newton', 'rmx_energies', 'rmx_linsolve_stats', 'rmx_debug_schedule', 'rmx_body_frames',
-    'rmx_fp64_probe', 'rmx_host_register', 'rmx_host_unregister', 'rmx_eval_krylov',
+    'rmx_fp64_probe', 'rmx_host_register', 'rmx_host_unregister', 'rmx_eval_krylov', 'rmx_rollout_multi_dev',
 ]
 
 _lib = None
@@ -131,6 +131,7 @@ def lib():
     L.rmx_adjoint_tape_bytes.restype = C.c_int64
     L.rmx_eval.argtypes = [vp, vp, vp, vp, vp, C.c_double, C.c_double, vp, vp, vp, vp, vp]
     L.rmx_eval_newton.argtypes = [vp, vp, vp, vp, vp, C.c_double, C.c_double, vp, vp]
+    L.rmx_rollout_multi_dev.argtypes = [vp, C.POINTER(rmx_opts), C.c_int32, vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp, C.c_int32]
     L.rmx_eval_krylov.argtypes = [vp, vp, vp, vp, vp, C.c_double, C.c_double, vp, vp, vp]
     L.rmx_energies.argtypes = [vp, C.c_int64, vp, vp, vp, vp]
     L.rmx_body_frames.argtypes = [vp, C.c_int64, vp, vp]

@@ -1265,3 +1265,4 @@ extern "C" int rmx_debug_schedule(int64_t B, int32_t nsteps, int64_t slots, int3
 }
 
 #include "rmx_api_adjoint.inc"
+#include "rmx_api_multi.inc"

@@ -1571,109 +1571,18 @@ __device__ __noinline__ void lu_solve_warp_t(int nr, int ld, double* H, int* per
     __syncwarp();
 }
 
-// ---------------------------------------------------------------------------------------------
-// Same factorisation, pivot rule and arithmetic (one fma per trailing entry, correctly rounded reciprocal) as
-// lu_solve_warp_t, but the pivot row of step k travels through shared memory instead of 2 x 32-bit shuffles per entry:
-// the pivot lane stores its trailing row as 128-bit pairs into one of two alternating row buffers (one __syncwarp per
-// step), every lane reads the pairs back with 128-bit broadcast loads.  Per trailing entry that is 1/2 store + 1/2 load
-// + 1 fma instead of 2 shuffles + register moves + 1 fma; the back substitution broadcasts x_k the same way.
-// ---------------------------------------------------------------------------------------------
-template <int NR>
-__device__ __noinline__ void lu_solve_warp_sm(int nr, int ld, double* H, int* perm, const double* rhs, double scale, double* dx,
-                                                 bool write_back, double2* rowbuf) {
-    constexpr int NP = NR / 2 + 1;  // pairs per row buffer: NR/2 matrix pairs + {b, -}
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    double a[NR];
-#pragma unroll
-    for (int cI = 0; cI < NR; ++cI) a[cI] = (cI < nr && lane < nr) ? H[(size_t)cI * ld + lane] : ((cI == lane) ? 1.0 : 0.0);
-    double b = (lane < nr) ? scale * rhs[lane] : 0.0;
-    bool done = lane >= NR;
-    int pos = lane, mypos = -1;
-    double rdiag = 1.0;
-#pragma unroll
-    for (int k = 0; k < NR; ++k) {
-        const double v = fabs(a[k]);
-        const unsigned hi = done ? 0u : (unsigned)__double2hiint(v);
-        const unsigned mh = __reduce_max_sync(FULL, hi);
-        const bool c1 = !done && hi == mh;
-        unsigned cand = __ballot_sync(FULL, c1);
-        if (cand & (cand - 1)) {
-            const unsigned lo = c1 ? (unsigned)__double2loint(v) : 0u;
-            const unsigned ml = __reduce_max_sync(FULL, lo);
-            const bool c2 = c1 && lo == ml;
-            const unsigned pm = __reduce_min_sync(FULL, c2 ? (unsigned)pos : 0xffffu);
-            cand = __ballot_sync(FULL, c2 && (unsigned)pos == pm);
-        }
-        const int src = __ffs(cand) - 1;
-        double2* buf = rowbuf + (k & 1) * NP;
-        if (lane == src) {  // publish the pivot row: entries k.. (pair-aligned) and the right-hand side
-#pragma unroll
-            for (int j = k / 2; j < NR / 2; ++j) buf[j] = make_double2(a[2 * j], a[2 * j + 1]);
-            buf[NR / 2] = make_double2(b, 0.0);
-        }
-        const int kl = __ffs(__ballot_sync(FULL, !done && pos == k)) - 1;
-        const int pos_src = __shfl_sync(FULL, pos, src);
-        if (lane == kl) pos = pos_src;
-        if (lane == src) {
-            pos = k;
-            done = true;
-            mypos = k;
-        }
-        if (lane == k) perm[k] = src;
-        __syncwarp();
-        const double2 pv = buf[k / 2];
-        const double piv = (k & 1) ? pv.y : pv.x;
-        const double rp = __drcp_rn(piv);  // == 1.0 / piv, correctly rounded
-        rdiag = (lane == src) ? rp : rdiag;
-        const double l = done ? 0.0 : a[k] * rp;
-        a[k] = done ? a[k] : l;
-        if (((k + 1) & 1) && k + 1 < NR) a[k + 1] = fma(-l, pv.y, a[k + 1]);  // k even: its pair partner k+1 is trailing
-#pragma unroll
-        for (int j = k / 2 + 1; j < NR / 2; ++j) {
-            const double2 u = buf[j];
-            a[2 * j] = fma(-l, u.x, a[2 * j]);  // l == 0 for rows that are already pivots
-            a[2 * j + 1] = fma(-l, u.y, a[2 * j + 1]);
-        }
-        b = fma(-l, buf[NR / 2].x, b);
-    }
-    __syncwarp();
-    if (write_back && lane < nr) {
-#pragma unroll
-        for (int cI = 0; cI < NR; ++cI)
-            if (cI < nr) H[(size_t)cI * ld + mypos] = a[cI];
-    }
-    // back substitution U x = y : row `mypos` of U lives in this lane, y_mypos = b; x_k is published through shared memory
-    double* xs = reinterpret_cast<double*>(rowbuf);
-#pragma unroll
-    for (int k = NR - 1; k >= 0; --k) {
-        if (mypos == k) xs[k] = b * rdiag;
-        __syncwarp();
-        const double xk = xs[k];
-        b = (mypos < k) ? fma(-a[k], xk, b) : b;
-    }
-    if (lane < nr) dx[lane] = xs[lane];
-    __syncwarp();
-}
-
-// Measured on B200 (profiles/r01_ab_lu_occupancy.log): both broadcasts run the headline shape at the same speed (the
-// factorisation is bound by its per-pivot dependency chain, not by the broadcast); the shuffle form is the default.
-#ifdef RMX_LU_SM
-#define RMX_LU_WARP lu_solve_warp_sm
-#else
-#define RMX_LU_WARP lu_solve_warp_t
-#endif
-
+// (A variant that broadcast the pivot row through shared memory instead of shuffles ran at the same speed on B200 --
+// profiles/r01_ab_lu_occupancy.log -- and was removed in round 2; the tensor-core kernels have their own blocked LU, rmx_tc.cuh.)
 __device__ __forceinline__ void lu_solve_warp(int nr, int ld, double* H, int* perm, const double* rhs, double scale, double* dx,
                                               bool write_back, double2* rowbuf) {
     if (nr <= 8)
-        RMX_LU_WARP<8>(nr, ld, H, perm, rhs, scale, dx, write_back, rowbuf);
+        lu_solve_warp_t<8>(nr, ld, H, perm, rhs, scale, dx, write_back, rowbuf);
     else if (nr <= 16)
-        RMX_LU_WARP<16>(nr, ld, H, perm, rhs, scale, dx, write_back, rowbuf);
+        lu_solve_warp_t<16>(nr, ld, H, perm, rhs, scale, dx, write_back, rowbuf);
     else if (nr <= 24)
-        RMX_LU_WARP<24>(nr, ld, H, perm, rhs, scale, dx, write_back, rowbuf);
+        lu_solve_warp_t<24>(nr, ld, H, perm, rhs, scale, dx, write_back, rowbuf);
     else
-        RMX_LU_WARP<32>(nr, ld, H, perm, rhs, scale, dx, write_back, rowbuf);
+        lu_solve_warp_t<32>(nr, ld, H, perm, rhs, scale, dx, write_back, rowbuf);
 }
 
 }  // namespace rmx

@@ -715,6 +715,26 @@ class Scene:
         _ffi.check(L.rmx_rollout_dev(self._handle, C.byref(o), B, ptr(q0), ptr(qdot0), ptr(tau), ptr(q_out),
                                      ptr(qdot_out), ptr(status), ptr(iters), st), 'rmx_rollout_dev')
 
+    def rollout_multi_dev(self, q0, qdot0, q_out, qdot_out, status, iters=None, tau=None, scheme=1, nsteps=None, gather=True, **kw):
+        """rmx_rollout_multi_dev: one process drives G GPUs.  Every argument is a list with one torch CUDA tensor per device:
+        q0[g], qdot0[g] (and tau[g], status[g], iters[g]) hold device g's shard, q_out[g] / qdot_out[g] are full-size
+        [B, nsteps, nr]; with gather=True one NCCL all-gather per array leaves all trajectories on every device."""
+        L = self._require()
+        G = len(q0)
+        devs = (C.c_int32 * G)(*[int(t.device.index) for t in q0])
+        B = int(q_out[0].shape[0])
+        tau_mode = _ffi.RMX_TAU_NONE
+        if tau is not None:
+            tau_mode = _ffi.RMX_TAU_CONST if tau[0].dim() == 2 else _ffi.RMX_TAU_PER_STEP
+        o = self.opts(scheme=scheme, nsteps=nsteps, tau_mode=tau_mode, **kw)
+
+        def plist(ts):
+            if ts is None:
+                return None
+            return (C.c_void_p * G)(*[None if t is None else t.data_ptr() for t in ts])
+        keep = [plist(x) for x in (q0, qdot0, tau, q_out, qdot_out, status, iters)]
+        _ffi.check(L.rmx_rollout_multi_dev(self._handle, C.byref(o), G, devs, B, *keep, int(bool(gather))), 'rmx_rollout_multi_dev')
+
     @staticmethod
     def check_status(status):
         """Raise if a device-buffer launch flagged an internal scheduling failure (RMX_ST_SCHED): those trajectories are not

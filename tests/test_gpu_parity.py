@@ -311,3 +311,43 @@ def test_load_balanced_schedule_is_bitwise_identical(rb, scheme):
         np.testing.assert_array_equal(out['qdot'][lo:lo + 500], ref['qdot'])
         np.testing.assert_array_equal(out['iters'][lo:lo + 500], ref['iters'])
         np.testing.assert_array_equal(out['status'][lo:lo + 500], ref['status'])
+
+
+def test_one_process_multi_gpu_device_rollout_with_nccl_gather(rb):
+    """rmx_rollout_multi_dev: one process, G devices, device-resident shards, no communication during the
+    rollouts and ONE in-place NCCL all-gather of the trajectory shards after them.  Every device must end up with the whole
+    batch, bitwise equal to the one-GPU run.  Needs at least two GPUs (gpurun --gpus 2)."""
+    import torch
+    G = min(_ffi_device_count(rb), 4)
+    if G < 2:
+        pytest.skip('needs >= 2 GPUs (run under gpurun --gpus 2)')
+    sg = rb.chain_scene(12, nsteps=15, h=1e-3)
+    sg.init()
+    B = 96 * G
+    q0, qd0 = rb.synthetic_inputs(sg, B, seed=4)
+    ref = sg.rollout(q0, qd0, scheme=2)
+    nr, ns = sg.nr, sg.nsteps
+    n = B // G
+    dq0 = [torch.from_numpy(q0[g * n:(g + 1) * n].copy()).to('cuda:%d' % g) for g in range(G)]
+    dqd0 = [torch.from_numpy(qd0[g * n:(g + 1) * n].copy()).to('cuda:%d' % g) for g in range(G)]
+    qo = [torch.full((B, ns, nr), float('nan'), dtype=torch.float64, device='cuda:%d' % g) for g in range(G)]
+    qdo = [torch.full((B, ns, nr), float('nan'), dtype=torch.float64, device='cuda:%d' % g) for g in range(G)]
+    st = [torch.empty(n, dtype=torch.int32, device='cuda:%d' % g) for g in range(G)]
+    it = [torch.empty((n, 2), dtype=torch.int32, device='cuda:%d' % g) for g in range(G)]
+    for g in range(G):
+        torch.cuda.synchronize(g)
+    sg.rollout_multi_dev(dq0, dqd0, qo, qdo, st, it, scheme=2, gather=True)
+    for g in range(G):
+        np.testing.assert_array_equal(qo[g].cpu().numpy(), ref['q'])
+        np.testing.assert_array_equal(qdo[g].cpu().numpy(), ref['qdot'])
+        np.testing.assert_array_equal(st[g].cpu().numpy(), ref['status'][g * n:(g + 1) * n])
+        np.testing.assert_array_equal(it[g].cpu().numpy(), ref['iters'][g * n:(g + 1) * n])
+    # gather = False: only the device's own slice is written
+    qo2 = [torch.full((B, ns, nr), float('nan'), dtype=torch.float64, device='cuda:%d' % g) for g in range(G)]
+    for g in range(G):
+        torch.cuda.synchronize(g)
+    sg.rollout_multi_dev(dq0, dqd0, qo2, None, st, None, scheme=2, gather=False)
+    for g in range(G):
+        a = qo2[g].cpu().numpy()
+        np.testing.assert_array_equal(a[g * n:(g + 1) * n], ref['q'][g * n:(g + 1) * n])
+        assert np.isnan(np.delete(a, np.s_[g * n:(g + 1) * n], axis=0)).all()
