@@ -441,11 +441,9 @@ __device__ void ground_body(const JointConst& J, const double* R, const double* 
     double nb[3];
     mat3T_vec(R, J.gng, nb);
     const double dp = J.gng[0] * (p[0] - J.gxg[0]) + J.gng[1] * (p[1] - J.gxg[1]) + J.gng[2] * (p[2] - J.gxg[2]);
-#ifdef RMX_GROUND_UNROLL_CORNERS
-#pragma unroll
-#elif defined(RMX_GROUND_ROLL_CORNERS)
+    // (kept a loop on purpose: fully unrolled, the kernel grows from 9.9k to 15.9k instructions and runs 1.64x slower --
+    // profiles/r02_ground_unroll_ab.log -- the external-force kernels are bound by their executed code footprint)
 #pragma unroll 1
-#endif
     for (int ci = 0; ci < 8; ++ci) {
         // corner order of ForceGroundCuboid.m:73-82: x sign is the slowest bit
         double xl[3] = {(ci & 4) ? J.hs[0] : -J.hs[0], (ci & 2) ? J.hs[1] : -J.hs[1], (ci & 1) ? J.hs[2] : -J.hs[2]};
