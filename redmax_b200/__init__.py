@@ -10,12 +10,12 @@ from .scene import (Body, BodyCuboid, ForceCable, ForceGroundCuboid, ForcePointP
                     inertiaCuboid)
 from .drivers import (driverRedMaxAdjointBDF1, driverRedMaxAdjointBDF2, driverRedMaxBDF1, driverRedMaxBDF2, plotEnergies,
                       simLoop, taskObjective)
-from .scenes import BDF1, BDF2, chain_scene, hand_scene, scenesRedMax, synthetic_inputs
+from .scenes import BDF1, BDF2, chain_scene, hand_scene, scenesRedMax, synthetic_inputs, tree_scene
 
 __all__ = [
     'Scene', 'Body', 'BodyCuboid', 'Joint', 'JointRevolute', 'JointFixed', 'JointPrismatic', 'JointPlanar',
     'JointTranslational', 'JointFree2D', 'JointUniversal', 'JointSpherical', 'JointFree3D', 'ForceGroundCuboid', 'ForcePointPoint', 'ForceSpringDamper', 'ForceCable',
-    'TaskBDF1PointPos', 'TaskBDF2PointPos', 'inertiaCuboid', 'scenesRedMax', 'chain_scene', 'hand_scene',
+    'TaskBDF1PointPos', 'TaskBDF2PointPos', 'inertiaCuboid', 'scenesRedMax', 'chain_scene', 'hand_scene', 'tree_scene',
     'synthetic_inputs', 'BDF1', 'BDF2', 'RmxError', 'driverRedMaxBDF1', 'driverRedMaxBDF2', 'driverRedMaxAdjointBDF1',
     'driverRedMaxAdjointBDF2', 'taskObjective', 'simLoop', 'plotEnergies',
 ]

@@ -398,6 +398,47 @@ def chain_scene(n, ground=False, h=1e-2, nsteps=100, axis=(0, 1, 0), ground_z=-4
     return scene
 
 
+def tree_scene(n, seed=0, h=1e-3, nsteps=100, fixed_every=7, scheme=1, api=None):
+    """A seeded random joint tree of n cuboid links (test scenes for the tree code paths beyond the reference's own small
+    trees: branching, mixed revolute axes -- the three se3.aaToMat special cases and general axes --, some fixed joints, joint
+    damping).  Joint i hangs off a random earlier joint (parents are listed first, as Joint.m:134 requires).  The task is a
+    TaskBDF*PointPos on the last link's far end."""
+    api = api or _api
+    rng = np.random.Generator(np.random.PCG64(seed))
+    scene = api.Scene()
+    scene.name = 'random tree, %d links, seed %d' % (n, seed)
+    scene.h = h
+    scene.tEnd = nsteps * h
+    axes = [[1, 0, 0], [0, 1, 0], [0, 0, 1], [0, -1, 0], [1, 1, 0], [0.3, -0.5, 0.8]]
+    for i in range(n):
+        sides = [float(rng.uniform(3, 8)), float(rng.uniform(0.5, 1.5)), float(rng.uniform(0.5, 1.5))]
+        b = api.BodyCuboid(1.0, sides)
+        parent = None if i == 0 else scene.joints[int(rng.integers(max(0, i - 6), i))]
+        if i > 0 and fixed_every and i % fixed_every == 0:
+            j = api.JointFixed(parent, b)
+        else:
+            j = api.JointRevolute(parent, b, axes[int(rng.integers(len(axes)))])
+            j.q[0] = float(rng.uniform(-0.6, 0.6))
+            j.setDamping(float(rng.uniform(0.0, 50.0)))
+        if parent is None:
+            j.setJointTransform(np.eye(4))
+        else:
+            E = _trans([float(parent.body.sides[0]), float(rng.uniform(-1, 1)), float(rng.uniform(-1, 1))])
+            E[:3, :3] = _rot([0, 0, 1], float(rng.uniform(-0.5, 0.5)))[:3, :3]
+            j.setJointTransform(E)
+        b.setBodyTransform(_trans([sides[0] / 2, 0, 0]))
+        scene.bodies.append(b)
+        scene.joints.append(j)
+    scene.task = (api.TaskBDF1PointPos if scheme == 1 else api.TaskBDF2PointPos)(scene)
+    scene.task.setTime(scene.tEnd)
+    scene.task.setBody(scene.bodies[-1])
+    scene.task.setPoint([float(scene.bodies[-1].sides[0]) / 2, 0, 0])
+    scene.task.setTarget([5.0, -3.0, 2.0])
+    scene.task.setScale(1e3)
+    scene.task.setWeights(1e-2, 1e2)
+    return scene
+
+
 def hand_scene(h=1e-2, nsteps=100, scheme=1, api=None):
     """C4: fixed palm + 5 fingers x 4 revolute phalanges, TaskBDF*PointPos on the index fingertip, joint stiffness
     and damping as scene 100 (scenesRedMax.m:426-436)."""
