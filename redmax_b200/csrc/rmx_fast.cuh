@@ -109,9 +109,12 @@ struct TcLayoutA {
     static constexpr int H_OFF = F::XA * NS;          // 594: behind W, over S, V, U, composite blocks (ends before RB)
     static constexpr int SOA = (NS * F::TOTAL + 1) & ~1;
     static constexpr int RZ_OFF = SOA;
-    static constexpr int JROWS = RZ_OFF + CAP * F::NW_;  // 6 x CAP rows of J of the task body
+    // 6 x CAP rows of J of the task body: over the kept body frames, which are dead from the moment those rows are formed
+    // (adjoint_tape_md) to the next base evaluation -- the objective reads its row before that evaluation (rollout_fwd_kernel).
+    // Without a region of their own the block is 28 160 B with the kernel's static part: eight blocks per SM instead of seven.
+    static constexpr int JROWS = NS * F::RB;
     static constexpr int NV = 9;                      // q g (= dx) tau hq0 hqd0 hq1 hqd1 sp1 sp2
-    static constexpr int VEC = JROWS + 6 * CAP;
+    static constexpr int VEC = RZ_OFF + CAP * F::NW_;
     static constexpr int RED = VEC + NV * CAP;
     static constexpr int ROWBUF = RED;                 // (one warp: no reduction scratch)
     static constexpr int IE = ROWBUF + 20;
@@ -123,6 +126,8 @@ struct TcLayoutA {
     static constexpr int TOTAL = (TANC + CAP / 2 + 1) & ~1;
     static_assert(CAP * F::NW_ <= F::XA * NS, "W must fit region XA");
     static_assert(H_OFF + CAP * LD <= NS * F::RB, "H must end before the kept body frames");
+    static_assert(JROWS + 6 * CAP <= SOA, "J rows must fit the body-frame fields");
+    static_assert((TOTAL * 8 + 128 + 1024) * 8 <= 228 * 1024, "eight blocks per SM");
 };
 // the adjoint forward kernel of a scene runs on the tensor-core path if ...
 __host__ __device__ inline bool tc_adjoint(int n, int nr, bool ground) { return !ground && n <= 32 && nr <= 32; }

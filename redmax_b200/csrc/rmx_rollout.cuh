@@ -434,14 +434,16 @@ __device__ __forceinline__ void adjoint_tape_md(typename E::C& c, double* __rest
     if (want_J) {
         // J(idxM(body), :) : column of joint k is Ad(E_body^-1) s_k for ancestors-or-self k of the body, else 0
         double* Jb = E::jrows(c);
-        if (t < c.n && c.jc[t].idx >= 0) {
-            double col[6] = {0, 0, 0, 0, 0, 0};
-            if (t <= jb && jb < c.jc[t].end) {
-                double Rb[9], pb[3], st[6];
-                E::body_frame(c, jb, Rb, pb);
-                E::screw(c, t, st);
-                xm_w2b(Rb, pb, st, col);
-            }
+        const bool mine = t < c.n && c.jc[t].idx >= 0;
+        double col[6] = {0, 0, 0, 0, 0, 0};
+        if (mine && t <= jb && jb < c.jc[t].end) {
+            double Rb[9], pb[3], st[6];
+            E::body_frame(c, jb, Rb, pb);
+            E::screw(c, t, st);
+            xm_w2b(Rb, pb, st, col);
+        }
+        __syncwarp();  // the rows overlay the body frames just read (TcLayoutA::JROWS)
+        if (mine) {
 #pragma unroll
             for (int i = 0; i < 6; ++i) Jb[6 * c.jc[t].idx + i] = col[i];
         }
@@ -681,6 +683,12 @@ __global__ void RMX_FWD_BOUNDS rollout_fwd_kernel(RolloutArgs a) {
                 double dPdq = 0.0;
                 if (is_obj) {
                     bsync<NW>();
+                    double jr[6] = {0, 0, 0, 0, 0, 0};  // this thread's row of the tape's J: read before the evaluation below
+                    if (t < nr) {                        // rebuilds the body frames it may share storage with (TcLayoutA)
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) jr[i] = E::jrows(c)[6 * t + i];
+                    }
+                    bsync<NW>();
                     E::base(c, false);  // c.q holds the final iterate: FK at history(k).q
                     double rb[9], pbt[3];
                     E::body_frame(c, a.task.body, rb, pbt);
@@ -696,7 +704,7 @@ __global__ void RMX_FWD_BOUNDS rollout_fwd_kernel(RolloutArgs a) {
                         v6[i] *= a.task.wpos;
                         v6[3 + i] = y[i] * a.task.wpos;
                     }
-                    if (t < nr) dPdq = dot6(E::jrows(c) + 6 * t, v6);
+                    if (t < nr) dPdq = dot6(jr, v6);
                 }
                 if (t < nr) {
                     double* recA = a.tape.A + ((size_t)b * op.nsteps + k) * a.tape.sza;
