@@ -741,6 +741,9 @@ static int launch_fwd(const rmx_scene* s, const RolloutArgs& a, cudaStream_t st,
     size_t smem = (scene_smem_doubles(s, ADJ) + (ADJ ? 6 * (size_t)s->nr : 0)) * sizeof(double);
     // the one-warp adjoint forward kernel of a scene without external forces runs on the tensor-core path (TcLayoutA)
     if (ADJ && s->impl == 2 && nw == 1 && tc_adjoint(s->n, s->nr, g != 0)) smem = (size_t)TcLayoutA::TOTAL * sizeof(double);
+    // developer knob for residency experiments (tools/residency_ab.sh): unused shared memory per block, fewer blocks per SM
+    static const size_t pad = [] { const char* e = std::getenv("RMX_DEBUG_SMEM_PAD"); return e ? (size_t)std::atol(e) : (size_t)0; }();
+    smem += pad & ~(size_t)15;
     if (smem > 227 * 1024) return fail(RMX_ELIMIT, "scene does not fit the 227 KB shared memory of one SM");
     rmx_fwd_launcher f = fwd_launcher(s->impl, nw, g, ADJ, 0);
     if (!f) return fail(RMX_ELIMIT, "no forward kernel for this scene size");

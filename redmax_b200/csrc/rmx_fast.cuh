@@ -165,6 +165,29 @@ struct Ctx2 : Ctx {
                    // a dependent chain and must not wait for a global load each
 };
 
+// The pointer-jumping scans of eval_base2 run their rounds as a real loop (one copy of the round's code, the ancestor picked
+// from the register array by a select chain): unrolled six times they were 800 of the kernel's 6 800 instructions, and the
+// one-warp kernels are sensitive to their executed code footprint (instruction fetch from the GPC-level cache runs at 90 % of
+// its peak, profiles/r02_residency_ab.log).  -DRMX_SCAN_UNROLLED restores the unrolled rounds.
+#ifdef RMX_SCAN_UNROLLED
+#define RMX_SCAN_UNROLL _Pragma("unroll")
+#else
+#define RMX_SCAN_UNROLL _Pragma("unroll 1")
+#endif
+__device__ __forceinline__ int anc_round(const int (&a)[6], int r) {
+#ifdef RMX_SCAN_UNROLLED
+    return a[r];
+#else
+    int v = a[0];
+    v = r == 1 ? a[1] : v;
+    v = r == 2 ? a[2] : v;
+    v = r == 3 ? a[3] : v;
+    v = r == 4 ? a[4] : v;
+    v = r == 5 ? a[5] : v;
+    return v;
+#endif
+}
+
 __device__ __forceinline__ void ctx2_carve(Ctx2& c, double* sm, int n, int nr, bool ground, bool keep) {
     c.n = n;
     c.nr = nr;
@@ -1004,10 +1027,10 @@ __device__ void eval_base2(Ctx2& c, bool deriv) {
     }
     bsync<NW>();
     // ---- world frames: pointer-jumping prefix product  E_w,j = E_w,anc o E_(anc, j] -----------------------------
-#pragma unroll
+    RMX_SCAN_UNROLL
     for (int r = 0; r < 6; ++r) {
         if (r >= c.nrounds) break;  // uniform
-        const int a = c.anc_r[r];
+        const int a = anc_round(c.anc_r, r);
         if (a >= 0) {
             double Ra[9], pa[3], Rn[9], pn[3];
 #pragma unroll
@@ -1053,10 +1076,10 @@ __device__ void eval_base2(Ctx2& c, bool deriv) {
         }
     }
     bsync<NW>();
-#pragma unroll
+    RMX_SCAN_UNROLL
     for (int r = 0; r < 6; ++r) {
         if (r >= c.nrounds) break;  // uniform
-        const int a = c.anc_r[r];
+        const int a = anc_round(c.anc_r, r);
         if (a >= 0) {
 #pragma unroll
             for (int i = 0; i < 6; ++i) Vj[i] += SA(F::V, i, a);
@@ -1086,10 +1109,10 @@ __device__ void eval_base2(Ctx2& c, bool deriv) {
         for (int i = 0; i < 6; ++i) SA(F::U, i, t) = Uj[i];
     }
     bsync<NW>();
-#pragma unroll
+    RMX_SCAN_UNROLL
     for (int r = 0; r < 6; ++r) {
         if (r >= c.nrounds) break;  // uniform
-        const int a = c.anc_r[r];
+        const int a = anc_round(c.anc_r, r);
         if (a >= 0) {
 #pragma unroll
             for (int i = 0; i < 6; ++i) Uj[i] += SA(F::U, i, a);
@@ -1161,8 +1184,15 @@ __device__ void eval_base2(Ctx2& c, bool deriv) {
 #pragma unroll
                     for (int i = 0; i < 36; ++i) K[i] = D[i] = 0;
                     ground_body<true>(J, Rb, pb, phi, fb, K, D);
+#ifdef RMX_XTMX_TWO_COPIES
                     xtmx_store(c.sa, NS, F::AEXT, t, Rb, pb, D, -c.c);
                     xtmx_store(c.sa, NS, F::CEXT, t, Rb, pb, K, -c.c);
+#else
+                    // one copy of the congruence code for both blocks (code footprint: see anc_round above)
+#pragma unroll 1
+                    for (int pass = 0; pass < 2; ++pass)
+                        xtmx_store(c.sa, NS, pass ? F::CEXT : F::AEXT, t, Rb, pb, pass ? K : D, -c.c);
+#endif
                 } else {
                     ground_body<false>(J, Rb, pb, phi, fb, nullptr, nullptr);
                 }

@@ -80,12 +80,14 @@ def main():
     ap.add_argument('--lib', default=os.path.join(ROOT, 'redmax_b200', 'lib', 'libredmax_b200.so'))
     ap.add_argument('--units', type=float, default=0.0)
     ap.add_argument('--top', type=int, default=25)
+    ap.add_argument('--reason', default='# Samples',
+                    help="source-page column to use as the sample count, e.g. stall_no_inst, stall_long_sb (default: all samples)")
     a = ap.parse_args()
     src = sh(['ncu', '-i', a.report, '--page', 'source', '--csv'])
     rows = list(csv.reader(io.StringIO(src)))
     hdr = next(i for i, r in enumerate(rows) if r and r[0] == 'Address')
     names = rows[hdr]
-    ci, cs = names.index('Instructions Executed'), names.index('# Samples')
+    ci, cs = names.index('Instructions Executed'), names.index(a.reason)
     sass = rows[hdr + 1:]
     lt = line_table(a.lib, a.kernel)
     if len(lt) != len(sass):
@@ -100,6 +102,8 @@ def main():
             d[k][1] += float(r[ci])
     print('report %s' % os.path.basename(a.report))
     print('kernel %s' % a.kernel)
+    if a.reason != '# Samples':
+        print('samples counted: %s only' % a.reason)
     print('SASS instructions %d, warp-instructions executed %.0f%s, stall samples %.0f'
           % (len(sass), tot_i, (' (%.2fk per unit)' % (tot_i / a.units / 1e3)) if a.units else '', tot_s))
     print('--- regions (share of samples, share of executed warp-instructions%s)' % (', k instructions per unit' if a.units else ''))
