@@ -734,6 +734,19 @@ static int launch_fwd_pcg(const rmx_scene* s, const RolloutArgs& a, cudaStream_t
     return f(a, smem, st, nullptr);
 }
 
+// Rollouts per block of a one-warp forward launch (lockstep groups, group_barrier in rmx_device.cuh).  The kernels with
+// external forces are bound by instruction fetch, and warps that walk through the code together share the fetched lines:
+// they run as many warps per block as one SM holds.  RMX_GROUP=<n> overrides (1 = one rollout per block everywhere).
+static int fwd_group(const rmx_scene* s, int nw, int ground, size_t smem_per_rollout) {
+    if (nw != 1 || s->impl != 2) return 1;
+    const char* e = std::getenv("RMX_GROUP");  // read per launch: tests compare group sizes within one process
+    const int forced = e ? std::atoi(e) : 0;
+    int G = forced > 0 ? forced : (ground ? RMX_MAX_GROUP : 1);
+    const size_t room = 227 * 1024;
+    while (G > 1 && (size_t)G * smem_per_rollout > room) --G;
+    return G < 1 ? 1 : G;
+}
+
 template <bool ADJ>
 static int launch_fwd(const rmx_scene* s, const RolloutArgs& a, cudaStream_t st, DevCopy* dc = nullptr) {
     const int nw = warps_for(s);
@@ -747,7 +760,9 @@ static int launch_fwd(const rmx_scene* s, const RolloutArgs& a, cudaStream_t st,
     if (smem > 227 * 1024) return fail(RMX_ELIMIT, "scene does not fit the 227 KB shared memory of one SM");
     rmx_fwd_launcher f = fwd_launcher(s->impl, nw, g, ADJ, 0);
     if (!f) return fail(RMX_ELIMIT, "no forward kernel for this scene size");
-    return f(a, smem, st, dc);
+    RolloutArgs ag = a;
+    ag.group = ADJ ? 1 : fwd_group(s, nw, g, smem);
+    return f(ag, smem, st, dc);
 }
 
 // co-resident blocks of the forward kernel this scene runs on the current device (0 if unknown)

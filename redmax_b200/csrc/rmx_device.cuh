@@ -192,6 +192,28 @@ __device__ __forceinline__ void bsync() {
         __syncthreads();
 }
 
+// Lockstep groups (one-warp forward kernels launched with blockDim.y = G > 1): G independent rollouts, one per warp, meet at the
+// top of every evaluation pass, so that the G warps of a block walk through the same code at the same time and share its
+// instruction-cache lines -- the kernels with external forces are bound by instruction fetch (SM instruction-cache hit rate
+// 62 %, GPC-level cache requests at 90 % of peak: profiles/r02_residency_ab.log).  Named barrier 1 with an AND vote: a warp
+// that has finished all of its work keeps arriving with done = true until every warp of the block has.  Every blocking
+// wait of a grouped warp must keep calling this, or its partners stall.
+__device__ __forceinline__ bool group_barrier(int G, bool done) {
+    if (G <= 1) return done;
+    int r;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        "setp.ne.s32 q, %1, 0;\n\t"
+        "bar.red.and.pred p, 1, %2, q;\n\t"
+        "selp.s32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(r)
+        : "r"((int)done), "r"(G * 32)
+        : "memory");
+    return r != 0;
+}
+
 template <int NW>
 __device__ __forceinline__ double block_sum(double v, double* red) {
 #pragma unroll
@@ -246,6 +268,7 @@ __device__ __forceinline__ int block_argmax(double v, int idx, double* red) {
 // ---------------------------------------------------------------------------------------------
 struct Ctx {
     int n, nr, ld;
+    int group;  // one-warp forward kernels: rollouts (warps) per block that run their evaluation passes in lockstep (1: none)
     const JointConst* __restrict__ jc;
     const int* __restrict__ ends_list;
     double gx, gy, gz;

@@ -8,25 +8,33 @@ template <int NW, int GROUND, bool ADJ, int IMPL, int LIN>
 static int rmx_launch_fwd_t(const rmx::RolloutArgs& a0, size_t smem, cudaStream_t st, DevCopy* dc) {
     using namespace rmx;
     auto kernel = rollout_fwd_kernel<NW, GROUND, ADJ, IMPL, LIN>;
-    int rc = rmx_set_smem(kernel, smem);
-    if (rc) return rc;
+    int rc = 0;
     RolloutArgs a = a0;
+    // lockstep groups: G rollouts (warps) per block, G regions of `smem` bytes
+    const int G = (NW == 1 && !ADJ && LIN == 0 && a.group > 1) ? (a.group < RMX_MAX_GROUP ? a.group : RMX_MAX_GROUP) : 1;
+    a.group = G;
+    smem = (smem + 15) & ~(size_t)15;  // every slot's region starts 16-byte aligned (double2 pivot-row buffers)
+    a.group_stride = (int)(smem / sizeof(double));
+    smem *= (size_t)G;
+    if (smem > 227 * 1024) return rmx_fail(RMX_ELIMIT, "lockstep group does not fit the shared memory of one SM");
+    rc = rmx_set_smem(kernel, smem);
+    if (rc) return rc;
     if (a.B <= 0) {  // occupancy query only: how many blocks of this kernel are co-resident on the current device
         if (!dc) return RMX_OK;
         int nb = 0, dev = 0, sms = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, 32 * NW, smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, 32 * NW * G, smem));
         CUDA_TRY(cudaGetDevice(&dev));
         CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        dc->slots_query = (long long)nb * sms;
+        dc->slots_query = (long long)nb * sms * G;
         return RMX_OK;
     }
     long long grid = a.B;
     if (!ADJ && LIN == 0 && dc && a.qd_out && a.op.nsteps >= 2 && a.B < (1ll << 30) && rmx_sched_enabled()) {
         int nb = 0, dev = 0, sms = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, 32 * NW, smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, 32 * NW * G, smem));
         CUDA_TRY(cudaGetDevice(&dev));
         CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        const long long slots = (long long)nb * sms;
+        const long long slots = (long long)nb * sms * G;
         if (slots > 0 && a.B > slots && a.B % slots != 0) {
             SchedPlan& p = dc->plan;
             const bool fresh = !(p.B == a.B && p.nsteps == a.op.nsteps && p.slots == slots);
@@ -49,7 +57,8 @@ static int rmx_launch_fwd_t(const rmx::RolloutArgs& a0, size_t smem, cudaStream_
             grid = slots;
         }
     }
-    kernel<<<(unsigned)grid, 32 * NW, smem, st>>>(a);
+    grid = (grid + G - 1) / G;  // slots -> blocks (slots beyond the batch find no work)
+    kernel<<<(unsigned)grid, dim3(32 * NW, G), smem, st>>>(a);
     CUDA_TRY(cudaGetLastError());
     return RMX_OK;
 }

@@ -61,7 +61,14 @@ struct RolloutArgs {
     // no device-to-host copy afterwards.  The device copies stay the ones a cut rollout resumes from.  Null: not mirrored.
     double* q_host;
     double* qd_host;
+    // Lockstep groups (one-warp forward kernels; group_barrier in rmx_device.cuh): `group` warps per block, each an independent
+    // rollout slot with `group_stride` doubles of the block's dynamic shared memory.  group <= 1: one rollout per block.
+    int group;
+    int group_stride;
 };
+#ifndef RMX_MAX_GROUP
+#define RMX_MAX_GROUP 8
+#endif
 
 // Shared-memory scratch of the point forces sits behind everything any kernel variant places after the Newton matrix
 // (task Jacobian rows of the adjoint kernels, Krylov vectors), at the same offset for all of them.
@@ -278,6 +285,7 @@ __device__ __forceinline__ int newton_forward(typename E::C& c, const StepOpts& 
     int iterLs = 1;
     bool at_x0 = false;  // the trial being evaluated is x0 itself (and it is the last of this line search)
     while (true) {
+        if (NW == 1) group_barrier(c.group, false);  // lockstep groups: every evaluation pass starts together
         E::base(c, true);
         const double gt = (t < nr) ? c.g[t] : 0.0;
         const double gsum = block_sum<NW>(gt * gt, c.red);
@@ -525,12 +533,21 @@ template <int NW, int GROUND, bool ADJ, int IMPL, int LIN>
 __global__ void RMX_FWD_BOUNDS rollout_fwd_kernel(RolloutArgs a) {
     typedef Eval<IMPL, NW, GROUND, ADJ || LIN == 1, LIN, ADJ> E;
     extern __shared__ double2 smem_raw[];
-    double* sm = reinterpret_cast<double*>(smem_raw);
-    __shared__ int perm_s[32 * NW];
+    // lockstep group (group_barrier, rmx_device.cuh): warp threadIdx.y of the block is an independent rollout slot with its own
+    // shared-memory region; slots are numbered so that neighbouring slots (the two parts of a cut rollout) sit in different blocks
+    constexpr bool CAN_GROUP = NW == 1 && !ADJ && LIN == 0;
+    constexpr int MAXG = CAN_GROUP ? RMX_MAX_GROUP : 1;
+    const int G = CAN_GROUP ? (int)blockDim.y : 1;
+    const int gy = CAN_GROUP ? (int)threadIdx.y : 0;
+    double* sm = reinterpret_cast<double*>(smem_raw) + (size_t)gy * a.group_stride;
+    __shared__ int perm_all[32 * NW * MAXG];
+    int* perm_s = perm_all + 32 * NW * gy;
+    const long long slot = (long long)blockIdx.x + (long long)gy * gridDim.x, nslots = (long long)gridDim.x * G;
     const int t = threadIdx.x;
     const int nr = a.sc.nr;
     typename E::C c;
     E::setup(c, sm, a.sc, a.op);
+    c.group = G;
     const StepOpts op = a.op;
     const double h = op.h;
     const double ah = __dmul_rn(SDIRK_A_CONST, h);
@@ -538,9 +555,9 @@ __global__ void RMX_FWD_BOUNDS rollout_fwd_kernel(RolloutArgs a) {
 
     constexpr bool CAN_SCHED = !ADJ && LIN == 0;
     const bool sched = CAN_SCHED && a.seg != nullptr;
-    long long it = sched ? (long long)a.seg_off[blockIdx.x] : (long long)blockIdx.x;
-    const long long it_end = sched ? (long long)a.seg_off[blockIdx.x + 1] : a.B;
-    const long long it_step = sched ? 1 : (long long)gridDim.x;
+    long long it = sched ? (long long)a.seg_off[slot] : slot;
+    const long long it_end = sched ? (long long)a.seg_off[slot + 1] : a.B;
+    const long long it_step = sched ? 1 : nslots;
     for (; it < it_end; it += it_step) {
         long long b = it;
         int k_begin = 0, k_end = op.nsteps, seg_flags = 0;
@@ -557,7 +574,17 @@ __global__ void RMX_FWD_BOUNDS rollout_fwd_kernel(RolloutArgs a) {
         if (CAN_SCHED && (seg_flags & 1)) {
             // second part of a cut rollout: wait until the block that runs the first part has published it (bounded spin: a
             // lost signal becomes a status bit, never a hang), then resume from the trajectory already in global memory
-            if (t == 0) {
+            if (G > 1) {  // a grouped warp keeps meeting its partners while it waits (they check in once per evaluation pass)
+                unsigned spins = 0;
+                int ready = 0;
+                while (true) {
+                    if (t == 0) ready = atomicAdd(a.flags + b, 0);
+                    ready = __shfl_sync(0xffffffffu, ready, 0);
+                    if (ready || ++spins >= (1u << 22)) break;
+                    group_barrier(G, false);
+                }
+                if (!ready) status |= 16;
+            } else if (t == 0) {
                 unsigned spins = 0;
                 while (atomicAdd(a.flags + b, 0) == 0 && ++spins < (1u << 26)) __nanosleep(200);
                 if (spins >= (1u << 26)) status |= 16;
@@ -748,6 +775,10 @@ __global__ void RMX_FWD_BOUNDS rollout_fwd_kernel(RolloutArgs a) {
             }
         }
         bsync<NW>();
+    }
+    if (CAN_GROUP && G > 1) {  // out of work: keep the block's barrier going until every warp of the group is
+        while (!group_barrier(G, true)) {
+        }
     }
 }
 

@@ -131,3 +131,34 @@ def test_stalled_newton_shortcuts_are_bitwise_identical(rb, case, monkeypatch):
     assert stalled.any()
     for key in ('q', 'qdot', 'status', 'iters'):
         np.testing.assert_array_equal(fast[key], slow[key])
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize('case', ['ground', 'pointforce'])
+def test_lockstep_groups_are_bitwise_identical(rb, case, monkeypatch):
+    """The external-force kernels run several rollouts per block, one per warp, meeting at the top of every evaluation pass
+    (group_barrier, rmx_device.cuh: the warps then share their instruction-cache lines).  The rollouts stay independent, so
+    trajectories, status bits and iteration counts must not depend on the group size -- checked on a batch that is not a
+    multiple of the co-resident slots (rollouts cut in two, the second part waiting for the first across blocks) and that
+    contains stalled solves (warps that run hundreds of passes while their partners finish)."""
+    if case == 'ground':
+        sg = rb.chain_scene(32, ground=True, h=5e-4, nsteps=24)
+        B, scheme = 1500, 2
+    else:
+        sg = rb.scenesRedMax(12)     # ForceSpringDamper between bodies
+        B, scheme = 1201, 1
+    sg.init()
+    q0, qd0 = rb.synthetic_inputs(sg, B, seed=20260007)
+    kw = dict(scheme=scheme, iterMaxFactor=2, nsteps=24)
+    out = {}
+    for G in ('1', '2', '5', ''):
+        if G:
+            monkeypatch.setenv('RMX_GROUP', G)
+        else:
+            monkeypatch.delenv('RMX_GROUP')
+        out[G] = sg.rollout(q0, qd0, **kw)
+    if case == 'ground':
+        assert ((out['1']['status'] & 6) != 0).any()
+    for G in ('2', '5', ''):
+        for key in ('q', 'qdot', 'status', 'iters'):
+            np.testing.assert_array_equal(out[G][key], out['1'][key])

@@ -17,6 +17,9 @@ KEYS = [
     'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'lts__t_bytes.sum',
     'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
     'smsp__inst_executed_op_local_ld.sum', 'smsp__inst_executed_op_local_st.sum',
+    # instruction fetch: SM-level instruction cache and the GPC-level cache behind it
+    'sm__icc_requests.sum', 'sm__icc_request_hit_rate.pct', 'gcc__cache_requests_type_instruction.sum',
+    'gcc__cache_requests_type_instruction.sum.pct_of_peak_sustained_elapsed',
 ]
 
 
