@@ -17,7 +17,7 @@ static int rmx_launch_fwd_t(const rmx::RolloutArgs& a0, size_t smem, cudaStream_
     a.group_stride = (int)(smem / sizeof(double));
     smem *= (size_t)G;
     if (smem > 227 * 1024) return rmx_fail(RMX_ELIMIT, "lockstep group does not fit the shared memory of one SM");
-    rc = rmx_set_smem(kernel, smem);
+    rc = rmx_set_smem(kernel, smem, 32 * NW * G);
     if (rc) return rc;
     if (a.B <= 0) {  // occupancy query only: how many blocks of this kernel are co-resident on the current device
         if (!dc) return RMX_OK;
