@@ -1,6 +1,6 @@
 # Final measurement pass of round 2: every bench line, the launch list and the ncu captures committed under profiles/.
 set -x
-O=gpurun_out/r2z; mkdir -p $O
+O=gpurun_out/r2end; mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/smi.txt; nproc >> $O/smi.txt
 timeout 900 python -m pytest tests -m gpu -q > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu.log
 timeout 400 python bench.py --steps 20 --warmup 5 > $O/bench_chain32.log 2>&1
@@ -19,6 +19,6 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:adjo
 timeout 900 python tools/explore_r2b.py > $O/stalled_newton_shortcuts.log 2>&1
 timeout 300 python tools/ground_nocontact.py > $O/ground_nocontact.log 2>&1
 ls -la $O
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_adjoint.py tests/test_gpu_long_chains.py tests/test_mex_gateway.py -m gpu -q -x -k "scene100_101 or hand_c4 or newton_system_two_warps or eval_long_chain or gateway" > $O/memcheck.log 2>&1; echo "memcheck rc=$?" >> $O/memcheck.log
-timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_long_chains.py -m gpu -q -x -k "newton_system_two_warps" > $O/racecheck.log 2>&1; echo "racecheck rc=$?" >> $O/racecheck.log
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_adjoint.py tests/test_gpu_long_chains.py tests/test_mex_gateway.py tests/test_gpu_trees.py -m gpu -q -x -k "scene100_101 or hand_c4 or newton_system_two_warps or eval_long_chain or gateway or lockstep or tree_adjoint" > $O/memcheck.log 2>&1; echo "memcheck rc=$?" >> $O/memcheck.log
+timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_long_chains.py tests/test_gpu_adjoint.py -m gpu -q -x -k "newton_system_two_warps or lockstep or hand_c4" > $O/racecheck.log 2>&1; echo "racecheck rc=$?" >> $O/racecheck.log
 ls -la $O

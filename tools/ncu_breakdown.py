@@ -31,9 +31,10 @@ REGIONS = [
     ('rmx_tc.cuh', 393, 472, 'tc:LU trailing update'),
     ('rmx_tc.cuh', 473, 560, 'tc:LU back substitution'),
     ('rmx_rollout.cuh', 1, 10000, 'rollout (newton, line search, time loop, schedule, tape stores)'),
-    ('rmx_fast.cuh', 200, 320, 'fast: xtmx_store (X^T K X, X^T D X of the contact blocks)'),
+    ('rmx_fast.cuh', 312, 345, 'fast: xtmx_store (X^T K X, X^T D X of the contact blocks)'),
     ('rmx_fast.cuh', 1, 10000, 'fast: composite base evaluation'),
-    ('rmx_device.cuh', 390, 560, 'device: ground_body (ForceGroundCuboid)'),
+    ('rmx_device.cuh', 195, 222, 'device: group_barrier (lockstep groups: waiting for the slowest warp of the block)'),
+    ('rmx_device.cuh', 414, 590, 'device: ground_body (ForceGroundCuboid)'),
     ('rmx_device.cuh', 1, 10000, 'device helpers (se3, reductions)'),
 ]
 
