@@ -1028,7 +1028,9 @@ extern "C" int rmx_rollout_resume(rmx_scene* s, const rmx_opts* o, int64_t B, co
     for (int i = 0; i < 7; ++i)
         if (sz[i] && (rc = dev_reserve(dc->buf[i], sz[i]))) return rc;
     const size_t sb = seg.size() * sizeof(int4), ob = off.size() * sizeof(int);
-    if ((rc = dev_reserve(dc->buf[13], sb)) || (rc = dev_reserve(dc->buf[14], ob))) return rc;
+    if ((rc = dev_reserve(dc->buf[13], sb)) || (rc = dev_reserve(dc->buf[14], ob)) ||
+        (rc = dev_reserve(dc->buf[15], (size_t)B * sizeof(int))))
+        return rc;
     dc->plan = SchedPlan();  // the cached load-balancing plan no longer matches what is in buf[13], buf[14]
     dc->plan_dev = nullptr;
     cudaStream_t st = dc->stream;
@@ -1055,6 +1057,9 @@ extern "C" int rmx_rollout_resume(rmx_scene* s, const rmx_opts* o, int64_t B, co
     a.iters = (int*)dc->buf[6].p;
     a.seg = (const int4*)dc->buf[13].p;
     a.seg_off = (const int*)dc->buf[14].p;
+    a.cursor = (int*)dc->buf[15].p;  // one list per rollout: claimed once each (claim_segment)
+    a.nlists = (int)B;
+    CUDA_TRY(cudaMemsetAsync(dc->buf[15].p, 0, (size_t)B * sizeof(int), st));
     rc = launch_fwd<false>(s, a, st, nullptr);  // no DevCopy: the launch keeps our segments, grid = B
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(q_out, dc->buf[3].p, sz[3], cudaMemcpyDeviceToHost, st));

@@ -39,7 +39,8 @@ static int rmx_launch_fwd_t(const rmx::RolloutArgs& a0, size_t smem, cudaStream_
             SchedPlan& p = dc->plan;
             const bool fresh = !(p.B == a.B && p.nsteps == a.op.nsteps && p.slots == slots);
             if (fresh) rmx_build_plan(p, a.B, a.op.nsteps, slots);
-            const size_t sb = p.seg.size() * sizeof(int4), ob = p.off.size() * sizeof(int), fb = (size_t)a.B * sizeof(int);
+            const size_t sb = p.seg.size() * sizeof(int4), ob = p.off.size() * sizeof(int);
+            const size_t fb = ((size_t)a.B + (size_t)slots) * sizeof(int);  // flags[B] | cursor[slots]
             if ((rc = rmx_dev_reserve(dc->buf[13], sb)) || (rc = rmx_dev_reserve(dc->buf[14], ob)) ||
                 (rc = rmx_dev_reserve(dc->buf[15], fb)))
                 return rc;
@@ -54,6 +55,8 @@ static int rmx_launch_fwd_t(const rmx::RolloutArgs& a0, size_t smem, cudaStream_
             a.seg = (const int4*)dc->buf[13].p;
             a.seg_off = (const int*)dc->buf[14].p;
             a.flags = (int*)dc->buf[15].p;
+            a.cursor = a.flags + a.B;
+            a.nlists = (int)slots;
             grid = slots;
         }
     }

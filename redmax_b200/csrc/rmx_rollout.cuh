@@ -56,6 +56,12 @@ struct RolloutArgs {
     const int4* seg;
     const int* seg_off;
     int* flags;
+    // cursor[s]: how many segments of list s have been claimed (zeroed before the launch).  A block works through its own list
+    // and, once that is empty, takes unclaimed segments of other lists (claim_segment): the segments queued behind a stalled
+    // rollout -- one that runs 10 nr iterations x 20 halvings in some step -- are integrated by blocks that are out of work
+    // instead of waiting for it.  Who integrates a segment does not change its arithmetic: results stay bitwise the same.
+    int* cursor;
+    int nlists;  // number of segment lists (co-resident slots of a load-balanced launch; B for rmx_rollout_resume)
     // Optional mirrors of q_out / qd_out in mapped pinned HOST memory (device pointers of the caller's buffers): every step
     // is stored to both, so the trajectories cross PCIe while the rollout is still running and the host-pointer entry needs
     // no device-to-host copy afterwards.  The device copies stay the ones a cut rollout resumes from.  Null: not mirrored.
@@ -520,6 +526,56 @@ __device__ __forceinline__ int newton_adjoint_tc(typename E::C& c, const StepOpt
 // Forward rollout kernel: simLoop of driverRedMaxBDF1.m:57-91 / driverRedMaxBDF2.m:57-125 (ADJ = false) and of
 // driverRedMaxAdjointBDF1.m:65-102 / driverRedMaxAdjointBDF2.m:65-136 (ADJ = true), one block per rollout.
 // ---------------------------------------------------------------------------------------------
+// Next segment of a scheduled launch for this block (NW > 1) or warp (NW == 1; lockstep groups: every warp claims on its own):
+// from list `victim` while it has unclaimed segments, else from the next list that has (32 candidates per probe round).
+// Returns the segment index or -1 when every list is empty.  Uniform over the block / warp.
+template <int NW>
+__device__ __forceinline__ int claim_segment(const RolloutArgs& a, int& victim, int nslots, int* bc) {
+    const int lane = threadIdx.x & 31;
+    const bool w0 = threadIdx.x < 32;
+    int seg = -1;
+    if (w0) {
+        while (true) {
+            int idx = 0;
+            if (lane == 0) idx = atomicAdd(a.cursor + victim, 1);
+            idx = __shfl_sync(0xffffffffu, idx, 0);
+            const int lo = __ldg(a.seg_off + victim), hi = __ldg(a.seg_off + victim + 1);
+            if (lo + idx < hi) {
+                seg = lo + idx;
+                break;
+            }
+            int found = -1;
+            for (int base = 1; base < nslots && found < 0; base += 32) {
+                int v = victim + base + lane;
+                v -= (v >= nslots) ? nslots : 0;
+                bool has = false;
+                if (base + lane < nslots) {
+                    const int left = __ldg(a.seg_off + v + 1) - __ldg(a.seg_off + v);
+                    has = *reinterpret_cast<volatile int*>(a.cursor + v) < left;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, has);
+                if (m) {
+                    found = victim + base + __ffs(m) - 1;
+                    found -= (found >= nslots) ? nslots : 0;
+                }
+            }
+            if (found < 0) break;
+            victim = found;
+        }
+    }
+    if (NW > 1) {  // one block per rollout: warp 0 claimed for all
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            bc[0] = seg;
+            bc[1] = victim;
+        }
+        __syncthreads();
+        seg = bc[0];
+        victim = bc[1];
+    }
+    return seg;
+}
+
 // Register budget of the one-warp tensor-core forward kernel.  Measured on B200 (profiles/r01_residency_probe.log,
 // r01_regcap_ab.log): the kernel is latency-bound per warp -- time per block is almost flat in the number of resident blocks
 // (59.7 us per rollout-step alone on an SM, 71.4 us with 8 resident) -- but capping registers to fit 10 blocks per SM
@@ -555,18 +611,23 @@ __global__ void RMX_FWD_BOUNDS rollout_fwd_kernel(RolloutArgs a) {
 
     constexpr bool CAN_SCHED = !ADJ && LIN == 0;
     const bool sched = CAN_SCHED && a.seg != nullptr;
-    long long it = sched ? (long long)a.seg_off[slot] : slot;
-    const long long it_end = sched ? (long long)a.seg_off[slot + 1] : a.B;
-    const long long it_step = sched ? 1 : nslots;
-    for (; it < it_end; it += it_step) {
+    long long it = slot;   // plain launches: rollouts slot, slot + nslots, ...
+    // scheduled launches: the list this block is claiming segments from (claim_segment); slots beyond the lists only steal
+    int victim = sched ? (int)(slot % a.nlists) : 0;
+    while (true) {
         long long b = it;
         int k_begin = 0, k_end = op.nsteps, seg_flags = 0;
         if (sched) {
-            const int4 sg = __ldg(a.seg + it);
+            const int si = claim_segment<NW>(a, victim, a.nlists, perm_s);  // (perm_s is free between rollouts)
+            if (si < 0) break;
+            const int4 sg = __ldg(a.seg + si);
             b = sg.x;
             k_begin = sg.y;
             k_end = sg.z;
             seg_flags = sg.w;
+        } else {
+            if (it >= a.B) break;
+            it += nslots;
         }
         double qc = 0.0, qdc = 0.0;  // current state of dof t (joint.q / joint.qdot)
         double q0t = 0.0, qd0t = 0.0, q1t = 0.0, qdat = 0.0;
