@@ -78,3 +78,46 @@ def test_c_oracle_hits_reference_golden_energy(oracle, oc):
     s.update()
     T, V = s.computeEnergies()
     assert abs(T + V - V0 - s.Hexpected[0]) <= 1e-2
+
+
+@pytest.mark.parametrize('n,seed', [(12, 3), (21, 4), (36, 5)])
+def test_c_oracle_on_random_trees(rb, oracle, oc, n, seed):
+    """The checker of tests/test_gpu_trees.py (the C twin) against the NumPy oracle on the seeded random trees themselves:
+    branching, general and sign-flipped axes, fixed joints inside the tree, damping.  One evaluation and a short rollout."""
+    s = rb.tree_scene(n, seed=seed, api=oracle)
+    s.init()
+    rng = np.random.default_rng(100 + seed)
+    nr, h = s.nr, s.h
+    q = s.qInit + 0.4 * rng.uniform(-1, 1, nr)
+    q0 = q - 0.003 * rng.uniform(-1, 1, nr)
+    qdot0 = rng.uniform(-1, 1, nr)
+    tau = 100 * rng.uniform(-1, 1, nr)
+    s.setQ0(q0, qdot0)
+    for j in s.joints:
+        j.tau = tau[j.idxR].copy()
+    g, H, M, f, K, D, J = oracle.eval_bdf1(q, s, True, True)
+    out = oc.eval_direct(s, q, (q - q0) / h, q - q0 - h * qdot0, h, h * h, tau=tau)
+    for key, ref in (('g', g), ('H', H), ('M', M), ('D', D), ('K', K), ('f', f)):
+        assert rel_err(out[key], ref) < 1e-12, (key, rel_err(out[key], ref))
+    if n <= 21:
+        s2 = rb.tree_scene(n, seed=seed, api=oracle)
+        s2.init()
+        stats = []
+        qs, qds = oracle.run_forward(s2, 2, s2.qInit.copy(), s2.qdotInit.copy(), nsteps=6, stats=stats)
+        qc, qdc, st = oc.run_forward_batch(s2, 2, s2.qInit, s2.qdotInit, nsteps=6, threads=1)
+        assert rel_err(qc[0], qs) < 1e-11 and rel_err(qdc[0], qds) < 1e-9
+        assert st[0, 0] == np.array(stats)[:, 0].sum() and st[0, 2] == 0
+
+
+def test_tree_scene_host_mirror_matches_oracle_numbering(rb, oracle):
+    """Same seeded tree through the host mirror (what the library is given) and through the oracle's classes: same reduced
+    numbering (leaf-to-root, Scene.m:69-71), same initial state."""
+    for n, seed in ((12, 3), (40, 1), (73, 6)):
+        a = rb.tree_scene(n, seed=seed)
+        a.init()
+        b = rb.tree_scene(n, seed=seed, api=oracle)
+        b.init()
+        assert a.nr == b.nr
+        np.testing.assert_array_equal(a.qInit, b.qInit)
+        for ja, jb in zip(a.joints, b.joints):
+            assert list(np.atleast_1d(ja.idxR)) == list(np.atleast_1d(jb.idxR))
