@@ -201,6 +201,7 @@ __device__ __forceinline__ void bsync() {
 __device__ __forceinline__ bool group_barrier(int G, bool done) {
     if (G <= 1) return done;
     int r;
+    __syncwarp();  // the barrier instruction is .aligned: the whole warp has to arrive converged (compute-sanitizer synccheck)
     asm volatile(
         "{\n\t"
         ".reg .pred p, q;\n\t"

@@ -1,5 +1,8 @@
 // rmx_launch.cuh -- launch of one forward-kernel instance (included by the rmx_k_fwd_*.cu files only).
 #pragma once
+#include <algorithm>
+#include <cstdlib>
+
 #include "rmx_host.h"
 
 // One persistent launch of rollout_fwd_kernel<NW, GROUND, ADJ, IMPL, LIN>.  Forward launches whose batch is not a multiple of
@@ -34,7 +37,10 @@ static int rmx_launch_fwd_t(const rmx::RolloutArgs& a0, size_t smem, cudaStream_
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, 32 * NW * G, smem));
         CUDA_TRY(cudaGetDevice(&dev));
         CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        const long long slots = (long long)nb * sms * G;
+        long long slots = (long long)nb * sms * G;
+        // (developer knob: pretend more blocks are co-resident than are, to exercise the waits of cut rollouts and the hand-off
+        // of segments whose owner has not started -- tests/test_gpu_long_chains.py)
+        if (const char* e = std::getenv("RMX_DEBUG_SLOTS_SCALE")) slots *= std::max(1, std::atoi(e));
         if (slots > 0 && a.B > slots && a.B % slots != 0) {
             SchedPlan& p = dc->plan;
             const bool fresh = !(p.B == a.B && p.nsteps == a.op.nsteps && p.slots == slots);

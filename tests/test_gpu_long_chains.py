@@ -162,3 +162,28 @@ def test_lockstep_groups_are_bitwise_identical(rb, case, monkeypatch):
     for G in ('2', '5', ''):
         for key in ('q', 'qdot', 'status', 'iters'):
             np.testing.assert_array_equal(out[G][key], out['1'][key])
+
+
+@pytest.mark.timeout(900)
+def test_schedule_survives_oversubscription_bitwise(rb, monkeypatch):
+    """The load-balanced launch assumes its blocks are co-resident.  When they are not (here: the launcher is told to assume two
+    and three times the real residency, RMX_DEBUG_SLOTS_SCALE), the second parts of cut rollouts wait for first parts whose
+    owner has not started, and blocks that run out of work take over the lists of blocks that have not begun -- with and without
+    lockstep groups, whose waiting warps keep meeting their partners.  Everything still completes with bitwise the same
+    trajectories, status bits and counts."""
+    sg = rb.chain_scene(32, ground=True, h=5e-4, nsteps=24)
+    sg.init()
+    B = 3001
+    q0, qd0 = rb.synthetic_inputs(sg, B, seed=20260007)
+    kw = dict(scheme=2, iterMaxFactor=2, nsteps=24)
+    monkeypatch.setenv('RMX_GROUP', '1')
+    ref = sg.rollout(q0, qd0, **kw)
+    assert not (ref['status'] & 16).any()
+    for G in ('1', '2', '5'):
+        for scale in ('2', '3'):
+            monkeypatch.setenv('RMX_GROUP', G)
+            monkeypatch.setenv('RMX_DEBUG_SLOTS_SCALE', scale)
+            out = sg.rollout(q0, qd0, **kw)
+            monkeypatch.delenv('RMX_DEBUG_SLOTS_SCALE')
+            for key in ('q', 'qdot', 'status', 'iters'):
+                np.testing.assert_array_equal(out[key], ref[key])
