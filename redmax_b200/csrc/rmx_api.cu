@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 #include "rmx_host.h"
 
@@ -570,6 +571,8 @@ extern "C" void rmx_scene_destroy(rmx_scene* s) {
         if (kv.second.copy_stream) cudaStreamDestroy(kv.second.copy_stream);
         for (cudaEvent_t e : kv.second.chunk_done)
             if (e) cudaEventDestroy(e);
+        for (void* h : kv.second.stage)
+            if (h) cudaFreeHost(h);
     }
     cudaSetDevice(cur);
     cudaGetLastError();
@@ -818,6 +821,46 @@ extern "C" int rmx_rollout_dev(rmx_scene* s, const rmx_opts* o, int64_t B, const
     return rollout_dev_impl(s, o, B, q0, qdot0, tau, q_out, qdot_out, status, iters, cuda_stream, nullptr, nullptr);
 }
 
+// Staging for pageable outputs (rmx_rollout).  A device-to-host copy into pageable memory runs at half the rate of one into
+// page-locked memory and blocks the calling thread (measured on the B200 boxes, profiles/r02_pageable_probe.log: 20.8 against
+// 41.7 GB/s, no gain from more threads), while four host threads move page-locked memory to pageable memory at 50 GB/s.  So the
+// kernel writes the trajectories into library-owned page-locked memory while it runs (the same mirrored stores a page-locked
+// caller buffer gets) and the finished sub-batches are copied on by host threads.  RMX_STAGE=0 keeps the plain copies; so does
+// an allocation that fails or a request above 2 GiB per array and device.
+static bool stage_enabled() {
+    const char* e = std::getenv("RMX_STAGE");
+    return !(e && e[0] == '0');
+}
+static double* stage_reserve(DevCopy* dc, int which, size_t bytes) {
+    if (bytes == 0 || bytes > ((size_t)2 << 30)) return nullptr;
+    if (dc->stage_cap[which] < bytes) {
+        if (dc->stage[which]) cudaFreeHost(dc->stage[which]);
+        dc->stage[which] = nullptr;
+        dc->stage_cap[which] = 0;
+        void* h = nullptr;
+        if (cudaHostAlloc(&h, bytes, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        dc->stage[which] = h;
+        dc->stage_cap[which] = bytes;
+    }
+    return (double*)dc->stage[which];
+}
+static void host_copy_threads(void* dst, const void* src, size_t bytes) {
+    const int nt = bytes >= ((size_t)8 << 20) ? 4 : 1;
+    if (nt == 1) {
+        std::memcpy(dst, src, bytes);
+        return;
+    }
+    std::thread th[4];
+    for (int i = 0; i < nt; ++i) {
+        const size_t lo = (bytes / 64 * i / nt) * 64, hi = i == nt - 1 ? bytes : (bytes / 64 * (i + 1) / nt) * 64;
+        th[i] = std::thread([=] { std::memcpy((char*)dst + lo, (const char*)src + lo, hi - lo); });
+    }
+    for (int i = 0; i < nt; ++i) th[i].join();
+}
+
 // Device pointer of a caller's host buffer if the running kernel can store to it directly: page-locked memory
 // (cudaHostAlloc / cudaHostRegister; mapped on every device under unified addressing).  Null for pageable memory.
 // RMX_ZEROCOPY=0 (developer switch) forces the staged device-to-host copy.
@@ -869,7 +912,7 @@ extern "C" int rmx_rollout(rmx_scene* s, const rmx_opts* o, int64_t B, const dou
     std::vector<int> devs;
     for (int gi = 0; gi < G; ++gi) devs.push_back(G == 1 ? cur : gi);
     int ret = RMX_OK;
-    std::vector<int> nchunk(G, 1);
+    std::vector<int> nchunk(G, 1), staged(G, 0);
     for (int gi = 0; gi < G && ret == RMX_OK; ++gi) {
         const int64_t b0 = B * gi / G, b1 = B * (gi + 1) / G, nb = b1 - b0;
         CUDA_LOOP(cudaSetDevice(devs[gi]));
@@ -893,6 +936,28 @@ extern "C" int rmx_rollout(rmx_scene* s, const rmx_opts* o, int64_t B, const dou
         double* qh = mapped_host_ptr(q_out + b0 * per);
         double* qdh = qdot_out ? mapped_host_ptr(qdot_out + b0 * per) : nullptr;
         const bool paged = !qh || (qdot_out && !qdh);
+        // pageable outputs: through the page-locked staging if it can be had (the kernel then writes it like a caller's
+        // page-locked buffer, device pointer = host pointer under unified addressing)
+        staged[gi] = 0;
+        if (paged && stage_enabled()) {
+            double* sq = !qh ? stage_reserve(dc, 0, sz[3]) : nullptr;
+            double* sqd = (qdot_out && !qdh) ? stage_reserve(dc, 1, sz[4]) : nullptr;
+            if ((qh || sq) && (!qdot_out || qdh || sqd)) {
+                if (sq) {
+                    qh = mapped_host_ptr(sq);
+                    staged[gi] |= 1;
+                }
+                if (sqd) {
+                    qdh = mapped_host_ptr(sqd);
+                    staged[gi] |= 2;
+                }
+                if ((sq && !qh) || (sqd && !qdh)) {  // not mapped after all: plain copies
+                    staged[gi] = 0;
+                    qh = mapped_host_ptr(q_out + b0 * per);
+                    qdh = qdot_out ? mapped_host_ptr(qdot_out + b0 * per) : nullptr;
+                }
+            }
+        }
         int K = 1;
         if (paged && o1.linsolve == RMX_LINSOLVE_LU && !g_no_sched) {
             const long long slots = fwd_slots(s, dc);
@@ -929,6 +994,28 @@ extern "C" int rmx_rollout(rmx_scene* s, const rmx_opts* o, int64_t B, const dou
         double* qh = mapped_host_ptr(q_out + b0 * per);
         double* qdh = qdot_out ? mapped_host_ptr(qdot_out + b0 * per) : nullptr;
         const int K = nchunk[gi];
+        if (staged[gi]) {
+            // the trajectories are in the staging already when a sub-batch's event has fired: host threads copy them on
+            for (int c = 0; c < K && ret == RMX_OK; ++c) {
+                const int64_t c0 = nb * c / K, cn = nb * (c + 1) / K - c0;
+                CUDA_LOOP(K > 1 ? cudaEventSynchronize(dc->chunk_done[c]) : cudaStreamSynchronize(st));
+                if (staged[gi] & 1)
+                    host_copy_threads(q_out + (b0 + c0) * per, (const double*)dc->stage[0] + c0 * per, cn * per * sizeof(double));
+                else if (!qh)
+                    CUDA_LOOP(cudaMemcpyAsync(q_out + (b0 + c0) * per, (double*)dc->buf[3].p + c0 * per,
+                                              cn * per * sizeof(double), cudaMemcpyDeviceToHost, st));
+                if (staged[gi] & 2)
+                    host_copy_threads(qdot_out + (b0 + c0) * per, (const double*)dc->stage[1] + c0 * per,
+                                      cn * per * sizeof(double));
+                else if (qdot_out && !qdh)
+                    CUDA_LOOP(cudaMemcpyAsync(qdot_out + (b0 + c0) * per, (double*)dc->buf[4].p + c0 * per,
+                                              cn * per * sizeof(double), cudaMemcpyDeviceToHost, st));
+            }
+            if (ret) break;
+            CUDA_LOOP(cudaMemcpyAsync(status + b0, dc->buf[5].p, nb * sizeof(int), cudaMemcpyDeviceToHost, st));
+            if (iters) CUDA_LOOP(cudaMemcpyAsync(iters + 2 * b0, dc->buf[6].p, 2 * nb * sizeof(int), cudaMemcpyDeviceToHost, st));
+            continue;
+        }
         for (int c = 0; c < K && ret == RMX_OK; ++c) {
             const int64_t c0 = nb * c / K, cn = nb * (c + 1) / K - c0;
             cudaStream_t cs = K > 1 ? dc->copy_stream : st;

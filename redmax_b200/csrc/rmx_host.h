@@ -53,6 +53,10 @@ struct DevCopy {
     cudaEvent_t chunk_done[4] = {nullptr, nullptr, nullptr, nullptr};
     long long slots_query = 0;           // co-resident blocks of the last forward-kernel occupancy query (launcher called with B <= 0)
     DevBuf buf[16];
+    // page-locked, device-mapped staging for pageable outputs of rmx_rollout (q, qdot): the kernel writes them while it runs,
+    // host threads copy finished sub-batches on to the caller's arrays
+    void* stage[2] = {nullptr, nullptr};
+    size_t stage_cap[2] = {0, 0};
     void* plan_dev = nullptr;  // device copy of `plan` currently in buf[13]/buf[14]
 };
 
