@@ -854,11 +854,20 @@ static void host_copy_threads(void* dst, const void* src, size_t bytes) {
         return;
     }
     std::thread th[4];
+    int started = 0;
+    size_t done_to = 0;  // bytes [0, done_to) are covered by started threads
     for (int i = 0; i < nt; ++i) {
         const size_t lo = (bytes / 64 * i / nt) * 64, hi = i == nt - 1 ? bytes : (bytes / 64 * (i + 1) / nt) * 64;
-        th[i] = std::thread([=] { std::memcpy((char*)dst + lo, (const char*)src + lo, hi - lo); });
+        try {  // no exception may cross the C ABI: whatever cannot get a thread is copied here
+            th[i] = std::thread([=] { std::memcpy((char*)dst + lo, (const char*)src + lo, hi - lo); });
+        } catch (...) {
+            break;
+        }
+        ++started;
+        done_to = hi;
     }
-    for (int i = 0; i < nt; ++i) th[i].join();
+    if (done_to < bytes) std::memcpy((char*)dst + done_to, (const char*)src + done_to, bytes - done_to);
+    for (int i = 0; i < started; ++i) th[i].join();
 }
 
 // Device pointer of a caller's host buffer if the running kernel can store to it directly: page-locked memory
