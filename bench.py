@@ -384,7 +384,8 @@ def run_ours(args):
         h2d = 2 * B * nr * 8
         d2h = 2 * B * nsteps * nr * 8 + B * 4 + B * 8
         api = ('rmx_rollout (host pointers; with page-locked buffers q(t), qdot(t) are stored to the mapped host buffers by the '
-               'kernel as it runs, status/iters copied after; pageable buffers take a staged copy)')
+               'kernel as it runs, status/iters copied after; pageable buffers go through page-locked staging written the same way and '
+               'are copied on by host threads, sub-batch by sub-batch)')
 
     def time_e2e(hb):
         for _ in range(2):
