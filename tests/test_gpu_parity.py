@@ -291,6 +291,21 @@ def _ffi_device_count(rb):
     return int(_ffi.lib().rmx_device_count())
 
 
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize('n,B,chunk', [(40, 1301, 500), (70, 1001, 250)])
+def test_load_balanced_schedule_multi_warp_kernels(rb, n, B, chunk):
+    """The same for the kernels with several warps per rollout (two-warp tensor-core kernel, four-warp sweep kernel), where the
+    block's first warp claims the segments and broadcasts them (claim_segment)."""
+    sg = rb.chain_scene(n, nsteps=5, h=2e-4)
+    sg.init()
+    q0, qd0 = rb.synthetic_inputs(sg, B, seed=98)
+    out = sg.rollout(q0, qd0, scheme=1)
+    for lo in range(0, B, chunk):  # `chunk` rollouts fit the resident blocks: plain launches
+        ref = sg.rollout(q0[lo:lo + chunk], qd0[lo:lo + chunk], scheme=1)
+        for key in ('q', 'qdot', 'iters', 'status'):
+            np.testing.assert_array_equal(out[key][lo:lo + chunk], ref[key])
+
+
 @pytest.mark.timeout(300)
 @pytest.mark.parametrize('scheme', [1, 2])
 def test_load_balanced_schedule_is_bitwise_identical(rb, scheme):
