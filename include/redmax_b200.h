@@ -276,9 +276,10 @@ int rmx_debug_schedule(int64_t B, int32_t nsteps, int64_t slots, int32_t seg_cap
 int rmx_fp64_probe(double* dfma_tflops, double* dmma_tflops);
 
 /* Page-lock / release a caller-owned host buffer (cudaHostRegister, portable + mapped).  rmx_rollout stores q(t), qdot(t)
- * straight into page-locked output buffers while the kernel runs (no device-to-host copy afterwards); pageable buffers take
- * the staged copy.  Registration costs about as much as one copy of the buffer, so it pays for buffers that are reused
- * (MPC loops), not for arrays allocated per call. */
+ * straight into page-locked output buffers while the kernel runs (no device-to-host copy afterwards); pageable buffers are
+ * served through page-locked staging owned by the library (written the same way, copied on by host threads as sub-batches
+ * finish).  Registration costs about as much as one copy of the buffer, so it pays for buffers that are reused (MPC loops),
+ * not for arrays allocated per call. */
 int rmx_host_register(void* p, size_t bytes);
 int rmx_host_unregister(void* p);
 
