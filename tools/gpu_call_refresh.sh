@@ -1,5 +1,7 @@
+# Refresh of the numbers a round ends with: smoke, the GPU suite, every bench line (with the CPU arm), the launch list.
+#   gpurun --timeout 2400 -- 'bash tools/gpu_call_refresh.sh'   ->  gpurun_out/refresh/*  (copied to profiles/r02_* by hand)
 set -x
-O=gpurun_out/r2x2; mkdir -p $O
+O=gpurun_out/refresh; mkdir -p $O
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "smoke rc=$?" >> $O/smoke.log
 timeout 1200 python -m pytest tests -q -m gpu -n 4 > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu.log; tail -3 $O/pytest_gpu.log
 timeout 400 python bench.py --steps 20 --warmup 5 > $O/bench_chain32.log 2>&1
