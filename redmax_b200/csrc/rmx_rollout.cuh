@@ -635,16 +635,23 @@ __global__ void RMX_FWD_BOUNDS rollout_fwd_kernel(RolloutArgs a) {
         if (CAN_SCHED && (seg_flags & 1)) {
             // second part of a cut rollout: wait until the block that runs the first part has published it (bounded spin: a
             // lost signal becomes a status bit, never a hang), then resume from the trajectory already in global memory
-            if (G > 1) {  // a grouped warp keeps meeting its partners while it waits (they check in once per evaluation pass)
-                unsigned spins = 0;
+            if (G > 1) {  // a grouped warp keeps meeting its partners while it waits (they check in once per evaluation pass);
+                          // a round lasts as long as the partners' passes, so the wait is bounded by time (~13 s), not by rounds
+                unsigned long long t0 = 0;
+                if (t == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
                 int ready = 0;
                 while (true) {
-                    if (t == 0) ready = atomicAdd(a.flags + b, 0);
+                    if (t == 0) {
+                        ready = atomicAdd(a.flags + b, 0) != 0;
+                        unsigned long long now;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                        if (!ready && now - t0 > 13000000000ull) ready = 2;  // gave up
+                    }
                     ready = __shfl_sync(0xffffffffu, ready, 0);
-                    if (ready || ++spins >= (1u << 22)) break;
+                    if (ready) break;
                     group_barrier(G, false);
                 }
-                if (!ready) status |= 16;
+                if (ready == 2) status |= 16;
             } else if (t == 0) {
                 unsigned spins = 0;
                 while (atomicAdd(a.flags + b, 0) == 0 && ++spins < (1u << 26)) __nanosleep(200);
